@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- Wildtrack-shape warped frames/s of the warp_views hot path on B200.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5                      # our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference --steps 3 --warmup 1               # reference arm: the CPU oracle on host cores
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W                        # view-sharded, one rank per GPU
+
+One "step" = one pass of the hot path over one batch: forward gather-warp (+ view concat + coord_map)
+and the deterministic CSR backward, on synthetic features of the Wildtrack shape
+(7 views x 512 ch x 270x480 -> 3586 x 120x360).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Wildtrack-shape warped frames/s (7 views->120x360), warp_views forward+backward"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--rig", default="wildtrack", choices=["wildtrack", "multiviewx"])
+    ap.add_argument("--batch", type=int, default=1, help="frames per step per GPU")
+    ap.add_argument("--channels", type=int, default=512)
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--layout", default="cl", choices=["cl", "nchw"],
+                    help="physical layout of features/output: cl = channel-contiguous (fast path), nchw = reference layout")
+    ap.add_argument("--mode", default="fwdbwd", choices=["fwdbwd", "fwd"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-channels", type=int, default=64,
+                    help="reference arm: channels per step (a bounded 1/8-frame sample by default)")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region through NVML (same counters as the nvidia-smi query line)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int, period: float = 0.02):
+        self.samples, self.reasons, self.period, self._stop = [], set(), period, threading.Event()
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.ok:
+            self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.thread.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU oracle (restated kornia path) on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(spec, channels, steps, warmup, mode, threads=None):
+    """Times the oracle (V x warp_perspective + cat + coord_map, autograd backward) on `channels` of the
+    512 channels of one frame; cost is linear in channels, so frames/s = (channels/512) / seconds."""
+    import torch
+    from mvdet_b200.geometry import synthetic_rig
+    from oracle import kornia_warp as K
+    if threads:
+        torch.set_num_threads(threads)
+    pm = synthetic_rig(spec)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, spec.num_cam, channels, *spec.feat_shape, generator=g)
+    go = torch.randn(1, spec.num_cam * channels + 2, *spec.grid_shape, generator=torch.Generator().manual_seed(1))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        if mode == "fwd":
+            with torch.no_grad():
+                K.warp_views_oracle(x, pm, spec.grid_shape)
+        else:
+            xr = x.requires_grad_(True)
+            out = K.warp_views_oracle(xr, pm, spec.grid_shape)
+            torch.autograd.grad(out, xr, go)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return (channels / 512.0) / sec, sec, torch.get_num_threads()
+
+
+def run_reference(args):
+    import torch
+    from mvdet_b200.geometry import RIGS
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the reference is a single-process CPU path: rank 0 alone runs it
+    spec = RIGS[args.rig]
+    value, sec, threads = cpu_reference_run(spec, args.ref_channels, args.steps, args.warmup, args.mode)
+    sample = (f"{args.ref_channels}/512 channels of one {spec.name} frame per step ({spec.num_cam} views, fp32, "
+              f"NCHW), oracle {'fwd+autograd bwd' if args.mode == 'fwdbwd' else 'fwd'}, scaled linearly to full frames")
+    line = {
+        "impl": "reference", "metric": METRIC if args.mode == "fwdbwd" else METRIC.replace("forward+backward", "forward"),
+        "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, spec, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "host": {"cpu_count": os.cpu_count(), "torch_threads": threads},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, spec, world):
+    Hs, Ws = spec.feat_shape
+    Hg, Wg = spec.grid_shape
+    return {
+        "workload": f"{spec.name}: B={args.batch} x {spec.num_cam} views x {args.channels}ch x {Hs}x{Ws} -> "
+                    f"{spec.num_cam * args.channels + 2}ch x {Hg}x{Wg}, {args.dtype}, {args.mode}",
+        "rig": spec.name, "batch_per_gpu": args.batch, "views_per_gpu": spec.num_cam, "channels": args.channels,
+        "layout": "channels_last (NHWC physical, logical [B,V,C,H,W])" if args.layout == "cl" else "NCHW contiguous",
+        "mode": args.mode,
+        "parallelism": f"view-sharded: each of {world} ranks warps its own {spec.num_cam} cameras (no data-path collective)",
+        "l2": "inputs (>= 1.2 GB per step) larger than the 126 MB L2; no flush needed",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mvdet_b200 import ops, plan as P
+    from mvdet_b200.geometry import RIGS, RigSpec, synthetic_rig
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    base = RIGS[args.rig]
+    # rank r owns cameras [r*V, (r+1)*V) of a (world*V)-camera rig generated by the same recipe
+    spec = RigSpec(base.name, base.num_cam * world, base.img_shape, base.worldgrid_shape, base.img_reduce,
+                   base.grid_reduce, base.channels, base.seed)
+    V, Cc, B = base.num_cam, args.channels, args.batch
+    pm_all = synthetic_rig(spec)
+    pm = pm_all[rank * V:(rank + 1) * V]
+    Hs, Ws = base.feat_shape
+    Hg, Wg = base.grid_shape
+    plan = P.get_plan(pm, (Hs, Ws), (Hg, Wg), dev)
+    dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    elem = 4 if args.dtype == "fp32" else 2
+    ctot = V * Cc + 2
+
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    if args.layout == "cl":
+        feats = torch.randn((B, V, Hs, Ws, Cc), device=dev, generator=gen).to(dtype).permute(0, 1, 4, 2, 3)
+        out = torch.empty((B, Hg, Wg, ctot), device=dev, dtype=dtype).permute(0, 3, 1, 2)
+        grad_out = torch.randn((B, Hg, Wg, ctot), device=dev, generator=gen).to(dtype).permute(0, 3, 1, 2)
+        grad_feats = torch.empty((B, V, Hs, Ws, Cc), device=dev, dtype=dtype).permute(0, 1, 4, 2, 3)
+    else:
+        feats = torch.randn((B, V, Cc, Hs, Ws), device=dev, generator=gen).to(dtype)
+        out = torch.empty((B, ctot, Hg, Wg), device=dev, dtype=dtype)
+        grad_out = torch.randn((B, ctot, Hg, Wg), device=dev, generator=gen).to(dtype)
+        grad_feats = torch.empty((B, V, Cc, Hs, Ws), device=dev, dtype=dtype)
+    do_bwd = args.mode == "fwdbwd"
+
+    def step():
+        ops.warp_views_fwd_into(plan, feats, out, 0, 0, V * Cc)
+        if do_bwd:
+            ops.warp_views_bwd_into(plan, grad_out, grad_feats, 0, 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events on the launching (current) stream ------------------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_begin.record()
+        for k in range(args.steps):
+            ev[k][0].record()
+            ops.warp_views_fwd_into(plan, feats, out, 0, 0, V * Cc)
+            ev[k][1].record()
+            if do_bwd:
+                ops.warp_views_bwd_into(plan, grad_out, grad_feats, 0, 0)
+            ev[k][2].record()
+        t_end.record()
+        barrier()
+    total_ms = t_begin.elapsed_time(t_end)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps if do_bwd else 0.0
+    if world > 1:
+        t = torch.tensor([total_ms, fwd_ms, bwd_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, fwd_ms, bwd_ms = t.tolist()
+    ms_per_step = total_ms / args.steps
+    frames_per_step = B * world
+    value = frames_per_step / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    fwd_bytes = B * plan.fwd_bytes(Cc, elem)
+    bwd_bytes = B * plan.bwd_bytes(Cc, elem)
+    roof_fwd = {"kernel": "fwd_cl_kernel" if args.layout == "cl" else "fwd_generic_kernel", "bound": "hbm",
+                "achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "algorithmic_bytes": fwd_bytes, "ms": fwd_ms, "traffic": None}
+    roof_fwd["frac"] = roof_fwd["achieved"] / peak
+    roofline = roof_fwd
+    extra = {}
+    if do_bwd:
+        roof_bwd = {"kernel": "bwd_cl_kernel" if args.layout == "cl" else "bwd_generic_kernel", "bound": "hbm",
+                    "achieved": bwd_bytes / (bwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "algorithmic_bytes": bwd_bytes, "ms": bwd_ms, "traffic": None}
+        roof_bwd["frac"] = roof_bwd["achieved"] / peak
+        roofline = roof_bwd if bwd_ms >= fwd_ms else roof_fwd
+        extra["roofline_fwd"], extra["roofline_bwd"] = roof_fwd, roof_bwd
+        extra["roofline_step"] = {"achieved": (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9, "peak": peak,
+                                  "frac": (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"}
+    roofline["peak_source"] = peak_src
+    _load_traffic(roofline, extra)
+
+    # ---- e2e: host buffers through the public op, copies inside the timed region ---------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, plan, feats, grad_out, dev, world, dist if world > 1 else None)
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ch = 64
+        v_all, sec_all, thr = cpu_reference_run(base, ch, 2, 1, args.mode)
+        v_one, sec_one, _ = cpu_reference_run(base, ch, 1, 1, args.mode, threads=1)
+        cpu_baseline = {"value": v_all, "unit": UNIT, "cores": thr, "kind": "port",
+                        "sample": f"{ch}/512 channels of one {base.name} frame, oracle (restated kornia warp x V + cat + "
+                                  f"coord_map{', autograd bwd' if do_bwd else ''}), fp32 NCHW, mean of 2 after 1 warm-up, "
+                                  f"scaled linearly to full frames",
+                        "single_thread_value": v_one, "cpu_count": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC if do_bwd else METRIC.replace("forward+backward", "forward"),
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.dtype == "fp32" else "bf16 (fp32 coordinates/weights/accumulate)", "data": "synthetic",
+            "config": workload_config(args, base, world),
+            "roofline": roofline, **extra,
+            "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": args.steps * (2 if do_bwd else 1),
+            "clocks": clocks.summary(),
+            "plan": {k: plan.stats[k] for k in ("unique_texels", "nnz", "valid_cells", "max_row", "device_bytes")},
+            "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _load_traffic(roofline, extra):
+    """DRAM traffic per launch from the committed ncu capture (profiles/traffic.json), if present."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return
+    try:
+        with open(path) as f:
+            traffic = json.load(f)
+        for r in [roofline] + [v for k, v in extra.items() if k.startswith("roofline_") and "kernel" in v]:
+            key = r["kernel"]
+            if key in traffic and traffic[key].get("algorithmic_bytes") == r["algorithmic_bytes"]:
+                r["traffic"] = traffic[key]["dram_bytes"]
+    except Exception:
+        pass
+
+
+def run_e2e(args, plan, feats_dev, grad_out_dev, dev, world, dist):
+    """Same step through the public op with HOST buffers: every step copies the features (and grad_out)
+    from pinned host memory, runs warp_views (+ backward), and reads the results back to the host."""
+    import torch
+    import mvdet_b200 as mv
+    from mvdet_b200 import ops
+    do_bwd = args.mode == "fwdbwd"
+    B = feats_dev.shape[0]
+    # pinned host mirrors with the same physical layout as the device tensors
+    def pinned_like(t):
+        if t.dim() == 5 and t.stride(2) == 1:
+            return torch.empty(t.permute(0, 1, 3, 4, 2).shape, dtype=t.dtype, pin_memory=True).permute(0, 1, 4, 2, 3)
+        if t.dim() == 4 and t.stride(1) == 1:
+            return torch.empty(t.permute(0, 2, 3, 1).shape, dtype=t.dtype, pin_memory=True).permute(0, 3, 1, 2)
+        return torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h_feats = pinned_like(feats_dev)
+    h_feats.copy_(feats_dev)
+    h_out = pinned_like(grad_out_dev)
+    h_go = pinned_like(grad_out_dev)
+    h_go.copy_(grad_out_dev)
+    h_gf = pinned_like(feats_dev) if do_bwd else None
+    d_feats = torch.empty_like(feats_dev)
+    d_go = torch.empty_like(grad_out_dev)
+    steps = max(2, min(args.steps, 5))
+
+    def one():
+        d_feats.copy_(h_feats, non_blocking=True)
+        x = d_feats.requires_grad_(do_bwd)
+        out = ops.warp_views_with_plan(x, plan)
+        h_out.copy_(out.detach(), non_blocking=True)
+        if do_bwd:
+            d_go.copy_(h_go, non_blocking=True)
+            (gx,) = torch.autograd.grad(out, x, d_go)
+            h_gf.copy_(gx, non_blocking=True)
+        d_feats.requires_grad_(False)
+
+    one()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    nbytes = lambda t: t.numel() * t.element_size()
+    h2d = nbytes(h_feats) + (nbytes(h_go) if do_bwd else 0)
+    d2h = nbytes(h_out) + (nbytes(h_gf) if do_bwd else 0)
+    return {"value": B * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "api": "mvdet_b200.warp_views_with_plan + torch.autograd.grad, pinned host buffers, copies in the timed region"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+/* mvwarp.h -- C ABI of libmvwarp.so, the B200 (sm_100a) perspective-warp library.
+ *
+ * This is the drop-in boundary for MVDet's perspective-transformation hot path.  In the
+ * reference that path is a Python call sequence, not an FFI:
+ *
+ *   proj_mat = self.proj_mats[cam].repeat([B,1,1]).float().to('cuda:0')       persp_trans_detector.py:68
+ *   world_feature = kornia.geometry.transform.warp_perspective(                persp_trans_detector.py:69
+ *                       img_feature, proj_mat, self.reducedgrid_shape)
+ *   world_features = torch.cat(world_features + [coord_map.repeat(B)], dim=1)  persp_trans_detector.py:77
+ *   (autograd: CatBackward + grid_sampler_2d_backward, driven from trainer.py:48)
+ *
+ * (paths relative to /root/reference/multiview_detector/models/ resp. /root/reference/multiview_detector/).
+ * The entry points below are what a ctypes binding for that sequence binds; INTEGRATION.md
+ * shows the reference-side stub.  Conventions:
+ *   - every function returns 0 on success, a negative MVWARP_E* code on failure, and never
+ *     throws or aborts across the boundary; mvwarp_last_error() returns a thread-local message;
+ *   - the caller (PyTorch) owns every tensor; the library owns only the opaque plan;
+ *   - all device work is enqueued on the cudaStream_t passed as `stream` (void*), on the
+ *     plan's device (the library sets the device itself: backward is called from autograd's
+ *     worker thread, whose current device is not ours to assume);
+ *   - strides are in ELEMENTS of the tensor's dtype, logical index order given per argument;
+ *   - functions are re-entrant; a plan is immutable after creation and may be shared by threads.
+ */
+#ifndef MVWARP_H_
+#define MVWARP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVWARP_VERSION 1
+
+/* error codes */
+#define MVWARP_OK            0
+#define MVWARP_EINVAL       -1   /* bad argument (null pointer, non-positive size, bad dtype ...) */
+#define MVWARP_ECUDA        -2   /* a CUDA runtime call failed; see mvwarp_last_error() */
+#define MVWARP_ENOMEM       -3   /* host allocation failed */
+#define MVWARP_EUNSUPPORTED -4   /* valid request the library has no kernel for */
+
+/* element types of feature / output tensors (coordinates, weights and accumulation are always fp32) */
+#define MVWARP_F32  0
+#define MVWARP_BF16 1
+
+typedef struct mvwarp_plan mvwarp_plan_t;
+
+typedef struct mvwarp_stats {
+  int32_t  V, Hs, Ws, Hg, Wg;
+  int32_t  inline_coords;     /* 1: kernels recompute coordinates from the matrices; 0: read the grid table */
+  uint64_t unique_texels;     /* U: source texels with >= 1 in-bounds tap, summed over views */
+  uint64_t nnz;               /* in-bounds taps = entries of the inverse (texel -> cells) CSR map */
+  uint64_t valid_cells;       /* grid cells with >= 1 in-bounds tap, summed over views */
+  uint32_t max_row;           /* longest CSR row (taps landing on one texel) */
+  uint64_t device_bytes;      /* HBM held by the plan */
+} mvwarp_stats_t;
+
+/* Library identity / diagnostics. */
+int         mvwarp_version(void);
+const char* mvwarp_last_error(void);
+
+/* ---- host-only helpers (no GPU needed; used by the plan builder and by CPU tests) -------------
+ * mvwarp_host_grid: the normalised sampling grid [V,Hg,Wg,2] (x,y in [-1,1] source coordinates) that
+ * kornia's transform_points produces from src_norm_trans_dst_norm (fp32 [V,3,3], row-major, the
+ * matrix kornia calls `src_norm_trans_dst_norm`: inverse of the normalised homography).  Bit-identical
+ * to the CPU oracle's torch op sequence (create_meshgrid -> bmm -> convert_points_from_homogeneous).
+ * Replaces: kornia create_meshgrid + transform_points inside warp_perspective (persp_trans_detector.py:69). */
+int mvwarp_host_grid(const float* src_norm_trans_dst_norm, int V, int Hg, int Wg, float* grid_out);
+/* mvwarp_host_csr: build the inverse (texel -> cells) CSR map of a normalised grid [V,Hg,Wg,2] on the host
+ * and report its statistics (only unique_texels, nnz, valid_cells, max_row and the shape fields are set).
+ * If row_ptr_out / cells_out / weights_out are non-null they receive the map itself: row_ptr_out
+ * [V*(Hs*Ws+1)] offsets relative to each view's first entry, cells_out / weights_out [>= nnz] (pass
+ * capacity in `capacity`; MVWARP_EINVAL if too small).  Entry order in a row: ascending cell, then tap. */
+int mvwarp_host_csr(const float* grid_host, int V, int Hs, int Ws, int Hg, int Wg, mvwarp_stats_t* stats_out,
+                    uint32_t* row_ptr_out, uint32_t* cells_out, float* weights_out, uint64_t capacity);
+
+/* ---- plan: everything that depends only on the camera rig ---------------------------------------
+ * Built once per (proj_mats, shapes, device); holds the per-view matrices (or grid table) and the
+ * inverse CSR map used by the deterministic backward.
+ * mvwarp_plan_create:            kernels compute coordinates in-kernel from the matrices.
+ * mvwarp_plan_create_from_grid:  kernels read an explicit normalised grid [V,Hg,Wg,2] (host fp32),
+ *                                e.g. one produced by other torch code.  Same semantics as
+ *                                F.grid_sample(src, grid, 'bilinear', 'zeros', align_corners=True).
+ * Replaces: the per-forward matrix staging + kornia normalise/invert/meshgrid/transform chain
+ * (persp_trans_detector.py:68-69), which the reference redoes on every call. */
+int mvwarp_plan_create(const float* src_norm_trans_dst_norm, int V, int Hs, int Ws, int Hg, int Wg,
+                       int device, mvwarp_plan_t** plan_out);
+int mvwarp_plan_create_from_grid(const float* grid_host, int V, int Hs, int Ws, int Hg, int Wg,
+                                 int device, mvwarp_plan_t** plan_out);
+int mvwarp_plan_destroy(mvwarp_plan_t* plan);
+int mvwarp_plan_stats(const mvwarp_plan_t* plan, mvwarp_stats_t* stats_out);
+/* Debug/test: run the device coordinate kernel and copy the normalised grid [V,Hg,Wg,2] to host. */
+int mvwarp_plan_device_grid(const mvwarp_plan_t* plan, float* grid_host_out, void* stream);
+
+/* ---- forward: warp + view concat + coord_map in one pass ----------------------------------------
+ * For views v in [view0, view0+nviews), batch b, channel c, grid cell (y,x):
+ *   out[b, out_chan0 + (v-view0)*C + c, y, x] = bilinear(feats[b, v-view0, c], src_xy(v, y, x)), zeros outside
+ * and, if coord_chan >= 0,
+ *   out[b, coord_chan, y, x] = x/(Wg-1)*2-1 ;  out[b, coord_chan+1, y, x] = y/(Hg-1)*2-1
+ * feats:  logical [B, nviews, C, Hs, Ws], strides feat_strides[5] = (B, V, C, H, W);  `feats` points at view0.
+ * out:    logical [B, Ctot, Hg, Wg],      strides out_strides[4]  = (B, C, H, W).
+ * Fast path: channel-contiguous (stride C == 1, "channels_last") feats and out; any other strides
+ * take the generic kernel.  Replaces persp_trans_detector.py:68-69,75,77 (warp_perspective x V, cat, coord_map). */
+int mvwarp_warp_views_fwd(const mvwarp_plan_t* plan, int view0, int nviews,
+                          const void* feats, const int64_t feat_strides[5],
+                          void* out, const int64_t out_strides[4], int out_chan0, int coord_chan,
+                          int B, int C, int dtype, void* stream);
+
+/* ---- backward: deterministic gather through the inverse CSR map ---------------------------------
+ *   grad_feats[b, v-view0, c, ys, xs] = sum over CSR row (v, ys, xs) of  w * grad_out[b, out_chan0+(v-view0)*C+c, cell]
+ * in a fixed order (ascending cell, then tap nw,ne,sw,se): bitwise run-to-run reproducible, no atomics.
+ * Every texel of grad_feats is written (zeros where no cell samples it): no memset needed.
+ * The coord_map channels and the matrices receive no gradient (they never require grad in the reference).
+ * Replaces CatBackward + grid_sampler_2d_backward (atomicAdd scatter) reached from trainer.py:48. */
+int mvwarp_warp_views_bwd(const mvwarp_plan_t* plan, int view0, int nviews,
+                          const void* grad_out, const int64_t out_strides[4], int out_chan0,
+                          void* grad_feats, const int64_t feat_strides[5],
+                          int B, int C, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVWARP_H_ */

@@ -1,0 +1,88 @@
+"""ctypes binding of libmvwarp.so (include/mvwarp.h).  There is no fallback: if the CUDA library
+is missing or fails to load, every op raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from .build import LIB_PATH
+
+OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
+F32, BF16 = 0, 1
+
+
+class Stats(C.Structure):
+    _fields_ = [("V", C.c_int32), ("Hs", C.c_int32), ("Ws", C.c_int32), ("Hg", C.c_int32), ("Wg", C.c_int32),
+                ("inline_coords", C.c_int32), ("unique_texels", C.c_uint64), ("nnz", C.c_uint64),
+                ("valid_cells", C.c_uint64), ("max_row", C.c_uint32), ("device_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {name: int(getattr(self, name)) for name, _ in self._fields_}
+
+
+_P = C.c_void_p
+_I64P = C.POINTER(C.c_int64)
+_F32P = C.POINTER(C.c_float)
+_U32P = C.POINTER(C.c_uint32)
+
+# name -> (restype, argtypes); must list every symbol include/mvwarp.h declares (tests check this)
+SIGNATURES = {
+    "mvwarp_version": (C.c_int, []),
+    "mvwarp_last_error": (C.c_char_p, []),
+    "mvwarp_host_grid": (C.c_int, [_F32P, C.c_int, C.c_int, C.c_int, _F32P]),
+    "mvwarp_host_csr": (C.c_int, [_F32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Stats),
+                                  _U32P, _U32P, _F32P, C.c_uint64]),
+    "mvwarp_plan_create": (C.c_int, [_F32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "mvwarp_plan_create_from_grid": (C.c_int, [_F32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(_P)]),
+    "mvwarp_plan_destroy": (C.c_int, [_P]),
+    "mvwarp_plan_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "mvwarp_plan_device_grid": (C.c_int, [_P, _F32P, _P]),
+    "mvwarp_warp_views_fwd": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, _P, _I64P, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, _P]),
+    "mvwarp_warp_views_bwd": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, C.c_int, _P, _I64P,
+                                        C.c_int, C.c_int, C.c_int, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class MvwarpError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises MvwarpError when the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise MvwarpError(
+                f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m mvdet_b200.build` "
+                "(or __graft_entry__.build()). There is no CPU or PyTorch fallback for warp_views.")
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise MvwarpError(f"failed to load {LIB_PATH}: {e}") from e
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.mvwarp_version() != 1:
+            raise MvwarpError(f"libmvwarp.so ABI version {lib.mvwarp_version()} != 1: rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != OK:
+        msg = load().mvwarp_last_error()
+        raise MvwarpError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def i64x(values):
+    return (C.c_int64 * len(values))(*[int(v) for v in values])

@@ -1,0 +1,468 @@
+// mvwarp_kernels.cu -- sm_100a kernels of the perspective-warp path.
+//
+//  fwd_cl_kernel      forward gather-warp on channel-contiguous ("channels_last") tensors: one warp per grid
+//                     cell, lanes across channels with 128-bit loads of the four bilinear taps, the view
+//                     concat and the coord_map channels fused into the store.
+//                     Replaces kornia.warp_perspective x V + torch.cat + coord_map
+//                     (/root/reference/multiview_detector/models/persp_trans_detector.py:68-69,75,77).
+//  bwd_cl_kernel      deterministic backward: one warp per SOURCE texel gathers w * grad_out over the texel's row
+//                     of the inverse CSR map in a fixed order; zero rows are written as zeros (no memset, no atomics).
+//                     Replaces CatBackward + grid_sampler_2d_backward.
+//  *_generic_kernel   same arithmetic for arbitrary strides (e.g. the NCHW tensors the reference call site hands over).
+//
+// All arithmetic that decides bits (coordinates, weights, the 4-term blend) follows mvwarp_coords.h.
+#include <cuda_bf16.h>
+
+#include "mvwarp_coords.h"
+#include "mvwarp_internal.h"
+
+namespace mvw {
+
+struct KParams {
+  const float* T;        // [V,9] or unused
+  const float2* grid;    // [V,Hg,Wg] normalised (x,y) or nullptr (inline coordinates)
+  const float* coord_x;  // [Wg]
+  const float* coord_y;  // [Hg]
+  const uint32_t* row_ptr;
+  const CsrEntry* entries;
+  const uint64_t* view_base;
+  int Hs, Ws, Hg, Wg;
+  int view0, nviews, B, C;
+  const void* src;  // forward: feats      backward: grad_out
+  void* dst;        // forward: out        backward: grad_feats
+  int64_t fB, fV, fC, fH, fW;
+  int64_t oB, oC, oH, oW;
+  int out_chan0, coord_chan;
+  int tiles_x, tiles_y, cchunk;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// 16-byte vectors of T <-> fp32 lanes
+// ---------------------------------------------------------------------------------------------------
+template <typename T> struct VecTraits;
+template <> struct VecTraits<float> {
+  static constexpr int EPV = 4;
+  __device__ static __forceinline__ void unpack(const uint4& v, float (&f)[4]) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&f)[4]) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+};
+template <> struct VecTraits<__nv_bfloat16> {
+  static constexpr int EPV = 8;
+  __device__ static __forceinline__ void unpack(const uint4& v, float (&f)[8]) {
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&f)[8]) {
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const unsigned*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// read-only 16-byte gather, kept in L1 (neighbouring cells re-use the same texels)
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// 16 bytes from an address that is only 8- or 4-byte aligned (odd cells of the 3586-channel concat row)
+__device__ __forceinline__ uint4 ldg16_any(const void* p, unsigned align_mask) {
+  if (align_mask == 0) return __ldg(reinterpret_cast<const uint4*>(p));
+  if ((align_mask & 7u) == 0) {
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(p)), b = __ldg(reinterpret_cast<const uint2*>(p) + 1);
+    return make_uint4(a.x, a.y, b.x, b.y);
+  }
+  const unsigned* q = reinterpret_cast<const unsigned*>(p);
+  return make_uint4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+}
+
+// streaming 16-byte store (the output is not re-read by this kernel) to an address of any 4-byte alignment
+__device__ __forceinline__ void stcs16_any(void* p, const uint4& v, unsigned align_mask) {
+  if (align_mask == 0) {
+    __stcs(reinterpret_cast<uint4*>(p), v);
+  } else if ((align_mask & 7u) == 0) {
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(v.x, v.y));
+    __stcs(reinterpret_cast<uint2*>(p) + 1, make_uint2(v.z, v.w));
+  } else {
+    unsigned* q = reinterpret_cast<unsigned*>(p);
+    __stcs(q, v.x); __stcs(q + 1, v.y); __stcs(q + 2, v.z); __stcs(q + 3, v.w);
+  }
+}
+
+template <bool kInline>
+__device__ __forceinline__ Taps cell_taps(const KParams& p, const float (&Tm)[9], int v, int x, int y) {
+  float sx, sy;
+  if (kInline) {
+    norm_src_coord(Tm, x, y, p.Hg, p.Wg, sx, sy);
+  } else {
+    const float2 g = __ldg(p.grid + ((size_t)v * p.Hg + y) * p.Wg + x);
+    sx = g.x; sy = g.y;
+  }
+  return make_taps(sx, sy, p.Hs, p.Ws);
+}
+
+// The oracle's blend: ((a*nw + b*ne) + c*sw) + d*se with the additions fused (ATen CPU kernel as compiled).
+__device__ __forceinline__ float blend4(float a, float b, float c, float d, const float (&w)[4]) {
+  return __fmaf_rn(d, w[3], __fmaf_rn(c, w[2], __fmaf_rn(b, w[1], __fmul_rn(a, w[0]))));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward, channels-last
+// ---------------------------------------------------------------------------------------------------
+constexpr int FWD_TILE_W = 8, FWD_TILE_H = 8, FWD_WARPS = 8, FWD_UNROLL = 2;
+
+template <typename T, bool kInline>
+__global__ void __launch_bounds__(FWD_WARPS * 32) fwd_cl_kernel(const KParams p) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+  const int vl = blockIdx.y, b = blockIdx.z;
+  const int v = p.view0 + vl;
+  float Tm[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Tm[i] = kInline ? __ldg(p.T + 9 * v + i) : 0.f;
+
+  const T* __restrict__ src = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.fB + (int64_t)vl * p.fV;
+  T* __restrict__ dst = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
+  const int nvec = p.C / EPV;
+
+  for (int i = warp; i < FWD_TILE_W * FWD_TILE_H; i += FWD_WARPS) {
+    const int x = tx * FWD_TILE_W + (i % FWD_TILE_W), y = ty * FWD_TILE_H + (i / FWD_TILE_W);
+    if (x >= p.Wg || y >= p.Hg) continue;
+    const Taps tp = cell_taps<kInline>(p, Tm, v, x, y);
+    T* o = dst + (int64_t)y * p.oH + (int64_t)x * p.oW;
+    const unsigned oalign = (unsigned)(reinterpret_cast<uintptr_t>(o) & 15u);
+
+    if (p.coord_chan >= 0 && vl == 0 && lane == 0) {
+      T* cm = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (int64_t)y * p.oH + (int64_t)x * p.oW + (int64_t)p.coord_chan * p.oC;
+      cm[0] = from_float<T>(__ldg(p.coord_x + x));
+      cm[p.oC] = from_float<T>(__ldg(p.coord_y + y));
+    }
+
+    if (tp.mask == 0) {
+      // every tap outside: 0*w chain (NaN weights propagate exactly as in the oracle)
+      const float z = blend4(0.f, 0.f, 0.f, 0.f, tp.w);
+      float zf[EPV];
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) zf[e] = z;
+      const uint4 zv = VecTraits<T>::pack(zf);
+      for (int c = lane; c < nvec; c += 32) stcs16_any(o + c * EPV, zv, oalign);
+      continue;
+    }
+    // tap base pointers (a masked-off tap keeps a valid dummy address and is never dereferenced)
+    const T* tap[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xx = tp.x0 + (k & 1), yy = tp.y0 + (k >> 1);
+      tap[k] = (tp.mask >> k & 1) ? src + (int64_t)yy * p.fH + (int64_t)xx * p.fW : src;
+    }
+    for (int c0 = lane; c0 < nvec; c0 += 32 * FWD_UNROLL) {
+      uint4 val[FWD_UNROLL][4];
+#pragma unroll
+      for (int u = 0; u < FWD_UNROLL; ++u) {
+        const int c = c0 + 32 * u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          val[u][k] = (c < nvec && (tp.mask >> k & 1)) ? ldg16(tap[k] + c * EPV) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < FWD_UNROLL; ++u) {
+        const int c = c0 + 32 * u;
+        if (c < nvec) {
+          float f[4][EPV], r[EPV];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) VecTraits<T>::unpack(val[u][k], f[k]);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) r[e] = blend4(f[0][e], f[1][e], f[2][e], f[3][e], tp.w);
+          stcs16_any(o + c * EPV, VecTraits<T>::pack(r), oalign);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward, arbitrary strides: thread per grid cell (x fastest), loop over a chunk of channels
+// ---------------------------------------------------------------------------------------------------
+template <typename T, bool kInline>
+__global__ void __launch_bounds__(256) fwd_generic_kernel(const KParams p) {
+  const int ncell = p.Hg * p.Wg;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  const int vl = blockIdx.y, v = p.view0 + vl;
+  const int nchunk = (p.C + p.cchunk - 1) / p.cchunk;
+  const int b = blockIdx.z / nchunk, chunk = blockIdx.z % nchunk;
+  if (cell >= ncell) return;
+  const int y = cell / p.Wg, x = cell - y * p.Wg;
+  float Tm[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Tm[i] = kInline ? __ldg(p.T + 9 * v + i) : 0.f;
+  const Taps tp = cell_taps<kInline>(p, Tm, v, x, y);
+  const T* __restrict__ src = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.fB + (int64_t)vl * p.fV;
+  T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (int64_t)y * p.oH + (int64_t)x * p.oW;
+  if (p.coord_chan >= 0 && vl == 0 && chunk == 0) {
+    o[(int64_t)p.coord_chan * p.oC] = from_float<T>(__ldg(p.coord_x + x));
+    o[(int64_t)(p.coord_chan + 1) * p.oC] = from_float<T>(__ldg(p.coord_y + y));
+  }
+  int64_t off[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    off[k] = (tp.mask >> k & 1) ? (int64_t)(tp.y0 + (k >> 1)) * p.fH + (int64_t)(tp.x0 + (k & 1)) * p.fW : 0;
+  const int c_end = min(p.C, (chunk + 1) * p.cchunk);
+  for (int c = chunk * p.cchunk; c < c_end; ++c) {
+    const T* s = src + (int64_t)c * p.fC;
+    float f[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = (tp.mask >> k & 1) ? to_float(__ldg(s + off[k])) : 0.f;
+    o[(int64_t)(p.out_chan0 + (int64_t)vl * p.C + c) * p.oC] = from_float<T>(blend4(f[0], f[1], f[2], f[3], tp.w));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward, channels-last: warp per source texel, fixed-order gather over its CSR row
+// ---------------------------------------------------------------------------------------------------
+constexpr int BWD_WARPS = 8, BWD_TEX_PER_CTA = 64, BWD_ACC_FLOATS = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(BWD_WARPS * 32) bwd_cl_kernel(const KParams p) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  constexpr int NACC = BWD_ACC_FLOATS / EPV;  // 16-byte vectors per lane per pass
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vl = blockIdx.y, b = blockIdx.z, v = p.view0 + vl;
+  const int ntex = p.Hs * p.Ws;
+  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (ntex + 1);
+  const CsrEntry* __restrict__ en = p.entries + __ldg(p.view_base + v);
+  const T* __restrict__ go = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
+  T* __restrict__ gf = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV;
+  const int nvec = p.C / EPV;
+
+  for (int i = warp; i < BWD_TEX_PER_CTA; i += BWD_WARPS) {
+    const int tex = blockIdx.x * BWD_TEX_PER_CTA + i;
+    if (tex >= ntex) break;
+    const uint32_t r0 = __ldg(rp + tex), r1 = __ldg(rp + tex + 1);
+    const int ys = tex / p.Ws, xs = tex - ys * p.Ws;
+    T* o = gf + (int64_t)ys * p.fH + (int64_t)xs * p.fW;
+    for (int cbase = 0; cbase < nvec; cbase += 32 * NACC) {
+      float acc[NACC][EPV];
+#pragma unroll
+      for (int j = 0; j < NACC; ++j)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[j][e] = 0.f;
+      uint32_t k = r0;
+      // two entries per trip: all loads first, then the FMAs in row order
+      for (; k + 1 < r1; k += 2) {
+        const CsrEntry e0 = en[k], e1 = en[k + 1];
+        const int y0 = e0.cell / p.Wg, x0 = e0.cell - y0 * p.Wg, y1 = e1.cell / p.Wg, x1 = e1.cell - y1 * p.Wg;
+        const T* g0 = go + (int64_t)y0 * p.oH + (int64_t)x0 * p.oW;
+        const T* g1 = go + (int64_t)y1 * p.oH + (int64_t)x1 * p.oW;
+        const unsigned a0 = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15u), a1 = (unsigned)(reinterpret_cast<uintptr_t>(g1) & 15u);
+        uint4 v0[NACC], v1[NACC];
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+          const int c = cbase + 32 * j + lane;
+          v0[j] = c < nvec ? ldg16_any(g0 + c * EPV, a0) : make_uint4(0, 0, 0, 0);
+          v1[j] = c < nvec ? ldg16_any(g1 + c * EPV, a1) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+          float f0[EPV], f1[EPV];
+          VecTraits<T>::unpack(v0[j], f0);
+          VecTraits<T>::unpack(v1[j], f1);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) acc[j][e] = __fmaf_rn(e1.w, f1[e], __fmaf_rn(e0.w, f0[e], acc[j][e]));
+        }
+      }
+      if (k < r1) {
+        const CsrEntry e0 = en[k];
+        const int y0 = e0.cell / p.Wg, x0 = e0.cell - y0 * p.Wg;
+        const T* g0 = go + (int64_t)y0 * p.oH + (int64_t)x0 * p.oW;
+        const unsigned a0 = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15u);
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+          const int c = cbase + 32 * j + lane;
+          if (c < nvec) {
+            float f0[EPV];
+            VecTraits<T>::unpack(ldg16_any(g0 + c * EPV, a0), f0);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) acc[j][e] = __fmaf_rn(e0.w, f0[e], acc[j][e]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NACC; ++j) {
+        const int c = cbase + 32 * j + lane;
+        if (c < nvec) __stcs(reinterpret_cast<uint4*>(o + c * EPV), VecTraits<T>::pack(acc[j]));
+      }
+    }
+  }
+}
+
+// backward, arbitrary strides: thread per source texel (x fastest), loop over a chunk of channels
+template <typename T>
+__global__ void __launch_bounds__(256) bwd_generic_kernel(const KParams p) {
+  const int ntex = p.Hs * p.Ws;
+  const int tex = blockIdx.x * blockDim.x + threadIdx.x;
+  const int vl = blockIdx.y, v = p.view0 + vl;
+  const int nchunk = (p.C + p.cchunk - 1) / p.cchunk;
+  const int b = blockIdx.z / nchunk, chunk = blockIdx.z % nchunk;
+  if (tex >= ntex) return;
+  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (ntex + 1);
+  const CsrEntry* __restrict__ en = p.entries + __ldg(p.view_base + v);
+  const uint32_t r0 = __ldg(rp + tex), r1 = __ldg(rp + tex + 1);
+  const int ys = tex / p.Ws, xs = tex - ys * p.Ws;
+  const T* __restrict__ go = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.oB;
+  T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV + (int64_t)ys * p.fH + (int64_t)xs * p.fW;
+  const int c_end = min(p.C, (chunk + 1) * p.cchunk);
+  for (int c = chunk * p.cchunk; c < c_end; ++c) {
+    const T* g = go + (int64_t)(p.out_chan0 + (int64_t)vl * p.C + c) * p.oC;
+    float acc = 0.f;
+    for (uint32_t k = r0; k < r1; ++k) {
+      const CsrEntry e = en[k];
+      const int y = e.cell / p.Wg, x = e.cell - y * p.Wg;
+      acc = __fmaf_rn(e.w, to_float(__ldg(g + (int64_t)y * p.oH + (int64_t)x * p.oW)), acc);
+    }
+    o[(int64_t)c * p.fC] = from_float<T>(acc);
+  }
+}
+
+// device-side normalised grid (test hook: proves host == device coordinate bits)
+template <bool kInline>
+__global__ void device_grid_kernel(const KParams p, int V, float2* __restrict__ out) {
+  const int ncell = p.Hg * p.Wg;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (cell >= ncell || v >= V) return;
+  const int y = cell / p.Wg, x = cell - y * p.Wg;
+  float sx, sy;
+  if (kInline) {
+    float Tm[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Tm[i] = __ldg(p.T + 9 * v + i);
+    norm_src_coord(Tm, x, y, p.Hg, p.Wg, sx, sy);
+  } else {
+    const float2 g = __ldg(p.grid + (size_t)v * ncell + cell);
+    sx = g.x; sy = g.y;
+  }
+  out[(size_t)v * ncell + cell] = make_float2(sx, sy);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------
+static KParams make_params(const LaunchArgs& a) {
+  const mvwarp_plan* pl = a.plan;
+  KParams p{};
+  p.T = pl->d_T; p.grid = reinterpret_cast<const float2*>(pl->d_grid);
+  p.coord_x = pl->d_coord_x; p.coord_y = pl->d_coord_y;
+  p.row_ptr = pl->d_row_ptr; p.entries = pl->d_entries; p.view_base = pl->d_view_base;
+  p.Hs = pl->Hs; p.Ws = pl->Ws; p.Hg = pl->Hg; p.Wg = pl->Wg;
+  p.view0 = a.view0; p.nviews = a.nviews; p.B = a.B; p.C = a.C;
+  p.src = a.feats_or_grad_out; p.dst = a.out_or_grad_feats;
+  p.fB = a.fs[0]; p.fV = a.fs[1]; p.fC = a.fs[2]; p.fH = a.fs[3]; p.fW = a.fs[4];
+  p.oB = a.os[0]; p.oC = a.os[1]; p.oH = a.os[2]; p.oW = a.os[3];
+  p.out_chan0 = a.out_chan0; p.coord_chan = a.coord_chan;
+  p.tiles_x = (pl->Wg + FWD_TILE_W - 1) / FWD_TILE_W;
+  p.tiles_y = (pl->Hg + FWD_TILE_H - 1) / FWD_TILE_H;
+  p.cchunk = 32;
+  return p;
+}
+
+// channel-contiguous feature tensor whose every texel row starts 16-byte aligned
+static bool feats_vector_ok(const void* ptr, const int64_t fs[5], int C, int epv) {
+  if (fs[2] != 1 || C % epv != 0) return false;
+  if (reinterpret_cast<uintptr_t>(ptr) & 15u) return false;
+  for (int i : {0, 1, 3, 4})
+    if (fs[i] % epv != 0) return false;
+  return true;
+}
+
+static int check_grid_dims(const LaunchArgs& a, int64_t z) {
+  if (a.nviews > 65535 || z > 65535) {
+    set_error("launch: nviews or B*chunks exceeds the CUDA grid limit (65535)");
+    return MVWARP_EUNSUPPORTED;
+  }
+  return MVWARP_OK;
+}
+
+template <typename T>
+static int launch_fwd_t(const LaunchArgs& a) {
+  KParams p = make_params(a);
+  const bool inl = a.plan->inline_coords != 0;
+  constexpr int EPV = VecTraits<T>::EPV;
+  const bool fast = feats_vector_ok(a.feats_or_grad_out, a.fs, a.C, EPV) && a.os[1] == 1 &&
+                    (reinterpret_cast<uintptr_t>(a.out_or_grad_feats) % sizeof(float) == 0) &&
+                    (sizeof(T) == 4 || (a.os[0] % 2 == 0 && a.os[2] % 2 == 0 && a.os[3] % 2 == 0 && a.out_chan0 % 2 == 0));
+  if (fast) {
+    int rc = check_grid_dims(a, a.B);
+    if (rc) return rc;
+    dim3 grid(p.tiles_x * p.tiles_y, a.nviews, a.B), block(FWD_WARPS * 32);
+    if (inl) fwd_cl_kernel<T, true><<<grid, block, 0, a.stream>>>(p);
+    else fwd_cl_kernel<T, false><<<grid, block, 0, a.stream>>>(p);
+  } else {
+    const int nchunk = (a.C + p.cchunk - 1) / p.cchunk;
+    int rc = check_grid_dims(a, (int64_t)a.B * nchunk);
+    if (rc) return rc;
+    dim3 grid((p.Hg * p.Wg + 255) / 256, a.nviews, a.B * nchunk), block(256);
+    if (inl) fwd_generic_kernel<T, true><<<grid, block, 0, a.stream>>>(p);
+    else fwd_generic_kernel<T, false><<<grid, block, 0, a.stream>>>(p);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "warp_views_fwd launch");
+}
+
+template <typename T>
+static int launch_bwd_t(const LaunchArgs& a) {
+  KParams p = make_params(a);
+  constexpr int EPV = VecTraits<T>::EPV;
+  const bool fast = feats_vector_ok(a.out_or_grad_feats, a.fs, a.C, EPV) && a.os[1] == 1 &&
+                    (reinterpret_cast<uintptr_t>(a.feats_or_grad_out) % sizeof(float) == 0) &&
+                    (sizeof(T) == 4 || (a.os[0] % 2 == 0 && a.os[2] % 2 == 0 && a.os[3] % 2 == 0 && a.out_chan0 % 2 == 0));
+  const int ntex = p.Hs * p.Ws;
+  if (fast) {
+    int rc = check_grid_dims(a, a.B);
+    if (rc) return rc;
+    dim3 grid((ntex + BWD_TEX_PER_CTA - 1) / BWD_TEX_PER_CTA, a.nviews, a.B), block(BWD_WARPS * 32);
+    bwd_cl_kernel<T><<<grid, block, 0, a.stream>>>(p);
+  } else {
+    const int nchunk = (a.C + p.cchunk - 1) / p.cchunk;
+    int rc = check_grid_dims(a, (int64_t)a.B * nchunk);
+    if (rc) return rc;
+    dim3 grid((ntex + 255) / 256, a.nviews, a.B * nchunk), block(256);
+    bwd_generic_kernel<T><<<grid, block, 0, a.stream>>>(p);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "warp_views_bwd launch");
+}
+
+int launch_fwd(const LaunchArgs& a) {
+  return a.dtype == MVWARP_F32 ? launch_fwd_t<float>(a) : launch_fwd_t<__nv_bfloat16>(a);
+}
+
+int launch_bwd(const LaunchArgs& a) {
+  return a.dtype == MVWARP_F32 ? launch_bwd_t<float>(a) : launch_bwd_t<__nv_bfloat16>(a);
+}
+
+int launch_device_grid(const mvwarp_plan* pl, float* d_grid_out, cudaStream_t stream) {
+  KParams p{};
+  p.T = pl->d_T; p.grid = reinterpret_cast<const float2*>(pl->d_grid);
+  p.Hs = pl->Hs; p.Ws = pl->Ws; p.Hg = pl->Hg; p.Wg = pl->Wg;
+  dim3 grid((pl->Hg * pl->Wg + 255) / 256, pl->V), block(256);
+  if (pl->inline_coords) device_grid_kernel<true><<<grid, block, 0, stream>>>(p, pl->V, reinterpret_cast<float2*>(d_grid_out));
+  else device_grid_kernel<false><<<grid, block, 0, stream>>>(p, pl->V, reinterpret_cast<float2*>(d_grid_out));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "device_grid launch");
+}
+
+}  // namespace mvw

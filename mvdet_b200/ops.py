@@ -1,0 +1,242 @@
+"""``warp_views``: the drop-in PyTorch op for MVDet's perspective-transformation path.
+
+Replaces, at /root/reference/multiview_detector/models/persp_trans_detector.py:
+
+    :68  proj_mat = self.proj_mats[cam].repeat([B, 1, 1]).float().to('cuda:0')
+    :69  world_feature = kornia.geometry.transform.warp_perspective(img_feature, proj_mat, self.reducedgrid_shape)
+    :75  world_features.append(world_feature)
+    :77  world_features = torch.cat(world_features + [self.coord_map.repeat([B, 1, 1, 1])], dim=1)
+
+with ``warp_views(img_feats[B,V,C,H,W], proj_mats[V,3,3], grid_shape) -> [B, V*C+2, Hg, Wg]``.
+
+CUDA only.  There is no CPU, PyTorch or Triton fallback: a CPU tensor or a missing libmvwarp.so
+raises.  The CPU oracle lives in ``oracle/`` and is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .plan import WarpPlan, get_plan, get_plan_from_grid
+
+_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+# plans are looked up by integer id inside the custom op (op schemas carry only tensors / ints)
+_plans_by_id = {}
+
+
+def _register(plan: WarpPlan) -> int:
+    pid = id(plan)
+    _plans_by_id[pid] = plan
+    return pid
+
+
+def _check_feats(img_feats: torch.Tensor):
+    if not isinstance(img_feats, torch.Tensor):
+        raise TypeError(f"Input src type is not a torch.Tensor. Got {type(img_feats)}")
+    if not img_feats.is_cuda:
+        raise _lib.MvwarpError("warp_views is CUDA-only (no CPU fallback): got a tensor on " + str(img_feats.device))
+    if img_feats.dtype not in _DTYPES:
+        raise TypeError(f"warp_views supports float32 and bfloat16 features. Got {img_feats.dtype}")
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _out_strides_cl(B: int, ctot: int, Hg: int, Wg: int):
+    return (Hg * Wg * ctot, 1, Wg * ctot, ctot)
+
+
+def _launch_fwd(plan: WarpPlan, feats: torch.Tensor, out: torch.Tensor, view0: int, out_chan0: int, coord_chan: int):
+    """feats [B,nv,C,Hs,Ws] (any strides) -> out [B,Ctot,Hg,Wg] (any strides)."""
+    B, nv, Cc = feats.shape[:3]
+    rc = _lib.load().mvwarp_warp_views_fwd(
+        plan.handle, view0, nv, C.c_void_p(feats.data_ptr()), _lib.i64x(feats.stride()),
+        C.c_void_p(out.data_ptr()), _lib.i64x(out.stride()), out_chan0, coord_chan,
+        B, Cc, _DTYPES[feats.dtype], _stream_ptr(feats.device))
+    _lib.check(rc, "mvwarp_warp_views_fwd")
+
+
+def _launch_bwd(plan: WarpPlan, grad_out: torch.Tensor, grad_feats: torch.Tensor, view0: int, out_chan0: int):
+    B, nv, Cc = grad_feats.shape[:3]
+    rc = _lib.load().mvwarp_warp_views_bwd(
+        plan.handle, view0, nv, C.c_void_p(grad_out.data_ptr()), _lib.i64x(grad_out.stride()), out_chan0,
+        C.c_void_p(grad_feats.data_ptr()), _lib.i64x(grad_feats.stride()),
+        B, Cc, _DTYPES[grad_feats.dtype], _stream_ptr(grad_feats.device))
+    _lib.check(rc, "mvwarp_warp_views_bwd")
+
+
+def _is_channels_last_5d(t: torch.Tensor) -> bool:
+    return t.dim() == 5 and t.stride(2) == 1 and t.shape[2] > 1
+
+
+def _empty_feats_like(shape, like: torch.Tensor) -> torch.Tensor:
+    """grad buffer [B,V,C,H,W] with the same physical layout family as ``like``."""
+    B, V, Cc, H, W = shape
+    if _is_channels_last_5d(like):
+        return torch.empty((B, V, H, W, Cc), dtype=like.dtype, device=like.device).permute(0, 1, 4, 2, 3)
+    return torch.empty(shape, dtype=like.dtype, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------------------
+# torch.library custom op (forward + registered backward)
+# ------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("mvwarp::warp_views_plan", mutates_args=(), device_types="cuda")
+def _warp_views_plan(img_feats: torch.Tensor, plan_id: int, with_coord: bool, channels_last_out: bool) -> torch.Tensor:
+    plan = _plans_by_id[plan_id]
+    B, V, Cc, Hs, Ws = img_feats.shape
+    Hg, Wg = plan.grid_hw
+    ctot = V * Cc + (2 if with_coord else 0)
+    if channels_last_out:
+        out = torch.empty((B, Hg, Wg, ctot), dtype=img_feats.dtype, device=img_feats.device).permute(0, 3, 1, 2)
+    else:
+        out = torch.empty((B, ctot, Hg, Wg), dtype=img_feats.dtype, device=img_feats.device)
+    _launch_fwd(plan, img_feats, out, 0, 0, V * Cc if with_coord else -1)
+    return out
+
+
+@_warp_views_plan.register_fake
+def _(img_feats, plan_id, with_coord, channels_last_out):
+    plan = _plans_by_id[plan_id]
+    B, V, Cc = img_feats.shape[:3]
+    Hg, Wg = plan.grid_hw
+    ctot = V * Cc + (2 if with_coord else 0)
+    out = img_feats.new_empty((B, ctot, Hg, Wg))
+    return out.contiguous(memory_format=torch.channels_last) if channels_last_out else out
+
+
+@torch.library.custom_op("mvwarp::warp_views_plan_bwd", mutates_args=(), device_types="cuda")
+def _warp_views_plan_bwd(grad_out: torch.Tensor, plan_id: int, C_: int, feats_channels_last: bool) -> torch.Tensor:
+    plan = _plans_by_id[plan_id]
+    B = grad_out.shape[0]
+    Hs, Ws = plan.src_hw
+    V = plan.V
+    if feats_channels_last:
+        grad_feats = torch.empty((B, V, Hs, Ws, C_), dtype=grad_out.dtype, device=grad_out.device).permute(0, 1, 4, 2, 3)
+    else:
+        grad_feats = torch.empty((B, V, C_, Hs, Ws), dtype=grad_out.dtype, device=grad_out.device)
+    _launch_bwd(plan, grad_out, grad_feats, 0, 0)
+    return grad_feats
+
+
+@_warp_views_plan_bwd.register_fake
+def _(grad_out, plan_id, C_, feats_channels_last):
+    plan = _plans_by_id[plan_id]
+    Hs, Ws = plan.src_hw
+    return grad_out.new_empty((grad_out.shape[0], plan.V, C_, Hs, Ws))
+
+
+def _setup_ctx(ctx, inputs, output):
+    img_feats, plan_id, with_coord, channels_last_out = inputs
+    ctx.plan_id = plan_id
+    ctx.plan = _plans_by_id[plan_id]          # keep the plan alive while the graph is
+    ctx.C = img_feats.shape[2]
+    ctx.feats_cl = _is_channels_last_5d(img_feats)
+
+
+def _backward(ctx, grad_out):
+    grad_feats = _warp_views_plan_bwd(grad_out, ctx.plan_id, ctx.C, ctx.feats_cl)
+    return grad_feats, None, None, None
+
+
+_warp_views_plan.register_autograd(_backward, setup_context=_setup_ctx)
+
+
+# ------------------------------------------------------------------------------------------------------
+# public API
+# ------------------------------------------------------------------------------------------------------
+def warp_views(img_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Sequence[int],
+               with_coord_map: bool = True, channels_last_out: Optional[bool] = None) -> torch.Tensor:
+    """Warp every camera's feature map onto the ground-plane grid, concatenate the views along the
+    channel axis (view-major: channel ``v*C + c``) and append the two coord_map channels.
+
+    img_feats  [B,V,C,H,W] CUDA fp32/bf16, any strides (channel-contiguous = fast path).
+    proj_mats  [V,3,3] source-pixel -> grid-pixel homographies (the reference's ``proj_mats``, float64 on
+               CPU is fine: they are rounded to fp32 first, as persp_trans_detector.py:68 does).
+    grid_shape [Hg, Wg] (the reference's ``reducedgrid_shape``).
+    Returns    [B, V*C+2, Hg, Wg] in ``img_feats.dtype``; differentiable w.r.t. ``img_feats`` only.
+    The physical layout of the result follows the input (channels-last in -> channels-last out) unless
+    ``channels_last_out`` says otherwise.
+    """
+    _check_feats(img_feats)
+    if not isinstance(proj_mats, torch.Tensor):
+        raise TypeError(f"Input M type is not a torch.Tensor. Got {type(proj_mats)}")
+    if img_feats.dim() != 5:
+        raise ValueError(f"Input img_feats must be a BxVxCxHxW tensor. Got {tuple(img_feats.shape)}")
+    if not (proj_mats.dim() == 3 and tuple(proj_mats.shape[-2:]) == (3, 3)):
+        raise ValueError(f"Input M must be a Vx3x3 tensor. Got {tuple(proj_mats.shape)}")
+    if proj_mats.shape[0] != img_feats.shape[1]:
+        raise ValueError(f"proj_mats has {proj_mats.shape[0]} views, img_feats has {img_feats.shape[1]}")
+    if len(grid_shape) != 2:
+        raise ValueError(f"grid_shape must be [Hg, Wg]. Got {grid_shape}")
+    plan = get_plan(proj_mats, img_feats.shape[-2:], grid_shape, img_feats.device)
+    if channels_last_out is None:
+        channels_last_out = _is_channels_last_5d(img_feats)
+    return _warp_views_plan(img_feats, _register(plan), bool(with_coord_map), bool(channels_last_out))
+
+
+def warp_views_with_plan(img_feats: torch.Tensor, plan: WarpPlan, with_coord_map: bool = True,
+                         channels_last_out: Optional[bool] = None) -> torch.Tensor:
+    """Same as :func:`warp_views` with a prebuilt plan (skips the cache lookup)."""
+    _check_feats(img_feats)
+    if img_feats.dim() != 5 or img_feats.shape[1] != plan.V or tuple(img_feats.shape[-2:]) != plan.src_hw:
+        raise ValueError(f"img_feats {tuple(img_feats.shape)} does not match the plan (V={plan.V}, src={plan.src_hw})")
+    if channels_last_out is None:
+        channels_last_out = _is_channels_last_5d(img_feats)
+    return _warp_views_plan(img_feats, _register(plan), bool(with_coord_map), bool(channels_last_out))
+
+
+def warp_perspective(src: torch.Tensor, M: torch.Tensor, dsize: Sequence[int], mode: str = "bilinear",
+                     padding_mode: str = "zeros", align_corners: bool = True) -> torch.Tensor:
+    """kornia-signature seam: ``kornia.geometry.transform.warp_perspective(src[B,C,H,W], M[B,3,3], dsize)``
+    as called at persp_trans_detector.py:69 (one camera per call, the concat stays in torch).
+    Same argument checks and error types as kornia 0.6.11.  Every batch element must carry the same
+    homography (the reference builds M with ``.repeat([B,1,1])``)."""
+    if not isinstance(src, torch.Tensor):
+        raise TypeError(f"Input src type is not a torch.Tensor. Got {type(src)}")
+    if not isinstance(M, torch.Tensor):
+        raise TypeError(f"Input M type is not a torch.Tensor. Got {type(M)}")
+    if not len(src.shape) == 4:
+        raise ValueError(f"Input src must be a BxCxHxW tensor. Got {src.shape}")
+    if not (len(M.shape) == 3 and M.shape[-2:] == (3, 3)):
+        raise ValueError(f"Input M must be a Bx3x3 tensor. Got {M.shape}")
+    if mode != "bilinear" or padding_mode != "zeros" or align_corners is not True:
+        raise NotImplementedError("mvwarp.warp_perspective implements the reference's call only: "
+                                  "mode='bilinear', padding_mode='zeros', align_corners=True")
+    if M.shape[0] not in (1, src.shape[0]):
+        raise ValueError(f"Batch of M ({M.shape[0]}) must match batch of src ({src.shape[0]})")
+    Mc = M.detach().to("cpu")
+    if Mc.shape[0] > 1 and not bool((Mc == Mc[:1]).all()):
+        raise NotImplementedError("mvwarp.warp_perspective needs one homography per call (a camera rig is "
+                                  "batch-invariant); use one call per distinct M")
+    _check_feats(src)
+    plan = get_plan(Mc[:1], src.shape[-2:], dsize, src.device)
+    feats5 = src.unsqueeze(1)
+    cl = src.dim() == 4 and src.stride(1) == 1 and src.shape[1] > 1
+    return _warp_views_plan(feats5, _register(plan), False, cl)
+
+
+def grid_sample_views(img_feats: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
+    """Table mode: sample ``img_feats`` [B,V,C,H,W] with an explicit normalised grid [V,Hg,Wg,2]
+    (F.grid_sample bilinear/zeros/align_corners=True semantics), views concatenated, no coord channels."""
+    _check_feats(img_feats)
+    plan = get_plan_from_grid(grid, img_feats.shape[-2:], img_feats.device)
+    return _warp_views_plan(img_feats, _register(plan), False, _is_channels_last_5d(img_feats))
+
+
+# ---- raw (non-autograd) launches, used by the view-sharded path and the benchmark ----------------------
+def warp_views_fwd_into(plan: WarpPlan, feats: torch.Tensor, out: torch.Tensor, view0: int = 0,
+                        out_chan0: int = 0, coord_chan: int = -1) -> None:
+    """Warp views [view0, view0+feats.shape[1]) of ``plan`` into a caller-provided output tensor."""
+    _check_feats(feats)
+    _launch_fwd(plan, feats, out, view0, out_chan0, coord_chan)
+
+
+def warp_views_bwd_into(plan: WarpPlan, grad_out: torch.Tensor, grad_feats: torch.Tensor, view0: int = 0,
+                        out_chan0: int = 0) -> None:
+    _check_feats(grad_out)
+    _launch_bwd(plan, grad_out, grad_feats, view0, out_chan0)

@@ -1,0 +1,256 @@
+"""Parity of the CUDA path (through the C ABI / the torch op) with the CPU oracle.  Needs a B200.
+
+Tolerances: fp32  max|a-o|/max|o| <= 1e-5 and ||a-o||/||o|| <= 1e-5 on the output and
+on the gradient; bf16  |a-o| <= 2^-8 |o| + 1e-6 max|o| against the fp32 oracle run on the bf16-rounded
+inputs.  The forward is additionally expected to be BIT-IDENTICAL to the oracle in fp32 (same
+coordinate chain, same FMA order); the fraction is asserted where stated.
+"""
+import pytest
+import torch
+
+import mvdet_b200 as mv
+from mvdet_b200 import ops, plan as P
+from mvdet_b200.geometry import MULTIVIEWX, RIG32, WILDTRACK, RigSpec, synthetic_rig
+from oracle import kornia_warp as K
+from tests.util import bit_equal_fraction, rel_errors, small_rig, to_channels_last_5d
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+
+def _feats(B, V, C, hw, seed=0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, V, C, *hw, generator=g).to(dtype)
+
+
+def _layout(x, layout):
+    return to_channels_last_5d(x) if layout == "cl" else x.contiguous()
+
+
+@pytest.mark.parametrize("spec", [WILDTRACK, MULTIVIEWX, RIG32], ids=lambda s: s.name)
+def test_device_coordinates_bit_identical_to_oracle(spec):
+    pm = synthetic_rig(spec)
+    plan = P.get_plan(pm, spec.feat_shape, spec.grid_shape, DEV)
+    dev_grid = plan.device_grid()
+    og = K.sampling_grids(pm, spec.feat_shape, spec.grid_shape)
+    assert torch.equal(dev_grid.view(torch.int32), og.view(torch.int32))
+    assert plan.stats["inline_coords"] == 1
+
+
+@pytest.mark.parametrize("layout", ["cl", "nchw"])
+@pytest.mark.parametrize("spec", [WILDTRACK, MULTIVIEWX], ids=lambda s: s.name)
+def test_forward_parity_full_rig(spec, layout):
+    """Full-size rig geometry (every cell / texel of the real shapes), C reduced so the oracle takes seconds."""
+    pm = synthetic_rig(spec)
+    B, C = 1, 16
+    x = _feats(B, spec.num_cam, C, spec.feat_shape)
+    ref = K.warp_views_oracle(x, pm, spec.grid_shape)
+    out = mv.warp_views(_layout(x, layout).to(DEV), pm, spec.grid_shape)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert out.stride(1) == (1 if layout == "cl" else spec.grid_shape[0] * spec.grid_shape[1])
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= TOL and el2 <= TOL, (emax, el2)
+    assert bit_equal_fraction(out, ref) == 1.0          # "bit-for-bit" (BASELINE.json configs[1])
+
+
+@pytest.mark.parametrize("layout", ["cl", "nchw"])
+@pytest.mark.parametrize("spec", [WILDTRACK, MULTIVIEWX], ids=lambda s: s.name)
+def test_backward_parity_full_rig(spec, layout):
+    pm = synthetic_rig(spec)
+    B, C = 1, 8
+    x = _feats(B, spec.num_cam, C, spec.feat_shape)
+    xo = x.clone().requires_grad_(True)
+    ref = K.warp_views_oracle(xo, pm, spec.grid_shape)
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (gref,) = torch.autograd.grad(ref, xo, go)
+
+    xd = _layout(x, layout).to(DEV).requires_grad_(True)
+    out = mv.warp_views(xd, pm, spec.grid_shape)
+    god = go.to(DEV)
+    if layout == "cl":
+        god = god.contiguous(memory_format=torch.channels_last)
+    (gx,) = torch.autograd.grad(out, xd, god)
+    assert gx.shape == x.shape
+    emax, el2 = rel_errors(gx, gref)
+    assert emax <= TOL and el2 <= TOL, (emax, el2)
+    # determinism: a second backward is bitwise identical (fixed-order CSR gather, no atomics)
+    out2 = mv.warp_views(xd, pm, spec.grid_shape)
+    (gx2,) = torch.autograd.grad(out2, xd, god)
+    assert torch.equal(gx, gx2)
+
+
+def test_full_channel_width_matches_oracle_on_one_view():
+    """C = 512 (the real width) on one Wildtrack camera, forward and backward."""
+    spec = WILDTRACK
+    pm = synthetic_rig(spec)[2:3]
+    x = _feats(1, 1, 512, spec.feat_shape)
+    xo = x.clone().requires_grad_(True)
+    ref = K.warp_views_oracle(xo, pm, spec.grid_shape)
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (gref,) = torch.autograd.grad(ref, xo, go)
+    xd = to_channels_last_5d(x).to(DEV).requires_grad_(True)
+    out = mv.warp_views(xd, pm, spec.grid_shape)
+    assert bit_equal_fraction(out, ref) == 1.0
+    (gx,) = torch.autograd.grad(out, xd, go.to(DEV).contiguous(memory_format=torch.channels_last))
+    emax, el2 = rel_errors(gx, gref)
+    assert emax <= TOL and el2 <= TOL, (emax, el2)
+
+
+@pytest.mark.parametrize("layout", ["cl", "nchw"])
+def test_bf16_within_documented_bound(layout):
+    pm, src_hw, grid_hw = small_rig(num_cam=3)
+    B, V, C = 2, 3, 64
+    x = _feats(B, V, C, src_hw).bfloat16()
+    ref = K.warp_views_oracle(x.float(), pm, grid_hw)          # fp32 oracle on the bf16-rounded inputs
+    out = mv.warp_views(_layout(x, layout).to(DEV), pm, grid_hw)
+    assert out.dtype == torch.bfloat16
+    bound = 2.0 ** -8 * ref.abs() + 1e-6 * ref.abs().max()
+    assert bool(((out.float().cpu() - ref).abs() <= bound).all())
+    # gradient: same bound against the fp32 oracle gradient of bf16-rounded grad_out
+    xo = x.float().requires_grad_(True)
+    ref2 = K.warp_views_oracle(xo, pm, grid_hw)
+    go = torch.randn(ref2.shape, generator=torch.Generator().manual_seed(1)).bfloat16()
+    (gref,) = torch.autograd.grad(ref2, xo, go.float())
+    xd = _layout(x, layout).to(DEV).requires_grad_(True)
+    outd = mv.warp_views(xd, pm, grid_hw)
+    god = go.to(DEV)
+    if layout == "cl":
+        god = god.contiguous(memory_format=torch.channels_last)
+    (gx,) = torch.autograd.grad(outd, xd, god)
+    bound = 2.0 ** -8 * gref.abs() + 1e-6 * gref.abs().max()
+    assert bool(((gx.float().cpu() - gref).abs() <= bound).all())
+
+
+@pytest.mark.parametrize("B,V,C", [(1, 1, 1), (2, 3, 3), (3, 2, 20), (1, 4, 132), (2, 1, 260)])
+@pytest.mark.parametrize("layout", ["cl", "nchw"])
+def test_ragged_shapes_forward_backward(B, V, C, layout):
+    """Channel counts off the vector width (generic kernel), batch > 1, single view."""
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=11 + V)
+    x = _feats(B, V, C, src_hw)
+    xo = x.clone().requires_grad_(True)
+    ref = K.warp_views_oracle(xo, pm, grid_hw)
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (gref,) = torch.autograd.grad(ref, xo, go)
+    xd = _layout(x, layout).to(DEV).requires_grad_(True)
+    out = mv.warp_views(xd, pm, grid_hw)
+    assert bit_equal_fraction(out, ref) == 1.0
+    (gx,) = torch.autograd.grad(out, xd, go.to(DEV))
+    emax, el2 = rel_errors(gx, gref)
+    assert emax <= TOL and el2 <= TOL, (emax, el2)
+
+
+def test_non_contiguous_view_of_larger_buffer():
+    pm, src_hw, grid_hw = small_rig(num_cam=2)
+    big = _feats(2, 2, 24, (src_hw[0] + 3, src_hw[1] + 5)).to(DEV)
+    x = big[:, :, 4:20, 1:1 + src_hw[0], 2:2 + src_hw[1]]
+    assert not x.is_contiguous()
+    ref = K.warp_views_oracle(x.cpu().contiguous(), pm, grid_hw)
+    out = mv.warp_views(x, pm, grid_hw)
+    assert bit_equal_fraction(out, ref) == 1.0
+
+
+def test_identity_and_translation_properties():
+    x = _feats(2, 1, 8, (17, 23))
+    eye = torch.eye(3, dtype=torch.float64)[None]
+    out = mv.warp_views(x.to(DEV), eye, (17, 23), with_coord_map=False)
+    assert float((out.cpu() - x[:, 0]).abs().max()) < 2e-5
+    shift = torch.tensor([[[1.0, 0, 3], [0, 1, 2], [0, 0, 1]]], dtype=torch.float64)
+    out = mv.warp_views(x.to(DEV), shift, (17, 23), with_coord_map=False).cpu()
+    expect = torch.zeros_like(x[:, 0])
+    expect[..., 2:, 3:] = x[:, 0, :, :-2, :-3]
+    assert float((out - expect).abs().max()) < 5e-5
+
+
+def test_adjoint_identity_at_full_size():
+    """<warp(x), g> == <x, warp^T(g)> at the real Wildtrack size (C=512, 7 views): oracle-free check of bwd."""
+    spec = WILDTRACK
+    pm = synthetic_rig(spec)
+    x = torch.randn(1, spec.num_cam, spec.feat_shape[0], spec.feat_shape[1], 512, device=DEV).permute(0, 1, 4, 2, 3)
+    x.requires_grad_(True)
+    out = mv.warp_views(x, pm, spec.grid_shape)
+    g = torch.randn(1, spec.grid_shape[0], spec.grid_shape[1], out.shape[1], device=DEV).permute(0, 3, 1, 2)
+    (gx,) = torch.autograd.grad(out, x, g)
+    lhs = float((out[:, :-2].double() * g[:, :-2].double()).sum())
+    rhs = float((x.detach().double() * gx.double()).sum())
+    assert abs(lhs - rhs) <= 1e-6 * (out[:, :-2].double().norm() * g.double().norm()).item()
+    # coord channels exact
+    cm = mv.create_coord_map(spec.grid_shape)
+    assert torch.equal(out[:, -2:].cpu(), cm)
+
+
+def test_linearity_at_full_size():
+    spec = MULTIVIEWX
+    pm = synthetic_rig(spec)
+    shape = (1, spec.num_cam, spec.feat_shape[0], spec.feat_shape[1], 128)
+    a = torch.randn(shape, device=DEV).permute(0, 1, 4, 2, 3)
+    b = torch.randn(shape, device=DEV).permute(0, 1, 4, 2, 3)
+    fa = mv.warp_views(a, pm, spec.grid_shape, with_coord_map=False)
+    fb = mv.warp_views(b, pm, spec.grid_shape, with_coord_map=False)
+    fab = mv.warp_views(2 * a - 3 * b, pm, spec.grid_shape, with_coord_map=False)
+    assert float((fab - (2 * fa - 3 * fb)).abs().max()) < 1e-4
+
+
+def test_kornia_signature_seam_matches_oracle():
+    """ops.warp_perspective == oracle warp_perspective for the exact call of persp_trans_detector.py:68-69."""
+    spec = WILDTRACK
+    pm = synthetic_rig(spec)
+    B, C = 2, 12
+    for cam in (0, 3):
+        src = _feats(B, 1, C, spec.feat_shape, seed=cam)[:, 0]
+        proj_mat = pm[cam].repeat([B, 1, 1]).float()
+        ref = K.warp_perspective(src, proj_mat, list(spec.grid_shape))
+        out = ops.warp_perspective(src.to(DEV), proj_mat.to(DEV), list(spec.grid_shape))
+        assert out.shape == ref.shape
+        assert bit_equal_fraction(out, ref) == 1.0
+
+
+def test_table_mode_matches_grid_sample():
+    """Explicit-grid plans reproduce F.grid_sample for an arbitrary grid (incl. out-of-range and NaN cells)."""
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    V, C, Hs, Ws, Hg, Wg = 2, 8, 20, 30, 9, 13
+    grid = torch.rand(V, Hg, Wg, 2) * 2.6 - 1.3
+    grid[0, 0, 0] = float("nan")
+    grid[1, 2, 3, 0] = float("inf")
+    x = _feats(1, V, C, (Hs, Ws))
+    ref = torch.cat([F.grid_sample(x[:, v], grid[v:v + 1], mode="bilinear", padding_mode="zeros", align_corners=True)
+                     for v in range(V)], dim=1)
+    out = ops.grid_sample_views(to_channels_last_5d(x).to(DEV), grid).cpu()
+    same = (out == ref) | (out.isnan() & ref.isnan())
+    assert bool(same.all())
+
+
+def test_errors_and_no_cpu_fallback():
+    pm, src_hw, grid_hw = small_rig()
+    x = _feats(1, 3, 4, src_hw)
+    with pytest.raises(mv.MvwarpError):
+        mv.warp_views(x, pm, grid_hw)                       # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        mv.warp_views(x.to(DEV)[0], pm, grid_hw)            # not 5-D
+    with pytest.raises(ValueError):
+        mv.warp_views(x.to(DEV), pm[:2], grid_hw)           # view count mismatch
+    with pytest.raises(TypeError):
+        mv.warp_views(x.to(DEV).half(), pm, grid_hw)
+    with pytest.raises(TypeError):
+        ops.warp_perspective(x[0].numpy(), pm[:1], grid_hw)
+    with pytest.raises(ValueError):
+        ops.warp_perspective(x.to(DEV)[0], pm[0], grid_hw)
+
+
+def test_rig32_slice_forward_backward():
+    """The 32-camera full-resolution rig (480x1440 grid, CSR rows up to 1360 taps), 4 of its views, small C."""
+    spec = RIG32
+    pm = synthetic_rig(spec)[[0, 9, 17, 30]]
+    C = 4
+    x = _feats(1, 4, C, spec.feat_shape)
+    xo = x.clone().requires_grad_(True)
+    ref = K.warp_views_oracle(xo, pm, spec.grid_shape)
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (gref,) = torch.autograd.grad(ref, xo, go)
+    xd = to_channels_last_5d(x).to(DEV).requires_grad_(True)
+    out = mv.warp_views(xd, pm, spec.grid_shape)
+    assert bit_equal_fraction(out, ref) == 1.0
+    (gx,) = torch.autograd.grad(out, xd, go.to(DEV).contiguous(memory_format=torch.channels_last))
+    emax, el2 = rel_errors(gx, gref)
+    assert emax <= TOL and el2 <= TOL, (emax, el2)

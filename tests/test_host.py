@@ -1,0 +1,134 @@
+"""Host-side logic of the product (CPU): the C-ABI library loads and exports what include/mvwarp.h
+declares, the host coordinate chain is bit-identical to the oracle's torch op sequence, and the
+inverse CSR map is the exact adjoint of the oracle's forward."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from mvdet_b200 import _lib, plan as P
+from mvdet_b200.geometry import MULTIVIEWX, RIG32, WILDTRACK, create_coord_map, synthetic_rig
+from oracle import kornia_warp as K
+from tests.util import small_rig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mvwarp.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(mvwarp_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 10
+    lib = ctypes.CDLL(os.path.join(ROOT, "mvdet_b200", "libmvwarp.so"))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in mvwarp.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes binding and header disagree"
+    assert _lib.load().mvwarp_version() == 1
+
+
+def test_stats_struct_layout_matches_header():
+    # int32 x6, then uint64 x3, uint32 (+pad), uint64: 24 + 24 + 8 + 8
+    assert ctypes.sizeof(_lib.Stats) == 64
+
+
+def test_bad_arguments_return_error_codes_not_crashes():
+    lib = _lib.load()
+    assert lib.mvwarp_host_grid(None, 1, 4, 4, None) == _lib.EINVAL
+    assert b"host_grid" in lib.mvwarp_last_error()
+    st = _lib.Stats()
+    assert lib.mvwarp_host_csr(None, 1, 4, 4, 4, 4, ctypes.byref(st), None, None, None, 0) == _lib.EINVAL
+    handle = ctypes.c_void_p()
+    assert lib.mvwarp_plan_create(None, 1, 4, 4, 4, 4, 0, ctypes.byref(handle)) == _lib.EINVAL
+    assert lib.mvwarp_plan_destroy(None) == _lib.OK
+    with pytest.raises(_lib.MvwarpError):
+        _lib.check(_lib.EINVAL, "demo")
+
+
+def test_matrix_chain_matches_oracle_bits():
+    for spec in (WILDTRACK, MULTIVIEWX):
+        pm = synthetic_rig(spec)
+        T = P.src_norm_trans_dst_norm(pm, spec.feat_shape, spec.grid_shape)
+        for v in range(spec.num_cam):
+            ref = K._torch_inverse_cast(K.normalize_homography(pm[v][None].float(), spec.feat_shape, spec.grid_shape))[0]
+            assert torch.equal(T[v], ref)
+
+
+@pytest.mark.parametrize("spec", [WILDTRACK, MULTIVIEWX, RIG32], ids=lambda s: s.name)
+def test_host_grid_bit_identical_to_oracle(spec):
+    pm = synthetic_rig(spec)
+    T = P.src_norm_trans_dst_norm(pm, spec.feat_shape, spec.grid_shape)
+    g = P.host_grid(T, spec.grid_shape)
+    og = K.sampling_grids(pm, spec.feat_shape, spec.grid_shape)
+    assert torch.equal(g.view(torch.int32), og.view(torch.int32))
+
+
+# U / nnz / max_row measured independently during the survey (SURVEY.md 7 hard part 4, 8d)
+KNOWN = {"wildtrack": (237509, 980278, 95), "multiviewx": (174222, 688362, 84), "rig32": (1702864, 67136331, 1360)}
+
+
+@pytest.mark.parametrize("spec", [WILDTRACK, MULTIVIEWX, RIG32], ids=lambda s: s.name)
+def test_csr_statistics_match_survey(spec):
+    pm = synthetic_rig(spec)
+    g = P.host_grid(P.src_norm_trans_dst_norm(pm, spec.feat_shape, spec.grid_shape), spec.grid_shape)
+    st = P.host_csr(g, spec.feat_shape)
+    assert (st["unique_texels"], st["nnz"], st["max_row"]) == KNOWN[spec.name]
+
+
+def _csr_backward(row_ptr, cells, weights, grad_out_v, ntex):
+    """grad_in[c, texel] = sum_k w_k * grad_out[c, cell_k], rows in CSR order (dense torch emulation)."""
+    C = grad_out_v.shape[0]
+    lens = (row_ptr[1:] - row_ptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(ntex), lens)
+    contrib = grad_out_v.reshape(C, -1)[:, cells.long()] * weights[None]
+    out = torch.zeros(C, ntex, dtype=grad_out_v.dtype)
+    out.index_add_(1, rows, contrib)
+    return out
+
+
+def test_csr_is_adjoint_of_oracle_forward():
+    pm, src_hw, grid_hw = small_rig()
+    V, C = pm.shape[0], 5
+    T = P.src_norm_trans_dst_norm(pm, src_hw, grid_hw)
+    g = P.host_grid(T, grid_hw)
+    st, row_ptr, cells, weights = P.host_csr(g, src_hw, with_map=True)
+    assert int(row_ptr[:, -1].sum()) == st["nnz"]
+    torch.manual_seed(0)
+    x = torch.randn(1, V, C, *src_hw, requires_grad=True)
+    out = K.warp_views_oracle(x, pm, grid_hw)
+    go = torch.randn_like(out)
+    (gx,) = torch.autograd.grad(out, x, go)
+    ntex = src_hw[0] * src_hw[1]
+    base = 0
+    for v in range(V):
+        n = int(row_ptr[v, -1])
+        mine = _csr_backward(row_ptr[v], cells[base:base + n], weights[base:base + n], go[0, v * C:(v + 1) * C], ntex)
+        base += n
+        ref = gx[0, v].reshape(C, ntex)
+        assert float((mine - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    # row entries are sorted by cell (fixed summation order = determinism)
+    r = row_ptr[0].long()
+    c0 = cells[: int(r[-1])].long()
+    for t in torch.nonzero(r[1:] - r[:-1] > 1)[:200, 0]:
+        seg = c0[r[t]:r[t + 1]]
+        assert bool((seg[1:] >= seg[:-1]).all())
+
+
+def test_csr_handles_degenerate_grids():
+    # all out of range, NaN and inf coordinates: no taps, no crash
+    g = torch.full((1, 4, 5, 2), 7.0)
+    g[0, 0, 0] = float("nan")
+    g[0, 0, 1] = float("inf")
+    g[0, 0, 2] = -float("inf")
+    st = P.host_csr(g, (6, 6))
+    assert st["nnz"] == 0 and st["unique_texels"] == 0 and st["valid_cells"] == 0
+    # exact corner hit: the four taps of the last texel, three of them outside
+    g = torch.ones((1, 1, 1, 2))
+    st, row_ptr, cells, weights = P.host_csr(g, (6, 6), with_map=True)
+    assert st["nnz"] == 1 and float(weights[0]) == 1.0 and int(row_ptr[0, -1]) == 1
+
+
+def test_coord_map_matches_reference_formula():
+    cm = create_coord_map((120, 360))
+    assert torch.equal(cm, K.create_coord_map([120, 360, 1]))
