@@ -1,0 +1,130 @@
+"""View sharding of the perspective-warp path across the GPUs of one box.
+
+Each camera's warp reads only its own feature map and writes a disjoint channel slice
+``[v*C, (v+1)*C)`` of the concat (/root/reference/multiview_detector/models/persp_trans_detector.py:62-77),
+so cameras partition across ranks with NO collective on the warp itself: a rank keeps its channel
+slice.  The one real exchange on this path is downstream, when ``map_classifier[0]``
+(persp_trans_detector.py:51,81) consumes the concat: a convolution is linear in its input channels,
+so every rank convolves its own slice with the matching slice of the weight and the partial sums are
+combined with one NCCL sum-reduce over NVLink; the bias and the coord_map term are added by one rank
+and the ReLU runs after the reduce.
+
+One process per GPU; ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the plumbing.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from .geometry import create_coord_map
+
+
+def view_partition(num_views: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced blocks ``(first_view, count)`` per rank; the first ``V % R`` ranks take one extra.
+    Ranks beyond the number of views get an empty block (7 Wildtrack cameras on 8 GPUs leave one idle)."""
+    if num_views <= 0 or world_size <= 0:
+        raise ValueError("num_views and world_size must be positive")
+    base, extra = divmod(num_views, world_size)
+    out, start = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        out.append((start, n))
+        start += n
+    return out
+
+
+@dataclass(frozen=True)
+class ViewShard:
+    """What one rank owns of a V-camera rig."""
+    rank: int
+    world_size: int
+    num_views: int
+    first_view: int
+    count: int
+
+    @property
+    def owns_coord_map(self) -> bool:
+        """The rank that carries the two coord_map channels (and conv1's bias): the last rank that has views,
+        because the coord channels sit right after its slice in the reference's concat order."""
+        return self.count > 0 and self.first_view + self.count == self.num_views
+
+    def channel_slice(self, C: int) -> slice:
+        """This rank's slice of the reference's V*C+2 concat channels (coord channels included for their owner)."""
+        stop = (self.first_view + self.count) * C + (2 if self.owns_coord_map else 0)
+        return slice(self.first_view * C, stop)
+
+    @staticmethod
+    def for_rank(num_views: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> "ViewShard":
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        if world_size is None:
+            world_size = dist.get_world_size() if dist.is_initialized() else 1
+        first, count = view_partition(num_views, world_size)[rank]
+        return ViewShard(rank, world_size, num_views, first, count)
+
+
+def _cuda_warp(local_feats, local_mats, grid_shape, with_coord_map):
+    from .ops import warp_views  # CUDA only; raises when the extension is missing
+    return warp_views(local_feats, local_mats, grid_shape, with_coord_map=with_coord_map)
+
+
+def warp_views_local(local_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Sequence[int],
+                     shard: ViewShard, warp_fn: Optional[Callable] = None) -> torch.Tensor:
+    """This rank's channel slice of ``warp_views``: ``[B, count*C (+2 on the coord owner), Hg, Wg]``.
+
+    ``local_feats`` [B, count, C, H, W] are the features of this rank's cameras (they are produced per
+    camera by the trunk, so they are born sharded); ``proj_mats`` [V,3,3] is the full rig.
+    ``warp_fn(feats, mats, grid_shape, with_coord_map)`` defaults to the CUDA op; the CPU tests inject the oracle.
+    """
+    if local_feats.shape[1] != shard.count:
+        raise ValueError(f"rank {shard.rank} owns {shard.count} views, got features for {local_feats.shape[1]}")
+    warp_fn = warp_fn or _cuda_warp
+    B = local_feats.shape[0]
+    Hg, Wg = int(grid_shape[0]), int(grid_shape[1])
+    if shard.count == 0:
+        return local_feats.new_zeros((B, 0, Hg, Wg))
+    mats = proj_mats[shard.first_view:shard.first_view + shard.count]
+    return warp_fn(local_feats, mats, grid_shape, shard.owns_coord_map)
+
+
+def gather_views(local_out: torch.Tensor, shard: ViewShard, C: int, group=None) -> torch.Tensor:
+    """All-gather the rank slices into the reference's full ``[B, V*C+2, Hg, Wg]`` concat (test / debugging aid:
+    the production path never materialises it on one GPU)."""
+    if shard.world_size == 1:
+        return local_out
+    parts = view_partition(shard.num_views, shard.world_size)
+    sizes = [n * C + (2 if (n > 0 and f + n == shard.num_views) else 0) for f, n in parts]
+    B, _, Hg, Wg = local_out.shape
+    widest = max(sizes)                      # all_gather wants equal shapes: pad the narrower slices
+    mine = local_out.new_zeros((B, widest, Hg, Wg))
+    mine[:, :local_out.shape[1]] = local_out
+    bufs = [torch.empty_like(mine) for _ in sizes]
+    dist.all_gather(bufs, mine, group=group)
+    return torch.cat([b[:, :s] for b, s in zip(bufs, sizes)], dim=1)
+
+
+def conv1_partial(local_out: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], shard: ViewShard,
+                  C: int) -> torch.Tensor:
+    """This rank's partial sum of ``map_classifier[0]`` = Conv2d(V*C+2, Cout, 3, padding=1)
+    (persp_trans_detector.py:51): its slice of the concat convolved with the matching input-channel slice
+    of ``weight`` [Cout, V*C+2, 3, 3]; the coord-map owner also contributes the coord term and the bias."""
+    B, _, Hg, Wg = local_out.shape
+    if shard.count == 0:
+        return local_out.new_zeros((B, weight.shape[0], Hg, Wg))
+    w = weight[:, shard.channel_slice(C)]
+    return F.conv2d(local_out, w, bias if shard.owns_coord_map else None, padding=1)
+
+
+def reduce_partials(partial: torch.Tensor, group=None, relu: bool = True) -> torch.Tensor:
+    """Sum the conv1 partials over the view shards (NCCL all-reduce over NVLink / NVSwitch), then ReLU."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+    return F.relu_(partial) if relu else partial
+
+
+def coord_map_for(grid_shape: Sequence[int], batch: int, like: torch.Tensor) -> torch.Tensor:
+    return create_coord_map(grid_shape).to(device=like.device, dtype=like.dtype).repeat(batch, 1, 1, 1)
