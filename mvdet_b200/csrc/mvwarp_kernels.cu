@@ -12,6 +12,7 @@
 //
 // All arithmetic that decides bits (coordinates, weights, the 4-term blend) follows mvwarp_coords.h.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "mvwarp_coords.h"
 #include "mvwarp_internal.h"
@@ -122,43 +123,72 @@ __device__ __forceinline__ float blend4(float a, float b, float c, float d, cons
 
 // ---------------------------------------------------------------------------------------------------
 // forward, channels-last
+//
+// CTA = 8x8 tile of grid cells of one (batch, view).  Phase 1: 64 threads run the coordinate chain, one
+// cell each, and park the taps in shared memory (the divisions leave the load-issue critical path).
+// Phase 2: one warp per cell, lanes across channels (16 B each): UNROLL x 4 independent 128-bit gathers
+// in flight per lane, blended in fp32 in the oracle's FMA order and stored straight into the view's channel
+// slice of the concat row (view concat and coord_map fused into the store).  In each round the 8 warps work
+// on 8 horizontally adjacent cells, and rounds walk down the tile: neighbouring cells share texels, which
+// L1 serves (hit-on-miss for the concurrent ones).
 // ---------------------------------------------------------------------------------------------------
-constexpr int FWD_TILE_W = 8, FWD_TILE_H = 8, FWD_WARPS = 8, FWD_UNROLL = 2;
+constexpr int FWD_TILE_W = 8, FWD_TILE_H = 8, FWD_WARPS = 8, FWD_CELLS = FWD_TILE_W * FWD_TILE_H;
 
-template <typename T, bool kInline>
-__global__ void __launch_bounds__(FWD_WARPS * 32) fwd_cl_kernel(const KParams p) {
+struct TapRec {
+  float w[4];
+  int x0, y0;
+  unsigned mask;
+  float zero;  // value of an all-outside cell: the 0*w chain (propagates NaN weights like the oracle)
+};
+
+template <typename T, bool kInline, int UNROLL, int MINB>
+__global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_cl_kernel(const KParams p) {
   constexpr int EPV = VecTraits<T>::EPV;
+  __shared__ TapRec taps[FWD_CELLS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
   const int vl = blockIdx.y, b = blockIdx.z;
   const int v = p.view0 + vl;
-  float Tm[9];
+
+  if (threadIdx.x < FWD_CELLS) {
+    const int x = tx * FWD_TILE_W + (threadIdx.x % FWD_TILE_W), y = ty * FWD_TILE_H + (threadIdx.x / FWD_TILE_W);
+    TapRec r;
+    r.mask = 0; r.x0 = r.y0 = 0; r.zero = 0.f;
+    r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.f;
+    if (x < p.Wg && y < p.Hg) {
+      float Tm[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) Tm[i] = kInline ? __ldg(p.T + 9 * v + i) : 0.f;
+      for (int i = 0; i < 9; ++i) Tm[i] = kInline ? __ldg(p.T + 9 * v + i) : 0.f;
+      const Taps tp = cell_taps<kInline>(p, Tm, v, x, y);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r.w[k] = tp.w[k];
+      r.x0 = tp.x0; r.y0 = tp.y0; r.mask = tp.mask;
+      r.zero = blend4(0.f, 0.f, 0.f, 0.f, tp.w);
+      if (p.coord_chan >= 0 && vl == 0) {
+        T* cm = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (int64_t)y * p.oH + (int64_t)x * p.oW + (int64_t)p.coord_chan * p.oC;
+        cm[0] = from_float<T>(__ldg(p.coord_x + x));
+        cm[p.oC] = from_float<T>(__ldg(p.coord_y + y));
+      }
+    }
+    taps[threadIdx.x] = r;
+  }
+  __syncthreads();
 
   const T* __restrict__ src = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.fB + (int64_t)vl * p.fV;
   T* __restrict__ dst = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
   const int nvec = p.C / EPV;
 
-  for (int i = warp; i < FWD_TILE_W * FWD_TILE_H; i += FWD_WARPS) {
+  for (int i = warp; i < FWD_CELLS; i += FWD_WARPS) {
     const int x = tx * FWD_TILE_W + (i % FWD_TILE_W), y = ty * FWD_TILE_H + (i / FWD_TILE_W);
     if (x >= p.Wg || y >= p.Hg) continue;
-    const Taps tp = cell_taps<kInline>(p, Tm, v, x, y);
+    const TapRec tp = taps[i];
     T* o = dst + (int64_t)y * p.oH + (int64_t)x * p.oW;
     const unsigned oalign = (unsigned)(reinterpret_cast<uintptr_t>(o) & 15u);
 
-    if (p.coord_chan >= 0 && vl == 0 && lane == 0) {
-      T* cm = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (int64_t)y * p.oH + (int64_t)x * p.oW + (int64_t)p.coord_chan * p.oC;
-      cm[0] = from_float<T>(__ldg(p.coord_x + x));
-      cm[p.oC] = from_float<T>(__ldg(p.coord_y + y));
-    }
-
     if (tp.mask == 0) {
-      // every tap outside: 0*w chain (NaN weights propagate exactly as in the oracle)
-      const float z = blend4(0.f, 0.f, 0.f, 0.f, tp.w);
       float zf[EPV];
 #pragma unroll
-      for (int e = 0; e < EPV; ++e) zf[e] = z;
+      for (int e = 0; e < EPV; ++e) zf[e] = tp.zero;
       const uint4 zv = VecTraits<T>::pack(zf);
       for (int c = lane; c < nvec; c += 32) stcs16_any(o + c * EPV, zv, oalign);
       continue;
@@ -170,17 +200,17 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) fwd_cl_kernel(const KParams p)
       const int xx = tp.x0 + (k & 1), yy = tp.y0 + (k >> 1);
       tap[k] = (tp.mask >> k & 1) ? src + (int64_t)yy * p.fH + (int64_t)xx * p.fW : src;
     }
-    for (int c0 = lane; c0 < nvec; c0 += 32 * FWD_UNROLL) {
-      uint4 val[FWD_UNROLL][4];
+    for (int c0 = lane; c0 < nvec; c0 += 32 * UNROLL) {
+      uint4 val[UNROLL][4];
 #pragma unroll
-      for (int u = 0; u < FWD_UNROLL; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         const int c = c0 + 32 * u;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           val[u][k] = (c < nvec && (tp.mask >> k & 1)) ? ldg16(tap[k] + c * EPV) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int u = 0; u < FWD_UNROLL; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         const int c = c0 + 32 * u;
         if (c < nvec) {
           float f[4][EPV], r[EPV];
@@ -232,81 +262,243 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const KParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// backward, channels-last: warp per source texel, fixed-order gather over its CSR row
+// backward, channels-last: deterministic gather through the inverse CSR map
+//
+// CTA = 8x8 tile of SOURCE texels, warp w = the 8 consecutive texels of tile row w (16 KB of contiguous
+// output).  The rows of consecutive texels are contiguous in the CSR arrays, so a warp fetches its nine
+// row pointers with one coalesced load and its entries 32 at a time with one coalesced load, and
+// broadcasts them with shuffles: the only dependent global round trip per entry is the grad_out
+// gather itself.  The 2-D tile keeps the four texels that share a grid cell (x..x+1, y..y+1) in the
+// same CTA, so the 2 KB grad_out slice of a cell is fetched from L2 once and re-read from L1.
+// Lanes run across channels (16 B each); a row is summed in CSR order (ascending cell, then tap)
+// with fp32 FMAs: the result is bitwise reproducible.  Empty rows store zeros: no memset pass.
 // ---------------------------------------------------------------------------------------------------
-constexpr int BWD_WARPS = 8, BWD_TEX_PER_CTA = 64, BWD_ACC_FLOATS = 16;
+constexpr int BWD_WARPS = 8, BWD_TW = 8, BWD_TH = 8, BWD_ACC_FLOATS = 16;
+static_assert(BWD_TH == BWD_WARPS, "one warp per tile row");
 
-template <typename T>
-__global__ void __launch_bounds__(BWD_WARPS * 32) bwd_cl_kernel(const KParams p) {
+template <typename T, int MINB, int DBG = 0>
+__global__ void __launch_bounds__(BWD_WARPS * 32, MINB) bwd_cl_kernel(const KParams p) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr int NACC = BWD_ACC_FLOATS / EPV;  // 16-byte vectors per lane per pass
+  constexpr unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int vl = blockIdx.y, b = blockIdx.z, v = p.view0 + vl;
+  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+  const int ys = ty * BWD_TH + warp, x0 = tx * BWD_TW;
+  if (ys >= p.Hs) return;
+  const int nx = min(BWD_TW, p.Ws - x0);
   const int ntex = p.Hs * p.Ws;
-  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (ntex + 1);
-  const CsrEntry* __restrict__ en = p.entries + __ldg(p.view_base + v);
+  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (ntex + 1) + ((size_t)ys * p.Ws + x0);
+  const uint2* __restrict__ en = reinterpret_cast<const uint2*>(p.entries + __ldg(p.view_base + v));
   const T* __restrict__ go = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
-  T* __restrict__ gf = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV;
+  T* __restrict__ orow = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV + (int64_t)ys * p.fH + (int64_t)x0 * p.fW;
   const int nvec = p.C / EPV;
 
-  for (int i = warp; i < BWD_TEX_PER_CTA; i += BWD_WARPS) {
-    const int tex = blockIdx.x * BWD_TEX_PER_CTA + i;
-    if (tex >= ntex) break;
-    const uint32_t r0 = __ldg(rp + tex), r1 = __ldg(rp + tex + 1);
-    const int ys = tex / p.Ws, xs = tex - ys * p.Ws;
-    T* o = gf + (int64_t)ys * p.fH + (int64_t)xs * p.fW;
-    for (int cbase = 0; cbase < nvec; cbase += 32 * NACC) {
+  const uint32_t rpl = (lane <= nx) ? __ldg(rp + lane) : 0u;
+  const uint32_t r_begin = __shfl_sync(FULL, rpl, 0), r_end = __shfl_sync(FULL, rpl, nx);
+
+  for (int cbase = 0; cbase < nvec; cbase += 32 * NACC) {
+    uint32_t chunk0 = r_begin;  // first entry held in the chunk registers
+    uint2 ent = (chunk0 + lane < r_end) ? __ldg(en + chunk0 + lane) : make_uint2(0u, 0u);
+    for (int j = 0; j < nx; ++j) {
+      const uint32_t a = __shfl_sync(FULL, rpl, j), e = (DBG == 1) ? a : __shfl_sync(FULL, rpl, j + 1);
       float acc[NACC][EPV];
 #pragma unroll
-      for (int j = 0; j < NACC; ++j)
+      for (int q = 0; q < NACC; ++q)
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) acc[j][e] = 0.f;
-      uint32_t k = r0;
-      // two entries per trip: all loads first, then the FMAs in row order
-      for (; k + 1 < r1; k += 2) {
-        const CsrEntry e0 = en[k], e1 = en[k + 1];
-        const int y0 = e0.cell / p.Wg, x0 = e0.cell - y0 * p.Wg, y1 = e1.cell / p.Wg, x1 = e1.cell - y1 * p.Wg;
-        const T* g0 = go + (int64_t)y0 * p.oH + (int64_t)x0 * p.oW;
-        const T* g1 = go + (int64_t)y1 * p.oH + (int64_t)x1 * p.oW;
-        const unsigned a0 = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15u), a1 = (unsigned)(reinterpret_cast<uintptr_t>(g1) & 15u);
-        uint4 v0[NACC], v1[NACC];
-#pragma unroll
-        for (int j = 0; j < NACC; ++j) {
-          const int c = cbase + 32 * j + lane;
-          v0[j] = c < nvec ? ldg16_any(g0 + c * EPV, a0) : make_uint4(0, 0, 0, 0);
-          v1[j] = c < nvec ? ldg16_any(g1 + c * EPV, a1) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < EPV; ++i) acc[q][i] = 0.f;
+      uint32_t k = a;
+      while (k < e) {
+        if (k >= chunk0 + 32) {  // warp-uniform: next 32 entries
+          chunk0 += 32 * ((k - chunk0) / 32);
+          ent = (chunk0 + lane < r_end) ? __ldg(en + chunk0 + lane) : make_uint2(0u, 0u);
         }
+        const int s0 = (int)(k - chunk0);
+        const bool two = (k + 1 < e) && (s0 + 1 < 32);
+        const uint32_t c0 = __shfl_sync(FULL, ent.x, s0), c1 = __shfl_sync(FULL, ent.x, (s0 + 1) & 31);
+        const float w0 = __uint_as_float(__shfl_sync(FULL, ent.y, s0));
+        const float w1 = __uint_as_float(__shfl_sync(FULL, ent.y, (s0 + 1) & 31));
+        const int cy0 = c0 / p.Wg, cx0 = c0 - cy0 * p.Wg;
+        const T* g0 = go + (int64_t)cy0 * p.oH + (int64_t)cx0 * p.oW;
+        const unsigned al0 = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15u);
+        if (two) {
+          const int cy1 = c1 / p.Wg, cx1 = c1 - cy1 * p.Wg;
+          const T* g1 = go + (int64_t)cy1 * p.oH + (int64_t)cx1 * p.oW;
+          const unsigned al1 = (unsigned)(reinterpret_cast<uintptr_t>(g1) & 15u);
+          uint4 v0[NACC], v1[NACC];
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) {
-          float f0[EPV], f1[EPV];
-          VecTraits<T>::unpack(v0[j], f0);
-          VecTraits<T>::unpack(v1[j], f1);
-#pragma unroll
-          for (int e = 0; e < EPV; ++e) acc[j][e] = __fmaf_rn(e1.w, f1[e], __fmaf_rn(e0.w, f0[e], acc[j][e]));
-        }
-      }
-      if (k < r1) {
-        const CsrEntry e0 = en[k];
-        const int y0 = e0.cell / p.Wg, x0 = e0.cell - y0 * p.Wg;
-        const T* g0 = go + (int64_t)y0 * p.oH + (int64_t)x0 * p.oW;
-        const unsigned a0 = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15u);
-#pragma unroll
-        for (int j = 0; j < NACC; ++j) {
-          const int c = cbase + 32 * j + lane;
-          if (c < nvec) {
-            float f0[EPV];
-            VecTraits<T>::unpack(ldg16_any(g0 + c * EPV, a0), f0);
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) acc[j][e] = __fmaf_rn(e0.w, f0[e], acc[j][e]);
+          for (int q = 0; q < NACC; ++q) {
+            const int c = cbase + 32 * q + lane;
+            v0[q] = c < nvec ? ldg16_any(g0 + c * EPV, al0) : make_uint4(0, 0, 0, 0);
+            v1[q] = c < nvec ? ldg16_any(g1 + c * EPV, al1) : make_uint4(0, 0, 0, 0);
           }
+#pragma unroll
+          for (int q = 0; q < NACC; ++q) {
+            float f0[EPV], f1[EPV];
+            VecTraits<T>::unpack(v0[q], f0);
+            VecTraits<T>::unpack(v1[q], f1);
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) acc[q][i] = __fmaf_rn(w1, f1[i], __fmaf_rn(w0, f0[i], acc[q][i]));
+          }
+          k += 2;
+        } else {
+#pragma unroll
+          for (int q = 0; q < NACC; ++q) {
+            const int c = cbase + 32 * q + lane;
+            if (c < nvec) {
+              float f0[EPV];
+              VecTraits<T>::unpack(ldg16_any(g0 + c * EPV, al0), f0);
+#pragma unroll
+              for (int i = 0; i < EPV; ++i) acc[q][i] = __fmaf_rn(w0, f0[i], acc[q][i]);
+            }
+          }
+          k += 1;
         }
       }
+      T* o = orow + (int64_t)j * p.fW;
 #pragma unroll
-      for (int j = 0; j < NACC; ++j) {
-        const int c = cbase + 32 * j + lane;
-        if (c < nvec) __stcs(reinterpret_cast<uint4*>(o + c * EPV), VecTraits<T>::pack(acc[j]));
+      for (int q = 0; q < NACC; ++q) {
+        const int c = cbase + 32 * q + lane;
+        if (DBG == 2) {  // measurement only: keep the gathers alive, drop the stores
+          if (c < nvec && acc[q][0] == 123.456f) __stcs(reinterpret_cast<uint4*>(o + c * EPV), VecTraits<T>::pack(acc[q]));
+        } else if (DBG == 3) {
+          if (c < nvec) *reinterpret_cast<uint4*>(o + c * EPV) = VecTraits<T>::pack(acc[q]);
+        } else {
+          if (c < nvec) __stcs(reinterpret_cast<uint4*>(o + c * EPV), VecTraits<T>::pack(acc[q]));
+        }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward, channels-last, asynchronous-copy ring (the production kernel)
+//
+// Same decomposition as bwd_cl_kernel (CTA = 8x8 texel tile, warp = 8 consecutive texels, lanes across
+// channels), but the grad_out gathers no longer land in registers: every lane streams the 16-byte
+// pieces it will consume through a private ring of S shared-memory slots with cp.async (LDGSTS, L1
+// allocating, so neighbouring texels still share cells through L1).  The ring keeps S-1 CSR entries
+// (2 KB each at C=512 fp32) in flight per warp at all times, independent of register pressure, and
+// the FMAs of entry i overlap the flight of entries i+1 .. i+S-1: the gather is no longer a chain of
+// exposed round trips.  Each lane reads back only bytes it copied itself, so cp.async.wait_group is
+// the only synchronisation.  Summation order is the CSR order: bitwise reproducible.
+// ---------------------------------------------------------------------------------------------------
+constexpr int RING_VECS = 128;  // 16-byte vectors per slot (2 KB): one pass covers C*sizeof(T) <= 2048 bytes
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 16 bytes global -> shared through the async-copy path, for a source of any 4-byte alignment
+__device__ __forceinline__ void cp_async_16_any(uint32_t dst, const char* src, unsigned align_mask) {
+  if (align_mask == 0) {
+    cp_async_16(dst, src);
+  } else if ((align_mask & 7u) == 0) {
+    cp_async_8(dst, src); cp_async_8(dst + 8, src + 8);
+  } else {
+    cp_async_4(dst, src); cp_async_4(dst + 4, src + 4); cp_async_4(dst + 8, src + 8); cp_async_4(dst + 12, src + 12);
+  }
+}
+
+template <typename T, int S, int MINB>
+__global__ void __launch_bounds__(BWD_WARPS * 32, MINB) bwd_cl_ring_kernel(const KParams p) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  constexpr int NQ = RING_VECS / 32;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ uint4 ring_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vl = blockIdx.y, b = blockIdx.z, v = p.view0 + vl;
+  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+  const int ys = ty * BWD_TH + warp, x0 = tx * BWD_TW;
+  if (ys >= p.Hs) return;
+  const int nx = min(BWD_TW, p.Ws - x0);
+  const int ntex = p.Hs * p.Ws;
+  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (ntex + 1) + ((size_t)ys * p.Ws + x0);
+  const uint2* __restrict__ en = reinterpret_cast<const uint2*>(p.entries + __ldg(p.view_base + v));
+  const T* __restrict__ go = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
+  T* __restrict__ orow = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV + (int64_t)ys * p.fH + (int64_t)x0 * p.fW;
+  const int nvec = p.C / EPV;
+  uint4* ring = ring_smem + (size_t)warp * S * RING_VECS;                 // this warp's S slots
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;  // this lane's column
+
+  const uint32_t rpl = (lane <= nx) ? __ldg(rp + lane) : 0u;
+  const uint32_t r_begin = __shfl_sync(FULL, rpl, 0);
+  const int n = (int)(__shfl_sync(FULL, rpl, nx) - r_begin);
+
+  for (int cbase = 0; cbase < nvec; cbase += RING_VECS) {
+    uint2 entp = make_uint2(0u, 0u), entc = make_uint2(0u, 0u);  // 32-entry metadata windows: producer / consumer
+    auto issue = [&](int i) {  // start the copy of entry i into slot i % S (warp-uniform i)
+      if ((i & 31) == 0) entp = (i + lane < n) ? __ldg(en + r_begin + i + lane) : make_uint2(0u, 0u);
+      const uint32_t cell = __shfl_sync(FULL, entp.x, i & 31);
+      const int cy = cell / p.Wg, cx = cell - cy * p.Wg;
+      const char* g = reinterpret_cast<const char*>(go + (int64_t)cy * p.oH + (int64_t)cx * p.oW + (int64_t)cbase * EPV);
+      const unsigned al = (unsigned)(reinterpret_cast<uintptr_t>(g) & 15u);
+      const uint32_t dst = ring_s + (uint32_t)(i % S) * (RING_VECS * 16);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (cbase + 32 * q + lane < nvec) cp_async_16_any(dst + q * 512, g + (32 * q + lane) * 16, al);
+    };
+
+    float acc[NQ][EPV];
+    auto clear = [&]() {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[q][e] = 0.f;
+    };
+    auto store = [&](int j) {
+      T* o = orow + (int64_t)j * p.fW;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int c = cbase + 32 * q + lane;
+        if (c < nvec) __stcs(reinterpret_cast<uint4*>(o + c * EPV), VecTraits<T>::pack(acc[q]));
+      }
+    };
+
+#pragma unroll
+    for (int i = 0; i < S - 1; ++i) {  // prologue: S-1 groups, empty ones keep the group count uniform
+      if (i < n) issue(i);
+      cp_async_commit();
+    }
+    clear();
+    int j = 0;
+    int row_end = (int)(__shfl_sync(FULL, rpl, 1) - r_begin);
+    for (int i = 0; i < n; ++i) {
+      if (i + S - 1 < n) issue(i + S - 1);
+      cp_async_commit();
+      while (i == row_end) {  // texel j complete (possibly empty): write it, move on
+        store(j);
+        clear();
+        ++j;
+        row_end = (int)(__shfl_sync(FULL, rpl, j + 1) - r_begin);
+      }
+      if ((i & 31) == 0) entc = (i + lane < n) ? __ldg(en + r_begin + i + lane) : make_uint2(0u, 0u);
+      const float w = __uint_as_float(__shfl_sync(FULL, entc.y, i & 31));
+      cp_async_wait<S - 1>();  // everything but the newest S-1 groups has landed: entry i is in its slot
+      const uint4* slot = ring + (size_t)(i % S) * RING_VECS + lane;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        if (cbase + 32 * q + lane < nvec) {
+          float f[EPV];
+          VecTraits<T>::unpack(slot[32 * q], f);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) acc[q][e] = __fmaf_rn(w, f[e], acc[q][e]);
+        }
+      }
+    }
+    for (; j < nx; ++j) {  // last non-empty texel and the trailing empty ones
+      store(j);
+      clear();
+    }
+    cp_async_wait<0>();
   }
 }
 
@@ -379,6 +571,11 @@ static KParams make_params(const LaunchArgs& a) {
   return p;
 }
 
+static int tuning_variant(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 // channel-contiguous feature tensor whose every texel row starts 16-byte aligned
 static bool feats_vector_ok(const void* ptr, const int64_t fs[5], int C, int epv) {
   if (fs[2] != 1 || C % epv != 0) return false;
@@ -408,8 +605,18 @@ static int launch_fwd_t(const LaunchArgs& a) {
     int rc = check_grid_dims(a, a.B);
     if (rc) return rc;
     dim3 grid(p.tiles_x * p.tiles_y, a.nviews, a.B), block(FWD_WARPS * 32);
-    if (inl) fwd_cl_kernel<T, true><<<grid, block, 0, a.stream>>>(p);
-    else fwd_cl_kernel<T, false><<<grid, block, 0, a.stream>>>(p);
+    switch (tuning_variant("MVWARP_FWD_VARIANT", 0)) {  // tuning knob (development only)
+#define MVW_FWD(U, M)                                                            \
+  if (inl) fwd_cl_kernel<T, true, U, M><<<grid, block, 0, a.stream>>>(p);        \
+  else fwd_cl_kernel<T, false, U, M><<<grid, block, 0, a.stream>>>(p);           \
+  break
+      case 1: MVW_FWD(4, 2);
+      case 2: MVW_FWD(1, 6);
+      case 3: MVW_FWD(2, 3);
+      case 4: MVW_FWD(4, 3);
+      default: MVW_FWD(2, 4);
+#undef MVW_FWD
+    }
   } else {
     const int nchunk = (a.C + p.cchunk - 1) / p.cchunk;
     int rc = check_grid_dims(a, (int64_t)a.B * nchunk);
@@ -433,8 +640,31 @@ static int launch_bwd_t(const LaunchArgs& a) {
   if (fast) {
     int rc = check_grid_dims(a, a.B);
     if (rc) return rc;
-    dim3 grid((ntex + BWD_TEX_PER_CTA - 1) / BWD_TEX_PER_CTA, a.nviews, a.B), block(BWD_WARPS * 32);
-    bwd_cl_kernel<T><<<grid, block, 0, a.stream>>>(p);
+    p.tiles_x = (p.Ws + BWD_TW - 1) / BWD_TW;
+    p.tiles_y = (p.Hs + BWD_TH - 1) / BWD_TH;
+    dim3 grid(p.tiles_x * p.tiles_y, a.nviews, a.B), block(BWD_WARPS * 32);
+    switch (tuning_variant("MVWARP_BWD_VARIANT", 0)) {  // tuning knob (development only)
+      case 1: bwd_cl_kernel<T, 4><<<grid, block, 0, a.stream>>>(p); break;
+      case 2: bwd_cl_kernel<T, 2><<<grid, block, 0, a.stream>>>(p); break;
+      case 11: bwd_cl_kernel<T, 3, 1><<<grid, block, 0, a.stream>>>(p); break;  // measurement: stores only
+      case 12: bwd_cl_kernel<T, 3, 2><<<grid, block, 0, a.stream>>>(p); break;  // measurement: gathers only
+      case 13: bwd_cl_kernel<T, 3, 3><<<grid, block, 0, a.stream>>>(p); break;  // default-policy stores
+      case 20: bwd_cl_kernel<T, 3><<<grid, block, 0, a.stream>>>(p); break;     // register-gather kernel
+#define MVW_RING(S_, M_)                                                                                          \
+  {                                                                                                               \
+    const int smem = BWD_WARPS * S_ * RING_VECS * 16;                                                             \
+    cudaError_t ea = cudaFuncSetAttribute(bwd_cl_ring_kernel<T, S_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(bwd ring)");                                \
+    bwd_cl_ring_kernel<T, S_, M_><<<grid, block, smem, a.stream>>>(p);                                            \
+  }                                                                                                               \
+  break
+      case 21: MVW_RING(6, 2);
+      case 22: MVW_RING(3, 4);
+      case 23: MVW_RING(8, 1);
+      case 24: MVW_RING(5, 2);
+      default: MVW_RING(4, 3);
+#undef MVW_RING
+    }
   } else {
     const int nchunk = (a.C + p.cchunk - 1) / p.cchunk;
     int rc = check_grid_dims(a, (int64_t)a.B * nchunk);

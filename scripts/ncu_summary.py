@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here, no GPU): per-kernel headline metrics + stall breakdown.
+usage: python scripts/ncu_summary.py gpurun_out/prof_x.ncu-rep [> profiles/rNN_x_summary.txt]"""
+import csv, io, subprocess, sys
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+idx = {h: i for i, h in enumerate(hdr)}
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sectors_srcunit_tex_op_read.sum',
+        'lts__t_sectors_srcunit_tex_op_write.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
+        'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__waves_per_multiprocessor',
+        'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_static',
+        'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'smsp__warps_eligible.avg.per_cycle_active', 'sm__cycles_active.avg', 'sm__cycles_active.max', 'sm__cycles_active.min',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
+for r in rows[2:]:
+    print("=" * 100)
+    print(r[idx['Kernel Name']], " grid", r[idx.get('Grid Size', 0)], "block", r[idx.get('Block Size', 0)])
+    for w in WANT:
+        if w in idx:
+            print(f"  {w:72s} {r[idx[w]]:>18s} {units[idx[w]]}")
+    st = []
+    for h, i in idx.items():
+        if h.startswith('smsp__average_warps_issue_stalled_') and h.endswith('_per_issue_active.ratio'):
+            try:
+                st.append((float(r[i].replace(',', '')), h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]))
+            except ValueError:
+                pass
+    st.sort(reverse=True)
+    print("  warp stall cycles per issued instruction (top):", ", ".join(f"{n}={v:.2f}" for v, n in st[:7]))
