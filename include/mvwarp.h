@@ -52,6 +52,9 @@ typedef struct mvwarp_stats {
   uint64_t nnz;               /* in-bounds taps = entries of the inverse (texel -> cells) CSR map */
   uint64_t valid_cells;       /* grid cells with >= 1 in-bounds tap, summed over views */
   uint32_t max_row;           /* longest CSR row (taps landing on one texel) */
+  uint32_t bwd_tasks;         /* backward: warp-sized tasks (runs of light rows) */
+  uint32_t heavy_rows;        /* backward: rows long enough to get a whole CTA */
+  uint32_t reserved_;
   uint64_t device_bytes;      /* HBM held by the plan */
 } mvwarp_stats_t;
 
@@ -67,12 +70,16 @@ const char* mvwarp_last_error(void);
  * Replaces: kornia create_meshgrid + transform_points inside warp_perspective (persp_trans_detector.py:69). */
 int mvwarp_host_grid(const float* src_norm_trans_dst_norm, int V, int Hg, int Wg, float* grid_out);
 /* mvwarp_host_csr: build the inverse (texel -> cells) CSR map of a normalised grid [V,Hg,Wg,2] on the host
- * and report its statistics (only unique_texels, nnz, valid_cells, max_row and the shape fields are set).
- * If row_ptr_out / cells_out / weights_out are non-null they receive the map itself: row_ptr_out
- * [V*(Hs*Ws+1)] offsets relative to each view's first entry, cells_out / weights_out [>= nnz] (pass
- * capacity in `capacity`; MVWARP_EINVAL if too small).  Entry order in a row: ascending cell, then tap. */
+ * and report its statistics (device_bytes and inline_coords are not set).
+ * Rows are ordered tile-major over 8x8 texel tiles (rows near in the array are near in the image):
+ * row r of view v is the texel tex_of[v*Hs*Ws + r] (= ys*Ws + xs).
+ * If tex_of_out / row_ptr_out / cells_out / weights_out are non-null they receive the map itself:
+ * tex_of_out [V*Hs*Ws], row_ptr_out [V*(Hs*Ws+1)] offsets relative to each view's first entry,
+ * cells_out / weights_out [>= nnz] (pass the capacity in `capacity`; MVWARP_EINVAL if too small).
+ * Entry order in a row: ascending cell, then tap (nw, ne, sw, se) -- the backward's summation order. */
 int mvwarp_host_csr(const float* grid_host, int V, int Hs, int Ws, int Hg, int Wg, mvwarp_stats_t* stats_out,
-                    uint32_t* row_ptr_out, uint32_t* cells_out, float* weights_out, uint64_t capacity);
+                    uint32_t* tex_of_out, uint32_t* row_ptr_out, uint32_t* cells_out, float* weights_out,
+                    uint64_t capacity);
 
 /* ---- plan: everything that depends only on the camera rig ---------------------------------------
  * Built once per (proj_mats, shapes, device); holds the per-view matrices (or grid table) and the

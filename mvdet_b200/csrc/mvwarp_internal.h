@@ -16,11 +16,29 @@ struct CsrEntry {
   float w;
 };
 
-// Host-side CSR for all views (built once per rig).
+// Backward work decomposition (built with the CSR): a regular task is a run of consecutive rows whose
+// weight (1 per texel + 1 per entry) fits TASK_BUDGET, processed by one warp; a row longer than HEAVY_LEN
+// is "heavy" and gets a whole CTA (its entries split over the warps, partials combined in warp order).
+constexpr uint32_t TASK_BUDGET = 64, TASK_MAX_TEX = 31, HEAVY_LEN = 48;
+constexpr int CSR_TILE = 8;  // rows are ordered tile-major over CSR_TILE x CSR_TILE texel tiles
+
+struct Task {
+  uint32_t row0;   // first row (tile-major texel position, view-relative)
+  uint16_t nrows;  // <= TASK_MAX_TEX
+  uint16_t view;
+};
+
+// Host-side CSR for all views (built once per rig).  Row r of view v describes the texel tex_of[v][r]:
+// rows follow a tile-major order of the source image so that rows close in the array are close in 2-D.
 struct HostCsr {
   std::vector<uint32_t> row_ptr;     // [V * (Hs*Ws + 1)], offsets relative to view_base[v]
-  std::vector<CsrEntry> entries;     // [nnz], per view, rows in texel order, row entries in (cell, tap) order
+  std::vector<uint32_t> tex_of;      // [V * Hs*Ws]  row -> linear texel index ys*Ws + xs
+  std::vector<CsrEntry> entries;     // [nnz], per view, rows in order, row entries in (cell, tap) order
   std::vector<uint64_t> view_base;   // [V + 1]
+  std::vector<Task> tasks;           // regular tasks, grouped by view
+  std::vector<uint32_t> task_base;   // [V + 1]
+  std::vector<uint32_t> heavy;       // heavy rows (view-relative row index), grouped by view
+  std::vector<uint32_t> heavy_base;  // [V + 1]
   uint64_t unique_texels = 0, valid_cells = 0;
   uint32_t max_row = 0;
 };
@@ -49,8 +67,13 @@ struct mvwarp_plan {
   float* d_coord_x = nullptr;      // [Wg]  coord_map channel 0 along x
   float* d_coord_y = nullptr;      // [Hg]  coord_map channel 1 along y
   uint32_t* d_row_ptr = nullptr;   // [V*(Hs*Ws+1)]
+  uint32_t* d_tex_of = nullptr;    // [V*Hs*Ws]
   mvw::CsrEntry* d_entries = nullptr;  // [nnz]
   uint64_t* d_view_base = nullptr; // [V+1]
+  mvw::Task* d_tasks = nullptr;    // regular backward tasks
+  uint32_t* d_heavy = nullptr;     // heavy rows
+  uint32_t* d_heavy_base = nullptr;  // [V+1]
+  std::vector<uint32_t> task_base, heavy_base;  // host copies, [V+1]
   mvwarp_stats_t stats{};
 };
 

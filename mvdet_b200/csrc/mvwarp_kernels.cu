@@ -25,8 +25,11 @@ struct KParams {
   const float* coord_x;  // [Wg]
   const float* coord_y;  // [Hg]
   const uint32_t* row_ptr;
+  const uint32_t* tex_of;
   const CsrEntry* entries;
   const uint64_t* view_base;
+  const Task* tasks;
+  const uint32_t* heavy;
   int Hs, Ws, Hg, Wg;
   int view0, nviews, B, C;
   const void* src;  // forward: feats      backward: grad_out
@@ -264,256 +267,193 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const KParams p) {
 // ---------------------------------------------------------------------------------------------------
 // backward, channels-last: deterministic gather through the inverse CSR map
 //
-// CTA = 8x8 tile of SOURCE texels, warp w = the 8 consecutive texels of tile row w (16 KB of contiguous
-// output).  The rows of consecutive texels are contiguous in the CSR arrays, so a warp fetches its nine
-// row pointers with one coalesced load and its entries 32 at a time with one coalesced load, and
-// broadcasts them with shuffles: the only dependent global round trip per entry is the grad_out
-// gather itself.  The 2-D tile keeps the four texels that share a grid cell (x..x+1, y..y+1) in the
-// same CTA, so the 2 KB grad_out slice of a cell is fetched from L2 once and re-read from L1.
-// Lanes run across channels (16 B each); a row is summed in CSR order (ascending cell, then tap)
-// with fp32 FMAs: the result is bitwise reproducible.  Empty rows store zeros: no memset pass.
+// The CSR rows (one per source texel, tile-major order) are very unevenly filled: 74 % are empty, the
+// median touched row has 2 entries, rows near a camera's horizon have up to 95 (1360 on the 32-camera
+// rig).  A gather row is a chain of dependent round trips, so work is balanced at plan time:
+//   * bwd_cl_task_kernel: one WARP per task = run of consecutive light rows with (rows + entries) <= 64.
+//     Row pointers, texel ids and entries are fetched with coalesced loads (consecutive rows are
+//     contiguous in the CSR arrays) and broadcast by shuffles; lanes run across channels (16 B each) and
+//     sum a row in CSR order (ascending cell, then tap) with fp32 FMAs, two entries (8 independent 128-bit
+//     gathers) in flight per lane.  Empty rows store zeros: there is no memset pass.
+//   * bwd_cl_heavy_kernel: one CTA per heavy row (> 48 entries): warp w sums the w-th eighth of the row,
+//     partials meet in shared memory and are added in warp order.
+// Both orders are fixed by the plan, so the gradient is bitwise reproducible (no atomics anywhere).
 // ---------------------------------------------------------------------------------------------------
-constexpr int BWD_WARPS = 8, BWD_TW = 8, BWD_TH = 8, BWD_ACC_FLOATS = 16;
-static_assert(BWD_TH == BWD_WARPS, "one warp per tile row");
+constexpr int BWD_WARPS = 8, BWD_ACC_FLOATS = 16;
 
-template <typename T, int MINB, int DBG = 0>
-__global__ void __launch_bounds__(BWD_WARPS * 32, MINB) bwd_cl_kernel(const KParams p) {
+// acc += sum over entries [k0, k1) of w * grad_out[cell]; entries come through 32-entry windows (coalesced)
+template <typename T, int NACC>
+__device__ __forceinline__ void gather_entries(float (&acc)[NACC][VecTraits<T>::EPV], const uint2* __restrict__ en,
+                                               uint32_t k0, uint32_t k1, uint32_t win_end, const T* __restrict__ go,
+                                               const KParams& p, int cbase, int nvec, int lane, uint32_t& win0, uint2& ent) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  constexpr unsigned FULL = 0xffffffffu;
+  uint32_t k = k0;
+  while (k < k1) {
+    if (k >= win0 + 32) {  // warp-uniform: slide the metadata window
+      win0 += 32 * ((k - win0) / 32);
+      ent = (win0 + lane < win_end) ? __ldg(en + win0 + lane) : make_uint2(0u, 0u);
+    }
+    const int s0 = (int)(k - win0);
+    const bool two = (k + 1 < k1) && (s0 + 1 < 32);
+    const uint32_t c0 = __shfl_sync(FULL, ent.x, s0), c1 = __shfl_sync(FULL, ent.x, (s0 + 1) & 31);
+    const float w0 = __uint_as_float(__shfl_sync(FULL, ent.y, s0));
+    const float w1 = __uint_as_float(__shfl_sync(FULL, ent.y, (s0 + 1) & 31));
+    const int cy0 = c0 / p.Wg, cx0 = c0 - cy0 * p.Wg;
+    const T* g0 = go + (int64_t)cy0 * p.oH + (int64_t)cx0 * p.oW;
+    const unsigned al0 = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15u);
+    if (two) {
+      const int cy1 = c1 / p.Wg, cx1 = c1 - cy1 * p.Wg;
+      const T* g1 = go + (int64_t)cy1 * p.oH + (int64_t)cx1 * p.oW;
+      const unsigned al1 = (unsigned)(reinterpret_cast<uintptr_t>(g1) & 15u);
+      uint4 v0[NACC], v1[NACC];
+#pragma unroll
+      for (int q = 0; q < NACC; ++q) {
+        const int c = cbase + 32 * q + lane;
+        v0[q] = c < nvec ? ldg16_any(g0 + c * EPV, al0) : make_uint4(0, 0, 0, 0);
+        v1[q] = c < nvec ? ldg16_any(g1 + c * EPV, al1) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int q = 0; q < NACC; ++q) {
+        float f0[EPV], f1[EPV];
+        VecTraits<T>::unpack(v0[q], f0);
+        VecTraits<T>::unpack(v1[q], f1);
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) acc[q][i] = __fmaf_rn(w1, f1[i], __fmaf_rn(w0, f0[i], acc[q][i]));
+      }
+      k += 2;
+    } else {
+#pragma unroll
+      for (int q = 0; q < NACC; ++q) {
+        const int c = cbase + 32 * q + lane;
+        if (c < nvec) {
+          float f0[EPV];
+          VecTraits<T>::unpack(ldg16_any(g0 + c * EPV, al0), f0);
+#pragma unroll
+          for (int i = 0; i < EPV; ++i) acc[q][i] = __fmaf_rn(w0, f0[i], acc[q][i]);
+        }
+      }
+      k += 1;
+    }
+  }
+}
+
+template <typename T, int MINB>
+__global__ void __launch_bounds__(BWD_WARPS * 32, MINB) bwd_cl_task_kernel(const KParams p, uint32_t task_lo, uint32_t task_hi) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr int NACC = BWD_ACC_FLOATS / EPV;  // 16-byte vectors per lane per pass
   constexpr unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int vl = blockIdx.y, b = blockIdx.z, v = p.view0 + vl;
-  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
-  const int ys = ty * BWD_TH + warp, x0 = tx * BWD_TW;
-  if (ys >= p.Hs) return;
-  const int nx = min(BWD_TW, p.Ws - x0);
+  const uint32_t tid = task_lo + blockIdx.x * BWD_WARPS + warp;
+  if (tid >= task_hi) return;
+  const Task task = p.tasks[tid];
+  const int v = task.view, vl = v - p.view0, b = blockIdx.z;
+  const int nrows = task.nrows;
   const int ntex = p.Hs * p.Ws;
-  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (ntex + 1) + ((size_t)ys * p.Ws + x0);
+  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (ntex + 1) + task.row0;
+  const uint32_t* __restrict__ tex_of = p.tex_of + (size_t)v * ntex + task.row0;
   const uint2* __restrict__ en = reinterpret_cast<const uint2*>(p.entries + __ldg(p.view_base + v));
   const T* __restrict__ go = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
-  T* __restrict__ orow = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV + (int64_t)ys * p.fH + (int64_t)x0 * p.fW;
+  T* __restrict__ gf = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV;
   const int nvec = p.C / EPV;
 
-  const uint32_t rpl = (lane <= nx) ? __ldg(rp + lane) : 0u;
-  const uint32_t r_begin = __shfl_sync(FULL, rpl, 0), r_end = __shfl_sync(FULL, rpl, nx);
+  const uint32_t rpl = (lane <= nrows) ? __ldg(rp + lane) : 0u;
+  const uint32_t texl = (lane < nrows) ? __ldg(tex_of + lane) : 0u;
+  const uint32_t r_begin = __shfl_sync(FULL, rpl, 0), r_end = __shfl_sync(FULL, rpl, nrows);
 
   for (int cbase = 0; cbase < nvec; cbase += 32 * NACC) {
-    uint32_t chunk0 = r_begin;  // first entry held in the chunk registers
-    uint2 ent = (chunk0 + lane < r_end) ? __ldg(en + chunk0 + lane) : make_uint2(0u, 0u);
-    for (int j = 0; j < nx; ++j) {
-      const uint32_t a = __shfl_sync(FULL, rpl, j), e = (DBG == 1) ? a : __shfl_sync(FULL, rpl, j + 1);
+    uint32_t win0 = r_begin;
+    uint2 ent = (win0 + lane < r_end) ? __ldg(en + win0 + lane) : make_uint2(0u, 0u);
+    for (int j = 0; j < nrows; ++j) {
+      const uint32_t a = __shfl_sync(FULL, rpl, j), e = __shfl_sync(FULL, rpl, j + 1);
+      const uint32_t tex = __shfl_sync(FULL, texl, j);
       float acc[NACC][EPV];
 #pragma unroll
       for (int q = 0; q < NACC; ++q)
 #pragma unroll
         for (int i = 0; i < EPV; ++i) acc[q][i] = 0.f;
-      uint32_t k = a;
-      while (k < e) {
-        if (k >= chunk0 + 32) {  // warp-uniform: next 32 entries
-          chunk0 += 32 * ((k - chunk0) / 32);
-          ent = (chunk0 + lane < r_end) ? __ldg(en + chunk0 + lane) : make_uint2(0u, 0u);
-        }
-        const int s0 = (int)(k - chunk0);
-        const bool two = (k + 1 < e) && (s0 + 1 < 32);
-        const uint32_t c0 = __shfl_sync(FULL, ent.x, s0), c1 = __shfl_sync(FULL, ent.x, (s0 + 1) & 31);
-        const float w0 = __uint_as_float(__shfl_sync(FULL, ent.y, s0));
-        const float w1 = __uint_as_float(__shfl_sync(FULL, ent.y, (s0 + 1) & 31));
-        const int cy0 = c0 / p.Wg, cx0 = c0 - cy0 * p.Wg;
-        const T* g0 = go + (int64_t)cy0 * p.oH + (int64_t)cx0 * p.oW;
-        const unsigned al0 = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15u);
-        if (two) {
-          const int cy1 = c1 / p.Wg, cx1 = c1 - cy1 * p.Wg;
-          const T* g1 = go + (int64_t)cy1 * p.oH + (int64_t)cx1 * p.oW;
-          const unsigned al1 = (unsigned)(reinterpret_cast<uintptr_t>(g1) & 15u);
-          uint4 v0[NACC], v1[NACC];
-#pragma unroll
-          for (int q = 0; q < NACC; ++q) {
-            const int c = cbase + 32 * q + lane;
-            v0[q] = c < nvec ? ldg16_any(g0 + c * EPV, al0) : make_uint4(0, 0, 0, 0);
-            v1[q] = c < nvec ? ldg16_any(g1 + c * EPV, al1) : make_uint4(0, 0, 0, 0);
-          }
-#pragma unroll
-          for (int q = 0; q < NACC; ++q) {
-            float f0[EPV], f1[EPV];
-            VecTraits<T>::unpack(v0[q], f0);
-            VecTraits<T>::unpack(v1[q], f1);
-#pragma unroll
-            for (int i = 0; i < EPV; ++i) acc[q][i] = __fmaf_rn(w1, f1[i], __fmaf_rn(w0, f0[i], acc[q][i]));
-          }
-          k += 2;
-        } else {
-#pragma unroll
-          for (int q = 0; q < NACC; ++q) {
-            const int c = cbase + 32 * q + lane;
-            if (c < nvec) {
-              float f0[EPV];
-              VecTraits<T>::unpack(ldg16_any(g0 + c * EPV, al0), f0);
-#pragma unroll
-              for (int i = 0; i < EPV; ++i) acc[q][i] = __fmaf_rn(w0, f0[i], acc[q][i]);
-            }
-          }
-          k += 1;
-        }
-      }
-      T* o = orow + (int64_t)j * p.fW;
+      gather_entries<T, NACC>(acc, en, a, e, r_end, go, p, cbase, nvec, lane, win0, ent);
+      const int ys = tex / p.Ws, xs = tex - ys * p.Ws;
+      T* o = gf + (int64_t)ys * p.fH + (int64_t)xs * p.fW;
 #pragma unroll
       for (int q = 0; q < NACC; ++q) {
         const int c = cbase + 32 * q + lane;
-        if (DBG == 2) {  // measurement only: keep the gathers alive, drop the stores
-          if (c < nvec && acc[q][0] == 123.456f) __stcs(reinterpret_cast<uint4*>(o + c * EPV), VecTraits<T>::pack(acc[q]));
-        } else if (DBG == 3) {
-          if (c < nvec) *reinterpret_cast<uint4*>(o + c * EPV) = VecTraits<T>::pack(acc[q]);
-        } else {
-          if (c < nvec) __stcs(reinterpret_cast<uint4*>(o + c * EPV), VecTraits<T>::pack(acc[q]));
-        }
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// backward, channels-last, asynchronous-copy ring (the production kernel)
-//
-// Same decomposition as bwd_cl_kernel (CTA = 8x8 texel tile, warp = 8 consecutive texels, lanes across
-// channels), but the grad_out gathers no longer land in registers: every lane streams the 16-byte
-// pieces it will consume through a private ring of S shared-memory slots with cp.async (LDGSTS, L1
-// allocating, so neighbouring texels still share cells through L1).  The ring keeps S-1 CSR entries
-// (2 KB each at C=512 fp32) in flight per warp at all times, independent of register pressure, and
-// the FMAs of entry i overlap the flight of entries i+1 .. i+S-1: the gather is no longer a chain of
-// exposed round trips.  Each lane reads back only bytes it copied itself, so cp.async.wait_group is
-// the only synchronisation.  Summation order is the CSR order: bitwise reproducible.
-// ---------------------------------------------------------------------------------------------------
-constexpr int RING_VECS = 128;  // 16-byte vectors per slot (2 KB): one pass covers C*sizeof(T) <= 2048 bytes
-
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// 16 bytes global -> shared through the async-copy path, for a source of any 4-byte alignment
-__device__ __forceinline__ void cp_async_16_any(uint32_t dst, const char* src, unsigned align_mask) {
-  if (align_mask == 0) {
-    cp_async_16(dst, src);
-  } else if ((align_mask & 7u) == 0) {
-    cp_async_8(dst, src); cp_async_8(dst + 8, src + 8);
-  } else {
-    cp_async_4(dst, src); cp_async_4(dst + 4, src + 4); cp_async_4(dst + 8, src + 8); cp_async_4(dst + 12, src + 12);
-  }
-}
-
-template <typename T, int S, int MINB>
-__global__ void __launch_bounds__(BWD_WARPS * 32, MINB) bwd_cl_ring_kernel(const KParams p) {
-  constexpr int EPV = VecTraits<T>::EPV;
-  constexpr int NQ = RING_VECS / 32;
-  constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ uint4 ring_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int vl = blockIdx.y, b = blockIdx.z, v = p.view0 + vl;
-  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
-  const int ys = ty * BWD_TH + warp, x0 = tx * BWD_TW;
-  if (ys >= p.Hs) return;
-  const int nx = min(BWD_TW, p.Ws - x0);
-  const int ntex = p.Hs * p.Ws;
-  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (ntex + 1) + ((size_t)ys * p.Ws + x0);
-  const uint2* __restrict__ en = reinterpret_cast<const uint2*>(p.entries + __ldg(p.view_base + v));
-  const T* __restrict__ go = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
-  T* __restrict__ orow = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV + (int64_t)ys * p.fH + (int64_t)x0 * p.fW;
-  const int nvec = p.C / EPV;
-  uint4* ring = ring_smem + (size_t)warp * S * RING_VECS;                 // this warp's S slots
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;  // this lane's column
-
-  const uint32_t rpl = (lane <= nx) ? __ldg(rp + lane) : 0u;
-  const uint32_t r_begin = __shfl_sync(FULL, rpl, 0);
-  const int n = (int)(__shfl_sync(FULL, rpl, nx) - r_begin);
-
-  for (int cbase = 0; cbase < nvec; cbase += RING_VECS) {
-    uint2 entp = make_uint2(0u, 0u), entc = make_uint2(0u, 0u);  // 32-entry metadata windows: producer / consumer
-    auto issue = [&](int i) {  // start the copy of entry i into slot i % S (warp-uniform i)
-      if ((i & 31) == 0) entp = (i + lane < n) ? __ldg(en + r_begin + i + lane) : make_uint2(0u, 0u);
-      const uint32_t cell = __shfl_sync(FULL, entp.x, i & 31);
-      const int cy = cell / p.Wg, cx = cell - cy * p.Wg;
-      const char* g = reinterpret_cast<const char*>(go + (int64_t)cy * p.oH + (int64_t)cx * p.oW + (int64_t)cbase * EPV);
-      const unsigned al = (unsigned)(reinterpret_cast<uintptr_t>(g) & 15u);
-      const uint32_t dst = ring_s + (uint32_t)(i % S) * (RING_VECS * 16);
-#pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        if (cbase + 32 * q + lane < nvec) cp_async_16_any(dst + q * 512, g + (32 * q + lane) * 16, al);
-    };
-
-    float acc[NQ][EPV];
-    auto clear = [&]() {
-#pragma unroll
-      for (int q = 0; q < NQ; ++q)
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) acc[q][e] = 0.f;
-    };
-    auto store = [&](int j) {
-      T* o = orow + (int64_t)j * p.fW;
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int c = cbase + 32 * q + lane;
         if (c < nvec) __stcs(reinterpret_cast<uint4*>(o + c * EPV), VecTraits<T>::pack(acc[q]));
       }
-    };
-
-#pragma unroll
-    for (int i = 0; i < S - 1; ++i) {  // prologue: S-1 groups, empty ones keep the group count uniform
-      if (i < n) issue(i);
-      cp_async_commit();
     }
-    clear();
-    int j = 0;
-    int row_end = (int)(__shfl_sync(FULL, rpl, 1) - r_begin);
-    for (int i = 0; i < n; ++i) {
-      if (i + S - 1 < n) issue(i + S - 1);
-      cp_async_commit();
-      while (i == row_end) {  // texel j complete (possibly empty): write it, move on
-        store(j);
-        clear();
-        ++j;
-        row_end = (int)(__shfl_sync(FULL, rpl, j + 1) - r_begin);
-      }
-      if ((i & 31) == 0) entc = (i + lane < n) ? __ldg(en + r_begin + i + lane) : make_uint2(0u, 0u);
-      const float w = __uint_as_float(__shfl_sync(FULL, entc.y, i & 31));
-      cp_async_wait<S - 1>();  // everything but the newest S-1 groups has landed: entry i is in its slot
-      const uint4* slot = ring + (size_t)(i % S) * RING_VECS + lane;
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        if (cbase + 32 * q + lane < nvec) {
-          float f[EPV];
-          VecTraits<T>::unpack(slot[32 * q], f);
-#pragma unroll
-          for (int e = 0; e < EPV; ++e) acc[q][e] = __fmaf_rn(w, f[e], acc[q][e]);
-        }
-      }
-    }
-    for (; j < nx; ++j) {  // last non-empty texel and the trailing empty ones
-      store(j);
-      clear();
-    }
-    cp_async_wait<0>();
   }
 }
 
-// backward, arbitrary strides: thread per source texel (x fastest), loop over a chunk of channels
+template <typename T>
+__global__ void __launch_bounds__(BWD_WARPS * 32) bwd_cl_heavy_kernel(const KParams p, uint32_t heavy_lo, int view_lo,
+                                                                      const uint32_t* __restrict__ heavy_base) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  constexpr int NACC = BWD_ACC_FLOATS / EPV;
+  constexpr int PASS_FLOATS = 32 * BWD_ACC_FLOATS;  // channels per pass (512)
+  __shared__ __align__(16) float part[BWD_WARPS][PASS_FLOATS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t hid = heavy_lo + blockIdx.x;
+  int v = view_lo;
+  while (hid >= __ldg(heavy_base + v + 1)) ++v;  // few views: linear search
+  const int vl = v - p.view0, b = blockIdx.z;
+  const int ntex = p.Hs * p.Ws;
+  const uint32_t row = __ldg(p.heavy + hid);
+  const uint32_t a = __ldg(p.row_ptr + (size_t)v * (ntex + 1) + row), e = __ldg(p.row_ptr + (size_t)v * (ntex + 1) + row + 1);
+  const uint32_t tex = __ldg(p.tex_of + (size_t)v * ntex + row);
+  const uint2* __restrict__ en = reinterpret_cast<const uint2*>(p.entries + __ldg(p.view_base + v));
+  const T* __restrict__ go = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
+  const int ys = tex / p.Ws, xs = tex - ys * p.Ws;
+  T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV + (int64_t)ys * p.fH + (int64_t)xs * p.fW;
+  const int nvec = p.C / EPV;
+  const uint32_t seg = (e - a + BWD_WARPS - 1) / BWD_WARPS;
+  const uint32_t k0 = min(e, a + warp * seg), k1 = min(e, k0 + seg);
+
+  for (int cbase = 0; cbase < nvec; cbase += 32 * NACC) {
+    float acc[NACC][EPV];
+#pragma unroll
+    for (int q = 0; q < NACC; ++q)
+#pragma unroll
+      for (int i = 0; i < EPV; ++i) acc[q][i] = 0.f;
+    uint32_t win0 = k0;
+    uint2 ent = (win0 + lane < k1) ? __ldg(en + win0 + lane) : make_uint2(0u, 0u);
+    gather_entries<T, NACC>(acc, en, k0, k1, k1, go, p, cbase, nvec, lane, win0, ent);
+    // partials in channel order: lane's q-th vector covers pass-channels [(32q + lane)*EPV, +EPV)
+#pragma unroll
+    for (int q = 0; q < NACC; ++q)
+#pragma unroll
+      for (int i = 0; i < EPV; i += 4)
+        *reinterpret_cast<float4*>(&part[warp][(32 * q + lane) * EPV + i]) = make_float4(acc[q][i], acc[q][i + 1], acc[q][i + 2], acc[q][i + 3]);
+    __syncthreads();
+    // combine in warp order; thread t owns pass-channels 2t, 2t+1
+    const int ch = 2 * threadIdx.x;
+    float s0 = part[0][ch], s1 = part[0][ch + 1];
+#pragma unroll
+    for (int w = 1; w < BWD_WARPS; ++w) {
+      s0 = __fadd_rn(s0, part[w][ch]);
+      s1 = __fadd_rn(s1, part[w][ch + 1]);
+    }
+    const int c_elem = cbase * EPV + ch;
+    if (c_elem < p.C) {  // C is a multiple of EPV (even)
+      o[c_elem] = from_float<T>(s0);
+      o[c_elem + 1] = from_float<T>(s1);
+    }
+    __syncthreads();
+  }
+}
+
+// backward, arbitrary strides: thread per CSR row (= source texel, tile-major order), loop over a chunk of channels
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_generic_kernel(const KParams p) {
   const int ntex = p.Hs * p.Ws;
-  const int tex = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
   const int vl = blockIdx.y, v = p.view0 + vl;
   const int nchunk = (p.C + p.cchunk - 1) / p.cchunk;
   const int b = blockIdx.z / nchunk, chunk = blockIdx.z % nchunk;
-  if (tex >= ntex) return;
+  if (row >= ntex) return;
   const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (ntex + 1);
   const CsrEntry* __restrict__ en = p.entries + __ldg(p.view_base + v);
-  const uint32_t r0 = __ldg(rp + tex), r1 = __ldg(rp + tex + 1);
+  const uint32_t r0 = __ldg(rp + row), r1 = __ldg(rp + row + 1);
+  const uint32_t tex = __ldg(p.tex_of + (size_t)v * ntex + row);
   const int ys = tex / p.Ws, xs = tex - ys * p.Ws;
   const T* __restrict__ go = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.oB;
   T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV + (int64_t)ys * p.fH + (int64_t)xs * p.fW;
@@ -558,7 +498,8 @@ static KParams make_params(const LaunchArgs& a) {
   KParams p{};
   p.T = pl->d_T; p.grid = reinterpret_cast<const float2*>(pl->d_grid);
   p.coord_x = pl->d_coord_x; p.coord_y = pl->d_coord_y;
-  p.row_ptr = pl->d_row_ptr; p.entries = pl->d_entries; p.view_base = pl->d_view_base;
+  p.row_ptr = pl->d_row_ptr; p.tex_of = pl->d_tex_of; p.entries = pl->d_entries; p.view_base = pl->d_view_base;
+  p.tasks = pl->d_tasks; p.heavy = pl->d_heavy;
   p.Hs = pl->Hs; p.Ws = pl->Ws; p.Hg = pl->Hg; p.Wg = pl->Wg;
   p.view0 = a.view0; p.nviews = a.nviews; p.B = a.B; p.C = a.C;
   p.src = a.feats_or_grad_out; p.dst = a.out_or_grad_feats;
@@ -640,30 +581,20 @@ static int launch_bwd_t(const LaunchArgs& a) {
   if (fast) {
     int rc = check_grid_dims(a, a.B);
     if (rc) return rc;
-    p.tiles_x = (p.Ws + BWD_TW - 1) / BWD_TW;
-    p.tiles_y = (p.Hs + BWD_TH - 1) / BWD_TH;
-    dim3 grid(p.tiles_x * p.tiles_y, a.nviews, a.B), block(BWD_WARPS * 32);
-    switch (tuning_variant("MVWARP_BWD_VARIANT", 0)) {  // tuning knob (development only)
-      case 1: bwd_cl_kernel<T, 4><<<grid, block, 0, a.stream>>>(p); break;
-      case 2: bwd_cl_kernel<T, 2><<<grid, block, 0, a.stream>>>(p); break;
-      case 11: bwd_cl_kernel<T, 3, 1><<<grid, block, 0, a.stream>>>(p); break;  // measurement: stores only
-      case 12: bwd_cl_kernel<T, 3, 2><<<grid, block, 0, a.stream>>>(p); break;  // measurement: gathers only
-      case 13: bwd_cl_kernel<T, 3, 3><<<grid, block, 0, a.stream>>>(p); break;  // default-policy stores
-      case 20: bwd_cl_kernel<T, 3><<<grid, block, 0, a.stream>>>(p); break;     // register-gather kernel
-#define MVW_RING(S_, M_)                                                                                          \
-  {                                                                                                               \
-    const int smem = BWD_WARPS * S_ * RING_VECS * 16;                                                             \
-    cudaError_t ea = cudaFuncSetAttribute(bwd_cl_ring_kernel<T, S_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-    if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(bwd ring)");                                \
-    bwd_cl_ring_kernel<T, S_, M_><<<grid, block, smem, a.stream>>>(p);                                            \
-  }                                                                                                               \
-  break
-      case 21: MVW_RING(6, 2);
-      case 22: MVW_RING(3, 4);
-      case 23: MVW_RING(8, 1);
-      case 24: MVW_RING(5, 2);
-      default: MVW_RING(4, 3);
-#undef MVW_RING
+    const mvwarp_plan* pl = a.plan;
+    const uint32_t t_lo = pl->task_base[a.view0], t_hi = pl->task_base[a.view0 + a.nviews];
+    const uint32_t h_lo = pl->heavy_base[a.view0], h_hi = pl->heavy_base[a.view0 + a.nviews];
+    if (t_hi > t_lo) {
+      dim3 grid((t_hi - t_lo + BWD_WARPS - 1) / BWD_WARPS, 1, a.B), block(BWD_WARPS * 32);
+      switch (tuning_variant("MVWARP_BWD_VARIANT", 0)) {  // tuning knob (development only)
+        case 1: bwd_cl_task_kernel<T, 4><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi); break;
+        case 2: bwd_cl_task_kernel<T, 2><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi); break;
+        default: bwd_cl_task_kernel<T, 3><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi); break;
+      }
+    }
+    if (h_hi > h_lo) {
+      dim3 grid(h_hi - h_lo, 1, a.B), block(BWD_WARPS * 32);
+      bwd_cl_heavy_kernel<T><<<grid, block, 0, a.stream>>>(p, h_lo, a.view0, pl->d_heavy_base);
     }
   } else {
     const int nchunk = (a.C + p.cchunk - 1) / p.cchunk;

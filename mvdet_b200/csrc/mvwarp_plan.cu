@@ -36,74 +36,131 @@ void host_grid(const float* T, int V, int Hg, int Wg, float* grid_out) {
       }
 }
 
-// Counting sort of the in-bounds taps of one view by texel; entry order inside a row is (cell, tap).
-static void build_view_csr(const float* grid, int Hs, int Ws, int Hg, int Wg, uint32_t* row_ptr,
-                           std::vector<CsrEntry>& entries, uint64_t& unique, uint64_t& valid, uint32_t& max_row) {
+// Tile-major order of the source image: CSR_TILE x CSR_TILE tiles row-major, texels row-major inside a tile.
+static void tile_major_order(int Hs, int Ws, std::vector<uint32_t>& tex_of, std::vector<uint32_t>& row_of) {
+  const size_t ntex = (size_t)Hs * Ws;
+  tex_of.resize(ntex);
+  row_of.resize(ntex);
+  size_t r = 0;
+  for (int ty = 0; ty < Hs; ty += CSR_TILE)
+    for (int tx = 0; tx < Ws; tx += CSR_TILE)
+      for (int y = ty; y < std::min(Hs, ty + CSR_TILE); ++y)
+        for (int x = tx; x < std::min(Ws, tx + CSR_TILE); ++x) {
+          const uint32_t tex = (uint32_t)((size_t)y * Ws + x);
+          tex_of[r] = tex;
+          row_of[tex] = (uint32_t)r++;
+        }
+}
+
+struct ViewCsr {
+  std::vector<CsrEntry> entries;
+  std::vector<Task> tasks;
+  std::vector<uint32_t> heavy;
+  uint64_t unique = 0, valid = 0;
+  uint32_t max_row = 0;
+};
+
+// Counting sort of the in-bounds taps of one view by row; entry order inside a row is (cell, tap).
+// Then the backward tasks: greedy runs of consecutive light rows under TASK_BUDGET, heavy rows apart.
+static void build_view_csr(const float* grid, int view, int Hs, int Ws, int Hg, int Wg, const std::vector<uint32_t>& row_of,
+                           uint32_t* row_ptr, ViewCsr& out) {
   const size_t ntex = (size_t)Hs * Ws, ncell = (size_t)Hg * Wg;
   std::vector<uint32_t> count(ntex + 1, 0);
   static const int dx[4] = {0, 1, 0, 1}, dy[4] = {0, 0, 1, 1};
-  valid = 0;
+  out.valid = 0;
   for (size_t cell = 0; cell < ncell; ++cell) {
     const Taps t = make_taps(grid[2 * cell], grid[2 * cell + 1], Hs, Ws);
-    if (t.mask) ++valid;
+    if (t.mask) ++out.valid;
     for (int k = 0; k < 4; ++k)
-      if (t.mask >> k & 1) ++count[(size_t)(t.y0 + dy[k]) * Ws + (t.x0 + dx[k])];
+      if (t.mask >> k & 1) ++count[row_of[(size_t)(t.y0 + dy[k]) * Ws + (t.x0 + dx[k])]];
   }
   uint32_t run = 0;
-  unique = 0;
-  max_row = 0;
+  out.unique = 0;
+  out.max_row = 0;
   for (size_t i = 0; i < ntex; ++i) {
     const uint32_t c = count[i];
     row_ptr[i] = run;
     count[i] = run;  // becomes the fill cursor
     run += c;
-    if (c) ++unique;
-    max_row = std::max(max_row, c);
+    if (c) ++out.unique;
+    out.max_row = std::max(out.max_row, c);
   }
   row_ptr[ntex] = run;
-  entries.resize(run);
+  out.entries.resize(run);
   for (size_t cell = 0; cell < ncell; ++cell) {
     const Taps t = make_taps(grid[2 * cell], grid[2 * cell + 1], Hs, Ws);
     for (int k = 0; k < 4; ++k)
       if (t.mask >> k & 1) {
-        const size_t tex = (size_t)(t.y0 + dy[k]) * Ws + (t.x0 + dx[k]);
-        entries[count[tex]++] = CsrEntry{(uint32_t)cell, t.w[k]};
+        const size_t row = row_of[(size_t)(t.y0 + dy[k]) * Ws + (t.x0 + dx[k])];
+        out.entries[count[row]++] = CsrEntry{(uint32_t)cell, t.w[k]};
       }
   }
+  // backward tasks
+  Task cur{0, 0, (uint16_t)view};
+  uint32_t weight = 0;
+  auto flush = [&]() {
+    if (cur.nrows) out.tasks.push_back(cur);
+    cur.nrows = 0;
+    weight = 0;
+  };
+  for (size_t r = 0; r < ntex; ++r) {
+    const uint32_t len = row_ptr[r + 1] - row_ptr[r];
+    if (len > HEAVY_LEN) {
+      flush();
+      out.heavy.push_back((uint32_t)r);
+      continue;
+    }
+    if (cur.nrows && (weight + 1 + len > TASK_BUDGET || cur.nrows >= TASK_MAX_TEX)) flush();
+    if (!cur.nrows) cur.row0 = (uint32_t)r;
+    ++cur.nrows;
+    weight += 1 + len;
+  }
+  flush();
 }
 
 void host_build_csr(const float* grid, int V, int Hs, int Ws, int Hg, int Wg, HostCsr& csr) {
   const size_t ntex = (size_t)Hs * Ws, ncell = (size_t)Hg * Wg;
+  std::vector<uint32_t> tex_of, row_of;
+  tile_major_order(Hs, Ws, tex_of, row_of);
   csr.row_ptr.assign((size_t)V * (ntex + 1), 0);
+  csr.tex_of.resize((size_t)V * ntex);
+  for (int v = 0; v < V; ++v) memcpy(csr.tex_of.data() + (size_t)v * ntex, tex_of.data(), ntex * sizeof(uint32_t));
   csr.view_base.assign(V + 1, 0);
-  std::vector<std::vector<CsrEntry>> per_view(V);
-  std::vector<uint64_t> uniq(V, 0), valid(V, 0);
-  std::vector<uint32_t> maxr(V, 0);
+  csr.task_base.assign(V + 1, 0);
+  csr.heavy_base.assign(V + 1, 0);
+  std::vector<ViewCsr> per_view(V);
   const int nthreads = std::max(1, std::min(V, (int)std::thread::hardware_concurrency()));
   std::vector<std::thread> pool;
   for (int t = 0; t < nthreads; ++t)
     pool.emplace_back([&, t]() {
       for (int v = t; v < V; v += nthreads)
-        build_view_csr(grid + (size_t)v * ncell * 2, Hs, Ws, Hg, Wg, csr.row_ptr.data() + (size_t)v * (ntex + 1),
-                       per_view[v], uniq[v], valid[v], maxr[v]);
+        build_view_csr(grid + (size_t)v * ncell * 2, v, Hs, Ws, Hg, Wg, row_of, csr.row_ptr.data() + (size_t)v * (ntex + 1),
+                       per_view[v]);
     });
   for (auto& th : pool) th.join();
   uint64_t total = 0;
   for (int v = 0; v < V; ++v) {
     csr.view_base[v] = total;
-    total += per_view[v].size();
+    total += per_view[v].entries.size();
+    csr.task_base[v + 1] = csr.task_base[v] + (uint32_t)per_view[v].tasks.size();
+    csr.heavy_base[v + 1] = csr.heavy_base[v] + (uint32_t)per_view[v].heavy.size();
   }
   csr.view_base[V] = total;
   csr.entries.resize(total);
+  csr.tasks.reserve(csr.task_base[V]);
+  csr.heavy.reserve(csr.heavy_base[V]);
   csr.unique_texels = csr.valid_cells = 0;
   csr.max_row = 0;
   for (int v = 0; v < V; ++v) {
-    if (!per_view[v].empty())
-      memcpy(csr.entries.data() + csr.view_base[v], per_view[v].data(), per_view[v].size() * sizeof(CsrEntry));
-    std::vector<CsrEntry>().swap(per_view[v]);
-    csr.unique_texels += uniq[v];
-    csr.valid_cells += valid[v];
-    csr.max_row = std::max(csr.max_row, maxr[v]);
+    ViewCsr& pv = per_view[v];
+    if (!pv.entries.empty())
+      memcpy(csr.entries.data() + csr.view_base[v], pv.entries.data(), pv.entries.size() * sizeof(CsrEntry));
+    csr.tasks.insert(csr.tasks.end(), pv.tasks.begin(), pv.tasks.end());
+    csr.heavy.insert(csr.heavy.end(), pv.heavy.begin(), pv.heavy.end());
+    std::vector<CsrEntry>().swap(pv.entries);
+    csr.unique_texels += pv.unique;
+    csr.valid_cells += pv.valid;
+    csr.max_row = std::max(csr.max_row, pv.max_row);
   }
 }
 
@@ -181,8 +238,12 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int Hs,
     const size_t o_grid = carve(T ? 0 : (size_t)V * ncell * 2 * sizeof(float));
     const size_t o_cx = carve(Wg * sizeof(float)), o_cy = carve(Hg * sizeof(float));
     const size_t o_rp = carve((size_t)V * (ntex + 1) * sizeof(uint32_t));
+    const size_t o_to = carve((size_t)V * ntex * sizeof(uint32_t));
     const size_t o_en = carve(csr.entries.size() * sizeof(CsrEntry));
     const size_t o_vb = carve((V + 1) * sizeof(uint64_t));
+    const size_t o_tk = carve(csr.tasks.size() * sizeof(Task));
+    const size_t o_hv = carve(csr.heavy.size() * sizeof(uint32_t));
+    const size_t o_hb = carve((V + 1) * sizeof(uint32_t));
     p->d_bytes = off;
     e = cudaMalloc(&p->d_base, p->d_bytes);
     if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(plan)"); }
@@ -192,8 +253,14 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int Hs,
     p->d_coord_x = (float*)(base + o_cx);
     p->d_coord_y = (float*)(base + o_cy);
     p->d_row_ptr = (uint32_t*)(base + o_rp);
+    p->d_tex_of = (uint32_t*)(base + o_to);
     p->d_entries = (CsrEntry*)(base + o_en);
     p->d_view_base = (uint64_t*)(base + o_vb);
+    p->d_tasks = (Task*)(base + o_tk);
+    p->d_heavy = (uint32_t*)(base + o_hv);
+    p->d_heavy_base = (uint32_t*)(base + o_hb);
+    p->task_base = csr.task_base;
+    p->heavy_base = csr.heavy_base;
 
     auto up = [&](void* dst, const void* src, size_t bytes) {
       if (e == cudaSuccess && bytes) e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
@@ -203,7 +270,11 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int Hs,
     up(p->d_coord_x, cx.data(), Wg * sizeof(float));
     up(p->d_coord_y, cy.data(), Hg * sizeof(float));
     up(p->d_row_ptr, csr.row_ptr.data(), csr.row_ptr.size() * sizeof(uint32_t));
+    up(p->d_tex_of, csr.tex_of.data(), csr.tex_of.size() * sizeof(uint32_t));
     up(p->d_entries, csr.entries.data(), csr.entries.size() * sizeof(CsrEntry));
+    up(p->d_tasks, csr.tasks.data(), csr.tasks.size() * sizeof(Task));
+    up(p->d_heavy, csr.heavy.data(), csr.heavy.size() * sizeof(uint32_t));
+    up(p->d_heavy_base, csr.heavy_base.data(), csr.heavy_base.size() * sizeof(uint32_t));
     up(p->d_view_base, csr.view_base.data(), csr.view_base.size() * sizeof(uint64_t));
     if (e != cudaSuccess) { cudaFree(p->d_base); delete p; return cuda_fail(e, "plan upload"); }
 
@@ -213,6 +284,8 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int Hs,
     p->stats.nnz = csr.view_base[V];
     p->stats.valid_cells = csr.valid_cells;
     p->stats.max_row = csr.max_row;
+    p->stats.bwd_tasks = csr.task_base[V];
+    p->stats.heavy_rows = csr.heavy_base[V];
     p->stats.device_bytes = p->d_bytes;
     *plan_out = p;
     return MVWARP_OK;
@@ -245,7 +318,8 @@ int mvwarp_host_grid(const float* T, int V, int Hg, int Wg, float* grid_out) {
 }
 
 int mvwarp_host_csr(const float* grid_host, int V, int Hs, int Ws, int Hg, int Wg, mvwarp_stats_t* stats_out,
-                    uint32_t* row_ptr_out, uint32_t* cells_out, float* weights_out, uint64_t capacity) {
+                    uint32_t* tex_of_out, uint32_t* row_ptr_out, uint32_t* cells_out, float* weights_out,
+                    uint64_t capacity) {
   if (!grid_host || !stats_out) { set_error("host_csr: null argument"); return MVWARP_EINVAL; }
   int rc = check_shapes(V, Hs, Ws, Hg, Wg);
   if (rc) return rc;
@@ -258,6 +332,9 @@ int mvwarp_host_csr(const float* grid_host, int V, int Hs, int Ws, int Hg, int W
     stats_out->nnz = csr.view_base[V];
     stats_out->valid_cells = csr.valid_cells;
     stats_out->max_row = csr.max_row;
+    stats_out->bwd_tasks = csr.task_base[V];
+    stats_out->heavy_rows = csr.heavy_base[V];
+    if (tex_of_out) memcpy(tex_of_out, csr.tex_of.data(), csr.tex_of.size() * sizeof(uint32_t));
     if (row_ptr_out) memcpy(row_ptr_out, csr.row_ptr.data(), csr.row_ptr.size() * sizeof(uint32_t));
     if (cells_out || weights_out) {
       if (capacity < csr.entries.size()) { set_error("host_csr: capacity smaller than nnz"); return MVWARP_EINVAL; }

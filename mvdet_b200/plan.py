@@ -69,24 +69,27 @@ def host_grid(T: torch.Tensor, dst_hw: Sequence[int]) -> torch.Tensor:
 
 
 def host_csr(grid: torch.Tensor, src_hw: Sequence[int], with_map: bool = False):
-    """Statistics (and optionally the arrays) of the inverse CSR map of ``grid`` [V,Hg,Wg,2]; host only."""
+    """Statistics (and optionally the arrays ``tex_of, row_ptr, cells, weights``) of the inverse CSR map of
+    ``grid`` [V,Hg,Wg,2]; host only.  Row r of view v is the texel ``tex_of[v, r]`` (tile-major order)."""
     lib = _lib.load()
     grid = grid.contiguous().float()
     V, Hg, Wg, _ = grid.shape
     Hs, Ws = int(src_hw[0]), int(src_hw[1])
     st = _lib.Stats()
     if not with_map:
-        _lib.check(lib.mvwarp_host_csr(_fptr(grid), V, Hs, Ws, Hg, Wg, C.byref(st), None, None, None, 0), "mvwarp_host_csr")
+        _lib.check(lib.mvwarp_host_csr(_fptr(grid), V, Hs, Ws, Hg, Wg, C.byref(st), None, None, None, None, 0), "mvwarp_host_csr")
         return st.as_dict()
     cap = 4 * V * Hg * Wg
+    tex_of = torch.empty(V * Hs * Ws, dtype=torch.int32)
     row_ptr = torch.empty(V * (Hs * Ws + 1), dtype=torch.int32)
     cells = torch.empty(cap, dtype=torch.int32)
     weights = torch.empty(cap, dtype=torch.float32)
     u32 = C.POINTER(C.c_uint32)
-    _lib.check(lib.mvwarp_host_csr(_fptr(grid), V, Hs, Ws, Hg, Wg, C.byref(st), C.cast(row_ptr.data_ptr(), u32),
-                                   C.cast(cells.data_ptr(), u32), _fptr(weights), cap), "mvwarp_host_csr")
+    _lib.check(lib.mvwarp_host_csr(_fptr(grid), V, Hs, Ws, Hg, Wg, C.byref(st), C.cast(tex_of.data_ptr(), u32),
+                                   C.cast(row_ptr.data_ptr(), u32), C.cast(cells.data_ptr(), u32), _fptr(weights), cap),
+               "mvwarp_host_csr")
     d = st.as_dict()
-    return d, row_ptr.view(V, Hs * Ws + 1), cells[:d["nnz"]], weights[:d["nnz"]]
+    return d, tex_of.view(V, Hs * Ws), row_ptr.view(V, Hs * Ws + 1), cells[:d["nnz"]], weights[:d["nnz"]]
 
 
 class WarpPlan:

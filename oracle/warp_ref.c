@@ -19,7 +19,8 @@ static float mesh(int i, int n) { return ((float)i / (float)(n - 1) - 0.5f) * 2.
 
 /* kornia transform_points + convert_points_from_homogeneous for one camera.
  * T: 3x3 row-major fp32 `src_norm_trans_dst_norm`; grid: [Hg,Wg,2].
- * torch.bmm (K=3) accumulates sequentially with FMA from a zero accumulator. */
+ * torch.bmm (K=3) on CPU: MKL sgemm accumulates sequentially with FMA from a zero accumulator; below
+ * 3*Wg*3 < 400 at::native uses its scalar small-matrix kernel instead (plain multiply-adds). */
 void warp_ref_grid(const float* T, int Hg, int Wg, float* grid) {
   for (int y = 0; y < Hg; ++y)
     for (int x = 0; x < Wg; ++x) {
@@ -27,8 +28,13 @@ void warp_ref_grid(const float* T, int Hg, int Wg, float* grid) {
       float q[3];
       for (int j = 0; j < 3; ++j) {
         float acc = p[0] * T[3 * j];
-        acc = fmaf(p[1], T[3 * j + 1], acc);
-        acc = fmaf(p[2], T[3 * j + 2], acc);
+        if (9 * Wg >= 400) {
+          acc = fmaf(p[1], T[3 * j + 1], acc);
+          acc = fmaf(p[2], T[3 * j + 2], acc);
+        } else {
+          acc = acc + p[1] * T[3 * j + 1];
+          acc = acc + p[2] * T[3 * j + 2];
+        }
         q[j] = acc;
       }
       const float eps = 1e-8f;

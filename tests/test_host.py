@@ -29,8 +29,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_stats_struct_layout_matches_header():
-    # int32 x6, then uint64 x3, uint32 (+pad), uint64: 24 + 24 + 8 + 8
-    assert ctypes.sizeof(_lib.Stats) == 64
+    # int32 x6, uint64 x3, uint32 x4, uint64: 24 + 24 + 16 + 8
+    assert ctypes.sizeof(_lib.Stats) == 72
 
 
 def test_bad_arguments_return_error_codes_not_crashes():
@@ -38,7 +38,7 @@ def test_bad_arguments_return_error_codes_not_crashes():
     assert lib.mvwarp_host_grid(None, 1, 4, 4, None) == _lib.EINVAL
     assert b"host_grid" in lib.mvwarp_last_error()
     st = _lib.Stats()
-    assert lib.mvwarp_host_csr(None, 1, 4, 4, 4, 4, ctypes.byref(st), None, None, None, 0) == _lib.EINVAL
+    assert lib.mvwarp_host_csr(None, 1, 4, 4, 4, 4, ctypes.byref(st), None, None, None, None, 0) == _lib.EINVAL
     handle = ctypes.c_void_p()
     assert lib.mvwarp_plan_create(None, 1, 4, 4, 4, 4, 0, ctypes.byref(handle)) == _lib.EINVAL
     assert lib.mvwarp_plan_destroy(None) == _lib.OK
@@ -76,11 +76,11 @@ def test_csr_statistics_match_survey(spec):
     assert (st["unique_texels"], st["nnz"], st["max_row"]) == KNOWN[spec.name]
 
 
-def _csr_backward(row_ptr, cells, weights, grad_out_v, ntex):
-    """grad_in[c, texel] = sum_k w_k * grad_out[c, cell_k], rows in CSR order (dense torch emulation)."""
+def _csr_backward(tex_of, row_ptr, cells, weights, grad_out_v, ntex):
+    """grad_in[c, tex_of[row]] = sum_k w_k * grad_out[c, cell_k], rows in CSR order (dense torch emulation)."""
     C = grad_out_v.shape[0]
     lens = (row_ptr[1:] - row_ptr[:-1]).long()
-    rows = torch.repeat_interleave(torch.arange(ntex), lens)
+    rows = torch.repeat_interleave(tex_of.long(), lens)
     contrib = grad_out_v.reshape(C, -1)[:, cells.long()] * weights[None]
     out = torch.zeros(C, ntex, dtype=grad_out_v.dtype)
     out.index_add_(1, rows, contrib)
@@ -92,8 +92,10 @@ def test_csr_is_adjoint_of_oracle_forward():
     V, C = pm.shape[0], 5
     T = P.src_norm_trans_dst_norm(pm, src_hw, grid_hw)
     g = P.host_grid(T, grid_hw)
-    st, row_ptr, cells, weights = P.host_csr(g, src_hw, with_map=True)
+    st, tex_of, row_ptr, cells, weights = P.host_csr(g, src_hw, with_map=True)
     assert int(row_ptr[:, -1].sum()) == st["nnz"]
+    ntex_ = src_hw[0] * src_hw[1]
+    assert torch.equal(torch.sort(tex_of[0].long()).values, torch.arange(ntex_))   # a permutation of the texels
     torch.manual_seed(0)
     x = torch.randn(1, V, C, *src_hw, requires_grad=True)
     out = K.warp_views_oracle(x, pm, grid_hw)
@@ -103,7 +105,7 @@ def test_csr_is_adjoint_of_oracle_forward():
     base = 0
     for v in range(V):
         n = int(row_ptr[v, -1])
-        mine = _csr_backward(row_ptr[v], cells[base:base + n], weights[base:base + n], go[0, v * C:(v + 1) * C], ntex)
+        mine = _csr_backward(tex_of[v], row_ptr[v], cells[base:base + n], weights[base:base + n], go[0, v * C:(v + 1) * C], ntex)
         base += n
         ref = gx[0, v].reshape(C, ntex)
         assert float((mine - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
@@ -125,8 +127,33 @@ def test_csr_handles_degenerate_grids():
     assert st["nnz"] == 0 and st["unique_texels"] == 0 and st["valid_cells"] == 0
     # exact corner hit: the four taps of the last texel, three of them outside
     g = torch.ones((1, 1, 1, 2))
-    st, row_ptr, cells, weights = P.host_csr(g, (6, 6), with_map=True)
+    st, tex_of, row_ptr, cells, weights = P.host_csr(g, (6, 6), with_map=True)
     assert st["nnz"] == 1 and float(weights[0]) == 1.0 and int(row_ptr[0, -1]) == 1
+    assert int(tex_of[0][int(torch.nonzero(row_ptr[0, 1:] - row_ptr[0, :-1])[0, 0])]) == 35   # the last texel
+
+
+def test_backward_task_decomposition_covers_every_row_once():
+    """Plan-time load balancing: light rows are packed into warp tasks, heavy rows get a CTA each."""
+    pm = synthetic_rig(WILDTRACK)
+    g = P.host_grid(P.src_norm_trans_dst_norm(pm, WILDTRACK.feat_shape, WILDTRACK.grid_shape), WILDTRACK.grid_shape)
+    st, tex_of, row_ptr, cells, weights = P.host_csr(g, WILDTRACK.feat_shape, with_map=True)
+    lens = (row_ptr[:, 1:] - row_ptr[:, :-1]).long()
+    heavy = int((lens > 48).sum())
+    assert st["heavy_rows"] == heavy and heavy > 0
+    light_weight = int((lens[lens <= 48] + 1).sum())
+    # every task is at most 64 heavy (rows + entries): the task count is bounded both ways
+    assert st["bwd_tasks"] >= light_weight / 64
+    assert st["bwd_tasks"] <= light_weight / 16 + heavy + 7 * 40000
+
+
+@pytest.mark.parametrize("Wg", [2, 44, 45, 64])
+def test_host_grid_follows_torch_bmm_dispatch(Wg):
+    """torch.bmm switches from its scalar small-matrix kernel to MKL at 9*Wg >= 400; the chain mirrors both."""
+    pm, src_hw, _ = small_rig(num_cam=2, seed=4)
+    grid_hw = (7, Wg)
+    g = P.host_grid(P.src_norm_trans_dst_norm(pm, src_hw, grid_hw), grid_hw)
+    og = K.sampling_grids(pm, src_hw, grid_hw)
+    assert torch.equal(g.view(torch.int32), og.view(torch.int32))
 
 
 def test_coord_map_matches_reference_formula():
