@@ -83,8 +83,33 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(f
 // read-only 16-byte gather, kept in L1 (neighbouring cells re-use the same texels)
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+// L2 "keep" policy for gathered rows: the backward streams 3x more bytes out than it gathers in, and without a
+// hint the write stream evicts grad_out rows from L2 before the next texel row re-uses them.
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg16_keep(const void* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint2 ldg8_keep(const void* p, uint64_t pol) {
+  uint2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+
 // 16 bytes from an address that is only 8- or 4-byte aligned (odd cells of the 3586-channel concat row)
-__device__ __forceinline__ uint4 ldg16_any(const void* p, unsigned align_mask) {
+template <bool KEEP>
+__device__ __forceinline__ uint4 ldg16_any(const void* p, unsigned align_mask, uint64_t pol) {
+  if (KEEP && (align_mask & 7u) == 0) {
+    if (align_mask == 0) return ldg16_keep(p, pol);
+    const uint2 a = ldg8_keep(p, pol), b = ldg8_keep(reinterpret_cast<const char*>(p) + 8, pol);
+    return make_uint4(a.x, a.y, b.x, b.y);
+  }
   if (align_mask == 0) return __ldg(reinterpret_cast<const uint4*>(p));
   if ((align_mask & 7u) == 0) {
     const uint2 a = __ldg(reinterpret_cast<const uint2*>(p)), b = __ldg(reinterpret_cast<const uint2*>(p) + 1);
@@ -144,9 +169,10 @@ struct TapRec {
   float zero;  // value of an all-outside cell: the 0*w chain (propagates NaN weights like the oracle)
 };
 
-template <typename T, bool kInline, int UNROLL, int MINB>
+template <typename T, bool kInline, int UNROLL, int MINB, bool KEEP = false>
 __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_cl_kernel(const KParams p) {
   constexpr int EPV = VecTraits<T>::EPV;
+  const uint64_t pol = KEEP ? l2_evict_last_policy() : 0ull;
   __shared__ TapRec taps[FWD_CELLS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
@@ -210,7 +236,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_cl_kernel(const KPar
         const int c = c0 + 32 * u;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          val[u][k] = (c < nvec && (tp.mask >> k & 1)) ? ldg16(tap[k] + c * EPV) : make_uint4(0, 0, 0, 0);
+          val[u][k] = (c < nvec && (tp.mask >> k & 1)) ? (KEEP ? ldg16_keep(tap[k] + c * EPV, pol) : ldg16(tap[k] + c * EPV))
+                                                       : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
@@ -282,10 +309,11 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const KParams p) {
 constexpr int BWD_WARPS = 8, BWD_ACC_FLOATS = 16;
 
 // acc += sum over entries [k0, k1) of w * grad_out[cell]; entries come through 32-entry windows (coalesced)
-template <typename T, int NACC>
+template <typename T, int NACC, bool KEEP>
 __device__ __forceinline__ void gather_entries(float (&acc)[NACC][VecTraits<T>::EPV], const uint2* __restrict__ en,
                                                uint32_t k0, uint32_t k1, uint32_t win_end, const T* __restrict__ go,
-                                               const KParams& p, int cbase, int nvec, int lane, uint32_t& win0, uint2& ent) {
+                                               const KParams& p, int cbase, int nvec, int lane, uint32_t& win0, uint2& ent,
+                                               uint64_t pol) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr unsigned FULL = 0xffffffffu;
   uint32_t k = k0;
@@ -310,8 +338,8 @@ __device__ __forceinline__ void gather_entries(float (&acc)[NACC][VecTraits<T>::
 #pragma unroll
       for (int q = 0; q < NACC; ++q) {
         const int c = cbase + 32 * q + lane;
-        v0[q] = c < nvec ? ldg16_any(g0 + c * EPV, al0) : make_uint4(0, 0, 0, 0);
-        v1[q] = c < nvec ? ldg16_any(g1 + c * EPV, al1) : make_uint4(0, 0, 0, 0);
+        v0[q] = c < nvec ? ldg16_any<KEEP>(g0 + c * EPV, al0, pol) : make_uint4(0, 0, 0, 0);
+        v1[q] = c < nvec ? ldg16_any<KEEP>(g1 + c * EPV, al1, pol) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int q = 0; q < NACC; ++q) {
@@ -328,7 +356,7 @@ __device__ __forceinline__ void gather_entries(float (&acc)[NACC][VecTraits<T>::
         const int c = cbase + 32 * q + lane;
         if (c < nvec) {
           float f0[EPV];
-          VecTraits<T>::unpack(ldg16_any(g0 + c * EPV, al0), f0);
+          VecTraits<T>::unpack(ldg16_any<KEEP>(g0 + c * EPV, al0, pol), f0);
 #pragma unroll
           for (int i = 0; i < EPV; ++i) acc[q][i] = __fmaf_rn(w0, f0[i], acc[q][i]);
         }
@@ -338,14 +366,14 @@ __device__ __forceinline__ void gather_entries(float (&acc)[NACC][VecTraits<T>::
   }
 }
 
-template <typename T, int MINB>
-__global__ void __launch_bounds__(BWD_WARPS * 32, MINB) bwd_cl_task_kernel(const KParams p, uint32_t task_lo, uint32_t task_hi) {
+template <typename T, bool KEEP>
+__device__ __forceinline__ void bwd_task(const KParams& p, uint32_t tid, uint32_t task_hi) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr int NACC = BWD_ACC_FLOATS / EPV;  // 16-byte vectors per lane per pass
   constexpr unsigned FULL = 0xffffffffu;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tid = task_lo + blockIdx.x * BWD_WARPS + warp;
+  const int lane = threadIdx.x & 31;
   if (tid >= task_hi) return;
+  const uint64_t pol = KEEP ? l2_evict_last_policy() : 0ull;
   const Task task = p.tasks[tid];
   const int v = task.view, vl = v - p.view0, b = blockIdx.z;
   const int nrows = task.nrows;
@@ -372,7 +400,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, MINB) bwd_cl_task_kernel(const
       for (int q = 0; q < NACC; ++q)
 #pragma unroll
         for (int i = 0; i < EPV; ++i) acc[q][i] = 0.f;
-      gather_entries<T, NACC>(acc, en, a, e, r_end, go, p, cbase, nvec, lane, win0, ent);
+      gather_entries<T, NACC, KEEP>(acc, en, a, e, r_end, go, p, cbase, nvec, lane, win0, ent, pol);
       const int ys = tex / p.Ws, xs = tex - ys * p.Ws;
       T* o = gf + (int64_t)ys * p.fH + (int64_t)xs * p.fW;
 #pragma unroll
@@ -384,15 +412,15 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, MINB) bwd_cl_task_kernel(const
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(BWD_WARPS * 32) bwd_cl_heavy_kernel(const KParams p, uint32_t heavy_lo, int view_lo,
-                                                                      const uint32_t* __restrict__ heavy_base) {
+constexpr int BWD_PASS_FLOATS = 32 * BWD_ACC_FLOATS;  // channels per pass (512)
+
+template <typename T, bool KEEP>
+__device__ __forceinline__ void bwd_heavy_row(const KParams& p, uint32_t hid, int view_lo, const uint32_t* __restrict__ heavy_base,
+                                              float (*part)[BWD_PASS_FLOATS]) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr int NACC = BWD_ACC_FLOATS / EPV;
-  constexpr int PASS_FLOATS = 32 * BWD_ACC_FLOATS;  // channels per pass (512)
-  __shared__ __align__(16) float part[BWD_WARPS][PASS_FLOATS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t hid = heavy_lo + blockIdx.x;
+  const uint64_t pol = KEEP ? l2_evict_last_policy() : 0ull;
   int v = view_lo;
   while (hid >= __ldg(heavy_base + v + 1)) ++v;  // few views: linear search
   const int vl = v - p.view0, b = blockIdx.z;
@@ -416,7 +444,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) bwd_cl_heavy_kernel(const KPar
       for (int i = 0; i < EPV; ++i) acc[q][i] = 0.f;
     uint32_t win0 = k0;
     uint2 ent = (win0 + lane < k1) ? __ldg(en + win0 + lane) : make_uint2(0u, 0u);
-    gather_entries<T, NACC>(acc, en, k0, k1, k1, go, p, cbase, nvec, lane, win0, ent);
+    gather_entries<T, NACC, KEEP>(acc, en, k0, k1, k1, go, p, cbase, nvec, lane, win0, ent, pol);
     // partials in channel order: lane's q-th vector covers pass-channels [(32q + lane)*EPV, +EPV)
 #pragma unroll
     for (int q = 0; q < NACC; ++q)
@@ -438,6 +466,20 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) bwd_cl_heavy_kernel(const KPar
       o[c_elem + 1] = from_float<T>(s1);
     }
     __syncthreads();
+  }
+}
+
+// One launch: the first n_heavy CTAs take one heavy row each (longest chains start first), the rest take
+// BWD_WARPS tasks each.
+template <typename T, int MINB, bool KEEP>
+__global__ void __launch_bounds__(BWD_WARPS * 32, MINB)
+    bwd_cl_kernel(const KParams p, uint32_t task_lo, uint32_t task_hi, uint32_t heavy_lo, uint32_t n_heavy, int view_lo,
+                  const uint32_t* __restrict__ heavy_base) {
+  __shared__ __align__(16) float part[BWD_WARPS][BWD_PASS_FLOATS];
+  if (blockIdx.x < n_heavy) {
+    bwd_heavy_row<T, KEEP>(p, heavy_lo + blockIdx.x, view_lo, heavy_base, part);
+  } else {
+    bwd_task<T, KEEP>(p, task_lo + (blockIdx.x - n_heavy) * BWD_WARPS + (threadIdx.x >> 5), task_hi);
   }
 }
 
@@ -547,15 +589,14 @@ static int launch_fwd_t(const LaunchArgs& a) {
     if (rc) return rc;
     dim3 grid(p.tiles_x * p.tiles_y, a.nviews, a.B), block(FWD_WARPS * 32);
     switch (tuning_variant("MVWARP_FWD_VARIANT", 0)) {  // tuning knob (development only)
-#define MVW_FWD(U, M)                                                            \
-  if (inl) fwd_cl_kernel<T, true, U, M><<<grid, block, 0, a.stream>>>(p);        \
-  else fwd_cl_kernel<T, false, U, M><<<grid, block, 0, a.stream>>>(p);           \
+#define MVW_FWD(U, M, K)                                                         \
+  if (inl) fwd_cl_kernel<T, true, U, M, K><<<grid, block, 0, a.stream>>>(p);     \
+  else fwd_cl_kernel<T, false, U, M, K><<<grid, block, 0, a.stream>>>(p);        \
   break
-      case 1: MVW_FWD(4, 2);
-      case 2: MVW_FWD(1, 6);
-      case 3: MVW_FWD(2, 3);
-      case 4: MVW_FWD(4, 3);
-      default: MVW_FWD(2, 4);
+      case 1: MVW_FWD(4, 2, false);
+      case 3: MVW_FWD(2, 3, false);
+      case 5: MVW_FWD(2, 4, true);
+      default: MVW_FWD(2, 4, false);
 #undef MVW_FWD
     }
   } else {
@@ -584,17 +625,14 @@ static int launch_bwd_t(const LaunchArgs& a) {
     const mvwarp_plan* pl = a.plan;
     const uint32_t t_lo = pl->task_base[a.view0], t_hi = pl->task_base[a.view0 + a.nviews];
     const uint32_t h_lo = pl->heavy_base[a.view0], h_hi = pl->heavy_base[a.view0 + a.nviews];
-    if (t_hi > t_lo) {
-      dim3 grid((t_hi - t_lo + BWD_WARPS - 1) / BWD_WARPS, 1, a.B), block(BWD_WARPS * 32);
+    const uint32_t n_heavy = h_hi - h_lo, n_task_ctas = (t_hi - t_lo + BWD_WARPS - 1) / BWD_WARPS;
+    if (n_heavy + n_task_ctas > 0) {
+      dim3 grid(n_heavy + n_task_ctas, 1, a.B), block(BWD_WARPS * 32);
       switch (tuning_variant("MVWARP_BWD_VARIANT", 0)) {  // tuning knob (development only)
-        case 1: bwd_cl_task_kernel<T, 4><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi); break;
-        case 2: bwd_cl_task_kernel<T, 2><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi); break;
-        default: bwd_cl_task_kernel<T, 3><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi); break;
+        case 1: bwd_cl_kernel<T, 3, false><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, pl->d_heavy_base); break;
+        case 2: bwd_cl_kernel<T, 2, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, pl->d_heavy_base); break;
+        default: bwd_cl_kernel<T, 3, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, pl->d_heavy_base); break;
       }
-    }
-    if (h_hi > h_lo) {
-      dim3 grid(h_hi - h_lo, 1, a.B), block(BWD_WARPS * 32);
-      bwd_cl_heavy_kernel<T><<<grid, block, 0, a.stream>>>(p, h_lo, a.view0, pl->d_heavy_base);
     }
   } else {
     const int nchunk = (a.C + p.cchunk - 1) / p.cchunk;

@@ -33,3 +33,23 @@ for r in rows[2:]:
                 pass
     st.sort(reverse=True)
     print("  warp stall cycles per issued instruction (top):", ", ".join(f"{n}={v:.2f}" for v, n in st[:7]))
+
+# --traffic OUT.json ALGO_JSON: also write per-kernel DRAM traffic (read+write bytes per launch, averaged over the
+# captured launches) keyed by short kernel name, for bench.py's roofline.traffic
+if "--traffic" in sys.argv:
+    import json, re, os
+    out = sys.argv[sys.argv.index("--traffic") + 1]
+    def to_bytes(v, u):
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+        return float(v.replace(",", "")) * mult
+    acc = {}
+    for r in rows[2:]:
+        name = re.sub(r"^void\s+", "", r[idx['Kernel Name']])
+        short = re.match(r"(?:mvw::)?([A-Za-z0-9_]+)", name).group(1)
+        rd = to_bytes(r[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']])
+        wr = to_bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
+        acc.setdefault(short, []).append(rd + wr)
+    prev = json.load(open(out)) if os.path.exists(out) else {}
+    for k, v in acc.items():
+        prev[k] = {"dram_bytes": sum(v) / len(v), "launches": len(v), "report": os.path.basename(rep)}
+    json.dump(prev, open(out, "w"), indent=1)
