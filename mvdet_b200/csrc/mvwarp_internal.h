@@ -17,9 +17,9 @@ struct CsrEntry {
 };
 
 // Backward work decomposition (built with the CSR): a regular task is a run of consecutive rows whose
-// weight (1 per texel + 1 per entry) fits TASK_BUDGET, processed by one warp; a row longer than HEAVY_LEN
+// weight (1 per texel + 1 per entry) fits TASK_BUDGET (32), processed by one warp; a row longer than HEAVY_LEN
 // is "heavy" and gets a whole CTA (its entries split over the warps, partials combined in warp order).
-constexpr uint32_t TASK_BUDGET = 64, TASK_MAX_TEX = 31, HEAVY_LEN = 48;
+constexpr uint32_t TASK_BUDGET = 32, TASK_MAX_TEX = 31, HEAVY_LEN = 31;  // swept on B200: profiles/README.md
 constexpr int CSR_TILE = 8;  // rows are ordered tile-major over CSR_TILE x CSR_TILE texel tiles
 
 struct Task {

@@ -169,14 +169,17 @@ struct TapRec {
   float zero;  // value of an all-outside cell: the 0*w chain (propagates NaN weights like the oracle)
 };
 
-template <typename T, bool kInline, int UNROLL, int MINB, bool KEEP = false>
+template <typename T, bool kInline, int UNROLL, int MINB, bool KEEP = false, int DBG = 0>
 __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_cl_kernel(const KParams p) {
   constexpr int EPV = VecTraits<T>::EPV;
   const uint64_t pol = KEEP ? l2_evict_last_policy() : 0ull;
   __shared__ TapRec taps[FWD_CELLS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
-  const int vl = blockIdx.y, b = blockIdx.z;
+  // grid: x = view (fastest), y = tile, z = batch.  CTAs are dispatched x-fastest, so the V CTAs of one cell tile
+  // run at about the same time and their V slices of each concat row reach L2 / DRAM together (one 14 KB row
+  // instead of V separate 2 KB pieces: measured 0.223 -> see profiles/README.md).
+  const int tx = blockIdx.y % p.tiles_x, ty = blockIdx.y / p.tiles_x;
+  const int vl = blockIdx.x, b = blockIdx.z;
   const int v = p.view0 + vl;
 
   if (threadIdx.x < FWD_CELLS) {
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_cl_kernel(const KPar
     T* o = dst + (int64_t)y * p.oH + (int64_t)x * p.oW;
     const unsigned oalign = (unsigned)(reinterpret_cast<uintptr_t>(o) & 15u);
 
-    if (tp.mask == 0) {
+    if (tp.mask == 0 || DBG == 1) {  // (DBG 1: measurement only -- stores without gathers)
       float zf[EPV];
 #pragma unroll
       for (int e = 0; e < EPV; ++e) zf[e] = tp.zero;
@@ -248,7 +251,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_cl_kernel(const KPar
           for (int k = 0; k < 4; ++k) VecTraits<T>::unpack(val[u][k], f[k]);
 #pragma unroll
           for (int e = 0; e < EPV; ++e) r[e] = blend4(f[0][e], f[1][e], f[2][e], f[3][e], tp.w);
-          stcs16_any(o + c * EPV, VecTraits<T>::pack(r), oalign);
+          if (DBG != 2 || r[0] == 123.456f)  // (DBG 2: measurement only -- gathers without stores)
+            stcs16_any(o + c * EPV, VecTraits<T>::pack(r), oalign);
         }
       }
     }
@@ -297,12 +301,12 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const KParams p) {
 // The CSR rows (one per source texel, tile-major order) are very unevenly filled: 74 % are empty, the
 // median touched row has 2 entries, rows near a camera's horizon have up to 95 (1360 on the 32-camera
 // rig).  A gather row is a chain of dependent round trips, so work is balanced at plan time:
-//   * bwd_cl_task_kernel: one WARP per task = run of consecutive light rows with (rows + entries) <= 64.
+//   * bwd_cl_task_kernel: one WARP per task = run of consecutive light rows with (rows + entries) <= 32.
 //     Row pointers, texel ids and entries are fetched with coalesced loads (consecutive rows are
 //     contiguous in the CSR arrays) and broadcast by shuffles; lanes run across channels (16 B each) and
 //     sum a row in CSR order (ascending cell, then tap) with fp32 FMAs, two entries (8 independent 128-bit
 //     gathers) in flight per lane.  Empty rows store zeros: there is no memset pass.
-//   * bwd_cl_heavy_kernel: one CTA per heavy row (> 48 entries): warp w sums the w-th eighth of the row,
+//   * bwd_cl_heavy_kernel: one CTA per heavy row (> 31 entries): warp w sums the w-th eighth of the row,
 //     partials meet in shared memory and are added in warp order.
 // Both orders are fixed by the plan, so the gradient is bitwise reproducible (no atomics anywhere).
 // ---------------------------------------------------------------------------------------------------
@@ -587,15 +591,21 @@ static int launch_fwd_t(const LaunchArgs& a) {
   if (fast) {
     int rc = check_grid_dims(a, a.B);
     if (rc) return rc;
-    dim3 grid(p.tiles_x * p.tiles_y, a.nviews, a.B), block(FWD_WARPS * 32);
+    if (p.tiles_x * p.tiles_y > 65535) {
+      set_error("warp_views_fwd: more than 65535 cell tiles per view");
+      return MVWARP_EUNSUPPORTED;
+    }
+    dim3 grid(a.nviews, p.tiles_x * p.tiles_y, a.B), block(FWD_WARPS * 32);
     switch (tuning_variant("MVWARP_FWD_VARIANT", 0)) {  // tuning knob (development only)
-#define MVW_FWD(U, M, K)                                                         \
-  if (inl) fwd_cl_kernel<T, true, U, M, K><<<grid, block, 0, a.stream>>>(p);     \
-  else fwd_cl_kernel<T, false, U, M, K><<<grid, block, 0, a.stream>>>(p);        \
+#define MVW_FWD(U, M, K, ...)                                                              \
+  if (inl) fwd_cl_kernel<T, true, U, M, K, ##__VA_ARGS__><<<grid, block, 0, a.stream>>>(p);   \
+  else fwd_cl_kernel<T, false, U, M, K, ##__VA_ARGS__><<<grid, block, 0, a.stream>>>(p);      \
   break
       case 1: MVW_FWD(4, 2, false);
       case 3: MVW_FWD(2, 3, false);
       case 5: MVW_FWD(2, 4, true);
+      case 11: MVW_FWD(2, 4, false, 1);
+      case 12: MVW_FWD(2, 4, false, 2);
       default: MVW_FWD(2, 4, false);
 #undef MVW_FWD
     }

@@ -95,7 +95,9 @@ static void build_view_csr(const float* grid, int view, int Hs, int Ws, int Hg, 
         out.entries[count[row]++] = CsrEntry{(uint32_t)cell, t.w[k]};
       }
   }
-  // backward tasks
+  // backward tasks (budget / heavy threshold overridable for tuning runs only)
+  static const uint32_t budget = getenv("MVWARP_TASK_BUDGET") ? (uint32_t)atoi(getenv("MVWARP_TASK_BUDGET")) : TASK_BUDGET;
+  static const uint32_t heavy_len = getenv("MVWARP_HEAVY_LEN") ? (uint32_t)atoi(getenv("MVWARP_HEAVY_LEN")) : HEAVY_LEN;
   Task cur{0, 0, (uint16_t)view};
   uint32_t weight = 0;
   auto flush = [&]() {
@@ -105,12 +107,12 @@ static void build_view_csr(const float* grid, int view, int Hs, int Ws, int Hg, 
   };
   for (size_t r = 0; r < ntex; ++r) {
     const uint32_t len = row_ptr[r + 1] - row_ptr[r];
-    if (len > HEAVY_LEN) {
+    if (len > heavy_len) {
       flush();
       out.heavy.push_back((uint32_t)r);
       continue;
     }
-    if (cur.nrows && (weight + 1 + len > TASK_BUDGET || cur.nrows >= TASK_MAX_TEX)) flush();
+    if (cur.nrows && (weight + 1 + len > budget || cur.nrows >= TASK_MAX_TEX)) flush();
     if (!cur.nrows) cur.row0 = (uint32_t)r;
     ++cur.nrows;
     weight += 1 + len;

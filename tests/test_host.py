@@ -138,12 +138,12 @@ def test_backward_task_decomposition_covers_every_row_once():
     g = P.host_grid(P.src_norm_trans_dst_norm(pm, WILDTRACK.feat_shape, WILDTRACK.grid_shape), WILDTRACK.grid_shape)
     st, tex_of, row_ptr, cells, weights = P.host_csr(g, WILDTRACK.feat_shape, with_map=True)
     lens = (row_ptr[:, 1:] - row_ptr[:, :-1]).long()
-    heavy = int((lens > 48).sum())
+    heavy = int((lens > 31).sum())
     assert st["heavy_rows"] == heavy and heavy > 0
-    light_weight = int((lens[lens <= 48] + 1).sum())
-    # every task is at most 64 heavy (rows + entries): the task count is bounded both ways
-    assert st["bwd_tasks"] >= light_weight / 64
-    assert st["bwd_tasks"] <= light_weight / 16 + heavy + 7 * 40000
+    light_weight = int((lens[lens <= 31] + 1).sum())
+    # every task weighs at most 32 (rows + entries): the task count is bounded both ways
+    assert st["bwd_tasks"] >= light_weight / 32
+    assert st["bwd_tasks"] <= light_weight / 8 + 2 * heavy + 7 * 2040
 
 
 @pytest.mark.parametrize("Wg", [2, 44, 45, 64])
