@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--mode", default="fwdbwd", choices=["fwdbwd", "fwd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--out-pitch", type=int, default=0,
+                    help="experiment: channel pitch of the channels-last output / grad_out (0 = dense V*C+2)")
     ap.add_argument("--ref-channels", type=int, default=64,
                     help="reference arm: channels per step (a bounded 1/8-frame sample by default)")
     return ap.parse_args()
@@ -218,8 +220,9 @@ def run_ours(args):
     gen = torch.Generator(device=dev).manual_seed(rank)
     if args.layout == "cl":
         feats = torch.randn((B, V, Hs, Ws, Cc), device=dev, generator=gen).to(dtype).permute(0, 1, 4, 2, 3)
-        out = torch.empty((B, Hg, Wg, ctot), device=dev, dtype=dtype).permute(0, 3, 1, 2)
-        grad_out = torch.randn((B, Hg, Wg, ctot), device=dev, generator=gen).to(dtype).permute(0, 3, 1, 2)
+        pitch = max(args.out_pitch, ctot)
+        out = torch.empty((B, Hg, Wg, pitch), device=dev, dtype=dtype)[..., :ctot].permute(0, 3, 1, 2)
+        grad_out = torch.randn((B, Hg, Wg, pitch), device=dev, generator=gen).to(dtype)[..., :ctot].permute(0, 3, 1, 2)
         grad_feats = torch.empty((B, V, Hs, Ws, Cc), device=dev, dtype=dtype).permute(0, 1, 4, 2, 3)
     else:
         feats = torch.randn((B, V, Cc, Hs, Ws), device=dev, generator=gen).to(dtype)

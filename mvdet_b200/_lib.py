@@ -6,7 +6,10 @@ import ctypes as C
 import os
 import threading
 
-from .build import LIB_PATH
+from .build import LIB_PATH as _DEFAULT_LIB_PATH
+
+# development: MVWARP_LIB=/path/to/variant.so selects another build of the same ABI (kernel tuning runs)
+LIB_PATH = os.environ.get("MVWARP_LIB", _DEFAULT_LIB_PATH)
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 F32, BF16 = 0, 1

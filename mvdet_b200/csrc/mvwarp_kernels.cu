@@ -169,7 +169,79 @@ struct TapRec {
   float zero;  // value of an all-outside cell: the 0*w chain (propagates NaN weights like the oracle)
 };
 
-template <typename T, bool kInline, int UNROLL, int MINB, bool KEEP = false, int DBG = 0>
+// streaming 16-byte store to an address whose alignment (16 / 8 / 4 bytes) is a compile-time constant
+template <int ALIGN>
+__device__ __forceinline__ void stcs16(void* p, const uint4& v) {
+  if (ALIGN == 16) {
+    __stcs(reinterpret_cast<uint4*>(p), v);
+  } else if (ALIGN == 8) {
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(v.x, v.y));
+    __stcs(reinterpret_cast<uint2*>(p) + 1, make_uint2(v.z, v.w));
+  } else {
+    unsigned* q = reinterpret_cast<unsigned*>(p);
+    __stcs(q, v.x); __stcs(q + 1, v.y); __stcs(q + 2, v.z); __stcs(q + 3, v.w);
+  }
+}
+
+// One grid cell, one warp: gather the four taps across the channels, blend, store.  Specialised on the
+// alignment of the cell's output row, on "all four taps inside" and on "C is a multiple of the warp's stride"
+// so that the common case carries no per-load predicates (the kernel is otherwise issue-bound in bf16).
+template <typename T, int UNROLL, int ALIGN, bool ALLTAPS, bool FULLC, bool KEEP>
+__device__ __forceinline__ void fwd_cell(const T* __restrict__ src, const KParams& p, const TapRec& tp, T* __restrict__ o,
+                                         int nvec, int lane, uint64_t pol) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  const T* tap[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {  // a masked-off tap keeps a valid dummy address and is never dereferenced
+    const int xx = tp.x0 + (k & 1), yy = tp.y0 + (k >> 1);
+    tap[k] = (ALLTAPS || (tp.mask >> k & 1)) ? src + (int64_t)yy * p.fH + (int64_t)xx * p.fW + lane * EPV : src;
+  }
+  T* ol = o + lane * EPV;
+  for (int c0 = 0; c0 < nvec; c0 += 32 * UNROLL) {
+    uint4 val[UNROLL][4];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int c = c0 + 32 * u;
+      const bool ok = FULLC || (c + lane < nvec);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool ld = ok && (ALLTAPS || (tp.mask >> k & 1));
+        val[u][k] = ld ? (KEEP ? ldg16_keep(tap[k] + c * EPV, pol) : ldg16(tap[k] + c * EPV)) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int c = c0 + 32 * u;
+      if (FULLC || (c + lane < nvec)) {
+        float f[4][EPV], r[EPV];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) VecTraits<T>::unpack(val[u][k], f[k]);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) r[e] = blend4(f[0][e], f[1][e], f[2][e], f[3][e], tp.w);
+        stcs16<ALIGN>(ol + c * EPV, VecTraits<T>::pack(r));
+      }
+    }
+  }
+}
+
+template <typename T, int UNROLL, int ALIGN, bool FULLC, bool KEEP>
+__device__ __forceinline__ void fwd_cell_dispatch(const T* __restrict__ src, const KParams& p, const TapRec& tp, T* __restrict__ o,
+                                                  int nvec, int lane, uint64_t pol) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  if (tp.mask == 15u) {
+    fwd_cell<T, UNROLL, ALIGN, true, FULLC, KEEP>(src, p, tp, o, nvec, lane, pol);
+  } else if (tp.mask != 0u) {
+    fwd_cell<T, UNROLL, ALIGN, false, FULLC, KEEP>(src, p, tp, o, nvec, lane, pol);
+  } else {
+    float zf[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) zf[e] = tp.zero;
+    const uint4 zv = VecTraits<T>::pack(zf);
+    for (int c = lane; c < nvec; c += 32) stcs16<ALIGN>(o + c * EPV, zv);
+  }
+}
+
+template <typename T, bool kInline, int UNROLL, int MINB, bool FULLC, bool KEEP>
 __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_cl_kernel(const KParams p) {
   constexpr int EPV = VecTraits<T>::EPV;
   const uint64_t pol = KEEP ? l2_evict_last_policy() : 0ull;
@@ -177,7 +249,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_cl_kernel(const KPar
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // grid: x = view (fastest), y = tile, z = batch.  CTAs are dispatched x-fastest, so the V CTAs of one cell tile
   // run at about the same time and their V slices of each concat row reach L2 / DRAM together (one 14 KB row
-  // instead of V separate 2 KB pieces: measured 0.223 -> see profiles/README.md).
+  // instead of V separate 2 KB pieces: 0.223 -> 0.199 ms at the Wildtrack shape, profiles/README.md).
   const int tx = blockIdx.y % p.tiles_x, ty = blockIdx.y / p.tiles_x;
   const int vl = blockIdx.x, b = blockIdx.z;
   const int v = p.view0 + vl;
@@ -215,47 +287,10 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_cl_kernel(const KPar
     if (x >= p.Wg || y >= p.Hg) continue;
     const TapRec tp = taps[i];
     T* o = dst + (int64_t)y * p.oH + (int64_t)x * p.oW;
-    const unsigned oalign = (unsigned)(reinterpret_cast<uintptr_t>(o) & 15u);
-
-    if (tp.mask == 0 || DBG == 1) {  // (DBG 1: measurement only -- stores without gathers)
-      float zf[EPV];
-#pragma unroll
-      for (int e = 0; e < EPV; ++e) zf[e] = tp.zero;
-      const uint4 zv = VecTraits<T>::pack(zf);
-      for (int c = lane; c < nvec; c += 32) stcs16_any(o + c * EPV, zv, oalign);
-      continue;
-    }
-    // tap base pointers (a masked-off tap keeps a valid dummy address and is never dereferenced)
-    const T* tap[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int xx = tp.x0 + (k & 1), yy = tp.y0 + (k >> 1);
-      tap[k] = (tp.mask >> k & 1) ? src + (int64_t)yy * p.fH + (int64_t)xx * p.fW : src;
-    }
-    for (int c0 = lane; c0 < nvec; c0 += 32 * UNROLL) {
-      uint4 val[UNROLL][4];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int c = c0 + 32 * u;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          val[u][k] = (c < nvec && (tp.mask >> k & 1)) ? (KEEP ? ldg16_keep(tap[k] + c * EPV, pol) : ldg16(tap[k] + c * EPV))
-                                                       : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int c = c0 + 32 * u;
-        if (c < nvec) {
-          float f[4][EPV], r[EPV];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) VecTraits<T>::unpack(val[u][k], f[k]);
-#pragma unroll
-          for (int e = 0; e < EPV; ++e) r[e] = blend4(f[0][e], f[1][e], f[2][e], f[3][e], tp.w);
-          if (DBG != 2 || r[0] == 123.456f)  // (DBG 2: measurement only -- gathers without stores)
-            stcs16_any(o + c * EPV, VecTraits<T>::pack(r), oalign);
-        }
-      }
-    }
+    const unsigned oalign = (unsigned)(reinterpret_cast<uintptr_t>(o) & 15u);  // warp-uniform
+    if (oalign == 0) fwd_cell_dispatch<T, UNROLL, 16, FULLC, KEEP>(src, p, tp, o, nvec, lane, pol);
+    else if ((oalign & 7u) == 0) fwd_cell_dispatch<T, UNROLL, 8, FULLC, KEEP>(src, p, tp, o, nvec, lane, pol);
+    else fwd_cell_dispatch<T, UNROLL, 4, FULLC, KEEP>(src, p, tp, o, nvec, lane, pol);
   }
 }
 
@@ -312,14 +347,58 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const KParams p) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int BWD_WARPS = 8, BWD_ACC_FLOATS = 16;
 
-// acc += sum over entries [k0, k1) of w * grad_out[cell]; entries come through 32-entry windows (coalesced)
-template <typename T, int NACC, bool KEEP>
+// NACC 16-byte vectors of one grad_out row (lane's columns), for a row base of compile-time alignment
+template <typename T, int NACC, int ALIGN, bool KEEP, bool FULLC>
+__device__ __forceinline__ void load_row(uint4 (&v)[NACC], const T* __restrict__ g, int cbase, int nvec, int lane, uint64_t pol) {
+  constexpr int EPV = VecTraits<T>::EPV;
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) {
+    const int c = cbase + 32 * q + lane;
+    if (FULLC || c < nvec) {
+      const char* ptr = reinterpret_cast<const char*>(g + c * EPV);
+      if (ALIGN == 16) {
+        v[q] = KEEP ? ldg16_keep(ptr, pol) : __ldg(reinterpret_cast<const uint4*>(ptr));
+      } else if (ALIGN == 8) {
+        const uint2 a = KEEP ? ldg8_keep(ptr, pol) : __ldg(reinterpret_cast<const uint2*>(ptr));
+        const uint2 b = KEEP ? ldg8_keep(ptr + 8, pol) : __ldg(reinterpret_cast<const uint2*>(ptr) + 1);
+        v[q] = make_uint4(a.x, a.y, b.x, b.y);
+      } else {
+        // 4-byte aligned row (bf16, 3 cells in 4).  Measured alternatives: two overlapping aligned 128-bit loads +
+        // word selection is 15-25 % slower than these four 32-bit loads (profiles/README.md).
+        {
+          const unsigned* w = reinterpret_cast<const unsigned*>(ptr);
+          v[q] = make_uint4(__ldg(w), __ldg(w + 1), __ldg(w + 2), __ldg(w + 3));
+        }
+      }
+    } else {
+      v[q] = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
+template <typename T, int NACC, bool KEEP, bool FULLC>
+__device__ __forceinline__ void load_row_any(uint4 (&v)[NACC], const T* __restrict__ g, int cbase, int nvec, int lane, uint64_t pol) {
+  const unsigned al = (unsigned)(reinterpret_cast<uintptr_t>(g) & 15u);  // warp-uniform
+  if (al == 0) load_row<T, NACC, 16, KEEP, FULLC>(v, g, cbase, nvec, lane, pol);
+  else if ((al & 7u) == 0) load_row<T, NACC, 8, KEEP, FULLC>(v, g, cbase, nvec, lane, pol);
+  else load_row<T, NACC, 4, KEEP, FULLC>(v, g, cbase, nvec, lane, pol);
+}
+
+// acc += sum over entries [k0, k1) of w * grad_out[cell]; entries come through 32-entry windows (coalesced).
+// DENSE: grad_out rows are cell*oW apart (dense channels-last), so no division turns a cell index into (y, x).
+template <typename T, int NACC, bool KEEP, bool FULLC, bool DENSE>
 __device__ __forceinline__ void gather_entries(float (&acc)[NACC][VecTraits<T>::EPV], const uint2* __restrict__ en,
                                                uint32_t k0, uint32_t k1, uint32_t win_end, const T* __restrict__ go,
                                                const KParams& p, int cbase, int nvec, int lane, uint32_t& win0, uint2& ent,
                                                uint64_t pol) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr unsigned FULL = 0xffffffffu;
+  auto row_of_cell = [&](uint32_t cell) -> const T* {
+    if (DENSE) return go + (int64_t)cell * p.oW;
+    const int cy = cell / p.Wg, cx = cell - cy * p.Wg;
+    return go + (int64_t)cy * p.oH + (int64_t)cx * p.oW;
+  };
+  constexpr int NE = 2;  // entries in flight per trip (4 for bf16 was measured slower: register pressure)
   uint32_t k = k0;
   while (k < k1) {
     if (k >= win0 + 32) {  // warp-uniform: slide the metadata window
@@ -327,50 +406,44 @@ __device__ __forceinline__ void gather_entries(float (&acc)[NACC][VecTraits<T>::
       ent = (win0 + lane < win_end) ? __ldg(en + win0 + lane) : make_uint2(0u, 0u);
     }
     const int s0 = (int)(k - win0);
-    const bool two = (k + 1 < k1) && (s0 + 1 < 32);
-    const uint32_t c0 = __shfl_sync(FULL, ent.x, s0), c1 = __shfl_sync(FULL, ent.x, (s0 + 1) & 31);
-    const float w0 = __uint_as_float(__shfl_sync(FULL, ent.y, s0));
-    const float w1 = __uint_as_float(__shfl_sync(FULL, ent.y, (s0 + 1) & 31));
-    const int cy0 = c0 / p.Wg, cx0 = c0 - cy0 * p.Wg;
-    const T* g0 = go + (int64_t)cy0 * p.oH + (int64_t)cx0 * p.oW;
-    const unsigned al0 = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15u);
-    if (two) {
-      const int cy1 = c1 / p.Wg, cx1 = c1 - cy1 * p.Wg;
-      const T* g1 = go + (int64_t)cy1 * p.oH + (int64_t)cx1 * p.oW;
-      const unsigned al1 = (unsigned)(reinterpret_cast<uintptr_t>(g1) & 15u);
-      uint4 v0[NACC], v1[NACC];
+    if ((int)(k1 - k) >= NE && s0 + NE <= 32) {  // warp-uniform: NE entries in flight, no predicates
+      uint4 v[NE][NACC];
+      float w[NE];
 #pragma unroll
-      for (int q = 0; q < NACC; ++q) {
-        const int c = cbase + 32 * q + lane;
-        v0[q] = c < nvec ? ldg16_any<KEEP>(g0 + c * EPV, al0, pol) : make_uint4(0, 0, 0, 0);
-        v1[q] = c < nvec ? ldg16_any<KEEP>(g1 + c * EPV, al1, pol) : make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < NE; ++i) {
+        const uint32_t cell = __shfl_sync(FULL, ent.x, s0 + i);
+        w[i] = __uint_as_float(__shfl_sync(FULL, ent.y, s0 + i));
+        load_row_any<T, NACC, KEEP, FULLC>(v[i], row_of_cell(cell), cbase, nvec, lane, pol);
       }
 #pragma unroll
-      for (int q = 0; q < NACC; ++q) {
-        float f0[EPV], f1[EPV];
-        VecTraits<T>::unpack(v0[q], f0);
-        VecTraits<T>::unpack(v1[q], f1);
+      for (int i = 0; i < NE; ++i) {  // FMAs strictly in entry order
 #pragma unroll
-        for (int i = 0; i < EPV; ++i) acc[q][i] = __fmaf_rn(w1, f1[i], __fmaf_rn(w0, f0[i], acc[q][i]));
-      }
-      k += 2;
-    } else {
+        for (int q = 0; q < NACC; ++q) {
+          float f[EPV];
+          VecTraits<T>::unpack(v[i][q], f);
 #pragma unroll
-      for (int q = 0; q < NACC; ++q) {
-        const int c = cbase + 32 * q + lane;
-        if (c < nvec) {
-          float f0[EPV];
-          VecTraits<T>::unpack(ldg16_any<KEEP>(g0 + c * EPV, al0, pol), f0);
-#pragma unroll
-          for (int i = 0; i < EPV; ++i) acc[q][i] = __fmaf_rn(w0, f0[i], acc[q][i]);
+          for (int e = 0; e < EPV; ++e) acc[q][e] = __fmaf_rn(w[i], f[e], acc[q][e]);
         }
+      }
+      k += NE;
+    } else {  // row tail / window edge: one entry
+      const uint32_t cell = __shfl_sync(FULL, ent.x, s0);
+      const float w0 = __uint_as_float(__shfl_sync(FULL, ent.y, s0));
+      uint4 v0[NACC];
+      load_row_any<T, NACC, KEEP, FULLC>(v0, row_of_cell(cell), cbase, nvec, lane, pol);
+#pragma unroll
+      for (int q = 0; q < NACC; ++q) {
+        float f[EPV];
+        VecTraits<T>::unpack(v0[q], f);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[q][e] = __fmaf_rn(w0, f[e], acc[q][e]);
       }
       k += 1;
     }
   }
 }
 
-template <typename T, bool KEEP>
+template <typename T, bool KEEP, bool FULLC, bool DENSE>
 __device__ __forceinline__ void bwd_task(const KParams& p, uint32_t tid, uint32_t task_hi) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr int NACC = BWD_ACC_FLOATS / EPV;  // 16-byte vectors per lane per pass
@@ -404,7 +477,7 @@ __device__ __forceinline__ void bwd_task(const KParams& p, uint32_t tid, uint32_
       for (int q = 0; q < NACC; ++q)
 #pragma unroll
         for (int i = 0; i < EPV; ++i) acc[q][i] = 0.f;
-      gather_entries<T, NACC, KEEP>(acc, en, a, e, r_end, go, p, cbase, nvec, lane, win0, ent, pol);
+      gather_entries<T, NACC, KEEP, FULLC, DENSE>(acc, en, a, e, r_end, go, p, cbase, nvec, lane, win0, ent, pol);
       const int ys = tex / p.Ws, xs = tex - ys * p.Ws;
       T* o = gf + (int64_t)ys * p.fH + (int64_t)xs * p.fW;
 #pragma unroll
@@ -418,7 +491,7 @@ __device__ __forceinline__ void bwd_task(const KParams& p, uint32_t tid, uint32_
 
 constexpr int BWD_PASS_FLOATS = 32 * BWD_ACC_FLOATS;  // channels per pass (512)
 
-template <typename T, bool KEEP>
+template <typename T, bool KEEP, bool FULLC, bool DENSE>
 __device__ __forceinline__ void bwd_heavy_row(const KParams& p, uint32_t hid, int view_lo, const uint32_t* __restrict__ heavy_base,
                                               float (*part)[BWD_PASS_FLOATS]) {
   constexpr int EPV = VecTraits<T>::EPV;
@@ -448,7 +521,7 @@ __device__ __forceinline__ void bwd_heavy_row(const KParams& p, uint32_t hid, in
       for (int i = 0; i < EPV; ++i) acc[q][i] = 0.f;
     uint32_t win0 = k0;
     uint2 ent = (win0 + lane < k1) ? __ldg(en + win0 + lane) : make_uint2(0u, 0u);
-    gather_entries<T, NACC, KEEP>(acc, en, k0, k1, k1, go, p, cbase, nvec, lane, win0, ent, pol);
+    gather_entries<T, NACC, KEEP, FULLC, DENSE>(acc, en, k0, k1, k1, go, p, cbase, nvec, lane, win0, ent, pol);
     // partials in channel order: lane's q-th vector covers pass-channels [(32q + lane)*EPV, +EPV)
 #pragma unroll
     for (int q = 0; q < NACC; ++q)
@@ -475,15 +548,15 @@ __device__ __forceinline__ void bwd_heavy_row(const KParams& p, uint32_t hid, in
 
 // One launch: the first n_heavy CTAs take one heavy row each (longest chains start first), the rest take
 // BWD_WARPS tasks each.
-template <typename T, int MINB, bool KEEP>
+template <typename T, int MINB, bool KEEP, bool FULLC, bool DENSE>
 __global__ void __launch_bounds__(BWD_WARPS * 32, MINB)
     bwd_cl_kernel(const KParams p, uint32_t task_lo, uint32_t task_hi, uint32_t heavy_lo, uint32_t n_heavy, int view_lo,
                   const uint32_t* __restrict__ heavy_base) {
   __shared__ __align__(16) float part[BWD_WARPS][BWD_PASS_FLOATS];
   if (blockIdx.x < n_heavy) {
-    bwd_heavy_row<T, KEEP>(p, heavy_lo + blockIdx.x, view_lo, heavy_base, part);
+    bwd_heavy_row<T, KEEP, FULLC, DENSE>(p, heavy_lo + blockIdx.x, view_lo, heavy_base, part);
   } else {
-    bwd_task<T, KEEP>(p, task_lo + (blockIdx.x - n_heavy) * BWD_WARPS + (threadIdx.x >> 5), task_hi);
+    bwd_task<T, KEEP, FULLC, DENSE>(p, task_lo + (blockIdx.x - n_heavy) * BWD_WARPS + (threadIdx.x >> 5), task_hi);
   }
 }
 
@@ -596,19 +669,20 @@ static int launch_fwd_t(const LaunchArgs& a) {
       return MVWARP_EUNSUPPORTED;
     }
     dim3 grid(a.nviews, p.tiles_x * p.tiles_y, a.B), block(FWD_WARPS * 32);
+    const bool fullc = (a.C / EPV) % 64 == 0;  // the warp's channel loop needs no tail predicate
+#define MVW_FWD(U, M, K)                                                                       \
+  do {                                                                                         \
+    if (inl && fullc) fwd_cl_kernel<T, true, U, M, true, K><<<grid, block, 0, a.stream>>>(p);   \
+    else if (inl) fwd_cl_kernel<T, true, U, M, false, K><<<grid, block, 0, a.stream>>>(p);      \
+    else if (fullc) fwd_cl_kernel<T, false, U, M, true, K><<<grid, block, 0, a.stream>>>(p);    \
+    else fwd_cl_kernel<T, false, U, M, false, K><<<grid, block, 0, a.stream>>>(p);              \
+  } while (0)
     switch (tuning_variant("MVWARP_FWD_VARIANT", 0)) {  // tuning knob (development only)
-#define MVW_FWD(U, M, K, ...)                                                              \
-  if (inl) fwd_cl_kernel<T, true, U, M, K, ##__VA_ARGS__><<<grid, block, 0, a.stream>>>(p);   \
-  else fwd_cl_kernel<T, false, U, M, K, ##__VA_ARGS__><<<grid, block, 0, a.stream>>>(p);      \
-  break
-      case 1: MVW_FWD(4, 2, false);
-      case 3: MVW_FWD(2, 3, false);
-      case 5: MVW_FWD(2, 4, true);
-      case 11: MVW_FWD(2, 4, false, 1);
-      case 12: MVW_FWD(2, 4, false, 2);
-      default: MVW_FWD(2, 4, false);
-#undef MVW_FWD
+      case 1: MVW_FWD(2, 3, false); break;
+      case 2: MVW_FWD(2, 4, true); break;
+      default: MVW_FWD(2, 4, false); break;
     }
+#undef MVW_FWD
   } else {
     const int nchunk = (a.C + p.cchunk - 1) / p.cchunk;
     int rc = check_grid_dims(a, (int64_t)a.B * nchunk);
@@ -638,12 +712,24 @@ static int launch_bwd_t(const LaunchArgs& a) {
     const uint32_t n_heavy = h_hi - h_lo, n_task_ctas = (t_hi - t_lo + BWD_WARPS - 1) / BWD_WARPS;
     if (n_heavy + n_task_ctas > 0) {
       dim3 grid(n_heavy + n_task_ctas, 1, a.B), block(BWD_WARPS * 32);
+      const bool fullc = (a.C / EPV) % (32 * (BWD_ACC_FLOATS / EPV)) == 0;   // a pass never has a channel tail
+      const bool dense = a.os[2] == (int64_t)pl->Wg * a.os[3];                // grad_out rows are cell * oW apart
+#define MVW_BWD(M, K)                                                                                            \
+  do {                                                                                                           \
+    if (fullc && dense) bwd_cl_kernel<T, M, K, true, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, pl->d_heavy_base); \
+    else bwd_cl_kernel<T, M, K, false, false><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, pl->d_heavy_base);             \
+  } while (0)
       switch (tuning_variant("MVWARP_BWD_VARIANT", 0)) {  // tuning knob (development only)
-        case 1: bwd_cl_kernel<T, 3, false><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, pl->d_heavy_base); break;
-        case 2: bwd_cl_kernel<T, 2, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, pl->d_heavy_base); break;
-        default: bwd_cl_kernel<T, 3, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, pl->d_heavy_base); break;
+        case 1: MVW_BWD(3, false); break;
+        case 2: MVW_BWD(4, true); break;
+        case 3: MVW_BWD(3, true); break;
+        default:
+          if (sizeof(T) == 2) MVW_BWD(4, true);  // bf16: half the bytes per entry, more warps hide the same latency
+          else MVW_BWD(3, true);
+          break;
       }
     }
+#undef MVW_BWD
   } else {
     const int nchunk = (a.C + p.cchunk - 1) / p.cchunk;
     int rc = check_grid_dims(a, (int64_t)a.B * nchunk);
