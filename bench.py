@@ -50,53 +50,66 @@ def parse_args():
 # --------------------------------------------------------------------------------------------------
 # clocks: sampled DURING the timed region through NVML (same counters as the nvidia-smi query line)
 # --------------------------------------------------------------------------------------------------
+_SAMPLER_CODE = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), reasons(h), flush=True)
+    time.sleep(0.002)
+"""
+
+
 class ClockSampler:
-    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+    """SM clock + clock-event reasons sampled through NVML by a child process (no GIL contention with the
+    launching thread) while the GPU works; `summary(t0, t1)` keeps the samples taken inside the timed region."""
+    REASONS = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index: int, period: float = 0.001):
-        self.samples, self.reasons, self.period, self._stop = [], set(), period, threading.Event()
-        self.max_mhz, self.ok = None, False
+    def __init__(self, index: int):
+        import subprocess
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
-        except Exception as e:  # pragma: no cover
-            self.err = str(e)
-        self.thread = threading.Thread(target=self._run, daemon=True)
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_CODE, str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            first = self.proc.stdout.readline().split()
+            self.max_mhz = int(first[1]) if first and first[0] == "max" else None
+            self.ok = self.max_mhz is not None
+        except Exception:  # pragma: no cover
+            self.proc, self.max_mhz, self.ok = None, None, False
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
-                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit and name != "gpu_idle":
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop.wait(self.period)
+    def stop(self):
+        if self.proc is None:
+            return []
+        self.proc.terminate()
+        out, _ = self.proc.communicate()
+        rows = []
+        for line in out.splitlines():
+            parts = line.split()
+            if len(parts) == 3:
+                rows.append((float(parts[0]), int(parts[1]), int(parts[2])))
+        self.proc = None
+        self.rows = rows
+        return rows
 
-    def __enter__(self):
-        if self.ok:
-            self.thread.start()
-        return self
-
-    def __exit__(self, *a):
-        self._stop.set()
-        if self.ok:
-            self.thread.join()
-
-    def summary(self):
-        if not self.ok or not self.samples:
+    def summary(self, t0: float, t1: float):
+        rows = getattr(self, "rows", None)
+        if rows is None:
+            rows = self.stop()
+        if not self.ok or not rows:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        inside = [r for r in rows if t0 <= r[0] <= t1] or [min(rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))]
+        mhz = sorted(r[1] for r in inside)
+        mask = 0
+        for r in inside:
+            mask |= r[2]
+        busy = sorted(r[1] for r in rows if r[0] >= t0)   # timed region + the end-to-end leg after it
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(inside),
+                "sm_mhz_busy_median": busy[len(busy) // 2] if busy else None, "samples_busy": len(busy)}
 
 
 def host_cores() -> int:
@@ -248,18 +261,20 @@ def run_ours(args):
     # ---- timed region: K steps, CUDA events on the launching (current) stream ------------------------
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
-        t_begin.record()
-        for k in range(args.steps):
-            ev[k][0].record()
-            ops.warp_views_fwd_into(plan, feats, out, 0, 0, V * Cc)
-            ev[k][1].record()
-            if do_bwd:
-                ops.warp_views_bwd_into(plan, grad_out, grad_feats, 0, 0)
-            ev[k][2].record()
-        t_end.record()
-        barrier()
+    clocks = ClockSampler(local)
+    barrier()
+    wall0 = time.time()
+    t_begin.record()
+    for k in range(args.steps):
+        ev[k][0].record()
+        ops.warp_views_fwd_into(plan, feats, out, 0, 0, V * Cc)
+        ev[k][1].record()
+        if do_bwd:
+            ops.warp_views_bwd_into(plan, grad_out, grad_feats, 0, 0)
+        ev[k][2].record()
+    t_end.record()
+    barrier()
+    wall1 = time.time()
     total_ms = t_begin.elapsed_time(t_end)
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps if do_bwd else 0.0
@@ -297,6 +312,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, plan, feats, grad_out, dev, world, dist if world > 1 else None)
+    clocks.stop()
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------------
     cpu_baseline = None
@@ -320,7 +336,7 @@ def run_ours(args):
             "roofline": roofline, **extra,
             "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": args.steps * (2 if do_bwd else 1),
-            "clocks": clocks.summary(),
+            "clocks": clocks.summary(wall0, wall1),
             "plan": {k: plan.stats[k] for k in ("unique_texels", "nnz", "valid_cells", "max_row", "device_bytes")},
             "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
         }
