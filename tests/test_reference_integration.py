@@ -1,0 +1,115 @@
+"""Wiring test against the UNMODIFIED reference model (CPU, this container only: /root/reference is not on
+the GPU box).  kornia and matplotlib are not installed, so they are stubbed in sys.modules; the kornia stub's
+warp_perspective is the oracle.  What is pinned: the arguments the reference passes at
+persp_trans_detector.py:68-69, that replacing :68-69,75,77 by one warp_views-shaped call leaves map_result
+unchanged, that mvdet_b200.geometry reproduces the reference's proj_mats / coord_map bit for bit, and that the
+kornia-signature seam (mvdet_b200.ops.warp_perspective) accepts exactly that call."""
+import inspect
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "multiview_detector")),
+                                reason="reference tree not present (GPU box)")
+
+
+class _Base:
+    pass
+
+
+class _Dataset:
+    pass
+
+
+def _fake_dataset(num_cam=3):
+    from mvdet_b200.geometry import synthetic_cameras
+    Ks, Es = synthetic_cameras(num_cam, seed=3)
+    scale = np.diag([0.2, 0.2, 1.0])                       # 1080x1920 calibration -> 216x384 images
+    base = _Base()
+    base.intrinsic_matrices = [scale @ K for K in Ks]
+    base.extrinsic_matrices = Es
+    base.worldgrid2worldcoord_mat = np.array([[2.5, 0, -300], [0, 2.5, -900], [0, 0, 1.0]])
+    ds = _Dataset()
+    ds.base, ds.num_cam = base, num_cam
+    ds.img_shape, ds.reducedgrid_shape = [216, 384], [24, 72]
+    ds.img_reduce, ds.grid_reduce = 4, 20
+    return ds
+
+
+@pytest.fixture()
+def reference_model(monkeypatch):
+    from oracle import kornia_warp as K
+    calls = []
+
+    def recording_warp(src, M, dsize, *args, **kwargs):
+        calls.append((tuple(src.shape), src.dtype, src.is_contiguous(), tuple(M.shape), M.dtype, dsize, args, kwargs))
+        return K.warp_perspective(src, M, dsize, *args, **kwargs)
+
+    kornia = types.ModuleType("kornia")
+    kornia.geometry = types.ModuleType("kornia.geometry")
+    kornia.geometry.transform = types.ModuleType("kornia.geometry.transform")
+    kornia.geometry.transform.warp_perspective = recording_warp
+    kornia.warp_perspective = recording_warp
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+    for name, mod in {"kornia": kornia, "kornia.geometry": kornia.geometry,
+                      "kornia.geometry.transform": kornia.geometry.transform,
+                      "matplotlib": mpl, "matplotlib.pyplot": mpl.pyplot}.items():
+        monkeypatch.setitem(sys.modules, name, mod)
+    monkeypatch.syspath_prepend(REF)
+    # the reference pins everything to 'cuda:0' (persp_trans_detector.py:37-54,63-81): redirect to CPU
+    t_to, m_to = torch.Tensor.to, torch.nn.Module.to
+    fix = lambda a: tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
+    monkeypatch.setattr(torch.Tensor, "to", lambda self, *a, **k: t_to(self, *fix(a), **k))
+    monkeypatch.setattr(torch.nn.Module, "to", lambda self, *a, **k: m_to(self, *fix(a), **k))
+    for m in [k for k in sys.modules if k.startswith("multiview_detector")]:
+        monkeypatch.delitem(sys.modules, m)
+    from multiview_detector.models.persp_trans_detector import PerspTransDetector
+    torch.manual_seed(0)
+    model = PerspTransDetector(_fake_dataset(), arch="resnet18").eval()
+    return model, calls
+
+
+def test_reference_forward_through_the_seams(reference_model):
+    from mvdet_b200 import geometry, ops
+    from oracle import kornia_warp as K
+    model, calls = reference_model
+    ds = _fake_dataset()
+    B = 2
+    imgs = torch.randn(B, ds.num_cam, 3, 144, 256, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        map_ref, img_res = model(imgs)
+    assert map_ref.shape == (B, 1, 24, 72) and len(img_res) == ds.num_cam
+
+    # (1) the call the seam must accept: positional (src, M, dsize), fp32 NCHW-contiguous, M = [B,3,3] fp32, dsize a list
+    assert len(calls) == ds.num_cam
+    for shape, dtype, contig, mshape, mdtype, dsize, args, kwargs in calls:
+        assert shape == (B, 512, 54, 96) and dtype == torch.float32 and contig
+        assert mshape == (B, 3, 3) and mdtype == torch.float32 and dsize == [24, 72] and not args and not kwargs
+    seam = inspect.signature(ops.warp_perspective)
+    ref_sig = inspect.signature(K.warp_perspective)
+    assert list(seam.parameters) == list(ref_sig.parameters)
+    assert [p.default for p in seam.parameters.values()] == [p.default for p in ref_sig.parameters.values()]
+
+    # (2) proj_mats and coord_map rebuilt by mvdet_b200.geometry == the reference's, bit for bit
+    pm = geometry.projection_matrices(ds.base.intrinsic_matrices, ds.base.extrinsic_matrices,
+                                      ds.base.worldgrid2worldcoord_mat, ds.img_shape, ds.img_reduce, ds.grid_reduce)
+    assert torch.equal(pm, torch.stack(model.proj_mats))
+    assert torch.equal(geometry.create_coord_map(ds.reducedgrid_shape), model.coord_map)
+
+    # (3) seam 2: lines 68-69, 75, 77 replaced by one warp_views-shaped call (oracle standing in for the CUDA op)
+    with torch.no_grad():
+        feats = []
+        for cam in range(ds.num_cam):
+            f = model.base_pt2(model.base_pt1(imgs[:, cam]))
+            feats.append(F.interpolate(f, model.upsample_shape, mode="bilinear"))
+        world = K.warp_views_oracle(torch.stack(feats, dim=1), torch.stack(model.proj_mats), model.reducedgrid_shape)
+        assert world.shape == (B, 512 * ds.num_cam + 2, 24, 72)
+        map_new = F.interpolate(model.map_classifier(world), model.reducedgrid_shape, mode="bilinear")
+    assert torch.equal(map_new, map_ref)
