@@ -231,18 +231,24 @@ def run_ours(args):
     ctot = V * Cc + 2
 
     gen = torch.Generator(device=dev).manual_seed(rank)
+    do_bwd = args.mode == "fwdbwd"
     if args.layout == "cl":
         feats = torch.randn((B, V, Hs, Ws, Cc), device=dev, generator=gen).to(dtype).permute(0, 1, 4, 2, 3)
         pitch = max(args.out_pitch, ctot)
         out = torch.empty((B, Hg, Wg, pitch), device=dev, dtype=dtype)[..., :ctot].permute(0, 3, 1, 2)
-        grad_out = torch.randn((B, Hg, Wg, pitch), device=dev, generator=gen).to(dtype)[..., :ctot].permute(0, 3, 1, 2)
-        grad_feats = torch.empty((B, V, Hs, Ws, Cc), device=dev, dtype=dtype).permute(0, 1, 4, 2, 3)
+        grad_out = grad_feats = None
+        if do_bwd or not args.no_e2e:
+            grad_out = torch.randn((B, Hg, Wg, pitch), device=dev, generator=gen).to(dtype)[..., :ctot].permute(0, 3, 1, 2)
+        if do_bwd:
+            grad_feats = torch.empty((B, V, Hs, Ws, Cc), device=dev, dtype=dtype).permute(0, 1, 4, 2, 3)
     else:
         feats = torch.randn((B, V, Cc, Hs, Ws), device=dev, generator=gen).to(dtype)
         out = torch.empty((B, ctot, Hg, Wg), device=dev, dtype=dtype)
-        grad_out = torch.randn((B, ctot, Hg, Wg), device=dev, generator=gen).to(dtype)
-        grad_feats = torch.empty((B, V, Cc, Hs, Ws), device=dev, dtype=dtype)
-    do_bwd = args.mode == "fwdbwd"
+        grad_out = grad_feats = None
+        if do_bwd or not args.no_e2e:
+            grad_out = torch.randn((B, ctot, Hg, Wg), device=dev, generator=gen).to(dtype)
+        if do_bwd:
+            grad_feats = torch.empty((B, V, Cc, Hs, Ws), device=dev, dtype=dtype)
 
     def step():
         ops.warp_views_fwd_into(plan, feats, out, 0, 0, V * Cc)

@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""View-sharded warp + map_classifier[0] partial sums + NCCL all-reduce (BASELINE.json configs[3]).
+
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P scripts/sharded_conv1.py
+
+Each rank warps its own cameras (mvdet_b200.warp_views, no collective), convolves its channel slice with the matching
+slice of conv1's weight (cuDNN; the bias and the coord-map term on the coord owner), and the [B,512,Hg,Wg] partial sums
+are combined with one NCCL all-reduce over NVLink, ReLU after.  Part 1 checks the result against the unsharded
+computation (oracle warp + F.conv2d, fp32, small channel count); part 2 times the three phases at full size in bf16.
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mvdet_b200 import sharding as S  # noqa: E402
+from mvdet_b200.geometry import RIG32, WILDTRACK, RigSpec, synthetic_rig  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    res = {"world": world}
+
+    # ---- part 1: parity with the unsharded reference computation (fp32, C=16, Wildtrack shape) ----------------
+    torch.backends.cudnn.allow_tf32 = False   # cuDNN convolutions default to TF32; the parity check wants fp32
+    spec = WILDTRACK
+    pm = synthetic_rig(spec)
+    V, C, Cout, B = spec.num_cam, 16, 32, 1
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, V, C, *spec.feat_shape, generator=g)
+    weight = torch.randn(Cout, V * C + 2, 3, 3, generator=g) * 0.05
+    bias = torch.randn(Cout, generator=g)
+    shard = S.ViewShard.for_rank(V)
+    local_x = x[:, shard.first_view:shard.first_view + shard.count].permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3).to(dev)
+    out_local = S.warp_views_local(local_x, pm, spec.grid_shape, shard)
+    partial = S.conv1_partial(out_local, weight.to(dev), bias.to(dev), shard, C)
+    reduced = S.reduce_partials(partial, relu=True)
+    if rank == 0:
+        from oracle import kornia_warp as K
+        ref = F.relu(F.conv2d(K.warp_views_oracle(x, pm, spec.grid_shape), weight, bias, padding=1))
+        err = float((reduced.cpu() - ref).abs().max() / ref.abs().max())
+        res["parity_max_rel_err_fp32"] = err
+        assert err <= 1e-4, err   # cuDNN fp32 conv (TF32 off) vs CPU conv: summation order only
+
+    # ---- part 2: timing at full size, bf16: 4 cameras per rank of the full-resolution rig --------------------
+    per_rank = 4
+    spec = RigSpec("rig32", per_rank * world, worldgrid_shape=RIG32.worldgrid_shape, grid_reduce=1, seed=2)
+    pm = synthetic_rig(spec)
+    V, C, Cout, B = spec.num_cam, 512, 512, 1
+    shard = S.ViewShard.for_rank(V)
+    Hs, Ws = spec.feat_shape
+    Hg, Wg = spec.grid_shape
+    feats = torch.randn(B, shard.count, Hs, Ws, C, device=dev, dtype=torch.bfloat16).permute(0, 1, 4, 2, 3)
+    weight = (torch.randn(Cout, V * C + 2, 3, 3, device=dev, dtype=torch.bfloat16) * 0.02).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(Cout, device=dev, dtype=torch.bfloat16)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    times = []
+    for it in range(4):
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record()
+        out_local = S.warp_views_local(feats, pm, (Hg, Wg), shard)
+        ev[1].record()
+        partial = S.conv1_partial(out_local, weight, bias, shard, C)
+        ev[2].record()
+        reduced = S.reduce_partials(partial, relu=True)
+        ev[3].record()
+        torch.cuda.synchronize()
+        times.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+        del out_local, partial, reduced
+    t = torch.tensor(times[1:], device=dev).mean(0)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        flops = 2.0 * Hg * Wg * Cout * (shard.count * C + 2) * 9
+        res.update({"rig": f"{V} cameras x 512ch x {Hs}x{Ws} -> {Hg}x{Wg}, bf16, {per_rank} cameras per rank",
+                    "warp_ms": float(t[0]), "conv1_partial_ms": float(t[1]), "allreduce_relu_ms": float(t[2]),
+                    "conv1_partial_tflops": flops / (float(t[1]) * 1e-3) / 1e12,
+                    "allreduce_bytes": B * Cout * Hg * Wg * 2,
+                    "allreduce_busbw_gbs": 2 * (world - 1) / world * B * Cout * Hg * Wg * 2 / (float(t[2]) * 1e-3) / 1e9})
+        print(json.dumps(res), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
