@@ -54,7 +54,9 @@ typedef struct mvwarp_stats {
   uint32_t max_row;           /* longest CSR row (taps landing on one texel) */
   uint32_t bwd_tasks;         /* backward: warp-sized tasks (runs of light rows) */
   uint32_t heavy_rows;        /* backward: rows long enough to get a whole CTA */
-  uint32_t reserved_;
+  uint32_t fwd_tasks;         /* fused up-sample plans: warp-sized tasks of the forward table gather (else 0) */
+  int32_t  lowres_h, lowres_w;/* fused up-sample plans: the low-res feature map the kernels read (else 0); for such plans
+                                 unique_texels / nnz / max_row describe the composed map on the low-res image */
   uint64_t device_bytes;      /* HBM held by the plan */
 } mvwarp_stats_t;
 
@@ -81,6 +83,12 @@ int mvwarp_host_csr(const float* grid_host, int V, int Hs, int Ws, int Hg, int W
                     uint32_t* tex_of_out, uint32_t* row_ptr_out, uint32_t* cells_out, float* weights_out,
                     uint64_t capacity);
 
+/* Same for the composed map of a fused up-sample plan (see mvwarp_plan_create_upsampled); hl = wl = 0 gives the plain map.
+ * tex_of_out then has V*hl*wl entries and row_ptr_out V*(hl*wl+1). */
+int mvwarp_host_csr_upsampled(const float* grid_host, int V, int hl, int wl, int Hs, int Ws, int Hg, int Wg,
+                              mvwarp_stats_t* stats_out, uint32_t* tex_of_out, uint32_t* row_ptr_out, uint32_t* cells_out,
+                              float* weights_out, uint64_t capacity);
+
 /* ---- plan: everything that depends only on the camera rig ---------------------------------------
  * Built once per (proj_mats, shapes, device); holds the per-view matrices (or grid table) and the
  * inverse CSR map used by the deterministic backward.
@@ -94,6 +102,16 @@ int mvwarp_plan_create(const float* src_norm_trans_dst_norm, int V, int Hs, int 
                        int device, mvwarp_plan_t** plan_out);
 int mvwarp_plan_create_from_grid(const float* grid_host, int V, int Hs, int Ws, int Hg, int Wg,
                                  int device, mvwarp_plan_t** plan_out);
+/* mvwarp_plan_create_upsampled: SURVEY.md 8(f) rank 1 -- fuse the trunk's bilinear up-sample into the warp.
+ * The reference warps  F.interpolate(feat[B,C,hl,wl], [Hs,Ws], mode='bilinear')  (persp_trans_detector.py:65, ATen
+ * upsample_bilinear2d, align_corners=False).  Both maps are linear and rig-constant, so their composition is one sparse
+ * operator from the LOW-RES feature map to the grid: every grid cell becomes <= 16 (typically 4-9) weighted low-res taps.
+ * With such a plan mvwarp_warp_views_fwd / _bwd take feats / grad_feats of shape [B, nviews, C, hl, wl]: the
+ * up-sampled tensor is never read (forward) nor written (backward).  Weights are composed in double and rounded once;
+ * results agree with the two-step reference to rounding (1e-6 relative), not bit for bit.
+ * Replaces: F.interpolate at persp_trans_detector.py:65 (for the warp's consumer) + :68-69,75,77. */
+int mvwarp_plan_create_upsampled(const float* src_norm_trans_dst_norm, int V, int hl, int wl, int Hs, int Ws,
+                                 int Hg, int Wg, int device, mvwarp_plan_t** plan_out);
 int mvwarp_plan_destroy(mvwarp_plan_t* plan);
 int mvwarp_plan_stats(const mvwarp_plan_t* plan, mvwarp_stats_t* stats_out);
 /* Debug/test: run the device coordinate kernel and copy the normalised grid [V,Hg,Wg,2] to host. */

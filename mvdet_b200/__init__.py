@@ -10,11 +10,11 @@ from ._lib import MvwarpError
 
 
 def __getattr__(name):  # ops import torch.library machinery lazily
-    if name in ("warp_views", "warp_views_with_plan", "warp_perspective", "grid_sample_views",
+    if name in ("warp_views", "warp_views_with_plan", "warp_views_upsampled", "warp_perspective", "grid_sample_views",
                 "warp_views_fwd_into", "warp_views_bwd_into"):
         from . import ops
         return getattr(ops, name)
-    if name in ("get_plan", "get_plan_from_grid", "WarpPlan", "src_norm_trans_dst_norm", "host_grid", "host_csr"):
+    if name in ("get_plan", "get_plan_from_grid", "get_plan_upsampled", "WarpPlan", "src_norm_trans_dst_norm", "host_grid", "host_csr"):
         from . import plan
         return getattr(plan, name)
     raise AttributeError(name)

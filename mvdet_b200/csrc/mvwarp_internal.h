@@ -10,37 +10,44 @@
 
 namespace mvw {
 
-// One inverse-map entry: grid cell (y*Wg + x) and the bilinear weight with which it samples the texel.
+// One sparse-map entry: column index (a grid cell y*Wg + x, or a source texel ys*Ws + xs) and its weight.
 struct CsrEntry {
-  uint32_t cell;
+  uint32_t col;
   float w;
 };
 
-// Backward work decomposition (built with the CSR): a regular task is a run of consecutive rows whose
-// weight (1 per texel + 1 per entry) fits TASK_BUDGET (32), processed by one warp; a row longer than HEAVY_LEN
+// Work decomposition of a CSR gather (built with the CSR): a regular task is a run of consecutive rows whose
+// weight (1 per row + 1 per entry) fits TASK_BUDGET (32), processed by one warp; a row longer than HEAVY_LEN
 // is "heavy" and gets a whole CTA (its entries split over the warps, partials combined in warp order).
-constexpr uint32_t TASK_BUDGET = 32, TASK_MAX_TEX = 31, HEAVY_LEN = 31;  // swept on B200: profiles/README.md
-constexpr int CSR_TILE = 8;  // rows are ordered tile-major over CSR_TILE x CSR_TILE texel tiles
+constexpr uint32_t TASK_BUDGET = 32, TASK_MAX_ROWS = 31, HEAVY_LEN = 31;  // swept on B200: profiles/README.md
+constexpr int CSR_TILE = 8;  // rows are ordered tile-major over CSR_TILE x CSR_TILE tiles of the row image
 
 struct Task {
-  uint32_t row0;   // first row (tile-major texel position, view-relative)
-  uint16_t nrows;  // <= TASK_MAX_TEX
+  uint32_t row0;   // first row (tile-major position, view-relative)
+  uint16_t nrows;  // <= TASK_MAX_ROWS
   uint16_t view;
 };
 
-// Host-side CSR for all views (built once per rig).  Row r of view v describes the texel tex_of[v][r]:
-// rows follow a tile-major order of the source image so that rows close in the array are close in 2-D.
+// Host-side CSR for all views (built once per rig): dst[row_id[r]] = sum over the row of w * src[col].
+// Rows follow a tile-major order of the destination image so that rows close in the array are close in 2-D.
 struct HostCsr {
-  std::vector<uint32_t> row_ptr;     // [V * (Hs*Ws + 1)], offsets relative to view_base[v]
-  std::vector<uint32_t> tex_of;      // [V * Hs*Ws]  row -> linear texel index ys*Ws + xs
-  std::vector<CsrEntry> entries;     // [nnz], per view, rows in order, row entries in (cell, tap) order
+  size_t rows_per_view = 0;
+  std::vector<uint32_t> row_ptr;     // [V * (rows_per_view + 1)], offsets relative to view_base[v]
+  std::vector<uint32_t> row_id;      // [V * rows_per_view]  row -> linear index y*W + x in the destination image
+  std::vector<CsrEntry> entries;     // [nnz], per view, rows in order, row entries in a fixed order
   std::vector<uint64_t> view_base;   // [V + 1]
   std::vector<Task> tasks;           // regular tasks, grouped by view
   std::vector<uint32_t> task_base;   // [V + 1]
   std::vector<uint32_t> heavy;       // heavy rows (view-relative row index), grouped by view
   std::vector<uint32_t> heavy_base;  // [V + 1]
-  uint64_t unique_texels = 0, valid_cells = 0;
+  uint64_t nonempty_rows = 0;
   uint32_t max_row = 0;
+};
+
+struct PlanMaps {
+  HostCsr bwd;            // rows = source texels, columns = grid cells (always built)
+  HostCsr fwd;            // rows = grid cells, columns = source texels (only for fused up-sample plans)
+  uint64_t valid_cells = 0;
 };
 
 void set_error(const std::string& msg);
@@ -48,8 +55,23 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // Host: normalised grid [V,Hg,Wg,2] from the matrices (bit-identical to the oracle's torch ops).
 void host_grid(const float* T, int V, int Hg, int Wg, float* grid_out);
-// Host: inverse CSR map from a normalised grid.
-void host_build_csr(const float* grid, int V, int Hs, int Ws, int Hg, int Wg, HostCsr& csr);
+// Host: inverse map (texel -> cells) of a normalised grid.
+void host_build_maps(const float* grid, int V, int Hs, int Ws, int Hg, int Wg, PlanMaps& maps);
+// Host: maps of  warp(bilinear_upsample(feats[hl,wl] -> [Hs,Ws]))  composed into one sparse operator on the low-res image.
+void host_build_maps_upsampled(const float* grid, int V, int hl, int wl, int Hs, int Ws, int Hg, int Wg, PlanMaps& maps);
+
+// Device-side CSR (pointers into the plan's allocation) + host copies of what launches need.
+struct DevCsr {
+  uint32_t rows_per_view = 0;
+  uint32_t* row_ptr = nullptr;
+  uint32_t* row_id = nullptr;
+  CsrEntry* entries = nullptr;
+  uint64_t* view_base = nullptr;
+  Task* tasks = nullptr;
+  uint32_t* heavy = nullptr;
+  uint32_t* heavy_base_dev = nullptr;
+  std::vector<uint32_t> task_base, heavy_base;  // host copies, [V+1]
+};
 
 }  // namespace mvw
 
@@ -57,6 +79,8 @@ void host_build_csr(const float* grid, int V, int Hs, int Ws, int Hg, int Wg, Ho
 struct mvwarp_plan {
   int device = 0;
   int V = 0, Hs = 0, Ws = 0, Hg = 0, Wg = 0;
+  int hl = 0, wl = 0;      // fused up-sample plans: size of the low-res feature map the kernels actually read
+  int upsampled = 0;
   int inline_coords = 0;
   int num_sms = 148;
   // device memory (one allocation, carved)
@@ -66,14 +90,7 @@ struct mvwarp_plan {
   float* d_grid = nullptr;         // [V,Hg,Wg,2]    (table mode)
   float* d_coord_x = nullptr;      // [Wg]  coord_map channel 0 along x
   float* d_coord_y = nullptr;      // [Hg]  coord_map channel 1 along y
-  uint32_t* d_row_ptr = nullptr;   // [V*(Hs*Ws+1)]
-  uint32_t* d_tex_of = nullptr;    // [V*Hs*Ws]
-  mvw::CsrEntry* d_entries = nullptr;  // [nnz]
-  uint64_t* d_view_base = nullptr; // [V+1]
-  mvw::Task* d_tasks = nullptr;    // regular backward tasks
-  uint32_t* d_heavy = nullptr;     // heavy rows
-  uint32_t* d_heavy_base = nullptr;  // [V+1]
-  std::vector<uint32_t> task_base, heavy_base;  // host copies, [V+1]
+  mvw::DevCsr bwd, fwd;
   mvwarp_stats_t stats{};
 };
 

@@ -19,17 +19,28 @@
 
 namespace mvw {
 
+// One side of a CSR gather: element strides of a [batch][view][y][x][channel] addressing,
+//   addr = base + b*B + vl*V + chan0 + c*C + y*H + x*W,   (y, x) = (id / width, id % width).
+struct Side {
+  int64_t B, V, H, W, C;
+  int64_t chan0;
+  int width;
+};
+
 struct KParams {
   const float* T;        // [V,9] or unused
   const float2* grid;    // [V,Hg,Wg] normalised (x,y) or nullptr (inline coordinates)
   const float* coord_x;  // [Wg]
   const float* coord_y;  // [Hg]
+  // CSR gather (backward of every plan; forward of fused up-sample plans): dst[row_id[r]] = sum_k w_k * src[col_k]
   const uint32_t* row_ptr;
-  const uint32_t* tex_of;
+  const uint32_t* row_id;
   const CsrEntry* entries;
   const uint64_t* view_base;
   const Task* tasks;
   const uint32_t* heavy;
+  uint32_t rows_per_view;
+  Side gsrc, gdst;
   int Hs, Ws, Hg, Wg;
   int view0, nviews, B, C;
   const void* src;  // forward: feats      backward: grad_out
@@ -39,6 +50,7 @@ struct KParams {
   int out_chan0, coord_chan;
   int tiles_x, tiles_y, cchunk;
 };
+
 
 // ---------------------------------------------------------------------------------------------------
 // 16-byte vectors of T <-> fp32 lanes
@@ -331,23 +343,25 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const KParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// backward, channels-last: deterministic gather through the inverse CSR map
+// CSR gather, channels-last:  dst[row] = sum over the row's entries of  w * src[col]
 //
-// The CSR rows (one per source texel, tile-major order) are very unevenly filled: 74 % are empty, the
-// median touched row has 2 entries, rows near a camera's horizon have up to 95 (1360 on the 32-camera
-// rig).  A gather row is a chain of dependent round trips, so work is balanced at plan time:
-//   * bwd_cl_task_kernel: one WARP per task = run of consecutive light rows with (rows + entries) <= 32.
-//     Row pointers, texel ids and entries are fetched with coalesced loads (consecutive rows are
-//     contiguous in the CSR arrays) and broadcast by shuffles; lanes run across channels (16 B each) and
-//     sum a row in CSR order (ascending cell, then tap) with fp32 FMAs, two entries (8 independent 128-bit
-//     gathers) in flight per lane.  Empty rows store zeros: there is no memset pass.
-//   * bwd_cl_heavy_kernel: one CTA per heavy row (> 31 entries): warp w sums the w-th eighth of the row,
-//     partials meet in shared memory and are added in warp order.
-// Both orders are fixed by the plan, so the gradient is bitwise reproducible (no atomics anywhere).
+// This is the deterministic backward of every plan (rows = source texels, columns = grid cells: the inverse
+// map of the warp) and the forward of fused up-sample plans (rows = grid cells, columns = low-res texels).
+//
+// The rows (tile-major order) are very unevenly filled -- for the backward 74 % are empty, the median
+// touched row has 2 entries, rows near a camera's horizon have up to 95 (1360 on the 32-camera rig) -- and a
+// gather row is a chain of dependent round trips, so work is balanced at plan time:
+//   * one WARP per task = run of consecutive light rows with (rows + entries) <= 32.  Row pointers, row ids
+//     and entries are fetched with coalesced loads (consecutive rows are contiguous in the CSR arrays) and
+//     broadcast by shuffles; lanes run across channels (16 B each) and sum a row in CSR order with fp32 FMAs,
+//     two entries (8 independent 128-bit gathers) in flight per lane.  Empty rows store zeros: no memset pass.
+//   * one CTA per heavy row (> 31 entries): warp w sums the w-th eighth of the row, partials meet in shared
+//     memory and are added in warp order.  Heavy CTAs come first in the same launch.
+// Both orders are fixed by the plan, so the result is bitwise reproducible (no atomics anywhere).
 // ---------------------------------------------------------------------------------------------------
 constexpr int BWD_WARPS = 8, BWD_ACC_FLOATS = 16;
 
-// NACC 16-byte vectors of one grad_out row (lane's columns), for a row base of compile-time alignment
+// NACC 16-byte vectors of one source row (lane's columns), for a row base of compile-time alignment
 template <typename T, int NACC, int ALIGN, bool KEEP, bool FULLC>
 __device__ __forceinline__ void load_row(uint4 (&v)[NACC], const T* __restrict__ g, int cbase, int nvec, int lane, uint64_t pol) {
   constexpr int EPV = VecTraits<T>::EPV;
@@ -363,12 +377,10 @@ __device__ __forceinline__ void load_row(uint4 (&v)[NACC], const T* __restrict__
         const uint2 b = KEEP ? ldg8_keep(ptr + 8, pol) : __ldg(reinterpret_cast<const uint2*>(ptr) + 1);
         v[q] = make_uint4(a.x, a.y, b.x, b.y);
       } else {
-        // 4-byte aligned row (bf16, 3 cells in 4).  Measured alternatives: two overlapping aligned 128-bit loads +
+        // 4-byte aligned row (bf16, 3 cells in 4).  Measured alternative: two overlapping aligned 128-bit loads +
         // word selection is 15-25 % slower than these four 32-bit loads (profiles/README.md).
-        {
-          const unsigned* w = reinterpret_cast<const unsigned*>(ptr);
-          v[q] = make_uint4(__ldg(w), __ldg(w + 1), __ldg(w + 2), __ldg(w + 3));
-        }
+        const unsigned* w = reinterpret_cast<const unsigned*>(ptr);
+        v[q] = make_uint4(__ldg(w), __ldg(w + 1), __ldg(w + 2), __ldg(w + 3));
       }
     } else {
       v[q] = make_uint4(0, 0, 0, 0);
@@ -384,19 +396,19 @@ __device__ __forceinline__ void load_row_any(uint4 (&v)[NACC], const T* __restri
   else load_row<T, NACC, 4, KEEP, FULLC>(v, g, cbase, nvec, lane, pol);
 }
 
-// acc += sum over entries [k0, k1) of w * grad_out[cell]; entries come through 32-entry windows (coalesced).
-// DENSE: grad_out rows are cell*oW apart (dense channels-last), so no division turns a cell index into (y, x).
+// acc += sum over entries [k0, k1) of w * src[col]; entries come through 32-entry windows (coalesced).
+// DENSE: source rows are col*W apart (dense channels-last), so no division turns a column index into (y, x).
 template <typename T, int NACC, bool KEEP, bool FULLC, bool DENSE>
 __device__ __forceinline__ void gather_entries(float (&acc)[NACC][VecTraits<T>::EPV], const uint2* __restrict__ en,
-                                               uint32_t k0, uint32_t k1, uint32_t win_end, const T* __restrict__ go,
+                                               uint32_t k0, uint32_t k1, uint32_t win_end, const T* __restrict__ gs,
                                                const KParams& p, int cbase, int nvec, int lane, uint32_t& win0, uint2& ent,
                                                uint64_t pol) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr unsigned FULL = 0xffffffffu;
-  auto row_of_cell = [&](uint32_t cell) -> const T* {
-    if (DENSE) return go + (int64_t)cell * p.oW;
-    const int cy = cell / p.Wg, cx = cell - cy * p.Wg;
-    return go + (int64_t)cy * p.oH + (int64_t)cx * p.oW;
+  auto row_of_col = [&](uint32_t col) -> const T* {
+    if (DENSE) return gs + (int64_t)col * p.gsrc.W;
+    const int cy = col / p.gsrc.width, cx = col - cy * p.gsrc.width;
+    return gs + (int64_t)cy * p.gsrc.H + (int64_t)cx * p.gsrc.W;
   };
   constexpr int NE = 2;  // entries in flight per trip (4 for bf16 was measured slower: register pressure)
   uint32_t k = k0;
@@ -411,9 +423,9 @@ __device__ __forceinline__ void gather_entries(float (&acc)[NACC][VecTraits<T>::
       float w[NE];
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
-        const uint32_t cell = __shfl_sync(FULL, ent.x, s0 + i);
+        const uint32_t col = __shfl_sync(FULL, ent.x, s0 + i);
         w[i] = __uint_as_float(__shfl_sync(FULL, ent.y, s0 + i));
-        load_row_any<T, NACC, KEEP, FULLC>(v[i], row_of_cell(cell), cbase, nvec, lane, pol);
+        load_row_any<T, NACC, KEEP, FULLC>(v[i], row_of_col(col), cbase, nvec, lane, pol);
       }
 #pragma unroll
       for (int i = 0; i < NE; ++i) {  // FMAs strictly in entry order
@@ -427,10 +439,10 @@ __device__ __forceinline__ void gather_entries(float (&acc)[NACC][VecTraits<T>::
       }
       k += NE;
     } else {  // row tail / window edge: one entry
-      const uint32_t cell = __shfl_sync(FULL, ent.x, s0);
+      const uint32_t col = __shfl_sync(FULL, ent.x, s0);
       const float w0 = __uint_as_float(__shfl_sync(FULL, ent.y, s0));
       uint4 v0[NACC];
-      load_row_any<T, NACC, KEEP, FULLC>(v0, row_of_cell(cell), cbase, nvec, lane, pol);
+      load_row_any<T, NACC, KEEP, FULLC>(v0, row_of_col(col), cbase, nvec, lane, pol);
 #pragma unroll
       for (int q = 0; q < NACC; ++q) {
         float f[EPV];
@@ -443,8 +455,18 @@ __device__ __forceinline__ void gather_entries(float (&acc)[NACC][VecTraits<T>::
   }
 }
 
-template <typename T, bool KEEP, bool FULLC, bool DENSE>
-__device__ __forceinline__ void bwd_task(const KParams& p, uint32_t tid, uint32_t task_hi) {
+// coord_map channels of grid cell `id` (only the forward table gather writes them, for the first local view)
+template <typename T>
+__device__ __forceinline__ void write_coord(const KParams& p, int b, uint32_t id) {
+  const int y = id / p.Wg, x = id - y * p.Wg;
+  T* cm = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (int64_t)y * p.oH + (int64_t)x * p.oW + (int64_t)p.coord_chan * p.oC;
+  cm[0] = from_float<T>(__ldg(p.coord_x + x));
+  cm[p.oC] = from_float<T>(__ldg(p.coord_y + y));
+}
+
+// DSTANY: destination rows may be only 8- / 4-byte aligned (the concat tensor); otherwise 16-byte aligned rows.
+template <typename T, bool KEEP, bool FULLC, bool DENSE, bool DSTANY>
+__device__ __forceinline__ void gather_task(const KParams& p, uint32_t tid, uint32_t task_hi) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr int NACC = BWD_ACC_FLOATS / EPV;  // 16-byte vectors per lane per pass
   constexpr unsigned FULL = 0xffffffffu;
@@ -454,36 +476,42 @@ __device__ __forceinline__ void bwd_task(const KParams& p, uint32_t tid, uint32_
   const Task task = p.tasks[tid];
   const int v = task.view, vl = v - p.view0, b = blockIdx.z;
   const int nrows = task.nrows;
-  const int ntex = p.Hs * p.Ws;
-  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (ntex + 1) + task.row0;
-  const uint32_t* __restrict__ tex_of = p.tex_of + (size_t)v * ntex + task.row0;
+  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (p.rows_per_view + 1) + task.row0;
+  const uint32_t* __restrict__ ids = p.row_id + (size_t)v * p.rows_per_view + task.row0;
   const uint2* __restrict__ en = reinterpret_cast<const uint2*>(p.entries + __ldg(p.view_base + v));
-  const T* __restrict__ go = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
-  T* __restrict__ gf = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV;
+  const T* __restrict__ gs = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.gsrc.B + (int64_t)vl * p.gsrc.V + p.gsrc.chan0;
+  T* __restrict__ gd = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.gdst.B + (int64_t)vl * p.gdst.V + p.gdst.chan0;
   const int nvec = p.C / EPV;
 
   const uint32_t rpl = (lane <= nrows) ? __ldg(rp + lane) : 0u;
-  const uint32_t texl = (lane < nrows) ? __ldg(tex_of + lane) : 0u;
+  const uint32_t idl = (lane < nrows) ? __ldg(ids + lane) : 0u;
   const uint32_t r_begin = __shfl_sync(FULL, rpl, 0), r_end = __shfl_sync(FULL, rpl, nrows);
+  if (DSTANY && p.coord_chan >= 0 && vl == 0 && lane < nrows) write_coord<T>(p, b, idl);
 
   for (int cbase = 0; cbase < nvec; cbase += 32 * NACC) {
     uint32_t win0 = r_begin;
     uint2 ent = (win0 + lane < r_end) ? __ldg(en + win0 + lane) : make_uint2(0u, 0u);
     for (int j = 0; j < nrows; ++j) {
       const uint32_t a = __shfl_sync(FULL, rpl, j), e = __shfl_sync(FULL, rpl, j + 1);
-      const uint32_t tex = __shfl_sync(FULL, texl, j);
+      const uint32_t id = __shfl_sync(FULL, idl, j);
       float acc[NACC][EPV];
 #pragma unroll
       for (int q = 0; q < NACC; ++q)
 #pragma unroll
         for (int i = 0; i < EPV; ++i) acc[q][i] = 0.f;
-      gather_entries<T, NACC, KEEP, FULLC, DENSE>(acc, en, a, e, r_end, go, p, cbase, nvec, lane, win0, ent, pol);
-      const int ys = tex / p.Ws, xs = tex - ys * p.Ws;
-      T* o = gf + (int64_t)ys * p.fH + (int64_t)xs * p.fW;
+      gather_entries<T, NACC, KEEP, FULLC, DENSE>(acc, en, a, e, r_end, gs, p, cbase, nvec, lane, win0, ent, pol);
+      const int yd = id / p.gdst.width, xd = id - yd * p.gdst.width;
+      T* o = gd + (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
+      const unsigned oal = DSTANY ? (unsigned)(reinterpret_cast<uintptr_t>(o) & 15u) : 0u;  // warp-uniform
 #pragma unroll
       for (int q = 0; q < NACC; ++q) {
         const int c = cbase + 32 * q + lane;
-        if (c < nvec) __stcs(reinterpret_cast<uint4*>(o + c * EPV), VecTraits<T>::pack(acc[q]));
+        if (FULLC || c < nvec) {
+          const uint4 r = VecTraits<T>::pack(acc[q]);
+          if (!DSTANY || oal == 0) stcs16<16>(o + c * EPV, r);
+          else if ((oal & 7u) == 0) stcs16<8>(o + c * EPV, r);
+          else stcs16<4>(o + c * EPV, r);
+        }
       }
     }
   }
@@ -491,9 +519,9 @@ __device__ __forceinline__ void bwd_task(const KParams& p, uint32_t tid, uint32_
 
 constexpr int BWD_PASS_FLOATS = 32 * BWD_ACC_FLOATS;  // channels per pass (512)
 
-template <typename T, bool KEEP, bool FULLC, bool DENSE>
-__device__ __forceinline__ void bwd_heavy_row(const KParams& p, uint32_t hid, int view_lo, const uint32_t* __restrict__ heavy_base,
-                                              float (*part)[BWD_PASS_FLOATS]) {
+template <typename T, bool KEEP, bool FULLC, bool DENSE, bool DSTANY>
+__device__ __forceinline__ void gather_heavy_row(const KParams& p, uint32_t hid, int view_lo, const uint32_t* __restrict__ heavy_base,
+                                                 float (*part)[BWD_PASS_FLOATS]) {
   constexpr int EPV = VecTraits<T>::EPV;
   constexpr int NACC = BWD_ACC_FLOATS / EPV;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -501,14 +529,16 @@ __device__ __forceinline__ void bwd_heavy_row(const KParams& p, uint32_t hid, in
   int v = view_lo;
   while (hid >= __ldg(heavy_base + v + 1)) ++v;  // few views: linear search
   const int vl = v - p.view0, b = blockIdx.z;
-  const int ntex = p.Hs * p.Ws;
   const uint32_t row = __ldg(p.heavy + hid);
-  const uint32_t a = __ldg(p.row_ptr + (size_t)v * (ntex + 1) + row), e = __ldg(p.row_ptr + (size_t)v * (ntex + 1) + row + 1);
-  const uint32_t tex = __ldg(p.tex_of + (size_t)v * ntex + row);
+  const uint32_t* rp = p.row_ptr + (size_t)v * (p.rows_per_view + 1) + row;
+  const uint32_t a = __ldg(rp), e = __ldg(rp + 1);
+  const uint32_t id = __ldg(p.row_id + (size_t)v * p.rows_per_view + row);
   const uint2* __restrict__ en = reinterpret_cast<const uint2*>(p.entries + __ldg(p.view_base + v));
-  const T* __restrict__ go = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
-  const int ys = tex / p.Ws, xs = tex - ys * p.Ws;
-  T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV + (int64_t)ys * p.fH + (int64_t)xs * p.fW;
+  const T* __restrict__ gs = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.gsrc.B + (int64_t)vl * p.gsrc.V + p.gsrc.chan0;
+  const int yd = id / p.gdst.width, xd = id - yd * p.gdst.width;
+  T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.gdst.B + (int64_t)vl * p.gdst.V + p.gdst.chan0 +
+                      (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
+  if (DSTANY && p.coord_chan >= 0 && vl == 0 && threadIdx.x == 0) write_coord<T>(p, b, id);
   const int nvec = p.C / EPV;
   const uint32_t seg = (e - a + BWD_WARPS - 1) / BWD_WARPS;
   const uint32_t k0 = min(e, a + warp * seg), k1 = min(e, k0 + seg);
@@ -521,7 +551,7 @@ __device__ __forceinline__ void bwd_heavy_row(const KParams& p, uint32_t hid, in
       for (int i = 0; i < EPV; ++i) acc[q][i] = 0.f;
     uint32_t win0 = k0;
     uint2 ent = (win0 + lane < k1) ? __ldg(en + win0 + lane) : make_uint2(0u, 0u);
-    gather_entries<T, NACC, KEEP, FULLC, DENSE>(acc, en, k0, k1, k1, go, p, cbase, nvec, lane, win0, ent, pol);
+    gather_entries<T, NACC, KEEP, FULLC, DENSE>(acc, en, k0, k1, k1, gs, p, cbase, nvec, lane, win0, ent, pol);
     // partials in channel order: lane's q-th vector covers pass-channels [(32q + lane)*EPV, +EPV)
 #pragma unroll
     for (int q = 0; q < NACC; ++q)
@@ -547,47 +577,70 @@ __device__ __forceinline__ void bwd_heavy_row(const KParams& p, uint32_t hid, in
 }
 
 // One launch: the first n_heavy CTAs take one heavy row each (longest chains start first), the rest take
-// BWD_WARPS tasks each.
+// BWD_WARPS tasks each.  Two entry points over the same body so that profiles name the two uses apart.
+template <typename T, bool KEEP, bool FULLC, bool DENSE, bool DSTANY>
+__device__ __forceinline__ void csr_gather_body(const KParams& p, uint32_t task_lo, uint32_t task_hi, uint32_t heavy_lo,
+                                                uint32_t n_heavy, int view_lo, const uint32_t* __restrict__ heavy_base,
+                                                float (*part)[BWD_PASS_FLOATS]) {
+  if (blockIdx.x < n_heavy) {
+    gather_heavy_row<T, KEEP, FULLC, DENSE, DSTANY>(p, heavy_lo + blockIdx.x, view_lo, heavy_base, part);
+  } else {
+    gather_task<T, KEEP, FULLC, DENSE, DSTANY>(p, task_lo + (blockIdx.x - n_heavy) * BWD_WARPS + (threadIdx.x >> 5), task_hi);
+  }
+}
+
+// backward of every plan: grad_feats[texel] = sum w * grad_out[cell]
 template <typename T, int MINB, bool KEEP, bool FULLC, bool DENSE>
 __global__ void __launch_bounds__(BWD_WARPS * 32, MINB)
     bwd_cl_kernel(const KParams p, uint32_t task_lo, uint32_t task_hi, uint32_t heavy_lo, uint32_t n_heavy, int view_lo,
                   const uint32_t* __restrict__ heavy_base) {
   __shared__ __align__(16) float part[BWD_WARPS][BWD_PASS_FLOATS];
-  if (blockIdx.x < n_heavy) {
-    bwd_heavy_row<T, KEEP, FULLC, DENSE>(p, heavy_lo + blockIdx.x, view_lo, heavy_base, part);
-  } else {
-    bwd_task<T, KEEP, FULLC, DENSE>(p, task_lo + (blockIdx.x - n_heavy) * BWD_WARPS + (threadIdx.x >> 5), task_hi);
-  }
+  csr_gather_body<T, KEEP, FULLC, DENSE, false>(p, task_lo, task_hi, heavy_lo, n_heavy, view_lo, heavy_base, part);
 }
 
-// backward, arbitrary strides: thread per CSR row (= source texel, tile-major order), loop over a chunk of channels
-template <typename T>
-__global__ void __launch_bounds__(256) bwd_generic_kernel(const KParams p) {
-  const int ntex = p.Hs * p.Ws;
+// forward of fused up-sample plans: out[cell] = sum w * feats_lowres[texel]  (+ coord_map channels)
+template <typename T, int MINB, bool FULLC, bool DENSE>
+__global__ void __launch_bounds__(BWD_WARPS * 32, MINB)
+    fwd_table_cl_kernel(const KParams p, uint32_t task_lo, uint32_t task_hi, uint32_t heavy_lo, uint32_t n_heavy, int view_lo,
+                        const uint32_t* __restrict__ heavy_base) {
+  __shared__ __align__(16) float part[BWD_WARPS][BWD_PASS_FLOATS];
+  csr_gather_body<T, false, FULLC, DENSE, true>(p, task_lo, task_hi, heavy_lo, n_heavy, view_lo, heavy_base, part);
+}
+
+// CSR gather, arbitrary strides: thread per CSR row (tile-major order), loop over a chunk of channels
+template <typename T, bool COORD>
+__device__ __forceinline__ void gather_generic_body(const KParams& p) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   const int vl = blockIdx.y, v = p.view0 + vl;
   const int nchunk = (p.C + p.cchunk - 1) / p.cchunk;
   const int b = blockIdx.z / nchunk, chunk = blockIdx.z % nchunk;
-  if (row >= ntex) return;
-  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (ntex + 1);
+  if (row >= (int)p.rows_per_view) return;
+  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (p.rows_per_view + 1);
   const CsrEntry* __restrict__ en = p.entries + __ldg(p.view_base + v);
   const uint32_t r0 = __ldg(rp + row), r1 = __ldg(rp + row + 1);
-  const uint32_t tex = __ldg(p.tex_of + (size_t)v * ntex + row);
-  const int ys = tex / p.Ws, xs = tex - ys * p.Ws;
-  const T* __restrict__ go = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.oB;
-  T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.fB + (int64_t)vl * p.fV + (int64_t)ys * p.fH + (int64_t)xs * p.fW;
+  const uint32_t id = __ldg(p.row_id + (size_t)v * p.rows_per_view + row);
+  if (COORD && p.coord_chan >= 0 && vl == 0 && chunk == 0) write_coord<T>(p, b, id);
+  const int yd = id / p.gdst.width, xd = id - yd * p.gdst.width;
+  const T* __restrict__ gs = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.gsrc.B + (int64_t)vl * p.gsrc.V + p.gsrc.chan0;
+  T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.gdst.B + (int64_t)vl * p.gdst.V + p.gdst.chan0 +
+                      (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
   const int c_end = min(p.C, (chunk + 1) * p.cchunk);
   for (int c = chunk * p.cchunk; c < c_end; ++c) {
-    const T* g = go + (int64_t)(p.out_chan0 + (int64_t)vl * p.C + c) * p.oC;
+    const T* g = gs + (int64_t)c * p.gsrc.C;
     float acc = 0.f;
     for (uint32_t k = r0; k < r1; ++k) {
       const CsrEntry e = en[k];
-      const int y = e.cell / p.Wg, x = e.cell - y * p.Wg;
-      acc = __fmaf_rn(e.w, to_float(__ldg(g + (int64_t)y * p.oH + (int64_t)x * p.oW)), acc);
+      const int y = e.col / p.gsrc.width, x = e.col - y * p.gsrc.width;
+      acc = __fmaf_rn(e.w, to_float(__ldg(g + (int64_t)y * p.gsrc.H + (int64_t)x * p.gsrc.W)), acc);
     }
-    o[(int64_t)c * p.fC] = from_float<T>(acc);
+    o[(int64_t)c * p.gdst.C] = from_float<T>(acc);
   }
 }
+
+template <typename T>
+__global__ void __launch_bounds__(256) bwd_generic_kernel(const KParams p) { gather_generic_body<T, false>(p); }
+template <typename T>
+__global__ void __launch_bounds__(256) fwd_table_generic_kernel(const KParams p) { gather_generic_body<T, true>(p); }
 
 // device-side normalised grid (test hook: proves host == device coordinate bits)
 template <bool kInline>
@@ -617,8 +670,6 @@ static KParams make_params(const LaunchArgs& a) {
   KParams p{};
   p.T = pl->d_T; p.grid = reinterpret_cast<const float2*>(pl->d_grid);
   p.coord_x = pl->d_coord_x; p.coord_y = pl->d_coord_y;
-  p.row_ptr = pl->d_row_ptr; p.tex_of = pl->d_tex_of; p.entries = pl->d_entries; p.view_base = pl->d_view_base;
-  p.tasks = pl->d_tasks; p.heavy = pl->d_heavy;
   p.Hs = pl->Hs; p.Ws = pl->Ws; p.Hg = pl->Hg; p.Wg = pl->Wg;
   p.view0 = a.view0; p.nviews = a.nviews; p.B = a.B; p.C = a.C;
   p.src = a.feats_or_grad_out; p.dst = a.out_or_grad_feats;
@@ -629,6 +680,18 @@ static KParams make_params(const LaunchArgs& a) {
   p.tiles_y = (pl->Hg + FWD_TILE_H - 1) / FWD_TILE_H;
   p.cchunk = 32;
   return p;
+}
+
+static void set_csr(KParams& p, const DevCsr& c) {
+  p.row_ptr = c.row_ptr; p.row_id = c.row_id; p.entries = c.entries; p.view_base = c.view_base;
+  p.tasks = c.tasks; p.heavy = c.heavy; p.rows_per_view = c.rows_per_view;
+}
+// feature-map side [B, V, C, H, W] and concat side [B, chan0 + vl*C + c, H, W] of a gather
+static Side feats_side(const LaunchArgs& a, int width) {
+  return Side{a.fs[0], a.fs[1], a.fs[3], a.fs[4], a.fs[2], 0, width};
+}
+static Side concat_side(const LaunchArgs& a, int width) {
+  return Side{a.os[0], (int64_t)a.C * a.os[1], a.os[2], a.os[3], a.os[1], (int64_t)a.out_chan0 * a.os[1], width};
 }
 
 static int tuning_variant(const char* name, int dflt) {
@@ -653,6 +716,52 @@ static int check_grid_dims(const LaunchArgs& a, int64_t z) {
   return MVWARP_OK;
 }
 
+// Launch a CSR gather (one CTA per heavy row, then BWD_WARPS tasks per CTA) or its any-stride fallback.
+template <typename T, bool FORWARD>
+static int launch_gather_t(const LaunchArgs& a, KParams& p, const DevCsr& csr, bool fast) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  if (fast) {
+    int rc = check_grid_dims(a, a.B);
+    if (rc) return rc;
+    const uint32_t t_lo = csr.task_base[a.view0], t_hi = csr.task_base[a.view0 + a.nviews];
+    const uint32_t h_lo = csr.heavy_base[a.view0], h_hi = csr.heavy_base[a.view0 + a.nviews];
+    const uint32_t n_heavy = h_hi - h_lo, n_task_ctas = (t_hi - t_lo + BWD_WARPS - 1) / BWD_WARPS;
+    if (n_heavy + n_task_ctas == 0) return MVWARP_OK;
+    dim3 grid(n_heavy + n_task_ctas, 1, a.B), block(BWD_WARPS * 32);
+    const bool fullc = (a.C / EPV) % (32 * (BWD_ACC_FLOATS / EPV)) == 0;      // a pass never has a channel tail
+    const bool dense = p.gsrc.H == (int64_t)p.gsrc.width * p.gsrc.W;           // source rows are col * W apart
+#define MVW_GATHER(KERNEL, ...)                                                                                                  \
+  do {                                                                                                                           \
+    if (fullc && dense) KERNEL<T, __VA_ARGS__, true, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev); \
+    else KERNEL<T, __VA_ARGS__, false, false><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev);             \
+  } while (0)
+    if (FORWARD) {
+      if (sizeof(T) == 2) MVW_GATHER(fwd_table_cl_kernel, 4);
+      else MVW_GATHER(fwd_table_cl_kernel, 3);
+    } else {
+      switch (tuning_variant("MVWARP_BWD_VARIANT", 0)) {  // tuning knob (development only)
+        case 1: MVW_GATHER(bwd_cl_kernel, 3, false); break;
+        case 2: MVW_GATHER(bwd_cl_kernel, 4, true); break;
+        case 3: MVW_GATHER(bwd_cl_kernel, 3, true); break;
+        default:
+          if (sizeof(T) == 2) MVW_GATHER(bwd_cl_kernel, 4, true);  // bf16: half the bytes per entry, more warps hide the same latency
+          else MVW_GATHER(bwd_cl_kernel, 3, true);
+          break;
+      }
+    }
+#undef MVW_GATHER
+  } else {
+    const int nchunk = (a.C + p.cchunk - 1) / p.cchunk;
+    int rc = check_grid_dims(a, (int64_t)a.B * nchunk);
+    if (rc) return rc;
+    dim3 grid((csr.rows_per_view + 255) / 256, a.nviews, a.B * nchunk), block(256);
+    if (FORWARD) fwd_table_generic_kernel<T><<<grid, block, 0, a.stream>>>(p);
+    else bwd_generic_kernel<T><<<grid, block, 0, a.stream>>>(p);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, FORWARD ? "warp_views_fwd (table) launch" : "warp_views_bwd launch");
+}
+
 template <typename T>
 static int launch_fwd_t(const LaunchArgs& a) {
   KParams p = make_params(a);
@@ -661,6 +770,12 @@ static int launch_fwd_t(const LaunchArgs& a) {
   const bool fast = feats_vector_ok(a.feats_or_grad_out, a.fs, a.C, EPV) && a.os[1] == 1 &&
                     (reinterpret_cast<uintptr_t>(a.out_or_grad_feats) % sizeof(float) == 0) &&
                     (sizeof(T) == 4 || (a.os[0] % 2 == 0 && a.os[2] % 2 == 0 && a.os[3] % 2 == 0 && a.out_chan0 % 2 == 0));
+  if (a.plan->upsampled) {  // fused up-sample plan: the forward is a table gather from the low-res feature map
+    set_csr(p, a.plan->fwd);
+    p.gsrc = feats_side(a, a.plan->wl);
+    p.gdst = concat_side(a, a.plan->Wg);
+    return launch_gather_t<T, true>(a, p, a.plan->fwd, fast);
+  }
   if (fast) {
     int rc = check_grid_dims(a, a.B);
     if (rc) return rc;
@@ -702,43 +817,11 @@ static int launch_bwd_t(const LaunchArgs& a) {
   const bool fast = feats_vector_ok(a.out_or_grad_feats, a.fs, a.C, EPV) && a.os[1] == 1 &&
                     (reinterpret_cast<uintptr_t>(a.feats_or_grad_out) % sizeof(float) == 0) &&
                     (sizeof(T) == 4 || (a.os[0] % 2 == 0 && a.os[2] % 2 == 0 && a.os[3] % 2 == 0 && a.out_chan0 % 2 == 0));
-  const int ntex = p.Hs * p.Ws;
-  if (fast) {
-    int rc = check_grid_dims(a, a.B);
-    if (rc) return rc;
-    const mvwarp_plan* pl = a.plan;
-    const uint32_t t_lo = pl->task_base[a.view0], t_hi = pl->task_base[a.view0 + a.nviews];
-    const uint32_t h_lo = pl->heavy_base[a.view0], h_hi = pl->heavy_base[a.view0 + a.nviews];
-    const uint32_t n_heavy = h_hi - h_lo, n_task_ctas = (t_hi - t_lo + BWD_WARPS - 1) / BWD_WARPS;
-    if (n_heavy + n_task_ctas > 0) {
-      dim3 grid(n_heavy + n_task_ctas, 1, a.B), block(BWD_WARPS * 32);
-      const bool fullc = (a.C / EPV) % (32 * (BWD_ACC_FLOATS / EPV)) == 0;   // a pass never has a channel tail
-      const bool dense = a.os[2] == (int64_t)pl->Wg * a.os[3];                // grad_out rows are cell * oW apart
-#define MVW_BWD(M, K)                                                                                            \
-  do {                                                                                                           \
-    if (fullc && dense) bwd_cl_kernel<T, M, K, true, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, pl->d_heavy_base); \
-    else bwd_cl_kernel<T, M, K, false, false><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, pl->d_heavy_base);             \
-  } while (0)
-      switch (tuning_variant("MVWARP_BWD_VARIANT", 0)) {  // tuning knob (development only)
-        case 1: MVW_BWD(3, false); break;
-        case 2: MVW_BWD(4, true); break;
-        case 3: MVW_BWD(3, true); break;
-        default:
-          if (sizeof(T) == 2) MVW_BWD(4, true);  // bf16: half the bytes per entry, more warps hide the same latency
-          else MVW_BWD(3, true);
-          break;
-      }
-    }
-#undef MVW_BWD
-  } else {
-    const int nchunk = (a.C + p.cchunk - 1) / p.cchunk;
-    int rc = check_grid_dims(a, (int64_t)a.B * nchunk);
-    if (rc) return rc;
-    dim3 grid((ntex + 255) / 256, a.nviews, a.B * nchunk), block(256);
-    bwd_generic_kernel<T><<<grid, block, 0, a.stream>>>(p);
-  }
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "warp_views_bwd launch");
+  set_csr(p, a.plan->bwd);
+  p.gsrc = concat_side(a, a.plan->Wg);
+  p.gdst = feats_side(a, a.plan->upsampled ? a.plan->wl : a.plan->Ws);
+  p.coord_chan = -1;
+  return launch_gather_t<T, false>(a, p, a.plan->bwd, fast);
 }
 
 int launch_fwd(const LaunchArgs& a) {

@@ -36,66 +36,56 @@ void host_grid(const float* T, int V, int Hg, int Wg, float* grid_out) {
       }
 }
 
-// Tile-major order of the source image: CSR_TILE x CSR_TILE tiles row-major, texels row-major inside a tile.
-static void tile_major_order(int Hs, int Ws, std::vector<uint32_t>& tex_of, std::vector<uint32_t>& row_of) {
-  const size_t ntex = (size_t)Hs * Ws;
-  tex_of.resize(ntex);
-  row_of.resize(ntex);
+// Tile-major order of an H x W image: CSR_TILE x CSR_TILE tiles row-major, pixels row-major inside a tile.
+static void tile_major_order(int H, int W, std::vector<uint32_t>& id_of_row, std::vector<uint32_t>& row_of_id) {
+  const size_t n = (size_t)H * W;
+  id_of_row.resize(n);
+  row_of_id.resize(n);
   size_t r = 0;
-  for (int ty = 0; ty < Hs; ty += CSR_TILE)
-    for (int tx = 0; tx < Ws; tx += CSR_TILE)
-      for (int y = ty; y < std::min(Hs, ty + CSR_TILE); ++y)
-        for (int x = tx; x < std::min(Ws, tx + CSR_TILE); ++x) {
-          const uint32_t tex = (uint32_t)((size_t)y * Ws + x);
-          tex_of[r] = tex;
-          row_of[tex] = (uint32_t)r++;
+  for (int ty = 0; ty < H; ty += CSR_TILE)
+    for (int tx = 0; tx < W; tx += CSR_TILE)
+      for (int y = ty; y < std::min(H, ty + CSR_TILE); ++y)
+        for (int x = tx; x < std::min(W, tx + CSR_TILE); ++x) {
+          const uint32_t id = (uint32_t)((size_t)y * W + x);
+          id_of_row[r] = id;
+          row_of_id[id] = (uint32_t)r++;
         }
 }
+
+struct Triplet {
+  uint32_t row;
+  CsrEntry e;
+};
 
 struct ViewCsr {
   std::vector<CsrEntry> entries;
   std::vector<Task> tasks;
   std::vector<uint32_t> heavy;
-  uint64_t unique = 0, valid = 0;
+  uint64_t nonempty = 0;
   uint32_t max_row = 0;
 };
 
-// Counting sort of the in-bounds taps of one view by row; entry order inside a row is (cell, tap).
-// Then the backward tasks: greedy runs of consecutive light rows under TASK_BUDGET, heavy rows apart.
-static void build_view_csr(const float* grid, int view, int Hs, int Ws, int Hg, int Wg, const std::vector<uint32_t>& row_of,
-                           uint32_t* row_ptr, ViewCsr& out) {
-  const size_t ntex = (size_t)Hs * Ws, ncell = (size_t)Hg * Wg;
-  std::vector<uint32_t> count(ntex + 1, 0);
-  static const int dx[4] = {0, 1, 0, 1}, dy[4] = {0, 0, 1, 1};
-  out.valid = 0;
-  for (size_t cell = 0; cell < ncell; ++cell) {
-    const Taps t = make_taps(grid[2 * cell], grid[2 * cell + 1], Hs, Ws);
-    if (t.mask) ++out.valid;
-    for (int k = 0; k < 4; ++k)
-      if (t.mask >> k & 1) ++count[row_of[(size_t)(t.y0 + dy[k]) * Ws + (t.x0 + dx[k])]];
-  }
+// Stable counting sort of one view's triplets by row (entry order inside a row = insertion order), then the
+// gather tasks: greedy runs of consecutive light rows under TASK_BUDGET, heavy rows apart.
+static void csr_from_triplets(const std::vector<Triplet>& trip, size_t nrows, int view, uint32_t* row_ptr, ViewCsr& out) {
+  std::vector<uint32_t> cursor(nrows + 1, 0);
+  for (const Triplet& t : trip) ++cursor[t.row];
   uint32_t run = 0;
-  out.unique = 0;
+  out.nonempty = 0;
   out.max_row = 0;
-  for (size_t i = 0; i < ntex; ++i) {
-    const uint32_t c = count[i];
+  for (size_t i = 0; i < nrows; ++i) {
+    const uint32_t c = cursor[i];
     row_ptr[i] = run;
-    count[i] = run;  // becomes the fill cursor
+    cursor[i] = run;
     run += c;
-    if (c) ++out.unique;
+    if (c) ++out.nonempty;
     out.max_row = std::max(out.max_row, c);
   }
-  row_ptr[ntex] = run;
+  row_ptr[nrows] = run;
   out.entries.resize(run);
-  for (size_t cell = 0; cell < ncell; ++cell) {
-    const Taps t = make_taps(grid[2 * cell], grid[2 * cell + 1], Hs, Ws);
-    for (int k = 0; k < 4; ++k)
-      if (t.mask >> k & 1) {
-        const size_t row = row_of[(size_t)(t.y0 + dy[k]) * Ws + (t.x0 + dx[k])];
-        out.entries[count[row]++] = CsrEntry{(uint32_t)cell, t.w[k]};
-      }
-  }
-  // backward tasks (budget / heavy threshold overridable for tuning runs only)
+  for (const Triplet& t : trip) out.entries[cursor[t.row]++] = t.e;
+
+  // tasks (budget / heavy threshold overridable for tuning runs only)
   static const uint32_t budget = getenv("MVWARP_TASK_BUDGET") ? (uint32_t)atoi(getenv("MVWARP_TASK_BUDGET")) : TASK_BUDGET;
   static const uint32_t heavy_len = getenv("MVWARP_HEAVY_LEN") ? (uint32_t)atoi(getenv("MVWARP_HEAVY_LEN")) : HEAVY_LEN;
   Task cur{0, 0, (uint16_t)view};
@@ -105,14 +95,14 @@ static void build_view_csr(const float* grid, int view, int Hs, int Ws, int Hg, 
     cur.nrows = 0;
     weight = 0;
   };
-  for (size_t r = 0; r < ntex; ++r) {
+  for (size_t r = 0; r < nrows; ++r) {
     const uint32_t len = row_ptr[r + 1] - row_ptr[r];
     if (len > heavy_len) {
       flush();
       out.heavy.push_back((uint32_t)r);
       continue;
     }
-    if (cur.nrows && (weight + 1 + len > budget || cur.nrows >= TASK_MAX_TEX)) flush();
+    if (cur.nrows && (weight + 1 + len > budget || cur.nrows >= TASK_MAX_ROWS)) flush();
     if (!cur.nrows) cur.row0 = (uint32_t)r;
     ++cur.nrows;
     weight += 1 + len;
@@ -120,26 +110,18 @@ static void build_view_csr(const float* grid, int view, int Hs, int Ws, int Hg, 
   flush();
 }
 
-void host_build_csr(const float* grid, int V, int Hs, int Ws, int Hg, int Wg, HostCsr& csr) {
-  const size_t ntex = (size_t)Hs * Ws, ncell = (size_t)Hg * Wg;
-  std::vector<uint32_t> tex_of, row_of;
-  tile_major_order(Hs, Ws, tex_of, row_of);
-  csr.row_ptr.assign((size_t)V * (ntex + 1), 0);
-  csr.tex_of.resize((size_t)V * ntex);
-  for (int v = 0; v < V; ++v) memcpy(csr.tex_of.data() + (size_t)v * ntex, tex_of.data(), ntex * sizeof(uint32_t));
+static void csr_init(HostCsr& csr, int V, size_t rows_per_view, const std::vector<uint32_t>& id_of_row) {
+  csr.rows_per_view = rows_per_view;
+  csr.row_ptr.assign((size_t)V * (rows_per_view + 1), 0);
+  csr.row_id.resize((size_t)V * rows_per_view);
+  for (int v = 0; v < V; ++v)
+    memcpy(csr.row_id.data() + (size_t)v * rows_per_view, id_of_row.data(), rows_per_view * sizeof(uint32_t));
   csr.view_base.assign(V + 1, 0);
   csr.task_base.assign(V + 1, 0);
   csr.heavy_base.assign(V + 1, 0);
-  std::vector<ViewCsr> per_view(V);
-  const int nthreads = std::max(1, std::min(V, (int)std::thread::hardware_concurrency()));
-  std::vector<std::thread> pool;
-  for (int t = 0; t < nthreads; ++t)
-    pool.emplace_back([&, t]() {
-      for (int v = t; v < V; v += nthreads)
-        build_view_csr(grid + (size_t)v * ncell * 2, v, Hs, Ws, Hg, Wg, row_of, csr.row_ptr.data() + (size_t)v * (ntex + 1),
-                       per_view[v]);
-    });
-  for (auto& th : pool) th.join();
+}
+
+static void csr_assemble(HostCsr& csr, int V, std::vector<ViewCsr>& per_view) {
   uint64_t total = 0;
   for (int v = 0; v < V; ++v) {
     csr.view_base[v] = total;
@@ -151,7 +133,7 @@ void host_build_csr(const float* grid, int V, int Hs, int Ws, int Hg, int Wg, Ho
   csr.entries.resize(total);
   csr.tasks.reserve(csr.task_base[V]);
   csr.heavy.reserve(csr.heavy_base[V]);
-  csr.unique_texels = csr.valid_cells = 0;
+  csr.nonempty_rows = 0;
   csr.max_row = 0;
   for (int v = 0; v < V; ++v) {
     ViewCsr& pv = per_view[v];
@@ -160,10 +142,126 @@ void host_build_csr(const float* grid, int V, int Hs, int Ws, int Hg, int Wg, Ho
     csr.tasks.insert(csr.tasks.end(), pv.tasks.begin(), pv.tasks.end());
     csr.heavy.insert(csr.heavy.end(), pv.heavy.begin(), pv.heavy.end());
     std::vector<CsrEntry>().swap(pv.entries);
-    csr.unique_texels += pv.unique;
-    csr.valid_cells += pv.valid;
+    csr.nonempty_rows += pv.nonempty;
     csr.max_row = std::max(csr.max_row, pv.max_row);
   }
+}
+
+template <typename F>
+static void for_each_view_parallel(int V, F&& fn) {
+  const int nthreads = std::max(1, std::min(V, (int)std::thread::hardware_concurrency()));
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; ++t)
+    pool.emplace_back([&, t]() {
+      for (int v = t; v < V; v += nthreads) fn(v);
+    });
+  for (auto& th : pool) th.join();
+}
+
+static const int kDx[4] = {0, 1, 0, 1}, kDy[4] = {0, 0, 1, 1};
+
+void host_build_maps(const float* grid, int V, int Hs, int Ws, int Hg, int Wg, PlanMaps& maps) {
+  const size_t ntex = (size_t)Hs * Ws, ncell = (size_t)Hg * Wg;
+  std::vector<uint32_t> tex_of_row, row_of_tex;
+  tile_major_order(Hs, Ws, tex_of_row, row_of_tex);
+  csr_init(maps.bwd, V, ntex, tex_of_row);
+  std::vector<ViewCsr> per_view(V);
+  std::vector<uint64_t> valid(V, 0);
+  for_each_view_parallel(V, [&](int v) {
+    const float* g = grid + (size_t)v * ncell * 2;
+    std::vector<Triplet> trip;
+    trip.reserve(4 * ncell);
+    for (size_t cell = 0; cell < ncell; ++cell) {  // ascending cell, then tap: the backward's summation order
+      const Taps t = make_taps(g[2 * cell], g[2 * cell + 1], Hs, Ws);
+      if (t.mask) ++valid[v];
+      for (int k = 0; k < 4; ++k)
+        if (t.mask >> k & 1)
+          trip.push_back({row_of_tex[(size_t)(t.y0 + kDy[k]) * Ws + (t.x0 + kDx[k])], CsrEntry{(uint32_t)cell, t.w[k]}});
+    }
+    csr_from_triplets(trip, ntex, v, maps.bwd.row_ptr.data() + (size_t)v * (ntex + 1), per_view[v]);
+  });
+  csr_assemble(maps.bwd, V, per_view);
+  maps.valid_cells = 0;
+  for (int v = 0; v < V; ++v) maps.valid_cells += valid[v];
+}
+
+// One axis of torch.nn.functional.interpolate(mode='bilinear', align_corners=False) (ATen upsample_bilinear2d,
+// persp_trans_detector.py:65): source index and weights of every output index, computed in fp32 as ATen does.
+struct UpsampleAxis {
+  std::vector<int> i0, i1;
+  std::vector<float> l0, l1;
+};
+static UpsampleAxis upsample_axis(int in, int out) {
+  UpsampleAxis a;
+  a.i0.resize(out); a.i1.resize(out); a.l0.resize(out); a.l1.resize(out);
+  const float scale = (float)in / (float)out;
+  for (int d = 0; d < out; ++d) {
+    float real = scale * ((float)d + 0.5f) - 0.5f;
+    if (real < 0.f) real = 0.f;
+    const int i0 = std::min((int)real, in - 1);
+    const float l1 = std::min(std::max(real - (float)i0, 0.f), 1.f);
+    a.i0[d] = i0;
+    a.i1[d] = i0 + (i0 < in - 1 ? 1 : 0);
+    a.l1[d] = l1;
+    a.l0[d] = 1.f - l1;
+  }
+  return a;
+}
+
+void host_build_maps_upsampled(const float* grid, int V, int hl, int wl, int Hs, int Ws, int Hg, int Wg, PlanMaps& maps) {
+  const size_t nlow = (size_t)hl * wl, ncell = (size_t)Hg * Wg;
+  std::vector<uint32_t> low_of_row, row_of_low, cell_of_row, row_of_cell;
+  tile_major_order(hl, wl, low_of_row, row_of_low);
+  tile_major_order(Hg, Wg, cell_of_row, row_of_cell);
+  csr_init(maps.bwd, V, nlow, low_of_row);
+  csr_init(maps.fwd, V, ncell, cell_of_row);
+  const UpsampleAxis ax = upsample_axis(wl, Ws), ay = upsample_axis(hl, Hs);
+  std::vector<ViewCsr> pv_bwd(V), pv_fwd(V);
+  std::vector<uint64_t> valid(V, 0);
+  for_each_view_parallel(V, [&](int v) {
+    const float* g = grid + (size_t)v * ncell * 2;
+    std::vector<Triplet> tb, tf;
+    tb.reserve(9 * ncell);
+    tf.reserve(9 * ncell);
+    for (size_t cell = 0; cell < ncell; ++cell) {
+      const Taps t = make_taps(g[2 * cell], g[2 * cell + 1], Hs, Ws);
+      if (!t.mask) continue;
+      ++valid[v];
+      // compose: each in-range high-res tap is itself 4 low-res taps; merge duplicates, weights summed in double
+      uint32_t col[16];
+      double wt[16];
+      int n = 0;
+      for (int k = 0; k < 4; ++k) {
+        if (!(t.mask >> k & 1)) continue;
+        const int X = t.x0 + kDx[k], Y = t.y0 + kDy[k];
+        const int xs[2] = {ax.i0[X], ax.i1[X]}, ys[2] = {ay.i0[Y], ay.i1[Y]};
+        const float lx[2] = {ax.l0[X], ax.l1[X]}, ly[2] = {ay.l0[Y], ay.l1[Y]};
+        for (int j = 0; j < 2; ++j)
+          for (int i = 0; i < 2; ++i) {
+            const double w = (double)t.w[k] * (double)ly[j] * (double)lx[i];
+            const uint32_t c = (uint32_t)((size_t)ys[j] * wl + xs[i]);
+            int m = 0;
+            while (m < n && col[m] != c) ++m;
+            if (m == n) { col[n] = c; wt[n] = 0.0; ++n; }
+            wt[m] += w;
+          }
+      }
+      // ascending low-res texel: the forward's summation order
+      for (int a = 1; a < n; ++a)
+        for (int b = a; b > 0 && col[b - 1] > col[b]; --b) { std::swap(col[b - 1], col[b]); std::swap(wt[b - 1], wt[b]); }
+      for (int m = 0; m < n; ++m) {
+        const float w = (float)wt[m];
+        tf.push_back({row_of_cell[cell], CsrEntry{col[m], w}});
+        tb.push_back({row_of_low[col[m]], CsrEntry{(uint32_t)cell, w}});   // ascending cell within a row
+      }
+    }
+    csr_from_triplets(tf, ncell, v, maps.fwd.row_ptr.data() + (size_t)v * (ncell + 1), pv_fwd[v]);
+    csr_from_triplets(tb, nlow, v, maps.bwd.row_ptr.data() + (size_t)v * (nlow + 1), pv_bwd[v]);
+  });
+  csr_assemble(maps.fwd, V, pv_fwd);
+  csr_assemble(maps.bwd, V, pv_bwd);
+  maps.valid_cells = 0;
+  for (int v = 0; v < V; ++v) maps.valid_cells += valid[v];
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -186,6 +284,10 @@ static int check_shapes(int V, int Hs, int Ws, int Hg, int Wg) {
     set_error("plan: V, Hs, Ws, Hg, Wg must all be positive");
     return MVWARP_EINVAL;
   }
+  if (V > 65535) {
+    set_error("plan: more than 65535 views");
+    return MVWARP_EUNSUPPORTED;
+  }
   if ((uint64_t)Hs * Ws >= (1ull << 31) || (uint64_t)Hg * Wg >= (1ull << 31)) {
     set_error("plan: image or grid too large for 32-bit texel/cell indices");
     return MVWARP_EUNSUPPORTED;
@@ -193,8 +295,21 @@ static int check_shapes(int V, int Hs, int Ws, int Hg, int Wg) {
   return MVWARP_OK;
 }
 
-static int plan_create_impl(const float* T, const float* grid_in, int V, int Hs, int Ws, int Hg, int Wg, int device,
-                            mvwarp_plan_t** plan_out) {
+static void fill_stats(mvwarp_stats_t& st, const PlanMaps& maps, int V, int Hs, int Ws, int Hg, int Wg, int hl, int wl) {
+  memset(&st, 0, sizeof(st));
+  st.V = V; st.Hs = Hs; st.Ws = Ws; st.Hg = Hg; st.Wg = Wg;
+  st.unique_texels = maps.bwd.nonempty_rows;
+  st.nnz = maps.bwd.view_base[V];
+  st.valid_cells = maps.valid_cells;
+  st.max_row = maps.bwd.max_row;
+  st.bwd_tasks = maps.bwd.task_base[V];
+  st.heavy_rows = maps.bwd.heavy_base[V];
+  st.lowres_h = hl; st.lowres_w = wl;
+  st.fwd_tasks = maps.fwd.task_base.empty() ? 0 : maps.fwd.task_base[V];
+}
+
+static int plan_create_impl(const float* T, const float* grid_in, int V, int hl, int wl, int Hs, int Ws, int Hg, int Wg,
+                            int device, mvwarp_plan_t** plan_out) {
   if (!plan_out || (!T && !grid_in)) {
     set_error("plan_create: null argument");
     return MVWARP_EINVAL;
@@ -202,8 +317,9 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int Hs,
   *plan_out = nullptr;
   int rc = check_shapes(V, Hs, Ws, Hg, Wg);
   if (rc) return rc;
+  const bool upsampled = hl > 0 && wl > 0;
   try {
-    const size_t ncell = (size_t)Hg * Wg, ntex = (size_t)Hs * Ws;
+    const size_t ncell = (size_t)Hg * Wg;
     std::vector<float> grid_local;
     const float* grid = grid_in;
     if (!grid) {
@@ -211,9 +327,10 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int Hs,
       host_grid(T, V, Hg, Wg, grid_local.data());
       grid = grid_local.data();
     }
-    HostCsr csr;
-    host_build_csr(grid, V, Hs, Ws, Hg, Wg, csr);
-    if (csr.view_base[V] >= (1ull << 32)) {
+    PlanMaps maps;
+    if (upsampled) host_build_maps_upsampled(grid, V, hl, wl, Hs, Ws, Hg, Wg, maps);
+    else host_build_maps(grid, V, Hs, Ws, Hg, Wg, maps);
+    if (maps.bwd.view_base[V] >= (1ull << 32)) {
       set_error("plan: more than 2^32 taps");
       return MVWARP_EUNSUPPORTED;
     }
@@ -224,6 +341,8 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int Hs,
     mvwarp_plan* p = new mvwarp_plan();
     p->device = device;
     p->V = V; p->Hs = Hs; p->Ws = Ws; p->Hg = Hg; p->Wg = Wg;
+    p->hl = upsampled ? hl : 0; p->wl = upsampled ? wl : 0;
+    p->upsampled = upsampled ? 1 : 0;
     p->inline_coords = T ? 1 : 0;
 
     DeviceGuard guard(device);
@@ -236,16 +355,23 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int Hs,
     // carve one allocation
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    struct CsrOff { size_t rp, id, en, vb, tk, hv, hb; };
+    auto carve_csr = [&](const HostCsr& c) {
+      CsrOff o{};
+      if (c.rows_per_view == 0) return o;
+      o.rp = carve(c.row_ptr.size() * sizeof(uint32_t));
+      o.id = carve(c.row_id.size() * sizeof(uint32_t));
+      o.en = carve(c.entries.size() * sizeof(CsrEntry));
+      o.vb = carve(c.view_base.size() * sizeof(uint64_t));
+      o.tk = carve(c.tasks.size() * sizeof(Task));
+      o.hv = carve(c.heavy.size() * sizeof(uint32_t));
+      o.hb = carve(c.heavy_base.size() * sizeof(uint32_t));
+      return o;
+    };
     const size_t o_T = carve((size_t)V * 9 * sizeof(float));
     const size_t o_grid = carve(T ? 0 : (size_t)V * ncell * 2 * sizeof(float));
     const size_t o_cx = carve(Wg * sizeof(float)), o_cy = carve(Hg * sizeof(float));
-    const size_t o_rp = carve((size_t)V * (ntex + 1) * sizeof(uint32_t));
-    const size_t o_to = carve((size_t)V * ntex * sizeof(uint32_t));
-    const size_t o_en = carve(csr.entries.size() * sizeof(CsrEntry));
-    const size_t o_vb = carve((V + 1) * sizeof(uint64_t));
-    const size_t o_tk = carve(csr.tasks.size() * sizeof(Task));
-    const size_t o_hv = carve(csr.heavy.size() * sizeof(uint32_t));
-    const size_t o_hb = carve((V + 1) * sizeof(uint32_t));
+    const CsrOff ob = carve_csr(maps.bwd), of = carve_csr(maps.fwd);
     p->d_bytes = off;
     e = cudaMalloc(&p->d_base, p->d_bytes);
     if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(plan)"); }
@@ -254,40 +380,35 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int Hs,
     p->d_grid = T ? nullptr : (float*)(base + o_grid);
     p->d_coord_x = (float*)(base + o_cx);
     p->d_coord_y = (float*)(base + o_cy);
-    p->d_row_ptr = (uint32_t*)(base + o_rp);
-    p->d_tex_of = (uint32_t*)(base + o_to);
-    p->d_entries = (CsrEntry*)(base + o_en);
-    p->d_view_base = (uint64_t*)(base + o_vb);
-    p->d_tasks = (Task*)(base + o_tk);
-    p->d_heavy = (uint32_t*)(base + o_hv);
-    p->d_heavy_base = (uint32_t*)(base + o_hb);
-    p->task_base = csr.task_base;
-    p->heavy_base = csr.heavy_base;
 
     auto up = [&](void* dst, const void* src, size_t bytes) {
       if (e == cudaSuccess && bytes) e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    auto up_csr = [&](DevCsr& d, const HostCsr& c, const CsrOff& o) {
+      if (c.rows_per_view == 0) return;
+      d.rows_per_view = (uint32_t)c.rows_per_view;
+      d.row_ptr = (uint32_t*)(base + o.rp); d.row_id = (uint32_t*)(base + o.id);
+      d.entries = (CsrEntry*)(base + o.en); d.view_base = (uint64_t*)(base + o.vb);
+      d.tasks = (Task*)(base + o.tk); d.heavy = (uint32_t*)(base + o.hv); d.heavy_base_dev = (uint32_t*)(base + o.hb);
+      d.task_base = c.task_base; d.heavy_base = c.heavy_base;
+      up(d.row_ptr, c.row_ptr.data(), c.row_ptr.size() * sizeof(uint32_t));
+      up(d.row_id, c.row_id.data(), c.row_id.size() * sizeof(uint32_t));
+      up(d.entries, c.entries.data(), c.entries.size() * sizeof(CsrEntry));
+      up(d.view_base, c.view_base.data(), c.view_base.size() * sizeof(uint64_t));
+      up(d.tasks, c.tasks.data(), c.tasks.size() * sizeof(Task));
+      up(d.heavy, c.heavy.data(), c.heavy.size() * sizeof(uint32_t));
+      up(d.heavy_base_dev, c.heavy_base.data(), c.heavy_base.size() * sizeof(uint32_t));
     };
     if (T) up(p->d_T, T, (size_t)V * 9 * sizeof(float));
     else { e = cudaMemset(p->d_T, 0, (size_t)V * 9 * sizeof(float)); up(p->d_grid, grid, (size_t)V * ncell * 2 * sizeof(float)); }
     up(p->d_coord_x, cx.data(), Wg * sizeof(float));
     up(p->d_coord_y, cy.data(), Hg * sizeof(float));
-    up(p->d_row_ptr, csr.row_ptr.data(), csr.row_ptr.size() * sizeof(uint32_t));
-    up(p->d_tex_of, csr.tex_of.data(), csr.tex_of.size() * sizeof(uint32_t));
-    up(p->d_entries, csr.entries.data(), csr.entries.size() * sizeof(CsrEntry));
-    up(p->d_tasks, csr.tasks.data(), csr.tasks.size() * sizeof(Task));
-    up(p->d_heavy, csr.heavy.data(), csr.heavy.size() * sizeof(uint32_t));
-    up(p->d_heavy_base, csr.heavy_base.data(), csr.heavy_base.size() * sizeof(uint32_t));
-    up(p->d_view_base, csr.view_base.data(), csr.view_base.size() * sizeof(uint64_t));
+    up_csr(p->bwd, maps.bwd, ob);
+    up_csr(p->fwd, maps.fwd, of);
     if (e != cudaSuccess) { cudaFree(p->d_base); delete p; return cuda_fail(e, "plan upload"); }
 
-    p->stats.V = V; p->stats.Hs = Hs; p->stats.Ws = Ws; p->stats.Hg = Hg; p->stats.Wg = Wg;
+    fill_stats(p->stats, maps, V, Hs, Ws, Hg, Wg, p->hl, p->wl);
     p->stats.inline_coords = p->inline_coords;
-    p->stats.unique_texels = csr.unique_texels;
-    p->stats.nnz = csr.view_base[V];
-    p->stats.valid_cells = csr.valid_cells;
-    p->stats.max_row = csr.max_row;
-    p->stats.bwd_tasks = csr.task_base[V];
-    p->stats.heavy_rows = csr.heavy_base[V];
     p->stats.device_bytes = p->d_bytes;
     *plan_out = p;
     return MVWARP_OK;
@@ -322,26 +443,29 @@ int mvwarp_host_grid(const float* T, int V, int Hg, int Wg, float* grid_out) {
 int mvwarp_host_csr(const float* grid_host, int V, int Hs, int Ws, int Hg, int Wg, mvwarp_stats_t* stats_out,
                     uint32_t* tex_of_out, uint32_t* row_ptr_out, uint32_t* cells_out, float* weights_out,
                     uint64_t capacity) {
+  return mvwarp_host_csr_upsampled(grid_host, V, 0, 0, Hs, Ws, Hg, Wg, stats_out, tex_of_out, row_ptr_out, cells_out,
+                                   weights_out, capacity);
+}
+
+int mvwarp_host_csr_upsampled(const float* grid_host, int V, int hl, int wl, int Hs, int Ws, int Hg, int Wg,
+                              mvwarp_stats_t* stats_out, uint32_t* tex_of_out, uint32_t* row_ptr_out, uint32_t* cells_out,
+                              float* weights_out, uint64_t capacity) {
   if (!grid_host || !stats_out) { set_error("host_csr: null argument"); return MVWARP_EINVAL; }
   int rc = check_shapes(V, Hs, Ws, Hg, Wg);
   if (rc) return rc;
+  if ((hl > 0) != (wl > 0) || hl < 0) { set_error("host_csr: bad low-res size"); return MVWARP_EINVAL; }
   try {
-    HostCsr csr;
-    host_build_csr(grid_host, V, Hs, Ws, Hg, Wg, csr);
-    memset(stats_out, 0, sizeof(*stats_out));
-    stats_out->V = V; stats_out->Hs = Hs; stats_out->Ws = Ws; stats_out->Hg = Hg; stats_out->Wg = Wg;
-    stats_out->unique_texels = csr.unique_texels;
-    stats_out->nnz = csr.view_base[V];
-    stats_out->valid_cells = csr.valid_cells;
-    stats_out->max_row = csr.max_row;
-    stats_out->bwd_tasks = csr.task_base[V];
-    stats_out->heavy_rows = csr.heavy_base[V];
-    if (tex_of_out) memcpy(tex_of_out, csr.tex_of.data(), csr.tex_of.size() * sizeof(uint32_t));
+    PlanMaps maps;
+    if (hl > 0) host_build_maps_upsampled(grid_host, V, hl, wl, Hs, Ws, Hg, Wg, maps);
+    else host_build_maps(grid_host, V, Hs, Ws, Hg, Wg, maps);
+    fill_stats(*stats_out, maps, V, Hs, Ws, Hg, Wg, hl, wl);
+    const HostCsr& csr = maps.bwd;
+    if (tex_of_out) memcpy(tex_of_out, csr.row_id.data(), csr.row_id.size() * sizeof(uint32_t));
     if (row_ptr_out) memcpy(row_ptr_out, csr.row_ptr.data(), csr.row_ptr.size() * sizeof(uint32_t));
     if (cells_out || weights_out) {
       if (capacity < csr.entries.size()) { set_error("host_csr: capacity smaller than nnz"); return MVWARP_EINVAL; }
       for (size_t i = 0; i < csr.entries.size(); ++i) {
-        if (cells_out) cells_out[i] = csr.entries[i].cell;
+        if (cells_out) cells_out[i] = csr.entries[i].col;
         if (weights_out) weights_out[i] = csr.entries[i].w;
       }
     }
@@ -354,13 +478,21 @@ int mvwarp_host_csr(const float* grid_host, int V, int Hs, int Ws, int Hg, int W
 
 int mvwarp_plan_create(const float* T, int V, int Hs, int Ws, int Hg, int Wg, int device, mvwarp_plan_t** plan_out) {
   if (!T) { set_error("plan_create: null matrices"); return MVWARP_EINVAL; }
-  return plan_create_impl(T, nullptr, V, Hs, Ws, Hg, Wg, device, plan_out);
+  return plan_create_impl(T, nullptr, V, 0, 0, Hs, Ws, Hg, Wg, device, plan_out);
 }
 
 int mvwarp_plan_create_from_grid(const float* grid_host, int V, int Hs, int Ws, int Hg, int Wg, int device,
                                  mvwarp_plan_t** plan_out) {
   if (!grid_host) { set_error("plan_create_from_grid: null grid"); return MVWARP_EINVAL; }
-  return plan_create_impl(nullptr, grid_host, V, Hs, Ws, Hg, Wg, device, plan_out);
+  return plan_create_impl(nullptr, grid_host, V, 0, 0, Hs, Ws, Hg, Wg, device, plan_out);
+}
+
+int mvwarp_plan_create_upsampled(const float* T, int V, int hl, int wl, int Hs, int Ws, int Hg, int Wg, int device,
+                                 mvwarp_plan_t** plan_out) {
+  if (!T) { set_error("plan_create_upsampled: null matrices"); return MVWARP_EINVAL; }
+  if (hl <= 0 || wl <= 0) { set_error("plan_create_upsampled: low-res size must be positive"); return MVWARP_EINVAL; }
+  if ((uint64_t)hl * wl >= (1ull << 31)) { set_error("plan_create_upsampled: low-res image too large"); return MVWARP_EUNSUPPORTED; }
+  return plan_create_impl(T, nullptr, V, hl, wl, Hs, Ws, Hg, Wg, device, plan_out);
 }
 
 int mvwarp_plan_destroy(mvwarp_plan_t* plan) {

@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from .plan import WarpPlan, get_plan, get_plan_from_grid
+from .plan import WarpPlan, get_plan, get_plan_from_grid, get_plan_upsampled
 
 _DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
 
@@ -113,7 +113,7 @@ def _(img_feats, plan_id, with_coord, channels_last_out):
 def _warp_views_plan_bwd(grad_out: torch.Tensor, plan_id: int, C_: int, feats_channels_last: bool) -> torch.Tensor:
     plan = _plans_by_id[plan_id]
     B = grad_out.shape[0]
-    Hs, Ws = plan.src_hw
+    Hs, Ws = plan.feat_hw
     V = plan.V
     if feats_channels_last:
         grad_feats = torch.empty((B, V, Hs, Ws, C_), dtype=grad_out.dtype, device=grad_out.device).permute(0, 1, 4, 2, 3)
@@ -126,7 +126,7 @@ def _warp_views_plan_bwd(grad_out: torch.Tensor, plan_id: int, C_: int, feats_ch
 @_warp_views_plan_bwd.register_fake
 def _(grad_out, plan_id, C_, feats_channels_last):
     plan = _plans_by_id[plan_id]
-    Hs, Ws = plan.src_hw
+    Hs, Ws = plan.feat_hw
     return grad_out.new_empty((grad_out.shape[0], plan.V, C_, Hs, Ws))
 
 
@@ -183,11 +183,37 @@ def warp_views_with_plan(img_feats: torch.Tensor, plan: WarpPlan, with_coord_map
                          channels_last_out: Optional[bool] = None) -> torch.Tensor:
     """Same as :func:`warp_views` with a prebuilt plan (skips the cache lookup)."""
     _check_feats(img_feats)
-    if img_feats.dim() != 5 or img_feats.shape[1] != plan.V or tuple(img_feats.shape[-2:]) != plan.src_hw:
-        raise ValueError(f"img_feats {tuple(img_feats.shape)} does not match the plan (V={plan.V}, src={plan.src_hw})")
+    if img_feats.dim() != 5 or img_feats.shape[1] != plan.V or tuple(img_feats.shape[-2:]) != plan.feat_hw:
+        raise ValueError(f"img_feats {tuple(img_feats.shape)} does not match the plan (V={plan.V}, feats={plan.feat_hw})")
     if channels_last_out is None:
         channels_last_out = _is_channels_last_5d(img_feats)
     return _warp_views_plan(img_feats, _register(plan), bool(with_coord_map), bool(channels_last_out))
+
+
+def warp_views_upsampled(img_feats_lowres: torch.Tensor, upsample_shape: Sequence[int], proj_mats: torch.Tensor,
+                         grid_shape: Sequence[int], with_coord_map: bool = True,
+                         channels_last_out: Optional[bool] = None) -> torch.Tensor:
+    """``warp_views(F.interpolate(feats, upsample_shape, mode='bilinear'), proj_mats, grid_shape)`` without ever
+    materialising the up-sampled tensor: replaces persp_trans_detector.py:65 for the warp's
+    consumer together with :68-69,75,77.
+
+    img_feats_lowres [B,V,C,hl,wl] is the trunk's output (90x160 in the reference), ``upsample_shape`` the reference's
+    ``upsample_shape`` ([270,480]) that ``proj_mats`` are built for.  Up-sample and warp are both linear and
+    rig-constant, so the plan composes them into one sparse operator (<= 16, typically 4-9 low-res taps per grid
+    cell, weights composed in double): the forward reads ~9x fewer bytes and the backward writes the 9x smaller
+    low-res gradient directly.  Agrees with the two-step reference to rounding (tests assert 1e-5), not bit for bit.
+    """
+    _check_feats(img_feats_lowres)
+    if img_feats_lowres.dim() != 5:
+        raise ValueError(f"Input img_feats must be a BxVxCxHxW tensor. Got {tuple(img_feats_lowres.shape)}")
+    if not (isinstance(proj_mats, torch.Tensor) and proj_mats.dim() == 3 and tuple(proj_mats.shape[-2:]) == (3, 3)):
+        raise ValueError("Input M must be a Vx3x3 tensor")
+    if proj_mats.shape[0] != img_feats_lowres.shape[1]:
+        raise ValueError(f"proj_mats has {proj_mats.shape[0]} views, img_feats has {img_feats_lowres.shape[1]}")
+    plan = get_plan_upsampled(proj_mats, img_feats_lowres.shape[-2:], upsample_shape, grid_shape, img_feats_lowres.device)
+    if channels_last_out is None:
+        channels_last_out = _is_channels_last_5d(img_feats_lowres)
+    return _warp_views_plan(img_feats_lowres, _register(plan), bool(with_coord_map), bool(channels_last_out))
 
 
 def warp_perspective(src: torch.Tensor, M: torch.Tensor, dsize: Sequence[int], mode: str = "bilinear",

@@ -68,28 +68,33 @@ def host_grid(T: torch.Tensor, dst_hw: Sequence[int]) -> torch.Tensor:
     return grid
 
 
-def host_csr(grid: torch.Tensor, src_hw: Sequence[int], with_map: bool = False):
+def host_csr(grid: torch.Tensor, src_hw: Sequence[int], with_map: bool = False, lowres_hw: Sequence[int] = None):
     """Statistics (and optionally the arrays ``tex_of, row_ptr, cells, weights``) of the inverse CSR map of
-    ``grid`` [V,Hg,Wg,2]; host only.  Row r of view v is the texel ``tex_of[v, r]`` (tile-major order)."""
+    ``grid`` [V,Hg,Wg,2]; host only.  Row r of view v is the texel ``tex_of[v, r]`` (tile-major order).
+    With ``lowres_hw`` the map is the composition with the bilinear up-sample ``lowres_hw -> src_hw`` and its
+    rows are the texels of the low-res image."""
     lib = _lib.load()
     grid = grid.contiguous().float()
     V, Hg, Wg, _ = grid.shape
     Hs, Ws = int(src_hw[0]), int(src_hw[1])
+    hl, wl = (int(lowres_hw[0]), int(lowres_hw[1])) if lowres_hw is not None else (0, 0)
     st = _lib.Stats()
     if not with_map:
-        _lib.check(lib.mvwarp_host_csr(_fptr(grid), V, Hs, Ws, Hg, Wg, C.byref(st), None, None, None, None, 0), "mvwarp_host_csr")
+        _lib.check(lib.mvwarp_host_csr_upsampled(_fptr(grid), V, hl, wl, Hs, Ws, Hg, Wg, C.byref(st), None, None, None,
+                                                 None, 0), "mvwarp_host_csr")
         return st.as_dict()
-    cap = 4 * V * Hg * Wg
-    tex_of = torch.empty(V * Hs * Ws, dtype=torch.int32)
-    row_ptr = torch.empty(V * (Hs * Ws + 1), dtype=torch.int32)
+    nrow = hl * wl if hl else Hs * Ws
+    cap = (16 if hl else 4) * V * Hg * Wg
+    tex_of = torch.empty(V * nrow, dtype=torch.int32)
+    row_ptr = torch.empty(V * (nrow + 1), dtype=torch.int32)
     cells = torch.empty(cap, dtype=torch.int32)
     weights = torch.empty(cap, dtype=torch.float32)
     u32 = C.POINTER(C.c_uint32)
-    _lib.check(lib.mvwarp_host_csr(_fptr(grid), V, Hs, Ws, Hg, Wg, C.byref(st), C.cast(tex_of.data_ptr(), u32),
-                                   C.cast(row_ptr.data_ptr(), u32), C.cast(cells.data_ptr(), u32), _fptr(weights), cap),
-               "mvwarp_host_csr")
+    _lib.check(lib.mvwarp_host_csr_upsampled(_fptr(grid), V, hl, wl, Hs, Ws, Hg, Wg, C.byref(st),
+                                             C.cast(tex_of.data_ptr(), u32), C.cast(row_ptr.data_ptr(), u32),
+                                             C.cast(cells.data_ptr(), u32), _fptr(weights), cap), "mvwarp_host_csr")
     d = st.as_dict()
-    return d, tex_of.view(V, Hs * Ws), row_ptr.view(V, Hs * Ws + 1), cells[:d["nnz"]], weights[:d["nnz"]]
+    return d, tex_of.view(V, nrow), row_ptr.view(V, nrow + 1), cells[:d["nnz"]], weights[:d["nnz"]]
 
 
 class WarpPlan:
@@ -124,6 +129,14 @@ class WarpPlan:
     @property
     def grid_hw(self) -> Tuple[int, int]: return self.stats["Hg"], self.stats["Wg"]
 
+    @property
+    def upsampled(self) -> bool: return self.stats["lowres_h"] > 0
+
+    @property
+    def feat_hw(self) -> Tuple[int, int]:
+        """Spatial size of the feature tensors the kernels read / write gradients for."""
+        return (self.stats["lowres_h"], self.stats["lowres_w"]) if self.upsampled else self.src_hw
+
     def device_grid(self) -> torch.Tensor:
         """Normalised grid [V,Hg,Wg,2] as the DEVICE computes it (test hook)."""
         Hg, Wg = self.grid_hw
@@ -139,7 +152,7 @@ class WarpPlan:
 
     def bwd_bytes(self, C_: int, elem: int) -> int:
         Hg, Wg = self.grid_hw
-        Hs, Ws = self.src_hw
+        Hs, Ws = self.feat_hw
         return elem * self.V * C_ * Hg * Wg + elem * self.V * C_ * Hs * Ws
 
 
@@ -172,6 +185,32 @@ def get_plan(proj_mats: torch.Tensor, src_hw: Sequence[int], grid_shape: Sequenc
     lib = _lib.load()
     _lib.check(lib.mvwarp_plan_create(_fptr(T), T.shape[0], src_hw[0], src_hw[1], dst_hw[0], dst_hw[1],
                                       device.index, C.byref(handle)), "mvwarp_plan_create")
+    plan = WarpPlan(handle, device, key)
+    with _cache_lock:
+        plan = _cache.setdefault(key, plan)
+    return plan
+
+
+def get_plan_upsampled(proj_mats: torch.Tensor, lowres_hw: Sequence[int], upsample_hw: Sequence[int],
+                       grid_shape: Sequence[int], device) -> WarpPlan:
+    """Plan for ``warp(F.interpolate(feats[.., hl, wl], upsample_hw, mode='bilinear'))`` as ONE sparse operator on
+    the low-res feature map (persp_trans_detector.py:65 + :68-69).  ``proj_mats`` are the
+    reference's matrices for the up-sampled (``upsample_hw``) feature map, unchanged."""
+    device = _device_index(device)
+    low = (int(lowres_hw[0]), int(lowres_hw[1]))
+    src_hw = (int(upsample_hw[0]), int(upsample_hw[1]))
+    dst_hw = (int(grid_shape[0]), int(grid_shape[1]))
+    m32 = proj_mats.detach().to("cpu").float().contiguous()
+    key = ("up", m32.numpy().tobytes(), low, src_hw, dst_hw, device.index)
+    with _cache_lock:
+        plan = _cache.get(key)
+    if plan is not None:
+        return plan
+    T = src_norm_trans_dst_norm(m32, src_hw, dst_hw)
+    handle = C.c_void_p()
+    _lib.check(_lib.load().mvwarp_plan_create_upsampled(_fptr(T), T.shape[0], low[0], low[1], src_hw[0], src_hw[1],
+                                                        dst_hw[0], dst_hw[1], device.index, C.byref(handle)),
+               "mvwarp_plan_create_upsampled")
     plan = WarpPlan(handle, device, key)
     with _cache_lock:
         plan = _cache.setdefault(key, plan)

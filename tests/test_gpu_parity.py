@@ -254,3 +254,72 @@ def test_rig32_slice_forward_backward():
     (gx,) = torch.autograd.grad(out, xd, go.to(DEV).contiguous(memory_format=torch.channels_last))
     emax, el2 = rel_errors(gx, gref)
     assert emax <= TOL and el2 <= TOL, (emax, el2)
+
+
+# ---- fused up-sample + warp ---------------------------------------------------------
+def _two_step_oracle(x_low, pm, up_hw, grid_hw):
+    import torch.nn.functional as F
+    V = x_low.shape[1]
+    up = torch.stack([F.interpolate(x_low[:, v], up_hw, mode="bilinear") for v in range(V)], dim=1)   # persp_trans_detector.py:65
+    return K.warp_views_oracle(up, pm, grid_hw)
+
+
+@pytest.mark.parametrize("layout", ["cl", "nchw"])
+@pytest.mark.parametrize("spec", [WILDTRACK, MULTIVIEWX], ids=lambda s: s.name)
+def test_upsampled_plan_matches_two_step_reference(spec, layout):
+    """warp_views_upsampled(feat[90x160]) == warp_views(F.interpolate(feat, [270,480])) at the real shapes."""
+    pm = synthetic_rig(spec)
+    B, C = 1, 8
+    low_hw = (90, 160)
+    x = _feats(B, spec.num_cam, C, low_hw)
+    xo = x.clone().requires_grad_(True)
+    ref = _two_step_oracle(xo, pm, spec.feat_shape, spec.grid_shape)
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (gref,) = torch.autograd.grad(ref, xo, go)
+    xd = _layout(x, layout).to(DEV).requires_grad_(True)
+    out = mv.warp_views_upsampled(xd, spec.feat_shape, pm, spec.grid_shape)
+    assert out.shape == ref.shape
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= TOL and el2 <= TOL, (emax, el2)
+    assert torch.equal(out[:, -2:].cpu(), ref[:, -2:])                 # coord_map channels exact
+    god = go.to(DEV)
+    if layout == "cl":
+        god = god.contiguous(memory_format=torch.channels_last)
+    (gx,) = torch.autograd.grad(out, xd, god)
+    assert gx.shape == x.shape
+    emax, el2 = rel_errors(gx, gref)
+    assert emax <= TOL and el2 <= TOL, (emax, el2)
+    out2 = mv.warp_views_upsampled(xd, spec.feat_shape, pm, spec.grid_shape)
+    (gx2,) = torch.autograd.grad(out2, xd, god)
+    assert torch.equal(gx, gx2) and torch.equal(out, out2)           # deterministic
+
+
+def test_upsampled_plan_full_width_and_bf16():
+    spec = WILDTRACK
+    pm = synthetic_rig(spec)[1:3]
+    low_hw = (90, 160)
+    x = _feats(2, 2, 512, low_hw)
+    ref = _two_step_oracle(x, pm, spec.feat_shape, spec.grid_shape)
+    out = mv.warp_views_upsampled(to_channels_last_5d(x).to(DEV), spec.feat_shape, pm, spec.grid_shape)
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= TOL and el2 <= TOL, (emax, el2)
+    xb = x.bfloat16()
+    refb = _two_step_oracle(xb.float(), pm, spec.feat_shape, spec.grid_shape)
+    outb = mv.warp_views_upsampled(to_channels_last_5d(xb).to(DEV), spec.feat_shape, pm, spec.grid_shape)
+    bound = 2.0 ** -8 * refb.abs() + 1e-5 * refb.abs().max()
+    assert bool(((outb.float().cpu() - refb).abs() <= bound).all())
+
+
+def test_upsampled_plan_ragged_channels():
+    pm, src_hw, grid_hw = small_rig(num_cam=2, seed=9)
+    low_hw = (src_hw[0] // 3, src_hw[1] // 3)
+    for C in (3, 20, 132):
+        x = _feats(2, 2, C, low_hw)
+        xo = x.clone().requires_grad_(True)
+        ref = _two_step_oracle(xo, pm, src_hw, grid_hw)
+        go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+        (gref,) = torch.autograd.grad(ref, xo, go)
+        xd = to_channels_last_5d(x).to(DEV).requires_grad_(True)
+        out = mv.warp_views_upsampled(xd, src_hw, pm, grid_hw)
+        (gx,) = torch.autograd.grad(out, xd, go.to(DEV))
+        assert max(rel_errors(out, ref)) <= TOL and max(rel_errors(gx, gref)) <= TOL

@@ -29,8 +29,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_stats_struct_layout_matches_header():
-    # int32 x6, uint64 x3, uint32 x4, uint64: 24 + 24 + 16 + 8
-    assert ctypes.sizeof(_lib.Stats) == 72
+    # int32 x6, uint64 x3, uint32 x4, int32 x2, uint64: 24 + 24 + 16 + 8 + 8
+    assert ctypes.sizeof(_lib.Stats) == 80
 
 
 def test_bad_arguments_return_error_codes_not_crashes():
@@ -159,3 +159,31 @@ def test_host_grid_follows_torch_bmm_dispatch(Wg):
 def test_coord_map_matches_reference_formula():
     cm = create_coord_map((120, 360))
     assert torch.equal(cm, K.create_coord_map([120, 360, 1]))
+
+
+def test_composed_upsample_map_is_adjoint_of_two_step_oracle():
+    """Fused up-sample plan: the composed CSR map on the low-res image reproduces the gradient of
+    warp(F.interpolate(x, bilinear)) -- the reference's persp_trans_detector.py:65 followed by :68-69."""
+    import torch.nn.functional as F
+    pm, src_hw, grid_hw = small_rig()
+    low_hw = (src_hw[0] // 3, src_hw[1] // 3)
+    V, C = pm.shape[0], 4
+    g = P.host_grid(P.src_norm_trans_dst_norm(pm, src_hw, grid_hw), grid_hw)
+    st, tex_of, row_ptr, cells, weights = P.host_csr(g, src_hw, with_map=True, lowres_hw=low_hw)
+    assert st["lowres_h"] == low_hw[0] and st["fwd_tasks"] > 0
+    torch.manual_seed(0)
+    x = torch.randn(1, V, C, *low_hw, requires_grad=True)
+    up = torch.stack([F.interpolate(x[:, v], src_hw, mode="bilinear") for v in range(V)], dim=1)
+    out = K.warp_views_oracle(up, pm, grid_hw)
+    go = torch.randn_like(out)
+    (gx,) = torch.autograd.grad(out, x, go)
+    nlow = low_hw[0] * low_hw[1]
+    base = 0
+    for v in range(V):
+        n = int(row_ptr[v, -1])
+        mine = _csr_backward(tex_of[v], row_ptr[v], cells[base:base + n], weights[base:base + n], go[0, v * C:(v + 1) * C], nlow)
+        base += n
+        ref = gx[0, v].reshape(C, nlow)
+        assert float((mine - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    # at most 16 low-res taps per cell, typically far fewer
+    assert st["nnz"] <= 16 * st["valid_cells"]
