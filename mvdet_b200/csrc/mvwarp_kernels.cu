@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const KParams p) {
   for (int k = 0; k < 4; ++k)
     off[k] = (tp.mask >> k & 1) ? (int64_t)(tp.y0 + (k >> 1)) * p.fH + (int64_t)(tp.x0 + (k & 1)) * p.fW : 0;
   const int c_end = min(p.C, (chunk + 1) * p.cchunk);
+#pragma unroll 4
   for (int c = chunk * p.cchunk; c < c_end; ++c) {
     const T* s = src + (int64_t)c * p.fC;
     float f[4];
@@ -607,7 +608,8 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, MINB)
   csr_gather_body<T, false, FULLC, DENSE, true>(p, task_lo, task_hi, heavy_lo, n_heavy, view_lo, heavy_base, part);
 }
 
-// CSR gather, arbitrary strides: thread per CSR row (tile-major order), loop over a chunk of channels
+// CSR gather, arbitrary strides: thread per CSR row (tile-major order), a chunk of GEN_CH channels per thread
+constexpr int GEN_CH = 16;
 template <typename T, bool COORD>
 __device__ __forceinline__ void gather_generic_body(const KParams& p) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -624,17 +626,25 @@ __device__ __forceinline__ void gather_generic_body(const KParams& p) {
   const T* __restrict__ gs = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.gsrc.B + (int64_t)vl * p.gsrc.V + p.gsrc.chan0;
   T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.gdst.B + (int64_t)vl * p.gdst.V + p.gdst.chan0 +
                       (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
-  const int c_end = min(p.C, (chunk + 1) * p.cchunk);
-  for (int c = chunk * p.cchunk; c < c_end; ++c) {
-    const T* g = gs + (int64_t)c * p.gsrc.C;
-    float acc = 0.f;
-    for (uint32_t k = r0; k < r1; ++k) {
-      const CsrEntry e = en[k];
-      const int y = e.col / p.gsrc.width, x = e.col - y * p.gsrc.width;
-      acc = __fmaf_rn(e.w, to_float(__ldg(g + (int64_t)y * p.gsrc.H + (int64_t)x * p.gsrc.W)), acc);
-    }
-    o[(int64_t)c * p.gdst.C] = from_float<T>(acc);
+  // entry-major: each (col, w) is fetched once and applied to the whole channel chunk (accumulators in registers),
+  // so the CSR walk is amortised over GEN_CH channels and GEN_CH independent loads are in flight per entry
+  const int c0 = chunk * p.cchunk, nc = min(p.C - c0, p.cchunk);
+  float acc[GEN_CH];
+#pragma unroll
+  for (int i = 0; i < GEN_CH; ++i) acc[i] = 0.f;
+  const T* __restrict__ g0 = gs + (int64_t)c0 * p.gsrc.C;
+  for (uint32_t k = r0; k < r1; ++k) {
+    const CsrEntry e = en[k];
+    const int y = e.col / p.gsrc.width, x = e.col - y * p.gsrc.width;
+    const T* g = g0 + (int64_t)y * p.gsrc.H + (int64_t)x * p.gsrc.W;
+#pragma unroll
+    for (int i = 0; i < GEN_CH; ++i)
+      if (i < nc) acc[i] = __fmaf_rn(e.w, to_float(__ldg(g + (int64_t)i * p.gsrc.C)), acc[i]);
   }
+  T* oc = o + (int64_t)c0 * p.gdst.C;
+#pragma unroll
+  for (int i = 0; i < GEN_CH; ++i)
+    if (i < nc) oc[(int64_t)i * p.gdst.C] = from_float<T>(acc[i]);
 }
 
 template <typename T>
@@ -678,7 +688,7 @@ static KParams make_params(const LaunchArgs& a) {
   p.out_chan0 = a.out_chan0; p.coord_chan = a.coord_chan;
   p.tiles_x = (pl->Wg + FWD_TILE_W - 1) / FWD_TILE_W;
   p.tiles_y = (pl->Hg + FWD_TILE_H - 1) / FWD_TILE_H;
-  p.cchunk = 32;
+  p.cchunk = GEN_CH;
   return p;
 }
 
