@@ -148,6 +148,19 @@ int mvwarp_warp_views_bwd(const mvwarp_plan_t* plan, int view0, int nviews,
  * (M % 128 == 0, K % 64 == 0, device pointers). */
 int mvwarp_debug_gemm(const void* A, const void* B, void* D, int M, int N, int K, void* stream);
 
+/* mvwarp_warp_conv1_fwd (north_star (c)): the warp fused into map_classifier[0] = Conv2d(V*C+2, 512, 3, padding=1)
+ * (persp_trans_detector.py:51,81) as a tcgen05 implicit GEMM; the warped tensor is never materialised.
+ *   out[b, n, y, x] = (bias ? bias[n] : 0) + sum_{dy,dx} sum_{ch} W[n, ch, dy, dx] * X[b, ch, y+dy-1, x+dx-1]   (+ ReLU if relu)
+ * with X = the warp of views [view0, view0+nviews) (+ the two coord_map channels if with_coord), zero padded.
+ * feats: bf16, logical [B, nviews, C, Hs, Ws], channel-contiguous, C % 64 == 0.  out: fp32 [B, 512, Hg, Wg] channels-last.
+ * wpack: the weight pre-packed by mvdet_b200.conv1.pack_conv1_weight: per (view, 64-channel block, tap) one
+ *        [512][64] bf16 block whose rows carry the 128-byte shared-memory swizzle, then one block for the coord channels.
+ * X is rounded to bf16 before the contraction (fp32 accumulate in TMEM).  View shards pass their own weight slices,
+ * bias / with_coord only on the coord-map owner, relu = 0, and all-reduce the partial sums (mvdet_b200.sharding). */
+int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
+                          const int64_t feat_strides[5], const void* wpack, const float* bias, float* out,
+                          const int64_t out_strides[4], int B, int C, int relu, int with_coord, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

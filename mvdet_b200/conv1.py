@@ -1,0 +1,77 @@
+"""Fused warp -> map_classifier[0] (north_star (c)): host side.
+
+``map_classifier[0]`` is ``Conv2d(V*C+2, 512, 3, padding=1)`` (/root/reference/multiview_detector/models/
+persp_trans_detector.py:51) applied to the concat that ``warp_views`` produces (:81).  ``warp_conv1`` computes
+``conv(warp_views(feats))`` as one tcgen05 implicit GEMM without materialising the warped tensor; this module
+packs the reference's weight ``[512, V*C+2, 3, 3]`` (e.g. straight from a reference checkpoint, ``main.py:121``)
+into the shared-memory image the kernel's B operand expects.  CUDA only, bf16 inputs, fp32 accumulate / output.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from .plan import get_plan
+
+KB = 64          # channels per K block
+N_OUT = 512
+
+
+def pack_conv1_weight(weight: torch.Tensor, num_views: int, channels: int, with_coord: bool = True) -> torch.Tensor:
+    """[512, V*C(+2), 3, 3] -> bf16 [(V * C/64 * 9 (+1)), 512, 64]: one block per (view, 64-channel block, tap), K-major,
+    every 128-byte row with its 16-byte chunks XOR-swizzled by (row & 7) -- the tensor core's SWIZZLE_128B layout.
+    The optional last block holds the two coord_map channels of all nine taps at k = tap*2 + ch (rest zero)."""
+    V, Cc = int(num_views), int(channels)
+    if weight.shape[0] != N_OUT or tuple(weight.shape[2:]) != (3, 3) or weight.shape[1] != V * Cc + (2 if with_coord else 0):
+        raise ValueError(f"weight must be [512, {V * Cc + (2 if with_coord else 0)}, 3, 3]. Got {tuple(weight.shape)}")
+    if Cc % KB:
+        raise ValueError("channels must be a multiple of 64")
+    w = weight.detach().to(torch.bfloat16)
+    ncb = Cc // KB
+    main = w[:, :V * Cc].reshape(N_OUT, V, ncb, KB, 9)                  # n, v, cb, k, tap
+    blocks = main.permute(1, 2, 4, 0, 3).reshape(V * ncb * 9, N_OUT, KB)  # (v, cb, tap), n, k
+    if with_coord:
+        cw = w[:, V * Cc:].reshape(N_OUT, 2, 9).permute(0, 2, 1).reshape(N_OUT, 18)   # n, tap*2 + ch
+        cblock = torch.zeros(1, N_OUT, KB, dtype=torch.bfloat16, device=w.device)
+        cblock[0, :, :18] = cw
+        blocks = torch.cat([blocks, cblock], dim=0)
+    # swizzle: chunk c of row n lands at chunk position c ^ (n & 7)
+    nb = blocks.shape[0]
+    chunks = blocks.reshape(nb, N_OUT, 8, 8)
+    n_idx = torch.arange(N_OUT, device=w.device)[:, None]
+    pos = torch.arange(8, device=w.device)[None, :]
+    src = pos ^ (n_idx & 7)                                              # chunk stored at position pos comes from chunk src
+    packed = torch.gather(chunks, 2, src[None, :, :, None].expand(nb, N_OUT, 8, 8))
+    return packed.reshape(nb, N_OUT, KB).contiguous()
+
+
+def warp_conv1(img_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Sequence[int], wpack: torch.Tensor,
+               bias: Optional[torch.Tensor] = None, relu: bool = True, with_coord: bool = True) -> torch.Tensor:
+    """relu(conv3x3(warp_views(img_feats, proj_mats, grid_shape), W) + bias) as one fused kernel (forward only).
+
+    img_feats [B,V,C,H,W] bf16 CUDA, channel-contiguous; wpack from :func:`pack_conv1_weight`; bias fp32 [512] or None.
+    Returns fp32 [B,512,Hg,Wg] (channels-last)."""
+    if not img_feats.is_cuda:
+        raise _lib.MvwarpError("warp_conv1 is CUDA-only (no CPU fallback)")
+    if img_feats.dtype != torch.bfloat16 or img_feats.dim() != 5 or img_feats.stride(2) != 1:
+        raise ValueError("warp_conv1 needs bf16 channel-contiguous features [B,V,C,H,W]")
+    B, V, Cc, Hs, Ws = img_feats.shape
+    nblocks = V * (Cc // KB) * 9 + (1 if with_coord else 0)
+    if wpack.dtype != torch.bfloat16 or tuple(wpack.shape) != (nblocks, N_OUT, KB) or not wpack.is_contiguous():
+        raise ValueError(f"wpack must be a contiguous bf16 [{nblocks}, 512, 64] tensor from pack_conv1_weight")
+    plan = get_plan(proj_mats, (Hs, Ws), grid_shape, img_feats.device)
+    Hg, Wg = plan.grid_hw
+    out = torch.empty((B, Hg, Wg, N_OUT), dtype=torch.float32, device=img_feats.device).permute(0, 3, 1, 2)
+    bias_ptr = None
+    if bias is not None:
+        bias = bias.detach().to(device=img_feats.device, dtype=torch.float32).contiguous()
+        bias_ptr = C.c_void_p(bias.data_ptr())
+    stream = C.c_void_p(torch.cuda.current_stream(img_feats.device).cuda_stream)
+    rc = _lib.load().mvwarp_warp_conv1_fwd(plan.handle, 0, V, C.c_void_p(img_feats.data_ptr()), _lib.i64x(img_feats.stride()),
+                                           C.c_void_p(wpack.data_ptr()), bias_ptr, C.c_void_p(out.data_ptr()),
+                                           _lib.i64x(out.stride()), B, Cc, int(relu), int(with_coord), stream)
+    _lib.check(rc, "mvwarp_warp_conv1_fwd")
+    return out

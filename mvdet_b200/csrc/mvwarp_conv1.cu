@@ -95,3 +95,247 @@ extern "C" int mvwarp_debug_gemm(const void* A, const void* B, void* D, int M, i
   e = cudaGetLastError();
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "debug_gemm launch");
 }
+
+// =====================================================================================================
+// Fused warp -> conv1 (north_star (c)):  out1[b, n, y, x] = bias[n] + sum_{dy,dx,ch} W[n, ch, dy, dx] * X[b, ch, y+dy-1, x+dx-1]
+// with X = warp_views(feats) (never materialised), zero padding, optional ReLU.
+// Implicit GEMM on tcgen05: M = grid cells (128 per CTA: an 8 x 16 tile), N = 512 output channels (all of TMEM),
+// K = 9 taps x (V*C + 2) channels in blocks of 64.  The A operand is PRODUCED: for each (view, 64-channel block)
+// the CTA warps the tile's 10 x 18 halo patch once (bilinear blend in fp32, rounded to bf16) and the nine conv
+// taps are shifted copies of that patch written into the 128-byte-swizzled K-major layout the tensor core reads.
+// The B operand (weights) is pre-packed on the host in exactly that shared-memory image, one 64 KB block per
+// (view, channel block, tap), and arrives by one bulk async copy (TMA engine) per block.
+// =====================================================================================================
+#include "mvwarp_coords.h"
+
+namespace mvw {
+
+constexpr int CT_H = 8, CT_W = 16, CP_H = CT_H + 2, CP_W = CT_W + 2, CP_CELLS = CP_H * CP_W;  // tile and halo patch
+constexpr int CV_N = 512, CV_KB = 64;
+constexpr uint32_t CV_B_BYTES = CV_N * CV_KB * 2;  // one packed weight block (64 KB)
+
+struct ConvParams {
+  const float* T;
+  const float* coord_x;
+  const float* coord_y;
+  int Hs, Ws, Hg, Wg, view0, nviews, C, B;
+  const __nv_bfloat16* feats;
+  int64_t fB, fV, fH, fW;
+  const __nv_bfloat16* wpack;  // [nviews * C/64 * 9 (+1 coord block)][512][64] bf16, rows pre-swizzled
+  const float* bias;           // [512] or nullptr
+  float* out;                  // [B, Hg, Wg, 512] fp32 (logical [B,512,Hg,Wg] channels-last)
+  int64_t oB, oH, oW;
+  int relu, with_coord, tiles_x, tiles_y;
+};
+
+struct ConvTap {
+  float w[4];
+  int x0, y0;
+  unsigned mask;
+  int pad;
+};
+
+__device__ __forceinline__ float bf_lo(unsigned v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(unsigned v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ unsigned pack_bf2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const unsigned*>(&h);
+}
+
+// Step A: correctness-first version -- one stage, every thread takes part in every phase.
+__global__ void __launch_bounds__(128) warp_conv1_kernel(const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                               // 128 x 128 B
+  uint8_t* sB = smem + 16384;                       // 512 x 128 B
+  uint8_t* sP = smem + 16384 + CV_B_BYTES;          // patch: 180 cells x 128 B (plain layout)
+  ConvTap* sT = reinterpret_cast<ConvTap*>(sP + CP_CELLS * 128);
+  __shared__ __align__(8) uint64_t b_full, mma_done;
+  __shared__ uint32_t tmem_holder;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x, tx0 = (tile % p.tiles_x) * CT_W, ty0 = (tile / p.tiles_x) * CT_H, b = blockIdx.z;
+
+  if (warp == 0) tmem_alloc(&tmem_holder, CV_N);
+  if (tid == 0) {
+    mbar_init(&b_full, 1);
+    mbar_init(&mma_done, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+  const uint32_t idesc = idesc_bf16_f32(128, 256);
+  uint32_t ph_b = 0, ph_m = 0;
+  int kcount = 0;
+  const int ncb = p.C / CV_KB;
+  const int my = tid / CT_W, mx = tid % CT_W;  // this thread's A row = tile cell (my, mx)
+
+  auto run_block = [&](const __nv_bfloat16* wblock) {  // A stage is in sA; fetch B, run the 128 x 512 x 64 MMA block
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&b_full, CV_B_BYTES);
+      bulk_g2s(sB, wblock, CV_B_BYTES, &b_full);
+      mbar_wait(&b_full, ph_b);
+      tc_fence_after();
+      const uint64_t da = smem_desc_sw128(smem_u32(sA)), db0 = smem_desc_sw128(smem_u32(sB)),
+                     db1 = smem_desc_sw128(smem_u32(sB) + 256 * 128);
+#pragma unroll
+      for (int k = 0; k < CV_KB / 16; ++k) {
+        mma_bf16(tmem, da + 2 * k, db0 + 2 * k, idesc, kcount > 0 || k > 0);
+        mma_bf16(tmem + 256, da + 2 * k, db1 + 2 * k, idesc, kcount > 0 || k > 0);
+      }
+      mma_commit(&mma_done);
+    }
+    ph_b ^= 1;
+    ++kcount;
+    mbar_wait(&mma_done, ph_m);  // sA / sB free again
+    ph_m ^= 1;
+    tc_fence_after();
+  };
+
+  for (int vl = 0; vl < p.nviews; ++vl) {
+    const int v = p.view0 + vl;
+    // taps of the halo patch for this view (cells outside the grid are the conv's zero padding)
+    for (int i = tid; i < CP_CELLS; i += 128) {
+      const int gy = ty0 + i / CP_W - 1, gx = tx0 + i % CP_W - 1;
+      ConvTap t;
+      t.mask = 0; t.x0 = t.y0 = 0; t.pad = 0;
+      t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
+      if (gy >= 0 && gy < p.Hg && gx >= 0 && gx < p.Wg) {
+        float Tm[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Tm[q] = __ldg(p.T + 9 * v + q);
+        float sx, sy;
+        norm_src_coord(Tm, gx, gy, p.Hg, p.Wg, sx, sy);
+        const Taps tp = make_taps(sx, sy, p.Hs, p.Ws);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t.w[k] = tp.w[k];
+        t.x0 = tp.x0; t.y0 = tp.y0; t.mask = tp.mask;
+      }
+      sT[i] = t;
+    }
+    __syncthreads();
+    const __nv_bfloat16* fv = p.feats + (int64_t)b * p.fB + (int64_t)vl * p.fV;
+    for (int cb = 0; cb < ncb; ++cb) {
+      // warp the patch: 180 cells x 8 chunks of 8 channels
+      for (int task = tid; task < CP_CELLS * 8; task += 128) {
+        const int cell = task >> 3, ch = task & 7;
+        const ConvTap t = sT[cell];
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (t.mask) {
+          uint4 tv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int xx = t.x0 + (k & 1), yy = t.y0 + (k >> 1);
+            tv[k] = (t.mask >> k & 1) ? __ldg(reinterpret_cast<const uint4*>(fv + (int64_t)yy * p.fH + (int64_t)xx * p.fW + cb * CV_KB + ch * 8))
+                                      : make_uint4(0, 0, 0, 0);
+          }
+          const unsigned* a = &tv[0].x; const unsigned* bq = &tv[1].x; const unsigned* c = &tv[2].x; const unsigned* d = &tv[3].x;
+          unsigned o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float lo = __fmaf_rn(bf_lo(d[q]), t.w[3], __fmaf_rn(bf_lo(c[q]), t.w[2], __fmaf_rn(bf_lo(bq[q]), t.w[1], __fmul_rn(bf_lo(a[q]), t.w[0]))));
+            const float hi = __fmaf_rn(bf_hi(d[q]), t.w[3], __fmaf_rn(bf_hi(c[q]), t.w[2], __fmaf_rn(bf_hi(bq[q]), t.w[1], __fmul_rn(bf_hi(a[q]), t.w[0]))));
+            o[q] = pack_bf2(lo, hi);
+          }
+          r = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        *reinterpret_cast<uint4*>(sP + cell * 128 + ch * 16) = r;
+      }
+      __syncthreads();
+      for (int tap = 0; tap < 9; ++tap) {
+        const int srcc = (my + tap / 3) * CP_W + (mx + tap % 3);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(sA + sw128_offset(tid, c)) = *reinterpret_cast<const uint4*>(sP + srcc * 128 + c * 16);
+        run_block(p.wpack + (size_t)((vl * ncb + cb) * 9 + tap) * (CV_N * CV_KB));
+      }
+    }
+    __syncthreads();
+  }
+  if (p.with_coord) {  // the two coord_map channels: all 9 taps x 2 channels in one K block (k = tap*2 + ch), rest zero
+    unsigned short vals[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) vals[k] = 0;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int gy = ty0 + my + tap / 3 - 1, gx = tx0 + mx + tap % 3 - 1;
+      if (gy >= 0 && gy < p.Hg && gx >= 0 && gx < p.Wg) {
+        vals[tap * 2] = __bfloat16_as_ushort(__float2bfloat16_rn(__ldg(p.coord_x + gx)));
+        vals[tap * 2 + 1] = __bfloat16_as_ushort(__float2bfloat16_rn(__ldg(p.coord_y + gy)));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 r;
+      r.x = vals[c * 8 + 0] | ((unsigned)vals[c * 8 + 1] << 16); r.y = vals[c * 8 + 2] | ((unsigned)vals[c * 8 + 3] << 16);
+      r.z = vals[c * 8 + 4] | ((unsigned)vals[c * 8 + 5] << 16); r.w = vals[c * 8 + 6] | ((unsigned)vals[c * 8 + 7] << 16);
+      *reinterpret_cast<uint4*>(sA + sw128_offset(tid, c)) = r;
+    }
+    run_block(p.wpack + (size_t)(p.nviews * ncb * 9) * (CV_N * CV_KB));
+  }
+
+  // epilogue: thread = tile cell = TMEM lane; 512 fp32 columns in chunks of 32
+  const int gy = ty0 + my, gx = tx0 + mx;
+  const bool inside = gy < p.Hg && gx < p.Wg;
+  float* orow = p.out + (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW;
+#pragma unroll 1
+  for (int c0 = 0; c0 < CV_N; c0 += 32) {
+    float vv[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, vv);
+    if (inside) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 o = make_float4(vv[i], vv[i + 1], vv[i + 2], vv[i + 3]);
+        if (p.bias) { o.x += __ldg(p.bias + c0 + i); o.y += __ldg(p.bias + c0 + i + 1); o.z += __ldg(p.bias + c0 + i + 2); o.w += __ldg(p.bias + c0 + i + 3); }
+        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(orow + c0 + i) = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, CV_N);
+}
+
+}  // namespace mvw
+
+extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
+                                     const int64_t feat_strides[5], const void* wpack, const float* bias, float* out,
+                                     const int64_t out_strides[4], int B, int C, int relu, int with_coord, void* stream) {
+  using namespace mvw;
+  if (!plan || !feats || !feat_strides || !wpack || !out || !out_strides) { set_error("warp_conv1_fwd: null argument"); return MVWARP_EINVAL; }
+  if (B <= 0 || nviews <= 0 || view0 < 0 || view0 + nviews > plan->V) { set_error("warp_conv1_fwd: bad B / view range"); return MVWARP_EINVAL; }
+  if (plan->upsampled || !plan->inline_coords) { set_error("warp_conv1_fwd: needs a plain matrix plan"); return MVWARP_EUNSUPPORTED; }
+  if (C <= 0 || C % CV_KB || feat_strides[2] != 1 || (reinterpret_cast<uintptr_t>(feats) & 15u) || feat_strides[0] % 8 ||
+      feat_strides[1] % 8 || feat_strides[3] % 8 || feat_strides[4] % 8) {
+    set_error("warp_conv1_fwd: feats must be bf16 channels-last with C % 64 == 0 and 16-byte aligned texel rows");
+    return MVWARP_EUNSUPPORTED;
+  }
+  if (out_strides[1] != 1 || out_strides[0] % 4 || out_strides[2] % 4 || out_strides[3] % 4 || (reinterpret_cast<uintptr_t>(out) & 15u)) {
+    set_error("warp_conv1_fwd: out must be fp32 channels-last [B,512,Hg,Wg] with 16-byte aligned cell rows");
+    return MVWARP_EUNSUPPORTED;
+  }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != plan->device && cudaSetDevice(plan->device) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+  ConvParams p{};
+  p.T = plan->d_T; p.coord_x = plan->d_coord_x; p.coord_y = plan->d_coord_y;
+  p.Hs = plan->Hs; p.Ws = plan->Ws; p.Hg = plan->Hg; p.Wg = plan->Wg;
+  p.view0 = view0; p.nviews = nviews; p.C = C; p.B = B;
+  p.feats = (const __nv_bfloat16*)feats;
+  p.fB = feat_strides[0]; p.fV = feat_strides[1]; p.fH = feat_strides[3]; p.fW = feat_strides[4];
+  p.wpack = (const __nv_bfloat16*)wpack; p.bias = bias; p.out = out;
+  p.oB = out_strides[0]; p.oH = out_strides[2]; p.oW = out_strides[3];
+  p.relu = relu; p.with_coord = with_coord;
+  p.tiles_x = (plan->Wg + CT_W - 1) / CT_W; p.tiles_y = (plan->Hg + CT_H - 1) / CT_H;
+  const int smem = 16384 + (int)CV_B_BYTES + CP_CELLS * 128 + CP_CELLS * (int)sizeof(ConvTap) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(warp_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) {
+    warp_conv1_kernel<<<dim3(p.tiles_x * p.tiles_y, 1, B), 128, smem, (cudaStream_t)stream>>>(p);
+    e = cudaGetLastError();
+  }
+  if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
+  return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "warp_conv1_fwd launch");
+}

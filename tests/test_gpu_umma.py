@@ -23,3 +23,30 @@ def test_tcgen05_gemm_matches_matmul(M, K):
     ref = A.float() @ B.float().T
     err = float((D - ref).abs().max() / ref.abs().max())
     assert err <= 1e-5, err          # bf16 products are exact in fp32; only the summation order differs
+
+
+def _conv1_reference(x_bf16, pm, grid_hw, weight, bias, relu):
+    """conv3x3(bf16(warp_views_oracle(feats))) with bf16-rounded weights, fp32 accumulate -- what the fused kernel computes."""
+    import torch.nn.functional as F
+    from oracle import kornia_warp as K
+    X = K.warp_views_oracle(x_bf16.float(), pm, grid_hw).bfloat16().float()
+    out = F.conv2d(X, weight.bfloat16().float(), bias, padding=1)
+    return F.relu(out) if relu else out
+
+
+@pytest.mark.parametrize("V,Cc,relu", [(1, 64, False), (2, 128, True)])
+def test_fused_warp_conv1_matches_reference(V, Cc, relu):
+    from mvdet_b200 import conv1
+    from tests.util import small_rig, to_channels_last_5d, rel_errors
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=31)      # 54x96 -> 24x72: partial tiles in x
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, V, Cc, *src_hw, generator=g).bfloat16()
+    weight = torch.randn(512, V * Cc + 2, 3, 3, generator=g) * 0.05
+    bias = torch.randn(512, generator=g)
+    ref = _conv1_reference(x, pm, grid_hw, weight, bias, relu)
+    wpack = conv1.pack_conv1_weight(weight, V, Cc).cuda()
+    out = conv1.warp_conv1(to_channels_last_5d(x).cuda(), pm, grid_hw, wpack, bias, relu=relu)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= 1e-4 and el2 <= 1e-4, (emax, el2)
