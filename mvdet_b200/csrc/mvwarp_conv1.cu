@@ -1,6 +1,7 @@
 // mvwarp_conv1.cu -- tensor-core side of the path (north_star (c)): tcgen05 / TMEM GEMM building blocks for the
 // fused warp -> map_classifier[0] implicit GEMM (/root/reference/multiview_detector/models/persp_trans_detector.py:51,81).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "mvwarp_internal.h"
 #include "mvwarp_umma.h"
@@ -299,6 +300,200 @@ __global__ void __launch_bounds__(128) warp_conv1_kernel(const ConvParams p) {
   if (warp == 0) tmem_dealloc(tmem, CV_N);
 }
 
+
+// -----------------------------------------------------------------------------------------------------
+// Pipelined version: warp-specialised, mbarrier rings.
+//   warps 0-3  producers: warp the halo patch (once per view x 64-channel block), write the nine shifted A stages,
+//              and at the end drain TMEM (epilogue);
+//   warp 4     one thread issues tcgen05.mma (8 per K block: 4 k-steps x 2 halves of N) and commits the stage barriers;
+//   warp 5     one thread streams the packed weight blocks with bulk async copies (64 KB each).
+// Rings: A = PA stages x 16 KB, B = PB stages x 64 KB.  full barriers: producers / TMA -> MMA; empty barriers:
+// tcgen05.commit -> producers / TMA.
+// -----------------------------------------------------------------------------------------------------
+constexpr int PA = 3, PB = 2;
+constexpr int PIPE_THREADS = 192;
+
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                                          // PA x 16 KB
+  uint8_t* sB = smem + PA * 16384;                             // PB x 64 KB
+  uint8_t* sP = sB + PB * CV_B_BYTES;                          // patch: 180 cells x 128 B (plain layout)
+  ConvTap* sT = reinterpret_cast<ConvTap*>(sP + CP_CELLS * 128);
+  __shared__ __align__(8) uint64_t a_full[PA], a_empty[PA], b_full[PB], b_empty[PB], acc_full;
+  __shared__ uint32_t tmem_holder;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, tx0 = (tile % p.tiles_x) * CT_W, ty0 = (tile / p.tiles_x) * CT_H, b = blockIdx.z;
+  const int ncb = p.C / CV_KB;
+  const int NK = p.nviews * ncb * 9 + (p.with_coord ? 1 : 0);
+
+  if (warp == 0) tmem_alloc(&tmem_holder, CV_N);
+  if (tid == 0) {
+    for (int i = 0; i < PA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < PB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+
+  if (warp == 5) {
+    // ===== weight streamer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < NK; ++kb) {
+        const int s = kb % PB;
+        if (kb >= PB) mbar_wait(&b_empty[s], ((kb / PB) - 1) & 1);
+        mbar_expect_tx(&b_full[s], CV_B_BYTES);
+        bulk_g2s(sB + (size_t)s * CV_B_BYTES, p.wpack + (size_t)kb * (CV_N * CV_KB), CV_B_BYTES, &b_full[s]);
+      }
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_f32(128, 256);
+      for (int kb = 0; kb < NK; ++kb) {
+        const int sa = kb % PA, sb = kb % PB;
+        mbar_wait(&a_full[sa], (kb / PA) & 1);
+        mbar_wait(&b_full[sb], (kb / PB) & 1);
+        tc_fence_after();
+        const uint32_t bbase = smem_u32(sB + (size_t)sb * CV_B_BYTES);
+        const uint64_t da = smem_desc_sw128(smem_u32(sA + sa * 16384)), db0 = smem_desc_sw128(bbase),
+                       db1 = smem_desc_sw128(bbase + 256 * 128);
+#pragma unroll
+        for (int k = 0; k < CV_KB / 16; ++k) {
+          mma_bf16(tmem, da + 2 * k, db0 + 2 * k, idesc, kb > 0 || k > 0);
+          mma_bf16(tmem + 256, da + 2 * k, db1 + 2 * k, idesc, kb > 0 || k > 0);
+        }
+        mma_commit(&a_empty[sa]);
+        mma_commit(&b_empty[sb]);
+      }
+      mma_commit(&acc_full);
+    }
+  } else {
+    // ===== producers (128 threads), then epilogue =====
+    const int my = tid / CT_W, mx = tid % CT_W;  // this thread's A row = tile cell (my, mx)
+    int kb = 0;
+    auto acquire_stage = [&]() -> uint8_t* {
+      const int sa = kb % PA;
+      if (kb >= PA) mbar_wait(&a_empty[sa], ((kb / PA) - 1) & 1);
+      return sA + sa * 16384;
+    };
+    auto publish_stage = [&]() {
+      fence_proxy_async();
+      mbar_arrive(&a_full[kb % PA]);
+      ++kb;
+    };
+    for (int vl = 0; vl < p.nviews; ++vl) {
+      const int v = p.view0 + vl;
+      producers_sync();  // previous view's taps are no longer read
+      for (int i = tid; i < CP_CELLS; i += 128) {
+        const int gy = ty0 + i / CP_W - 1, gx = tx0 + i % CP_W - 1;
+        ConvTap t;
+        t.mask = 0; t.x0 = t.y0 = 0; t.pad = 0;
+        t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
+        if (gy >= 0 && gy < p.Hg && gx >= 0 && gx < p.Wg) {
+          float Tm[9];
+#pragma unroll
+          for (int q = 0; q < 9; ++q) Tm[q] = __ldg(p.T + 9 * v + q);
+          float sx, sy;
+          norm_src_coord(Tm, gx, gy, p.Hg, p.Wg, sx, sy);
+          const Taps tp = make_taps(sx, sy, p.Hs, p.Ws);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) t.w[k] = tp.w[k];
+          t.x0 = tp.x0; t.y0 = tp.y0; t.mask = tp.mask;
+        }
+        sT[i] = t;
+      }
+      producers_sync();
+      const __nv_bfloat16* fv = p.feats + (int64_t)b * p.fB + (int64_t)vl * p.fV;
+      for (int cb = 0; cb < ncb; ++cb) {
+        for (int task = tid; task < CP_CELLS * 8; task += 128) {  // warp the patch: 180 cells x 8 chunks of 8 channels
+          const int cell = task >> 3, ch = task & 7;
+          const ConvTap t = sT[cell];
+          uint4 r = make_uint4(0, 0, 0, 0);
+          if (t.mask) {
+            uint4 tv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int xx = t.x0 + (k & 1), yy = t.y0 + (k >> 1);
+              tv[k] = (t.mask >> k & 1) ? __ldg(reinterpret_cast<const uint4*>(fv + (int64_t)yy * p.fH + (int64_t)xx * p.fW + cb * CV_KB + ch * 8))
+                                        : make_uint4(0, 0, 0, 0);
+            }
+            const unsigned* a = &tv[0].x; const unsigned* bq = &tv[1].x; const unsigned* c = &tv[2].x; const unsigned* d = &tv[3].x;
+            unsigned o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float lo = __fmaf_rn(bf_lo(d[q]), t.w[3], __fmaf_rn(bf_lo(c[q]), t.w[2], __fmaf_rn(bf_lo(bq[q]), t.w[1], __fmul_rn(bf_lo(a[q]), t.w[0]))));
+              const float hi = __fmaf_rn(bf_hi(d[q]), t.w[3], __fmaf_rn(bf_hi(c[q]), t.w[2], __fmaf_rn(bf_hi(bq[q]), t.w[1], __fmul_rn(bf_hi(a[q]), t.w[0]))));
+              o[q] = pack_bf2(lo, hi);
+            }
+            r = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          *reinterpret_cast<uint4*>(sP + cell * 128 + ch * 16) = r;
+        }
+        producers_sync();  // patch complete
+        for (int tap = 0; tap < 9; ++tap) {
+          uint8_t* stage = acquire_stage();
+          const int srcc = (my + tap / 3) * CP_W + (mx + tap % 3);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(stage + sw128_offset(tid, c)) = *reinterpret_cast<const uint4*>(sP + srcc * 128 + c * 16);
+          publish_stage();
+        }
+        producers_sync();  // every thread has finished reading the patch: it may be overwritten
+      }
+    }
+    if (p.with_coord) {  // the two coord_map channels: all 9 taps x 2 channels in one K block (k = tap*2 + ch), rest zero
+      unsigned short vals[64];
+#pragma unroll
+      for (int k = 0; k < 64; ++k) vals[k] = 0;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int gy = ty0 + my + tap / 3 - 1, gx = tx0 + mx + tap % 3 - 1;
+        if (gy >= 0 && gy < p.Hg && gx >= 0 && gx < p.Wg) {
+          vals[tap * 2] = __bfloat16_as_ushort(__float2bfloat16_rn(__ldg(p.coord_x + gx)));
+          vals[tap * 2 + 1] = __bfloat16_as_ushort(__float2bfloat16_rn(__ldg(p.coord_y + gy)));
+        }
+      }
+      uint8_t* stage = acquire_stage();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 r;
+        r.x = vals[c * 8 + 0] | ((unsigned)vals[c * 8 + 1] << 16); r.y = vals[c * 8 + 2] | ((unsigned)vals[c * 8 + 3] << 16);
+        r.z = vals[c * 8 + 4] | ((unsigned)vals[c * 8 + 5] << 16); r.w = vals[c * 8 + 6] | ((unsigned)vals[c * 8 + 7] << 16);
+        *reinterpret_cast<uint4*>(stage + sw128_offset(tid, c)) = r;
+      }
+      publish_stage();
+    }
+    // ----- epilogue: thread = tile cell = TMEM lane; 512 fp32 columns in chunks of 32 -----
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const int gy = ty0 + my, gx = tx0 + mx;
+    const bool inside = gy < p.Hg && gx < p.Wg;
+    float* orow = p.out + (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW;
+#pragma unroll 1
+    for (int c0 = 0; c0 < CV_N; c0 += 32) {
+      float vv[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, vv);
+      if (inside) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 o = make_float4(vv[i], vv[i + 1], vv[i + 2], vv[i + 3]);
+          if (p.bias) { o.x += __ldg(p.bias + c0 + i); o.y += __ldg(p.bias + c0 + i + 1); o.z += __ldg(p.bias + c0 + i + 2); o.w += __ldg(p.bias + c0 + i + 3); }
+          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          *reinterpret_cast<float4*>(orow + c0 + i) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, CV_N);
+}
+
 }  // namespace mvw
 
 extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
@@ -330,11 +525,22 @@ extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int n
   p.oB = out_strides[0]; p.oH = out_strides[2]; p.oW = out_strides[3];
   p.relu = relu; p.with_coord = with_coord;
   p.tiles_x = (plan->Wg + CT_W - 1) / CT_W; p.tiles_y = (plan->Hg + CT_H - 1) / CT_H;
-  const int smem = 16384 + (int)CV_B_BYTES + CP_CELLS * 128 + CP_CELLS * (int)sizeof(ConvTap) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(warp_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) {
-    warp_conv1_kernel<<<dim3(p.tiles_x * p.tiles_y, 1, B), 128, smem, (cudaStream_t)stream>>>(p);
-    e = cudaGetLastError();
+  cudaError_t e;
+  const char* variant = getenv("MVWARP_CONV1_VARIANT");   // development knob: "simple" = the unpipelined validation kernel
+  if (variant && variant[0] == 's') {
+    const int smem = 16384 + (int)CV_B_BYTES + CP_CELLS * 128 + CP_CELLS * (int)sizeof(ConvTap) + 1024;
+    e = cudaFuncSetAttribute(warp_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) {
+      warp_conv1_kernel<<<dim3(p.tiles_x * p.tiles_y, 1, B), 128, smem, (cudaStream_t)stream>>>(p);
+      e = cudaGetLastError();
+    }
+  } else {
+    const int smem = PA * 16384 + PB * (int)CV_B_BYTES + CP_CELLS * 128 + CP_CELLS * (int)sizeof(ConvTap) + 1024;
+    e = cudaFuncSetAttribute(warp_conv1_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) {
+      warp_conv1_pipe_kernel<<<dim3(p.tiles_x * p.tiles_y, 1, B), PIPE_THREADS, smem, (cudaStream_t)stream>>>(p);
+      e = cudaGetLastError();
+    }
   }
   if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "warp_conv1_fwd launch");
