@@ -303,54 +303,71 @@ __global__ void __launch_bounds__(128) warp_conv1_kernel(const ConvParams p) {
 
 // -----------------------------------------------------------------------------------------------------
 // Pipelined version: warp-specialised, mbarrier rings.
-//   warps 0-3  producers: warp the halo patch (once per view x 64-channel block), write the nine shifted A stages,
-//              and at the end drain TMEM (epilogue);
-//   warp 4     one thread issues tcgen05.mma (8 per K block: 4 k-steps x 2 halves of N) and commits the stage barriers;
-//   warp 5     one thread streams the packed weight blocks with bulk async copies (64 KB each).
+//   warps 0-7  producers (256 threads): warp the halo patch (once per view x 64-channel block) and write the nine
+//              shifted A stages; the gathers of the NEXT patch are issued before the nine copies of the current
+//              one and stay in flight in registers meanwhile, so their latency hides behind ~9 K blocks of MMA work.
+//              At the end the same warps drain TMEM (epilogue): warp w reads lane quarter w%4, column half w/4.
+//   warp 8     one thread issues tcgen05.mma (8 per K block: 4 k-steps x 2 halves of N) and commits the stage barriers;
+//   warp 9     one thread streams the packed weight blocks with bulk async copies (64 KB each).
 // Rings: A = PA stages x 16 KB, B = PB stages x 64 KB.  full barriers: producers / TMA -> MMA; empty barriers:
 // tcgen05.commit -> producers / TMA.
+// CL = thread-block cluster size: the CL CTAs of a cluster work on CL different cell tiles but stream the SAME weight
+// blocks, so each CTA fetches 1/CL of every block and multicasts it into all CL shared memories.
 // -----------------------------------------------------------------------------------------------------
 constexpr int PA = 3, PB = 2;
-constexpr int PIPE_THREADS = 192;
+constexpr int NPROD = 256, PIPE_THREADS = NPROD + 64;
+constexpr int PATCH_TASKS = CP_CELLS * 8, PATCH_ROUNDS = (PATCH_TASKS + NPROD - 1) / NPROD;  // 1440 tasks, 6 per thread
 
-__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+template <int CL>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;                                          // PA x 16 KB
   uint8_t* sB = smem + PA * 16384;                             // PB x 64 KB
   uint8_t* sP = sB + PB * CV_B_BYTES;                          // patch: 180 cells x 128 B (plain layout)
-  ConvTap* sT = reinterpret_cast<ConvTap*>(sP + CP_CELLS * 128);
+  ConvTap* sT = reinterpret_cast<ConvTap*>(sP + CP_CELLS * 128);  // taps of the halo cells: 2 buffers (current / next view)
   __shared__ __align__(8) uint64_t a_full[PA], a_empty[PA], b_full[PB], b_empty[PB], acc_full;
   __shared__ uint32_t tmem_holder;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x, tx0 = (tile % p.tiles_x) * CT_W, ty0 = (tile / p.tiles_x) * CT_H, b = blockIdx.z;
+  const int ntiles = p.tiles_x * p.tiles_y;
+  const bool real_tile = (int)blockIdx.x < ntiles;          // the grid is padded to a multiple of CL: a padding CTA
+  const int tile = real_tile ? blockIdx.x : ntiles - 1;      // recomputes the last tile (it must feed the multicast) and stores nothing
+  const int tx0 = (tile % p.tiles_x) * CT_W, ty0 = (tile / p.tiles_x) * CT_H, b = blockIdx.z;
   const int ncb = p.C / CV_KB;
   const int NK = p.nviews * ncb * 9 + (p.with_coord ? 1 : 0);
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0) tmem_alloc(&tmem_holder, CV_N);
   if (tid == 0) {
-    for (int i = 0; i < PA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < PB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < PA; ++i) { mbar_init(&a_full[i], NPROD); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < PB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL); }
     mbar_init(&acc_full, 1);
     fence_barrier_init();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync(); else __syncthreads();       // every CTA's barriers exist before any remote arrival
   tc_fence_after();
   const uint32_t tmem = tmem_holder;
 
-  if (warp == 5) {
+  if (warp == 9) {
     // ===== weight streamer =====
     if (lane == 0) {
       for (int kb = 0; kb < NK; ++kb) {
         const int s = kb % PB;
         if (kb >= PB) mbar_wait(&b_empty[s], ((kb / PB) - 1) & 1);
-        mbar_expect_tx(&b_full[s], CV_B_BYTES);
-        bulk_g2s(sB + (size_t)s * CV_B_BYTES, p.wpack + (size_t)kb * (CV_N * CV_KB), CV_B_BYTES, &b_full[s]);
+        mbar_expect_tx(&b_full[s], CV_B_BYTES);   // the whole block lands here: my slice and the peers' multicasts
+        if (CL == 1) {
+          bulk_g2s(sB + (size_t)s * CV_B_BYTES, p.wpack + (size_t)kb * (CV_N * CV_KB), CV_B_BYTES, &b_full[s]);
+        } else {
+          constexpr uint32_t SLICE = CV_B_BYTES / CL;
+          bulk_g2s_multicast(sB + (size_t)s * CV_B_BYTES + crank * SLICE,
+                             reinterpret_cast<const uint8_t*>(p.wpack + (size_t)kb * (CV_N * CV_KB)) + crank * SLICE, SLICE, &b_full[s], CMASK);
+        }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16_f32(128, 256);
@@ -368,13 +385,15 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
           mma_bf16(tmem + 256, da + 2 * k, db1 + 2 * k, idesc, kb > 0 || k > 0);
         }
         mma_commit(&a_empty[sa]);
-        mma_commit(&b_empty[sb]);
+        if (CL == 1) mma_commit(&b_empty[sb]);
+        else mma_commit_multicast(&b_empty[sb], CMASK);   // every CTA of the cluster writes into this stage of mine
       }
       mma_commit(&acc_full);
     }
   } else {
-    // ===== producers (128 threads), then epilogue =====
-    const int my = tid / CT_W, mx = tid % CT_W;  // this thread's A row = tile cell (my, mx)
+    // ===== producers (256 threads), then epilogue =====
+    const int m = tid & 127, half = tid >> 7;    // A row = tile cell (my, mx); this thread writes chunks [4*half, 4*half+4)
+    const int my = m / CT_W, mx = m % CT_W;
     int kb = 0;
     auto acquire_stage = [&]() -> uint8_t* {
       const int sa = kb % PA;
@@ -386,10 +405,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
       mbar_arrive(&a_full[kb % PA]);
       ++kb;
     };
-    for (int vl = 0; vl < p.nviews; ++vl) {
+    auto compute_taps = [&](int vl, ConvTap* dst) {  // taps of the halo patch for one view (outside the grid = conv zero padding)
       const int v = p.view0 + vl;
-      producers_sync();  // previous view's taps are no longer read
-      for (int i = tid; i < CP_CELLS; i += 128) {
+      for (int i = tid; i < CP_CELLS; i += NPROD) {
         const int gy = ty0 + i / CP_W - 1, gx = tx0 + i % CP_W - 1;
         ConvTap t;
         t.mask = 0; t.x0 = t.y0 = 0; t.pad = 0;
@@ -405,51 +423,78 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
           for (int k = 0; k < 4; ++k) t.w[k] = tp.w[k];
           t.x0 = tp.x0; t.y0 = tp.y0; t.mask = tp.mask;
         }
-        sT[i] = t;
+        dst[i] = t;
       }
-      producers_sync();
-      const __nv_bfloat16* fv = p.feats + (int64_t)b * p.fB + (int64_t)vl * p.fV;
-      for (int cb = 0; cb < ncb; ++cb) {
-        for (int task = tid; task < CP_CELLS * 8; task += 128) {  // warp the patch: 180 cells x 8 chunks of 8 channels
-          const int cell = task >> 3, ch = task & 7;
-          const ConvTap t = sT[cell];
-          uint4 r = make_uint4(0, 0, 0, 0);
-          if (t.mask) {
-            uint4 tv[4];
+    };
+    uint4 tv[PATCH_ROUNDS][4];   // gathers in flight for the next patch
+    auto issue_gathers = [&](int vl, int cb, const ConvTap* taps) {
+      const __nv_bfloat16* fv = p.feats + (int64_t)b * p.fB + (int64_t)vl * p.fV + cb * CV_KB;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int xx = t.x0 + (k & 1), yy = t.y0 + (k >> 1);
-              tv[k] = (t.mask >> k & 1) ? __ldg(reinterpret_cast<const uint4*>(fv + (int64_t)yy * p.fH + (int64_t)xx * p.fW + cb * CV_KB + ch * 8))
-                                        : make_uint4(0, 0, 0, 0);
-            }
-            const unsigned* a = &tv[0].x; const unsigned* bq = &tv[1].x; const unsigned* c = &tv[2].x; const unsigned* d = &tv[3].x;
-            unsigned o[4];
+      for (int j = 0; j < PATCH_ROUNDS; ++j) {
+        const int task = tid + j * NPROD;
+        const int cell = task >> 3, ch = task & 7;
+        if (task < PATCH_TASKS) {
+          const ConvTap t = taps[cell];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float lo = __fmaf_rn(bf_lo(d[q]), t.w[3], __fmaf_rn(bf_lo(c[q]), t.w[2], __fmaf_rn(bf_lo(bq[q]), t.w[1], __fmul_rn(bf_lo(a[q]), t.w[0]))));
-              const float hi = __fmaf_rn(bf_hi(d[q]), t.w[3], __fmaf_rn(bf_hi(c[q]), t.w[2], __fmaf_rn(bf_hi(bq[q]), t.w[1], __fmul_rn(bf_hi(a[q]), t.w[0]))));
-              o[q] = pack_bf2(lo, hi);
-            }
-            r = make_uint4(o[0], o[1], o[2], o[3]);
+          for (int k = 0; k < 4; ++k) {
+            const int xx = t.x0 + (k & 1), yy = t.y0 + (k >> 1);
+            tv[j][k] = (t.mask >> k & 1) ? __ldg(reinterpret_cast<const uint4*>(fv + (int64_t)yy * p.fH + (int64_t)xx * p.fW + ch * 8))
+                                         : make_uint4(0, 0, 0, 0);
           }
-          *reinterpret_cast<uint4*>(sP + cell * 128 + ch * 16) = r;
         }
-        producers_sync();  // patch complete
-        for (int tap = 0; tap < 9; ++tap) {
-          uint8_t* stage = acquire_stage();
-          const int srcc = (my + tap / 3) * CP_W + (mx + tap % 3);
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4*>(stage + sw128_offset(tid, c)) = *reinterpret_cast<const uint4*>(sP + srcc * 128 + c * 16);
-          publish_stage();
-        }
-        producers_sync();  // every thread has finished reading the patch: it may be overwritten
       }
+    };
+    auto blend_patch = [&](const ConvTap* taps) {
+#pragma unroll
+      for (int j = 0; j < PATCH_ROUNDS; ++j) {
+        const int task = tid + j * NPROD;
+        const int cell = task >> 3, ch = task & 7;
+        if (task < PATCH_TASKS) {
+          const ConvTap t = taps[cell];
+          const unsigned* a = &tv[j][0].x; const unsigned* bq = &tv[j][1].x; const unsigned* c = &tv[j][2].x; const unsigned* d = &tv[j][3].x;
+          unsigned o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float lo = __fmaf_rn(bf_lo(d[q]), t.w[3], __fmaf_rn(bf_lo(c[q]), t.w[2], __fmaf_rn(bf_lo(bq[q]), t.w[1], __fmul_rn(bf_lo(a[q]), t.w[0]))));
+            const float hi = __fmaf_rn(bf_hi(d[q]), t.w[3], __fmaf_rn(bf_hi(c[q]), t.w[2], __fmaf_rn(bf_hi(bq[q]), t.w[1], __fmul_rn(bf_hi(a[q]), t.w[0]))));
+            o[q] = pack_bf2(lo, hi);
+          }
+          *reinterpret_cast<uint4*>(sP + cell * 128 + ch * 16) = t.mask ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0, 0, 0, 0);
+        }
+      }
+    };
+
+    const int nblk = p.nviews * ncb;   // (view, channel-block) pairs
+    compute_taps(0, sT);
+    producers_sync();
+    issue_gathers(0, 0, sT);
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int vl = blk / ncb;
+      const ConvTap* taps = sT + (vl & 1) * CP_CELLS;
+      blend_patch(taps);                 // consumes the gathers issued one block earlier
+      producers_sync();                  // patch complete
+      if (blk + 1 < nblk) {              // start the next block's gathers; they fly during the nine copies below
+        const int nvl = (blk + 1) / ncb, ncbi = (blk + 1) % ncb;
+        if (ncbi == 0) {                 // next block opens a new view: its taps go to the other buffer
+          compute_taps(nvl, sT + (nvl & 1) * CP_CELLS);
+          producers_sync();
+        }
+        issue_gathers(nvl, ncbi, sT + (nvl & 1) * CP_CELLS);
+      }
+      for (int tap = 0; tap < 9; ++tap) {
+        uint8_t* stage = acquire_stage();
+        const int srcc = (my + tap / 3) * CP_W + (mx + tap % 3);
+#pragma unroll
+        for (int c = 4 * half; c < 4 * half + 4; ++c)
+          *reinterpret_cast<uint4*>(stage + sw128_offset(m, c)) = *reinterpret_cast<const uint4*>(sP + srcc * 128 + c * 16);
+        publish_stage();
+      }
+      producers_sync();                  // every thread has finished reading the patch: it may be overwritten
     }
     if (p.with_coord) {  // the two coord_map channels: all 9 taps x 2 channels in one K block (k = tap*2 + ch), rest zero
-      unsigned short vals[64];
+      unsigned short vals[32];
 #pragma unroll
-      for (int k = 0; k < 64; ++k) vals[k] = 0;
+      for (int k = 0; k < 32; ++k) vals[k] = 0;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const int gy = ty0 + my + tap / 3 - 1, gx = tx0 + mx + tap % 3 - 1;
@@ -460,24 +505,29 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
       }
       uint8_t* stage = acquire_stage();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 r;
-        r.x = vals[c * 8 + 0] | ((unsigned)vals[c * 8 + 1] << 16); r.y = vals[c * 8 + 2] | ((unsigned)vals[c * 8 + 3] << 16);
-        r.z = vals[c * 8 + 4] | ((unsigned)vals[c * 8 + 5] << 16); r.w = vals[c * 8 + 6] | ((unsigned)vals[c * 8 + 7] << 16);
-        *reinterpret_cast<uint4*>(stage + sw128_offset(tid, c)) = r;
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = 4 * half + cc;     // chunks 0..3 carry k = 0..31 (18 used), chunks 4..7 are zero
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (half == 0) {
+          r.x = vals[cc * 8 + 0] | ((unsigned)vals[cc * 8 + 1] << 16); r.y = vals[cc * 8 + 2] | ((unsigned)vals[cc * 8 + 3] << 16);
+          r.z = vals[cc * 8 + 4] | ((unsigned)vals[cc * 8 + 5] << 16); r.w = vals[cc * 8 + 6] | ((unsigned)vals[cc * 8 + 7] << 16);
+        }
+        *reinterpret_cast<uint4*>(stage + sw128_offset(m, c)) = r;
       }
       publish_stage();
     }
-    // ----- epilogue: thread = tile cell = TMEM lane; 512 fp32 columns in chunks of 32 -----
+    // ----- epilogue: thread = tile cell = TMEM lane (quarter warp%4); warps 0-3 take columns 0-255, warps 4-7 256-511 -----
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    const int gy = ty0 + my, gx = tx0 + mx;
-    const bool inside = gy < p.Hg && gx < p.Wg;
+    const int er = (warp & 3) * 32 + lane, ey = er / CT_W, ex = er % CT_W;
+    const int gy = ty0 + ey, gx = tx0 + ex;
+    const bool inside = real_tile && gy < p.Hg && gx < p.Wg;
     float* orow = p.out + (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW;
+    const int cbeg = (warp >> 2) * 256;
 #pragma unroll 1
-    for (int c0 = 0; c0 < CV_N; c0 += 32) {
+    for (int c0 = cbeg; c0 < cbeg + 256; c0 += 32) {
       float vv[32];
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, vv);
+      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, vv);
       if (inside) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -490,7 +540,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync(); else __syncthreads();       // nobody leaves while a peer may still multicast into it
   if (warp == 0) tmem_dealloc(tmem, CV_N);
 }
 
@@ -535,12 +585,25 @@ extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int n
       e = cudaGetLastError();
     }
   } else {
-    const int smem = PA * 16384 + PB * (int)CV_B_BYTES + CP_CELLS * 128 + CP_CELLS * (int)sizeof(ConvTap) + 1024;
-    e = cudaFuncSetAttribute(warp_conv1_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) {
-      warp_conv1_pipe_kernel<<<dim3(p.tiles_x * p.tiles_y, 1, B), PIPE_THREADS, smem, (cudaStream_t)stream>>>(p);
-      e = cudaGetLastError();
-    }
+    const int smem = PA * 16384 + PB * (int)CV_B_BYTES + CP_CELLS * 128 + 2 * CP_CELLS * (int)sizeof(ConvTap) + 1024;
+    const int cl = (variant && variant[0] >= '1' && variant[0] <= '4') ? variant[0] - '0' : 1;
+    auto launch = [&](auto kernel, int cluster) -> cudaError_t {
+      cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (err != cudaSuccess) return err;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((p.tiles_x * p.tiles_y + cluster - 1) / cluster * cluster, 1, B);
+      cfg.blockDim = dim3(PIPE_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&cfg, kernel, p);
+    };
+    if (cl == 1) e = launch(warp_conv1_pipe_kernel<1>, 1);
+    else if (cl == 4) e = launch(warp_conv1_pipe_kernel<4>, 4);
+    else e = launch(warp_conv1_pipe_kernel<2>, 2);
   }
   if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "warp_conv1_fwd launch");
