@@ -128,3 +128,23 @@ def reduce_partials(partial: torch.Tensor, group=None, relu: bool = True) -> tor
 
 def coord_map_for(grid_shape: Sequence[int], batch: int, like: torch.Tensor) -> torch.Tensor:
     return create_coord_map(grid_shape).to(device=like.device, dtype=like.dtype).repeat(batch, 1, 1, 1)
+
+
+def pack_conv1_weight_shard(weight: torch.Tensor, shard: ViewShard, C: int) -> torch.Tensor:
+    """This rank's slice of ``map_classifier[0].weight`` [512, V*C+2, 3, 3] packed for the fused kernel
+    (:func:`mvdet_b200.conv1.pack_conv1_weight`); the coord-map owner also carries the two coord channels."""
+    from .conv1 import pack_conv1_weight
+    return pack_conv1_weight(weight[:, shard.channel_slice(C)], shard.count, C, with_coord=shard.owns_coord_map)
+
+
+def conv1_partial_fused(local_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Sequence[int],
+                        wpack_local: torch.Tensor, bias: Optional[torch.Tensor], shard: ViewShard) -> torch.Tensor:
+    """:func:`conv1_partial` without materialising the rank's warped slice: warp + conv1 as one tcgen05 implicit GEMM
+    (north_star (c)); bf16 channel-contiguous features in, fp32 partial sums out (no ReLU: that follows the reduce)."""
+    from .conv1 import warp_conv1
+    if shard.count == 0:
+        B = local_feats.shape[0]
+        return torch.zeros((B, 512, int(grid_shape[0]), int(grid_shape[1])), dtype=torch.float32, device=local_feats.device)
+    mats = proj_mats[shard.first_view:shard.first_view + shard.count]
+    return warp_conv1(local_feats, mats, grid_shape, wpack_local, bias if shard.owns_coord_map else None, relu=False,
+                      with_coord=shard.owns_coord_map)

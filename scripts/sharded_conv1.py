@@ -61,8 +61,11 @@ def main():
     feats = torch.randn(B, shard.count, Hs, Ws, C, device=dev, dtype=torch.bfloat16).permute(0, 1, 4, 2, 3)
     weight = (torch.randn(Cout, V * C + 2, 3, 3, device=dev, dtype=torch.bfloat16) * 0.02).contiguous(memory_format=torch.channels_last)
     bias = torch.randn(Cout, device=dev, dtype=torch.bfloat16)
+    wpack = S.pack_conv1_weight_shard(weight.float(), shard, C)
+    bias32 = bias.float()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    times = []
+    fe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    times, ftimes = [], []
     for it in range(4):
         dist.barrier()
         torch.cuda.synchronize()
@@ -75,7 +78,16 @@ def main():
         ev[3].record()
         torch.cuda.synchronize()
         times.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+        ref_partial = partial.float() if it == 0 else None
         del out_local, partial, reduced
+        fe[0].record()
+        fpart = S.conv1_partial_fused(feats, pm, (Hg, Wg), wpack, bias32, shard)    # warp + conv1 partial in one kernel
+        fe[1].record()
+        torch.cuda.synchronize()
+        ftimes.append(fe[0].elapsed_time(fe[1]))
+        del fpart
+    ft = torch.tensor([sum(ftimes[1:]) / len(ftimes[1:])], device=dev)
+    dist.all_reduce(ft, op=dist.ReduceOp.MAX)
     t = torch.tensor(times[1:], device=dev).mean(0)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
@@ -83,6 +95,7 @@ def main():
         res.update({"rig": f"{V} cameras x 512ch x {Hs}x{Ws} -> {Hg}x{Wg}, bf16, {per_rank} cameras per rank",
                     "warp_ms": float(t[0]), "conv1_partial_ms": float(t[1]), "allreduce_relu_ms": float(t[2]),
                     "conv1_partial_tflops": flops / (float(t[1]) * 1e-3) / 1e12,
+                    "fused_warp_conv1_partial_ms": float(ft[0]), "fused_tflops": flops / (float(ft[0]) * 1e-3) / 1e12,
                     "allreduce_bytes": B * Cout * Hg * Wg * 2,
                     "allreduce_busbw_gbs": 2 * (world - 1) / world * B * Cout * Hg * Wg * 2 / (float(t[2]) * 1e-3) / 1e9})
         print(json.dumps(res), flush=True)

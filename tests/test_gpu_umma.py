@@ -50,3 +50,38 @@ def test_fused_warp_conv1_matches_reference(V, Cc, relu):
     assert out.shape == ref.shape
     emax, el2 = rel_errors(out, ref)
     assert emax <= 1e-4 and el2 <= 1e-4, (emax, el2)
+
+
+def test_fused_conv1_view_shards_sum_to_the_full_convolution():
+    """Two view shards (emulated one after the other on one GPU): the fused partial sums add up to conv1 of the concat."""
+    from mvdet_b200 import conv1, sharding as S
+    from tests.util import small_rig, to_channels_last_5d, rel_errors
+    V, Cc = 3, 64
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=33)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, V, Cc, *src_hw, generator=g).bfloat16()
+    weight = torch.randn(512, V * Cc + 2, 3, 3, generator=g) * 0.05
+    bias = torch.randn(512, generator=g)
+    ref = _conv1_reference(x, pm, grid_hw, weight, bias, relu=True)
+    total = None
+    for rank in range(2):
+        shard = S.ViewShard.for_rank(V, rank=rank, world_size=2)
+        local = to_channels_last_5d(x[:, shard.first_view:shard.first_view + shard.count]).cuda()
+        wp = S.pack_conv1_weight_shard(weight, shard, Cc).cuda()
+        part = S.conv1_partial_fused(local, pm, grid_hw, wp, bias.cuda(), shard)
+        total = part if total is None else total + part
+    out = torch.relu(total)
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= 1e-4 and el2 <= 1e-4, (emax, el2)
+
+
+def test_fused_conv1_rejects_what_it_cannot_run():
+    from mvdet_b200 import conv1
+    from tests.util import small_rig
+    pm, src_hw, grid_hw = small_rig(num_cam=1, seed=31)
+    x = torch.randn(1, 1, 64, *src_hw).cuda()                         # fp32: not supported
+    w = conv1.pack_conv1_weight(torch.randn(512, 66, 3, 3), 1, 64).cuda()
+    with pytest.raises(ValueError):
+        conv1.warp_conv1(x, pm, grid_hw, w)
+    with pytest.raises(ValueError):
+        conv1.pack_conv1_weight(torch.randn(512, 50, 3, 3), 1, 48)   # C % 64 != 0
