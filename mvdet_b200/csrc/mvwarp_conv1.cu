@@ -1,7 +1,10 @@
 // mvwarp_conv1.cu -- tensor-core side of the path (north_star (c)): tcgen05 / TMEM GEMM building blocks for the
 // fused warp -> map_classifier[0] implicit GEMM (/root/reference/multiview_detector/models/persp_trans_detector.py:51,81).
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "mvwarp_internal.h"
 #include "mvwarp_umma.h"
@@ -127,6 +130,7 @@ struct ConvParams {
   float* out;                  // [B, Hg, Wg, 512] fp32 (logical [B,512,Hg,Wg] channels-last)
   int64_t oB, oH, oW;
   int relu, with_coord, tiles_x, tiles_y;
+  unsigned long long* stats;   // development: per CTA {cycles waiting for A, for B, total} of the MMA thread, or nullptr
 };
 
 struct ConvTap {
@@ -371,10 +375,16 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16_f32(128, 256);
+      long long wa = 0, wb = 0;
+      const long long t_start = clock64();
       for (int kb = 0; kb < NK; ++kb) {
         const int sa = kb % PA, sb = kb % PB;
+        const long long t0 = clock64();
         mbar_wait(&a_full[sa], (kb / PA) & 1);
+        const long long t1 = clock64();
         mbar_wait(&b_full[sb], (kb / PB) & 1);
+        const long long t2 = clock64();
+        wa += t1 - t0; wb += t2 - t1;
         tc_fence_after();
         const uint32_t bbase = smem_u32(sB + (size_t)sb * CV_B_BYTES);
         const uint64_t da = smem_desc_sw128(smem_u32(sA + sa * 16384)), db0 = smem_desc_sw128(bbase),
@@ -389,6 +399,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
         else mma_commit_multicast(&b_empty[sb], CMASK);   // every CTA of the cluster writes into this stage of mine
       }
       mma_commit(&acc_full);
+      if (p.stats) {
+        unsigned long long* st = p.stats + 3 * (size_t)(blockIdx.x + gridDim.x * blockIdx.z);
+        st[0] = (unsigned long long)wa; st[1] = (unsigned long long)wb; st[2] = (unsigned long long)(clock64() - t_start);
+      }
     }
   } else {
     // ===== producers (256 threads), then epilogue =====
@@ -459,7 +473,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
             const float hi = __fmaf_rn(bf_hi(d[q]), t.w[3], __fmaf_rn(bf_hi(c[q]), t.w[2], __fmaf_rn(bf_hi(bq[q]), t.w[1], __fmul_rn(bf_hi(a[q]), t.w[0]))));
             o[q] = pack_bf2(lo, hi);
           }
-          *reinterpret_cast<uint4*>(sP + cell * 128 + ch * 16) = t.mask ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0, 0, 0, 0);
+          // the patch is XOR-swizzled like the stages (chunk position = ch ^ (cell & 7)): the tap copies below read one chunk
+          // of 8 consecutive cells per quarter-warp, which would otherwise be an 8-way bank conflict on every load
+          *reinterpret_cast<uint4*>(sP + cell * 128 + ((ch ^ (cell & 7)) << 4)) = t.mask ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0, 0, 0, 0);
         }
       }
     };
@@ -486,7 +502,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
         const int srcc = (my + tap / 3) * CP_W + (mx + tap % 3);
 #pragma unroll
         for (int c = 4 * half; c < 4 * half + 4; ++c)
-          *reinterpret_cast<uint4*>(stage + sw128_offset(m, c)) = *reinterpret_cast<const uint4*>(sP + srcc * 128 + c * 16);
+          *reinterpret_cast<uint4*>(stage + sw128_offset(m, c)) = *reinterpret_cast<const uint4*>(sP + srcc * 128 + ((c ^ (srcc & 7)) << 4));
         publish_stage();
       }
       producers_sync();                  // every thread has finished reading the patch: it may be overwritten
@@ -601,9 +617,24 @@ extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int n
       cfg.attrs = attr; cfg.numAttrs = 1;
       return cudaLaunchKernelEx(&cfg, kernel, p);
     };
+    unsigned long long* d_stats = nullptr;
+    const size_t nst = (size_t)3 * ((p.tiles_x * p.tiles_y + 3) / 4 * 4) * B;
+    if (getenv("MVWARP_CONV1_STATS")) {   // development only: synchronous, prints where the MMA thread waits
+      cudaMalloc(&d_stats, nst * sizeof(unsigned long long));
+      cudaMemset(d_stats, 0, nst * sizeof(unsigned long long));
+      p.stats = d_stats;
+    }
     if (cl == 1) e = launch(warp_conv1_pipe_kernel<1>, 1);
     else if (cl == 4) e = launch(warp_conv1_pipe_kernel<4>, 4);
     else e = launch(warp_conv1_pipe_kernel<2>, 2);
+    if (d_stats) {
+      std::vector<unsigned long long> h(nst);
+      cudaMemcpy(h.data(), d_stats, nst * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      double a = 0, bq = 0, t = 0; int n = 0;
+      for (size_t i = 0; i + 2 < nst; i += 3) if (h[i + 2]) { a += h[i]; bq += h[i + 1]; t += h[i + 2]; ++n; }
+      if (n) fprintf(stderr, "[conv1 stats] CTAs %d: MMA thread waits A %.1f%%, B %.1f%% of %.0f cycles per tile\n", n, 100 * a / t, 100 * bq / t, t / n);
+      cudaFree(d_stats);
+    }
   }
   if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "warp_conv1_fwd launch");
