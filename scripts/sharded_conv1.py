@@ -72,12 +72,22 @@ def main():
         ev[0].record()
         out_local = S.warp_views_local(feats, pm, (Hg, Wg), shard)
         ev[1].record()
-        partial = S.conv1_partial(out_local, weight, bias, shard, C)
+        partial = S.conv1_partial(out_local, weight, bias, shard, C).float().contiguous()
+        torch.cuda.synchronize()
+        dist.barrier()                       # time the exchange itself, not the skew between the ranks' convolutions
+        torch.cuda.synchronize()
         ev[2].record()
         reduced = S.reduce_partials(partial, relu=True)
         ev[3].record()
         torch.cuda.synchronize()
-        times.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+        times.append([ev[0].elapsed_time(ev[1]), 0.0, ev[2].elapsed_time(ev[3])])
+        ec = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ec[0].record()
+        _p = S.conv1_partial(out_local, weight, bias, shard, C)
+        ec[1].record()
+        torch.cuda.synchronize()
+        times[-1][1] = ec[0].elapsed_time(ec[1])
+        del _p
         ref_partial = partial.float() if it == 0 else None
         del out_local, partial, reduced
         fe[0].record()
@@ -96,8 +106,8 @@ def main():
                     "warp_ms": float(t[0]), "conv1_partial_ms": float(t[1]), "allreduce_relu_ms": float(t[2]),
                     "conv1_partial_tflops": flops / (float(t[1]) * 1e-3) / 1e12,
                     "fused_warp_conv1_partial_ms": float(ft[0]), "fused_tflops": flops / (float(ft[0]) * 1e-3) / 1e12,
-                    "allreduce_bytes": B * Cout * Hg * Wg * 2,
-                    "allreduce_busbw_gbs": 2 * (world - 1) / world * B * Cout * Hg * Wg * 2 / (float(t[2]) * 1e-3) / 1e9})
+                    "allreduce_bytes": B * Cout * Hg * Wg * 4,
+                    "allreduce_busbw_gbs": 2 * (world - 1) / world * B * Cout * Hg * Wg * 4 / (float(t[2]) * 1e-3) / 1e9})
         print(json.dumps(res), flush=True)
     dist.destroy_process_group()
 

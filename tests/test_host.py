@@ -187,3 +187,30 @@ def test_composed_upsample_map_is_adjoint_of_two_step_oracle():
         assert float((mine - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
     # at most 16 low-res taps per cell, typically far fewer
     assert st["nnz"] <= 16 * st["valid_cells"]
+
+
+def test_conv1_weight_packing_layout():
+    """pack_conv1_weight (host side of the fused warp->conv1 kernel): block order (view, channel block, tap), K-major rows,
+    16-byte chunks XOR-swizzled by (row & 7), coord channels of all nine taps in the last block."""
+    from mvdet_b200.conv1 import pack_conv1_weight
+    V, C = 2, 128
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(512, V * C + 2, 3, 3, generator=g)
+    packed = pack_conv1_weight(w, V, C)
+    assert packed.shape == (V * (C // 64) * 9 + 1, 512, 64) and packed.dtype == torch.bfloat16
+    wb = w.bfloat16()
+    for (v, cb, tap, n, k) in [(0, 0, 0, 0, 0), (1, 1, 5, 17, 33), (0, 1, 8, 511, 63), (1, 0, 4, 260, 9)]:
+        block = (v * (C // 64) + cb) * 9 + tap
+        chunk, j = k // 8, k % 8
+        pos = chunk ^ (n & 7)
+        assert packed[block, n, pos * 8 + j] == wb[n, v * C + cb * 64 + k, tap // 3, tap % 3]
+    last = packed[-1]
+    for (n, tap, ch) in [(0, 0, 0), (5, 8, 1), (300, 4, 0)]:
+        k = tap * 2 + ch
+        pos = (k // 8) ^ (n & 7)
+        assert last[n, pos * 8 + k % 8] == wb[n, V * C + ch, tap // 3, tap % 3]
+    # everything beyond k = 18 in the coord block is zero
+    unsw = torch.stack([last[n].reshape(8, 8)[[c ^ (n & 7) for c in range(8)]].reshape(64) for n in range(16)])
+    assert bool((unsw[:, 18:] == 0).all())
+    with pytest.raises(ValueError):
+        pack_conv1_weight(w, V, C + 64)
