@@ -156,10 +156,13 @@ int mvwarp_debug_gemm(const void* A, const void* B, void* D, int M, int N, int K
  * wpack: the weight pre-packed by mvdet_b200.conv1.pack_conv1_weight: per (view, 64-channel block, tap) one
  *        [512][64] bf16 block whose rows carry the 128-byte shared-memory swizzle, then one block for the coord channels.
  * X is rounded to bf16 before the contraction (fp32 accumulate in TMEM).  View shards pass their own weight slices,
- * bias / with_coord only on the coord-map owner, relu = 0, and all-reduce the partial sums (mvdet_b200.sharding). */
+ * bias / with_coord only on the coord-map owner, relu = 0, and all-reduce the partial sums (mvdet_b200.sharding).
+ * row0 / nrows restrict the launch to the grid rows [row0, row0+nrows) (row0 % 8 == 0; nrows <= 0 = the whole grid): the
+ * sharded path computes the map band by band so that the all-reduce of one band overlaps the GEMM of the next. */
 int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
                           const int64_t feat_strides[5], const void* wpack, const float* bias, float* out,
-                          const int64_t out_strides[4], int B, int C, int relu, int with_coord, void* stream);
+                          const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0, int nrows,
+                          void* stream);
 
 #ifdef __cplusplus
 }

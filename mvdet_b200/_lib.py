@@ -50,7 +50,7 @@ SIGNATURES = {
     "mvwarp_warp_views_fwd": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, _P, _I64P, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_int, _P]),
     "mvwarp_warp_conv1_fwd": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, _P, _P, _P, _I64P, C.c_int, C.c_int, C.c_int,
-                                        C.c_int, _P]),
+                                        C.c_int, C.c_int, C.c_int, _P]),
     "mvwarp_debug_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "mvwarp_warp_views_bwd": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, C.c_int, _P, _I64P,
                                         C.c_int, C.c_int, C.c_int, _P]),

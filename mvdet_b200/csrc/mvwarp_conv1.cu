@@ -130,6 +130,7 @@ struct ConvParams {
   float* out;                  // [B, Hg, Wg, 512] fp32 (logical [B,512,Hg,Wg] channels-last)
   int64_t oB, oH, oW;
   int relu, with_coord, tiles_x, tiles_y;
+  int tile0, ntiles;           // this launch covers tiles [tile0, tile0 + ntiles) (a band of tile rows)
   unsigned long long* stats;   // development: per CTA {cycles waiting for A, for B, total} of the MMA thread, or nullptr
 };
 
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(128) warp_conv1_kernel(const ConvParams p) {
   __shared__ __align__(8) uint64_t b_full, mma_done;
   __shared__ uint32_t tmem_holder;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int tile = blockIdx.x, tx0 = (tile % p.tiles_x) * CT_W, ty0 = (tile / p.tiles_x) * CT_H, b = blockIdx.z;
+  const int tile = p.tile0 + blockIdx.x, tx0 = (tile % p.tiles_x) * CT_W, ty0 = (tile / p.tiles_x) * CT_H, b = blockIdx.z;
 
   if (warp == 0) tmem_alloc(&tmem_holder, CV_N);
   if (tid == 0) {
@@ -334,9 +335,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
   __shared__ __align__(8) uint64_t a_full[PA], a_empty[PA], b_full[PB], b_empty[PB], acc_full;
   __shared__ uint32_t tmem_holder;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ntiles = p.tiles_x * p.tiles_y;
-  const bool real_tile = (int)blockIdx.x < ntiles;          // the grid is padded to a multiple of CL: a padding CTA
-  const int tile = real_tile ? blockIdx.x : ntiles - 1;      // recomputes the last tile (it must feed the multicast) and stores nothing
+  const bool real_tile = (int)blockIdx.x < p.ntiles;        // the grid is padded to a multiple of CL: a padding CTA
+  const int tile = p.tile0 + (real_tile ? blockIdx.x : p.ntiles - 1);  // recomputes the last tile (it must feed the multicast), stores nothing
   const int tx0 = (tile % p.tiles_x) * CT_W, ty0 = (tile / p.tiles_x) * CT_H, b = blockIdx.z;
   const int ncb = p.C / CV_KB;
   const int NK = p.nviews * ncb * 9 + (p.with_coord ? 1 : 0);
@@ -564,7 +564,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
 
 extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
                                      const int64_t feat_strides[5], const void* wpack, const float* bias, float* out,
-                                     const int64_t out_strides[4], int B, int C, int relu, int with_coord, void* stream) {
+                                     const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0, int nrows,
+                                     void* stream) {
   using namespace mvw;
   if (!plan || !feats || !feat_strides || !wpack || !out || !out_strides) { set_error("warp_conv1_fwd: null argument"); return MVWARP_EINVAL; }
   if (B <= 0 || nviews <= 0 || view0 < 0 || view0 + nviews > plan->V) { set_error("warp_conv1_fwd: bad B / view range"); return MVWARP_EINVAL; }
@@ -591,13 +592,21 @@ extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int n
   p.oB = out_strides[0]; p.oH = out_strides[2]; p.oW = out_strides[3];
   p.relu = relu; p.with_coord = with_coord;
   p.tiles_x = (plan->Wg + CT_W - 1) / CT_W; p.tiles_y = (plan->Hg + CT_H - 1) / CT_H;
+  if (nrows <= 0) { row0 = 0; nrows = plan->Hg; }
+  if (row0 < 0 || row0 % CT_H || row0 + nrows > plan->Hg || (nrows % CT_H && row0 + nrows != plan->Hg)) {
+    if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
+    set_error("warp_conv1_fwd: a row band must start on a multiple of 8 rows and end on one (or at the last row)");
+    return MVWARP_EINVAL;
+  }
+  p.tile0 = (row0 / CT_H) * p.tiles_x;
+  p.ntiles = ((nrows + CT_H - 1) / CT_H) * p.tiles_x;
   cudaError_t e;
   const char* variant = getenv("MVWARP_CONV1_VARIANT");   // development knob: "simple" = the unpipelined validation kernel
   if (variant && variant[0] == 's') {
     const int smem = 16384 + (int)CV_B_BYTES + CP_CELLS * 128 + CP_CELLS * (int)sizeof(ConvTap) + 1024;
     e = cudaFuncSetAttribute(warp_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) {
-      warp_conv1_kernel<<<dim3(p.tiles_x * p.tiles_y, 1, B), 128, smem, (cudaStream_t)stream>>>(p);
+      warp_conv1_kernel<<<dim3(p.ntiles, 1, B), 128, smem, (cudaStream_t)stream>>>(p);
       e = cudaGetLastError();
     }
   } else {
@@ -607,7 +616,7 @@ extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int n
       cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (err != cudaSuccess) return err;
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((p.tiles_x * p.tiles_y + cluster - 1) / cluster * cluster, 1, B);
+      cfg.gridDim = dim3((p.ntiles + cluster - 1) / cluster * cluster, 1, B);
       cfg.blockDim = dim3(PIPE_THREADS);
       cfg.dynamicSmemBytes = smem;
       cfg.stream = (cudaStream_t)stream;
@@ -618,7 +627,7 @@ extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int n
       return cudaLaunchKernelEx(&cfg, kernel, p);
     };
     unsigned long long* d_stats = nullptr;
-    const size_t nst = (size_t)3 * ((p.tiles_x * p.tiles_y + 3) / 4 * 4) * B;
+    const size_t nst = (size_t)3 * ((p.ntiles + 3) / 4 * 4) * B;
     if (getenv("MVWARP_CONV1_STATS")) {   // development only: synchronous, prints where the MMA thread waits
       cudaMalloc(&d_stats, nst * sizeof(unsigned long long));
       cudaMemset(d_stats, 0, nst * sizeof(unsigned long long));

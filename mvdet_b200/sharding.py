@@ -148,3 +148,42 @@ def conv1_partial_fused(local_feats: torch.Tensor, proj_mats: torch.Tensor, grid
     mats = proj_mats[shard.first_view:shard.first_view + shard.count]
     return warp_conv1(local_feats, mats, grid_shape, wpack_local, bias if shard.owns_coord_map else None, relu=False,
                       with_coord=shard.owns_coord_map)
+
+
+def conv1_fused_allreduce(local_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Sequence[int],
+                          wpack_local: torch.Tensor, bias: Optional[torch.Tensor], shard: ViewShard,
+                          bands: int = 4, relu: bool = True, group=None) -> torch.Tensor:
+    """relu(conv1(concat of all ranks' warps) + bias) on every rank: the fused warp->conv1 kernel computes this rank's
+    partial sums band by band (bands of grid rows, multiples of 8), and the NCCL all-reduce (+ ReLU) of band i runs on a
+    side stream while the tensor cores work on band i+1 -- the exchange hides behind the GEMM except for the last band."""
+    from .conv1 import warp_conv1
+    B = local_feats.shape[0]
+    Hg, Wg = int(grid_shape[0]), int(grid_shape[1])
+    dev = local_feats.device
+    phys = torch.empty((B, Hg, Wg, 512), dtype=torch.float32, device=dev)   # the channels-last storage of the result
+    out = phys.permute(0, 3, 1, 2)
+    distributed = dist.is_initialized() and dist.get_world_size(group) > 1
+    rows_per_band = max(8, ((Hg + bands - 1) // bands + 7) // 8 * 8)
+    edges = list(range(0, Hg, rows_per_band)) + [Hg]
+    mats = proj_mats[shard.first_view:shard.first_view + shard.count]
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev) if distributed else None
+    for y0, y1 in zip(edges[:-1], edges[1:]):
+        if shard.count:
+            warp_conv1(local_feats, mats, grid_shape, wpack_local, bias if shard.owns_coord_map else None, relu=False,
+                       with_coord=shard.owns_coord_map, out=out, rows=(y0, y1))
+        else:
+            phys[:, y0:y1].zero_()
+        if distributed:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for b in range(B):           # rows [y0, y1) of one batch element are one contiguous run of memory
+                    dist.all_reduce(phys[b, y0:y1], op=dist.ReduceOp.SUM, group=group)
+                if relu:
+                    phys[:, y0:y1].relu_()
+        elif relu:
+            phys[:, y0:y1].relu_()
+    if distributed:
+        main.wait_stream(side)
+        phys.record_stream(side)
+    return out
