@@ -113,6 +113,16 @@ int mvwarp_plan_create_from_grid(const float* grid_host, int V, int Hs, int Ws, 
 int mvwarp_plan_create_upsampled(const float* src_norm_trans_dst_norm, int V, int hl, int wl, int Hs, int Ws,
                                  int Hg, int Wg, int device, mvwarp_plan_t** plan_out);
 int mvwarp_plan_destroy(mvwarp_plan_t* plan);
+/* Plan persistence: a plan depends only on the calibration, so it can be stored next to it
+ * (the reference rebuilds its matrices from the calibration files on every start, persp_trans_detector.py:17-30, and the
+ * sampling grid on every forward).  mvwarp_plan_save writes the device-resident plan to `path` (atomic replace);
+ * mvwarp_plan_load re-creates it on `device` without running the host builder.  The file carries a checksum and the
+ * library's work-decomposition constants: a truncated / corrupt file or one written by an incompatible build is
+ * refused (MVWARP_EINVAL / MVWARP_EUNSUPPORTED), never half-loaded.  mvwarp_plan_matrices returns the [V,3,3]
+ * src_norm_trans_dst_norm matrices a plan was built from, so a caller can check a loaded plan against its rig. */
+int mvwarp_plan_save(const mvwarp_plan_t* plan, const char* path);
+int mvwarp_plan_load(const char* path, int device, mvwarp_plan_t** plan_out);
+int mvwarp_plan_matrices(const mvwarp_plan_t* plan, float* T_out);
 int mvwarp_plan_stats(const mvwarp_plan_t* plan, mvwarp_stats_t* stats_out);
 /* Debug/test: run the device coordinate kernel and copy the normalised grid [V,Hg,Wg,2] to host. */
 int mvwarp_plan_device_grid(const mvwarp_plan_t* plan, float* grid_host_out, void* stream);

@@ -14,7 +14,7 @@ def __getattr__(name):  # ops import torch.library machinery lazily
                 "warp_views_fwd_into", "warp_views_bwd_into"):
         from . import ops
         return getattr(ops, name)
-    if name in ("get_plan", "get_plan_from_grid", "get_plan_upsampled", "WarpPlan", "src_norm_trans_dst_norm", "host_grid", "host_csr"):
+    if name in ("get_plan", "get_plan_from_grid", "get_plan_upsampled", "load_plan", "WarpPlan", "src_norm_trans_dst_norm", "host_grid", "host_csr"):
         from . import plan
         return getattr(plan, name)
     raise AttributeError(name)

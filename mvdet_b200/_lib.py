@@ -45,6 +45,9 @@ SIGNATURES = {
     "mvwarp_plan_create_from_grid": (C.c_int, [_F32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.POINTER(_P)]),
     "mvwarp_plan_destroy": (C.c_int, [_P]),
+    "mvwarp_plan_save": (C.c_int, [_P, C.c_char_p]),
+    "mvwarp_plan_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
+    "mvwarp_plan_matrices": (C.c_int, [_P, _F32P]),
     "mvwarp_plan_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "mvwarp_plan_device_grid": (C.c_int, [_P, _F32P, _P]),
     "mvwarp_warp_views_fwd": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, _P, _I64P, C.c_int, C.c_int,

@@ -48,6 +48,49 @@ def pack_conv1_weight(weight: torch.Tensor, num_views: int, channels: int, with_
     return packed.reshape(nb, N_OUT, KB).contiguous()
 
 
+def unpack_conv1_weight(wpack: torch.Tensor, num_views: int, channels: int, with_coord: bool = True) -> torch.Tensor:
+    """Inverse of :func:`pack_conv1_weight`: the packed blocks back to the reference's ``map_classifier.0.weight`` layout
+    ``[512, V*C(+2), 3, 3]`` (bf16 values, exact), e.g. to write a checkpoint the reference's ``main.py:121`` can load."""
+    V, Cc = int(num_views), int(channels)
+    ncb = Cc // KB
+    nb = V * ncb * 9 + (1 if with_coord else 0)
+    if Cc % KB or tuple(wpack.shape) != (nb, N_OUT, KB):
+        raise ValueError(f"wpack must be [{nb}, 512, 64] for V={V}, C={Cc}. Got {tuple(wpack.shape)}")
+    chunks = wpack.reshape(nb, N_OUT, 8, 8)
+    n_idx = torch.arange(N_OUT, device=wpack.device)[:, None]
+    pos = torch.arange(8, device=wpack.device)[None, :]
+    src = pos ^ (n_idx & 7)                                              # the XOR swizzle is its own inverse
+    blocks = torch.gather(chunks, 2, src[None, :, :, None].expand(nb, N_OUT, 8, 8)).reshape(nb, N_OUT, KB)
+    main = blocks[:V * ncb * 9].reshape(V, ncb, 9, N_OUT, KB).permute(3, 0, 1, 4, 2).reshape(N_OUT, V * Cc, 3, 3)
+    if not with_coord:
+        return main.contiguous()
+    cw = blocks[-1][:, :18].reshape(N_OUT, 9, 2).permute(0, 2, 1).reshape(N_OUT, 2, 3, 3)
+    return torch.cat([main, cw], dim=1).contiguous()
+
+
+def conv1_from_state_dict(state_dict, num_views: int, channels: int = 512, prefix: str = "map_classifier.0.",
+                          device=None):
+    """``(wpack, bias)`` for :func:`warp_conv1` from a reference checkpoint's state dict (``torch.load`` of the file
+    ``main.py:121`` saves / ``main.py:125`` loads: keys ``map_classifier.0.weight`` [512, V*C+2, 3, 3] and ``.bias`` [512]).
+    Keys with a DataParallel ``module.`` prefix are accepted too."""
+    def find(name):
+        for k in (prefix + name, "module." + prefix + name):
+            if k in state_dict:
+                return state_dict[k]
+        raise KeyError(f"{prefix + name} not in the state dict")
+    w, b = find("weight"), find("bias")
+    if device is not None:
+        w, b = w.to(device), b.to(device)
+    return pack_conv1_weight(w, num_views, channels, with_coord=True), b.detach().float().contiguous()
+
+
+def conv1_to_state_dict(wpack: torch.Tensor, bias: torch.Tensor, num_views: int, channels: int = 512,
+                        prefix: str = "map_classifier.0.", dtype=torch.float32):
+    """The two reference state-dict entries back from the packed weight (values are the bf16-rounded ones)."""
+    return {prefix + "weight": unpack_conv1_weight(wpack, num_views, channels).to(dtype),
+            prefix + "bias": bias.detach().to(dtype).clone()}
+
+
 class _WarpConv1Fn(torch.autograd.Function):
     """Training wrapper: fused forward; the backward re-materialises the warped tensor (0.12 ms at the Wildtrack shape)
     and runs cuDNN's convolution backward and ``warp_views``' deterministic backward."""

@@ -73,6 +73,16 @@ struct DevCsr {
   std::vector<uint32_t> task_base, heavy_base;  // host copies, [V+1]
 };
 
+// Byte offsets of one CSR's arrays inside the plan's single device allocation (also the layout of a saved plan).
+struct CsrLayout {
+  uint64_t rows_per_view = 0;
+  uint64_t row_ptr = 0, row_id = 0, entries = 0, view_base = 0, tasks = 0, heavy = 0, heavy_base = 0;
+};
+struct PlanLayout {
+  uint64_t T = 0, grid = 0, coord_x = 0, coord_y = 0;
+  CsrLayout bwd, fwd;
+};
+
 }  // namespace mvw
 
 // The plan: immutable after creation.
@@ -91,6 +101,8 @@ struct mvwarp_plan {
   float* d_coord_x = nullptr;      // [Wg]  coord_map channel 0 along x
   float* d_coord_y = nullptr;      // [Hg]  coord_map channel 1 along y
   mvw::DevCsr bwd, fwd;
+  mvw::PlanLayout layout;          // where everything lives inside d_base (mvwarp_plan_save / _load)
+  std::vector<float> h_T;          // host copy of the matrices (inline mode), for mvwarp_plan_matrices
   mvwarp_stats_t stats{};
 };
 

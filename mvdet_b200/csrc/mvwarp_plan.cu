@@ -6,7 +6,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <stdio.h>
+
 #include <algorithm>
+#include <memory>
 #include <new>
 #include <thread>
 
@@ -308,6 +311,26 @@ static void fill_stats(mvwarp_stats_t& st, const PlanMaps& maps, int V, int Hs, 
   st.fwd_tasks = maps.fwd.task_base.empty() ? 0 : maps.fwd.task_base[V];
 }
 
+// Device pointers of a plan from its layout (shared by plan creation and mvwarp_plan_load).
+static void bind_pointers(mvwarp_plan* p) {
+  char* base = (char*)p->d_base;
+  const PlanLayout& L = p->layout;
+  p->d_T = (float*)(base + L.T);
+  p->d_grid = p->inline_coords ? nullptr : (float*)(base + L.grid);
+  p->d_coord_x = (float*)(base + L.coord_x);
+  p->d_coord_y = (float*)(base + L.coord_y);
+  auto bind = [&](DevCsr& d, const CsrLayout& o) {
+    if (o.rows_per_view == 0) return;
+    d.rows_per_view = (uint32_t)o.rows_per_view;
+    d.row_ptr = (uint32_t*)(base + o.row_ptr); d.row_id = (uint32_t*)(base + o.row_id);
+    d.entries = (CsrEntry*)(base + o.entries); d.view_base = (uint64_t*)(base + o.view_base);
+    d.tasks = (Task*)(base + o.tasks); d.heavy = (uint32_t*)(base + o.heavy);
+    d.heavy_base_dev = (uint32_t*)(base + o.heavy_base);
+  };
+  bind(p->bwd, L.bwd);
+  bind(p->fwd, L.fwd);
+}
+
 static int plan_create_impl(const float* T, const float* grid_in, int V, int hl, int wl, int Hs, int Ws, int Hg, int Wg,
                             int device, mvwarp_plan_t** plan_out) {
   if (!plan_out || (!T && !grid_in)) {
@@ -355,42 +378,39 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int hl,
     // carve one allocation
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    struct CsrOff { size_t rp, id, en, vb, tk, hv, hb; };
     auto carve_csr = [&](const HostCsr& c) {
-      CsrOff o{};
+      CsrLayout o{};
       if (c.rows_per_view == 0) return o;
-      o.rp = carve(c.row_ptr.size() * sizeof(uint32_t));
-      o.id = carve(c.row_id.size() * sizeof(uint32_t));
-      o.en = carve(c.entries.size() * sizeof(CsrEntry));
-      o.vb = carve(c.view_base.size() * sizeof(uint64_t));
-      o.tk = carve(c.tasks.size() * sizeof(Task));
-      o.hv = carve(c.heavy.size() * sizeof(uint32_t));
-      o.hb = carve(c.heavy_base.size() * sizeof(uint32_t));
+      o.rows_per_view = c.rows_per_view;
+      o.row_ptr = carve(c.row_ptr.size() * sizeof(uint32_t));
+      o.row_id = carve(c.row_id.size() * sizeof(uint32_t));
+      o.entries = carve(c.entries.size() * sizeof(CsrEntry));
+      o.view_base = carve(c.view_base.size() * sizeof(uint64_t));
+      o.tasks = carve(c.tasks.size() * sizeof(Task));
+      o.heavy = carve(c.heavy.size() * sizeof(uint32_t));
+      o.heavy_base = carve(c.heavy_base.size() * sizeof(uint32_t));
       return o;
     };
-    const size_t o_T = carve((size_t)V * 9 * sizeof(float));
-    const size_t o_grid = carve(T ? 0 : (size_t)V * ncell * 2 * sizeof(float));
-    const size_t o_cx = carve(Wg * sizeof(float)), o_cy = carve(Hg * sizeof(float));
-    const CsrOff ob = carve_csr(maps.bwd), of = carve_csr(maps.fwd);
+    PlanLayout& L = p->layout;
+    L.T = carve((size_t)V * 9 * sizeof(float));
+    L.grid = carve(T ? 0 : (size_t)V * ncell * 2 * sizeof(float));
+    L.coord_x = carve(Wg * sizeof(float));
+    L.coord_y = carve(Hg * sizeof(float));
+    L.bwd = carve_csr(maps.bwd);
+    L.fwd = carve_csr(maps.fwd);
     p->d_bytes = off;
     e = cudaMalloc(&p->d_base, p->d_bytes);
     if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(plan)"); }
-    char* base = (char*)p->d_base;
-    p->d_T = (float*)(base + o_T);
-    p->d_grid = T ? nullptr : (float*)(base + o_grid);
-    p->d_coord_x = (float*)(base + o_cx);
-    p->d_coord_y = (float*)(base + o_cy);
+    p->bwd.task_base = maps.bwd.task_base; p->bwd.heavy_base = maps.bwd.heavy_base;
+    p->fwd.task_base = maps.fwd.task_base; p->fwd.heavy_base = maps.fwd.heavy_base;
+    if (T) p->h_T.assign(T, T + (size_t)V * 9);
+    bind_pointers(p);
 
     auto up = [&](void* dst, const void* src, size_t bytes) {
       if (e == cudaSuccess && bytes) e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
     };
-    auto up_csr = [&](DevCsr& d, const HostCsr& c, const CsrOff& o) {
+    auto up_csr = [&](DevCsr& d, const HostCsr& c) {
       if (c.rows_per_view == 0) return;
-      d.rows_per_view = (uint32_t)c.rows_per_view;
-      d.row_ptr = (uint32_t*)(base + o.rp); d.row_id = (uint32_t*)(base + o.id);
-      d.entries = (CsrEntry*)(base + o.en); d.view_base = (uint64_t*)(base + o.vb);
-      d.tasks = (Task*)(base + o.tk); d.heavy = (uint32_t*)(base + o.hv); d.heavy_base_dev = (uint32_t*)(base + o.hb);
-      d.task_base = c.task_base; d.heavy_base = c.heavy_base;
       up(d.row_ptr, c.row_ptr.data(), c.row_ptr.size() * sizeof(uint32_t));
       up(d.row_id, c.row_id.data(), c.row_id.size() * sizeof(uint32_t));
       up(d.entries, c.entries.data(), c.entries.size() * sizeof(CsrEntry));
@@ -399,12 +419,13 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int hl,
       up(d.heavy, c.heavy.data(), c.heavy.size() * sizeof(uint32_t));
       up(d.heavy_base_dev, c.heavy_base.data(), c.heavy_base.size() * sizeof(uint32_t));
     };
+    e = cudaMemset(p->d_base, 0, p->d_bytes);  // alignment gaps are part of a saved plan's checksum
     if (T) up(p->d_T, T, (size_t)V * 9 * sizeof(float));
-    else { e = cudaMemset(p->d_T, 0, (size_t)V * 9 * sizeof(float)); up(p->d_grid, grid, (size_t)V * ncell * 2 * sizeof(float)); }
+    else up(p->d_grid, grid, (size_t)V * ncell * 2 * sizeof(float));
     up(p->d_coord_x, cx.data(), Wg * sizeof(float));
     up(p->d_coord_y, cy.data(), Hg * sizeof(float));
-    up_csr(p->bwd, maps.bwd, ob);
-    up_csr(p->fwd, maps.fwd, of);
+    up_csr(p->bwd, maps.bwd);
+    up_csr(p->fwd, maps.fwd);
     if (e != cudaSuccess) { cudaFree(p->d_base); delete p; return cuda_fail(e, "plan upload"); }
 
     fill_stats(p->stats, maps, V, Hs, Ws, Hg, Wg, p->hl, p->wl);
@@ -493,6 +514,182 @@ int mvwarp_plan_create_upsampled(const float* T, int V, int hl, int wl, int Hs, 
   if (hl <= 0 || wl <= 0) { set_error("plan_create_upsampled: low-res size must be positive"); return MVWARP_EINVAL; }
   if ((uint64_t)hl * wl >= (1ull << 31)) { set_error("plan_create_upsampled: low-res image too large"); return MVWARP_EUNSUPPORTED; }
   return plan_create_impl(T, nullptr, V, hl, wl, Hs, Ws, Hg, Wg, device, plan_out);
+}
+
+// ---- plan persistence ----------------------------------------------------------------------
+// File = PlanFileHeader | bwd task_base[V+1] | bwd heavy_base[V+1] | fwd task_base[V+1] | fwd heavy_base[V+1] (fused
+// up-sample plans only) | matrices [V*9] (inline plans only) | the device allocation, byte for byte.
+namespace {
+struct PlanFileHeader {
+  char magic[8];             // "MVWPLAN1"
+  uint32_t header_bytes;     // sizeof(PlanFileHeader): a struct change invalidates old files
+  uint32_t abi_version;      // MVWARP_VERSION
+  uint32_t task_budget, task_max_rows, heavy_len, csr_tile;  // work decomposition baked into the tasks
+  int32_t V, Hs, Ws, Hg, Wg, hl, wl, upsampled, inline_coords, has_fwd;
+  uint64_t d_bytes;
+  uint64_t blob_fnv1a;       // FNV-1a 64 of the device blob
+  mvw::PlanLayout layout;
+  mvwarp_stats_t stats;
+};
+const char kMagic[8] = {'M', 'V', 'W', 'P', 'L', 'A', 'N', '1'};
+
+uint64_t fnv1a64(const unsigned char* p, size_t n) {
+  // 8 bytes per step (word-wise FNV variant): a checksum against truncation / bit rot, not a cryptographic hash
+  uint64_t h = 1469598103934665603ull;
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    h = (h ^ w) * 1099511628211ull;
+  }
+  for (; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+  return h;
+}
+
+struct FileCloser {
+  FILE* f;
+  ~FileCloser() { if (f) fclose(f); }
+};
+}  // namespace
+
+int mvwarp_plan_save(const mvwarp_plan_t* plan, const char* path) {
+  if (!plan || !path) { set_error("plan_save: null argument"); return MVWARP_EINVAL; }
+  try {
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    std::vector<unsigned char> blob(plan->d_bytes);
+    cudaError_t e = cudaMemcpy(blob.data(), plan->d_base, plan->d_bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "plan_save: device -> host copy");
+    PlanFileHeader h;
+    memset((void*)&h, 0, sizeof(h));  // padding bytes are written to the file too
+    memcpy(h.magic, kMagic, 8);
+    h.header_bytes = sizeof(PlanFileHeader);
+    h.abi_version = MVWARP_VERSION;
+    h.task_budget = TASK_BUDGET; h.task_max_rows = TASK_MAX_ROWS; h.heavy_len = HEAVY_LEN; h.csr_tile = CSR_TILE;
+    h.V = plan->V; h.Hs = plan->Hs; h.Ws = plan->Ws; h.Hg = plan->Hg; h.Wg = plan->Wg; h.hl = plan->hl; h.wl = plan->wl;
+    h.upsampled = plan->upsampled; h.inline_coords = plan->inline_coords;
+    h.has_fwd = plan->fwd.rows_per_view ? 1 : 0;
+    h.d_bytes = plan->d_bytes;
+    h.blob_fnv1a = fnv1a64(blob.data(), blob.size());
+    h.layout = plan->layout;
+    h.stats = plan->stats;
+    const std::string tmp = std::string(path) + ".tmp";
+    {
+      FileCloser fc{fopen(tmp.c_str(), "wb")};
+      if (!fc.f) { set_error(std::string("plan_save: cannot open ") + tmp); return MVWARP_EINVAL; }
+      bool ok = fwrite(&h, sizeof(h), 1, fc.f) == 1;
+      auto put = [&](const std::vector<uint32_t>& v) {
+        ok = ok && v.size() == (size_t)plan->V + 1 && fwrite(v.data(), sizeof(uint32_t), v.size(), fc.f) == v.size();
+      };
+      put(plan->bwd.task_base); put(plan->bwd.heavy_base);
+      if (h.has_fwd) { put(plan->fwd.task_base); put(plan->fwd.heavy_base); }
+      if (h.inline_coords) ok = ok && plan->h_T.size() == (size_t)plan->V * 9 &&
+                                fwrite(plan->h_T.data(), sizeof(float), plan->h_T.size(), fc.f) == plan->h_T.size();
+      ok = ok && fwrite(blob.data(), 1, blob.size(), fc.f) == blob.size();
+      ok = ok && fflush(fc.f) == 0;
+      if (!ok) { set_error(std::string("plan_save: write to ") + tmp + " failed"); remove(tmp.c_str()); return MVWARP_EINVAL; }
+    }
+    if (rename(tmp.c_str(), path) != 0) {  // atomic replace: concurrent ranks may save the same rig
+      set_error(std::string("plan_save: cannot rename to ") + path);
+      remove(tmp.c_str());
+      return MVWARP_EINVAL;
+    }
+    return MVWARP_OK;
+  } catch (const std::bad_alloc&) {
+    set_error("plan_save: host allocation failed");
+    return MVWARP_ENOMEM;
+  }
+}
+
+int mvwarp_plan_load(const char* path, int device, mvwarp_plan_t** plan_out) {
+  if (!path || !plan_out) { set_error("plan_load: null argument"); return MVWARP_EINVAL; }
+  *plan_out = nullptr;
+  try {
+    FileCloser fc{fopen(path, "rb")};
+    if (!fc.f) { set_error(std::string("plan_load: cannot open ") + path); return MVWARP_EINVAL; }
+    PlanFileHeader h;
+    if (fread(&h, sizeof(h), 1, fc.f) != 1 || memcmp(h.magic, kMagic, 8) != 0) {
+      set_error(std::string("plan_load: ") + path + " is not a plan file");
+      return MVWARP_EINVAL;
+    }
+    if (h.header_bytes != sizeof(PlanFileHeader) || h.abi_version != MVWARP_VERSION || h.task_budget != TASK_BUDGET ||
+        h.task_max_rows != TASK_MAX_ROWS || h.heavy_len != HEAVY_LEN || h.csr_tile != CSR_TILE) {
+      set_error(std::string("plan_load: ") + path + " was written by an incompatible library build; rebuild the plan");
+      return MVWARP_EUNSUPPORTED;
+    }
+    int rc = check_shapes(h.V, h.Hs, h.Ws, h.Hg, h.Wg);
+    if (rc) return rc;
+    if (h.d_bytes == 0 || h.d_bytes > (1ull << 40)) { set_error("plan_load: implausible plan size"); return MVWARP_EINVAL; }
+    std::unique_ptr<mvwarp_plan> p(new mvwarp_plan());
+    p->device = device;
+    p->V = h.V; p->Hs = h.Hs; p->Ws = h.Ws; p->Hg = h.Hg; p->Wg = h.Wg; p->hl = h.hl; p->wl = h.wl;
+    p->upsampled = h.upsampled; p->inline_coords = h.inline_coords;
+    p->layout = h.layout;
+    p->stats = h.stats;
+    p->d_bytes = h.d_bytes;
+    bool ok = true;
+    auto get = [&](std::vector<uint32_t>& v) {
+      v.resize((size_t)h.V + 1);
+      ok = ok && fread(v.data(), sizeof(uint32_t), v.size(), fc.f) == v.size();
+    };
+    get(p->bwd.task_base); get(p->bwd.heavy_base);
+    if (h.has_fwd) { get(p->fwd.task_base); get(p->fwd.heavy_base); }
+    if (h.inline_coords) {
+      p->h_T.resize((size_t)h.V * 9);
+      ok = ok && fread(p->h_T.data(), sizeof(float), p->h_T.size(), fc.f) == p->h_T.size();
+    }
+    std::vector<unsigned char> blob(h.d_bytes);
+    ok = ok && fread(blob.data(), 1, blob.size(), fc.f) == blob.size();
+    if (!ok) { set_error(std::string("plan_load: ") + path + " is truncated"); return MVWARP_EINVAL; }
+    if (fnv1a64(blob.data(), blob.size()) != h.blob_fnv1a) {
+      set_error(std::string("plan_load: checksum mismatch in ") + path);
+      return MVWARP_EINVAL;
+    }
+    // every array must lie inside the blob (a corrupt header must not become a wild device pointer)
+    const uint64_t nrows_b = h.layout.bwd.rows_per_view, nrows_f = h.layout.fwd.rows_per_view;
+    auto inside = [&](uint64_t off, uint64_t bytes) { return off <= h.d_bytes && bytes <= h.d_bytes - off; };
+    auto csr_ok = [&](const CsrLayout& o, const std::vector<uint32_t>& tb, const std::vector<uint32_t>& hb) {
+      if (o.rows_per_view == 0) return true;
+      return inside(o.row_ptr, (uint64_t)h.V * (o.rows_per_view + 1) * 4) && inside(o.row_id, (uint64_t)h.V * o.rows_per_view * 4) &&
+             inside(o.view_base, ((uint64_t)h.V + 1) * 8) && inside(o.tasks, (uint64_t)tb.back() * sizeof(Task)) &&
+             inside(o.heavy, (uint64_t)hb.back() * 4) && inside(o.heavy_base, ((uint64_t)h.V + 1) * 4) && inside(o.entries, 0);
+    };
+    if (!inside(h.layout.T, (uint64_t)h.V * 36) || !inside(h.layout.coord_x, (uint64_t)h.Wg * 4) ||
+        !inside(h.layout.coord_y, (uint64_t)h.Hg * 4) || nrows_b == 0 || (h.has_fwd != 0) != (nrows_f != 0) ||
+        !csr_ok(h.layout.bwd, p->bwd.task_base, p->bwd.heavy_base) ||
+        (h.has_fwd && !csr_ok(h.layout.fwd, p->fwd.task_base, p->fwd.heavy_base)) ||
+        (!h.inline_coords && !inside(h.layout.grid, (uint64_t)h.V * h.Hg * h.Wg * 8))) {
+      set_error(std::string("plan_load: inconsistent layout in ") + path);
+      return MVWARP_EINVAL;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    p->num_sms = prop.multiProcessorCount;
+    e = cudaMalloc(&p->d_base, p->d_bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(plan)");
+    e = cudaMemcpy(p->d_base, blob.data(), p->d_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(p->d_base); return cuda_fail(e, "plan_load: upload"); }
+    bind_pointers(p.get());
+    p->stats.device_bytes = p->d_bytes;
+    *plan_out = p.release();
+    return MVWARP_OK;
+  } catch (const std::bad_alloc&) {
+    set_error("plan_load: host allocation failed");
+    return MVWARP_ENOMEM;
+  }
+}
+
+int mvwarp_plan_matrices(const mvwarp_plan_t* plan, float* T_out) {
+  if (!plan || !T_out) { set_error("plan_matrices: null argument"); return MVWARP_EINVAL; }
+  if (!plan->inline_coords || plan->h_T.size() != (size_t)plan->V * 9) {
+    set_error("plan_matrices: the plan was built from an explicit grid, it has no matrices");
+    return MVWARP_EUNSUPPORTED;
+  }
+  memcpy(T_out, plan->h_T.data(), plan->h_T.size() * sizeof(float));
+  return MVWARP_OK;
 }
 
 int mvwarp_plan_destroy(mvwarp_plan_t* plan) {

@@ -15,6 +15,8 @@ Plans are cached per (matrix bytes, shapes, device).
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
+import os
 import threading
 import weakref
 from typing import Dict, Sequence, Tuple
@@ -137,6 +139,17 @@ class WarpPlan:
         """Spatial size of the feature tensors the kernels read / write gradients for."""
         return (self.stats["lowres_h"], self.stats["lowres_w"]) if self.upsampled else self.src_hw
 
+    def matrices(self) -> torch.Tensor:
+        """fp32 [V,3,3] ``src_norm_trans_dst_norm`` matrices the plan was built from (not for explicit-grid plans)."""
+        out = torch.empty(self.V, 3, 3, dtype=torch.float32)
+        _lib.check(_lib.load().mvwarp_plan_matrices(self._handle, _fptr(out)), "mvwarp_plan_matrices")
+        return out
+
+    def save(self, path: str) -> None:
+        """Write the device-resident plan to ``path`` (store it next to the calibration, so a
+        start-up costs one file read + one H2D copy instead of the host builder: 0.1 s Wildtrack, 1.7 s 32-camera rig)."""
+        _lib.check(_lib.load().mvwarp_plan_save(self._handle, os.fsencode(path)), "mvwarp_plan_save")
+
     def device_grid(self) -> torch.Tensor:
         """Normalised grid [V,Hg,Wg,2] as the DEVICE computes it (test hook)."""
         Hg, Wg = self.grid_hw
@@ -169,8 +182,46 @@ def _device_index(device) -> torch.device:
     return device
 
 
-def get_plan(proj_mats: torch.Tensor, src_hw: Sequence[int], grid_shape: Sequence[int], device) -> WarpPlan:
-    """Plan for homographies ``proj_mats`` [V,3,3] (source pixel -> grid pixel), cached."""
+def load_plan(path: str, device, expect_matrices: torch.Tensor = None) -> WarpPlan:
+    """Re-create a plan saved with :meth:`WarpPlan.save` on ``device``.  The library refuses truncated / corrupt files
+    and files from an incompatible build.  ``expect_matrices`` (fp32 [V,3,3] ``src_norm_trans_dst_norm``) makes the
+    load fail unless the stored rig is bit-for-bit that one."""
+    device = _device_index(device)
+    handle = C.c_void_p()
+    _lib.check(_lib.load().mvwarp_plan_load(os.fsencode(path), device.index, C.byref(handle)), "mvwarp_plan_load")
+    plan = WarpPlan(handle, device, ("file", os.path.abspath(path), device.index))
+    if expect_matrices is not None:
+        want = expect_matrices.detach().to("cpu").float().contiguous()
+        if tuple(want.shape) != (plan.V, 3, 3) or not torch.equal(plan.matrices(), want):
+            raise _lib.MvwarpError(f"{path} holds the plan of a different camera rig")
+    return plan
+
+
+def _disk_cached(key: tuple, T: torch.Tensor, shapes: tuple, device: torch.device, cache_dir, build):
+    """Plan from ``cache_dir`` (or $MVWARP_PLAN_DIR) if a matching file is there, else built and stored there."""
+    cache_dir = cache_dir or os.environ.get("MVWARP_PLAN_DIR")
+    if not cache_dir:
+        return build()
+    name = hashlib.sha1(repr(key[:-1]).encode()).hexdigest()[:20] + ".mvwplan"
+    path = os.path.join(cache_dir, name)
+    if os.path.exists(path):
+        try:
+            plan = load_plan(path, device, expect_matrices=T)
+            st = plan.stats
+            if (st["Hs"], st["Ws"], st["Hg"], st["Wg"], st["lowres_h"], st["lowres_w"]) == shapes:
+                plan.key = key
+                return plan
+        except _lib.MvwarpError:
+            pass                      # stale or foreign file: rebuild and overwrite
+    plan = build()
+    os.makedirs(cache_dir, exist_ok=True)
+    plan.save(path)
+    return plan
+
+
+def get_plan(proj_mats: torch.Tensor, src_hw: Sequence[int], grid_shape: Sequence[int], device, cache_dir: str = None) -> WarpPlan:
+    """Plan for homographies ``proj_mats`` [V,3,3] (source pixel -> grid pixel), cached in the process and, with
+    ``cache_dir`` (or $MVWARP_PLAN_DIR), on disk."""
     device = _device_index(device)
     src_hw = (int(src_hw[0]), int(src_hw[1]))
     dst_hw = (int(grid_shape[0]), int(grid_shape[1]))
@@ -181,18 +232,21 @@ def get_plan(proj_mats: torch.Tensor, src_hw: Sequence[int], grid_shape: Sequenc
     if plan is not None:
         return plan
     T = src_norm_trans_dst_norm(m32, src_hw, dst_hw)
-    handle = C.c_void_p()
-    lib = _lib.load()
-    _lib.check(lib.mvwarp_plan_create(_fptr(T), T.shape[0], src_hw[0], src_hw[1], dst_hw[0], dst_hw[1],
-                                      device.index, C.byref(handle)), "mvwarp_plan_create")
-    plan = WarpPlan(handle, device, key)
+
+    def build():
+        handle = C.c_void_p()
+        _lib.check(_lib.load().mvwarp_plan_create(_fptr(T), T.shape[0], src_hw[0], src_hw[1], dst_hw[0], dst_hw[1],
+                                                  device.index, C.byref(handle)), "mvwarp_plan_create")
+        return WarpPlan(handle, device, key)
+
+    plan = _disk_cached(key, T, (*src_hw, *dst_hw, 0, 0), device, cache_dir, build)
     with _cache_lock:
         plan = _cache.setdefault(key, plan)
     return plan
 
 
 def get_plan_upsampled(proj_mats: torch.Tensor, lowres_hw: Sequence[int], upsample_hw: Sequence[int],
-                       grid_shape: Sequence[int], device) -> WarpPlan:
+                       grid_shape: Sequence[int], device, cache_dir: str = None) -> WarpPlan:
     """Plan for ``warp(F.interpolate(feats[.., hl, wl], upsample_hw, mode='bilinear'))`` as ONE sparse operator on
     the low-res feature map (persp_trans_detector.py:65 + :68-69).  ``proj_mats`` are the
     reference's matrices for the up-sampled (``upsample_hw``) feature map, unchanged."""
@@ -207,11 +261,15 @@ def get_plan_upsampled(proj_mats: torch.Tensor, lowres_hw: Sequence[int], upsamp
     if plan is not None:
         return plan
     T = src_norm_trans_dst_norm(m32, src_hw, dst_hw)
-    handle = C.c_void_p()
-    _lib.check(_lib.load().mvwarp_plan_create_upsampled(_fptr(T), T.shape[0], low[0], low[1], src_hw[0], src_hw[1],
-                                                        dst_hw[0], dst_hw[1], device.index, C.byref(handle)),
-               "mvwarp_plan_create_upsampled")
-    plan = WarpPlan(handle, device, key)
+
+    def build():
+        handle = C.c_void_p()
+        _lib.check(_lib.load().mvwarp_plan_create_upsampled(_fptr(T), T.shape[0], low[0], low[1], src_hw[0], src_hw[1],
+                                                            dst_hw[0], dst_hw[1], device.index, C.byref(handle)),
+                   "mvwarp_plan_create_upsampled")
+        return WarpPlan(handle, device, key)
+
+    plan = _disk_cached(key, T, (*src_hw, *dst_hw, *low), device, cache_dir, build)
     with _cache_lock:
         plan = _cache.setdefault(key, plan)
     return plan

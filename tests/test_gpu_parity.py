@@ -323,3 +323,102 @@ def test_upsampled_plan_ragged_channels():
         out = mv.warp_views_upsampled(xd, src_hw, pm, grid_hw)
         (gx,) = torch.autograd.grad(out, xd, go.to(DEV))
         assert max(rel_errors(out, ref)) <= TOL and max(rel_errors(gx, gref)) <= TOL
+
+
+# ---- ablation variants through the kornia-signature seam ---------------------------
+@pytest.mark.parametrize("C,strided", [(3, False), (1, True), (512, False)], ids=["image_proj_C3", "res_proj_C1", "no_joint_conv_C512"])
+def test_ablation_variant_shapes(C, strided):
+    """The calls pinned by tests/test_reference_integration.py::test_ablation_variants_call_the_same_seam:
+    image_proj_variant.py:69 warps the 3-channel image, res_proj_variant.py:72 warps ``img_res[:, 1].unsqueeze(1)`` (one
+    channel, a strided slice of a 2-channel tensor), no_joint_conv_variant.py:68 the 512-channel features; all NCHW."""
+    spec = WILDTRACK
+    pm = synthetic_rig(spec)
+    B, cam = 2, 4
+    if strided:
+        full = _feats(B, 1, 2, spec.feat_shape, seed=2)[:, 0]            # img_res [B,2,H,W]
+        src = full[:, 1].unsqueeze(1)
+        src_dev = full.to(DEV)[:, 1].unsqueeze(1)
+        assert not src_dev.is_contiguous()
+    else:
+        src = _feats(B, 1, C, spec.feat_shape, seed=2)[:, 0] if C <= 3 else _feats(1, 1, C, spec.feat_shape, seed=2)[:, 0]
+        src_dev = src.to(DEV)
+    Bc = src.shape[0]
+    proj_mat = pm[cam].repeat([Bc, 1, 1]).float()
+    so = src.clone().requires_grad_(True)
+    ref = K.warp_perspective(so, proj_mat, list(spec.grid_shape))
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(4))
+    (gref,) = torch.autograd.grad(ref, so, go)
+    sd = src_dev.detach().requires_grad_(True)
+    out = ops.warp_perspective(sd, proj_mat.to(DEV), list(spec.grid_shape))
+    assert out.shape == ref.shape == (Bc, C, *spec.grid_shape)
+    assert bit_equal_fraction(out, ref) == 1.0
+    (gx,) = torch.autograd.grad(out, sd, go.to(DEV))
+    emax, el2 = rel_errors(gx, gref)
+    assert emax <= TOL and el2 <= TOL, (emax, el2)
+
+
+def test_image_proj_variant_full_resolution_grid():
+    """C = 3 onto the un-reduced 480x1440 ground grid (SURVEY.md 8f rank 4's small-C edge at grid_reduce = 1)."""
+    spec = RIG32
+    pm = synthetic_rig(spec)[[3, 20]]
+    x = _feats(1, 2, 3, spec.feat_shape, seed=6)
+    ref = K.warp_views_oracle(x, pm, spec.grid_shape)
+    out = mv.warp_views(x.to(DEV), pm, spec.grid_shape)
+    assert bit_equal_fraction(out, ref) == 1.0
+
+
+# ---- plan persistence (SURVEY.md 8f rank 3) -----------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["plain", "upsampled"])
+def test_saved_plan_reproduces_the_built_plan(tmp_path, kind):
+    pm, src_hw, grid_hw = small_rig()
+    low = (src_hw[0] // 3, src_hw[1] // 3)
+    if kind == "plain":
+        plan = P.get_plan(pm, src_hw, grid_hw, DEV)
+        feat_hw = src_hw
+    else:
+        plan = P.get_plan_upsampled(pm, low, src_hw, grid_hw, DEV)
+        feat_hw = low
+    path = str(tmp_path / "rig.mvwplan")
+    plan.save(path)
+    T = P.src_norm_trans_dst_norm(pm, src_hw, grid_hw)
+    loaded = P.load_plan(path, DEV, expect_matrices=T)
+    assert loaded.stats == plan.stats
+    assert torch.equal(loaded.matrices(), T)
+    x = to_channels_last_5d(_feats(2, 3, 24, feat_hw)).to(DEV).requires_grad_(True)
+    a = ops.warp_views_with_plan(x, plan)
+    b = ops.warp_views_with_plan(x, loaded)
+    assert torch.equal(a, b)
+    go = torch.randn_like(a)
+    (ga,) = torch.autograd.grad(a, x, go)
+    (gb,) = torch.autograd.grad(b, x, go)
+    assert torch.equal(ga, gb)
+    # wrong rig, corrupt payload
+    with pytest.raises(mv.MvwarpError):
+        P.load_plan(path, DEV, expect_matrices=T.flip(0))
+    blob = bytearray(open(path, "rb").read())
+    blob[-100] ^= 0x40
+    bad = str(tmp_path / "bad.mvwplan")
+    open(bad, "wb").write(bytes(blob))
+    with pytest.raises(mv.MvwarpError, match="checksum"):
+        P.load_plan(bad, DEV)
+    open(bad, "wb").write(bytes(blob[:len(blob) // 2]))
+    with pytest.raises(mv.MvwarpError, match="truncated"):
+        P.load_plan(bad, DEV)
+
+
+def test_plan_disk_cache(tmp_path):
+    pm, src_hw, grid_hw = small_rig(seed=11)
+    P.clear_plan_cache()
+    p1 = P.get_plan(pm, src_hw, grid_hw, DEV, cache_dir=str(tmp_path))
+    files = list(tmp_path.iterdir())
+    assert len(files) == 1 and files[0].suffix == ".mvwplan"
+    P.clear_plan_cache()
+    p2 = P.get_plan(pm, src_hw, grid_hw, DEV, cache_dir=str(tmp_path))       # comes from the file
+    assert p2 is not p1 and p2.stats == p1.stats
+    x = to_channels_last_5d(_feats(1, 3, 8, src_hw)).to(DEV)
+    assert torch.equal(ops.warp_views_with_plan(x, p1), ops.warp_views_with_plan(x, p2))
+    files[0].write_bytes(b"garbage")                                        # a broken cache entry is rebuilt, not trusted
+    P.clear_plan_cache()
+    p3 = P.get_plan(pm, src_hw, grid_hw, DEV, cache_dir=str(tmp_path))
+    assert p3.stats == p1.stats and files[0].stat().st_size > 1000
+    P.clear_plan_cache()

@@ -214,3 +214,49 @@ def test_conv1_weight_packing_layout():
     assert bool((unsw[:, 18:] == 0).all())
     with pytest.raises(ValueError):
         pack_conv1_weight(w, V, C + 64)
+
+
+def test_conv1_weight_roundtrip_and_reference_state_dict():
+    """the reference checkpoint layout (main.py:121/125: map_classifier.0.weight [512, V*C+2, 3, 3],
+    .bias [512]) goes into the packed GEMM layout and comes back exactly (bf16 values)."""
+    from mvdet_b200.conv1 import conv1_from_state_dict, conv1_to_state_dict, pack_conv1_weight, unpack_conv1_weight
+    V, C = 3, 64
+    g = torch.Generator().manual_seed(3)
+    sd = {"map_classifier.0.weight": torch.randn(512, V * C + 2, 3, 3, generator=g),
+          "map_classifier.0.bias": torch.randn(512, generator=g),
+          "map_classifier.2.weight": torch.randn(4, 4)}
+    wpack, bias = conv1_from_state_dict(sd, V, C)
+    assert torch.equal(wpack, pack_conv1_weight(sd["map_classifier.0.weight"], V, C))
+    assert torch.equal(unpack_conv1_weight(wpack, V, C), sd["map_classifier.0.weight"].bfloat16())
+    back = conv1_to_state_dict(wpack, bias, V, C)
+    assert torch.equal(back["map_classifier.0.weight"], sd["map_classifier.0.weight"].bfloat16().float())
+    assert torch.equal(back["map_classifier.0.bias"], sd["map_classifier.0.bias"])
+    # DataParallel-style keys, view shards without the coord block
+    wp2, _ = conv1_from_state_dict({"module." + k: v for k, v in sd.items()}, V, C)
+    assert torch.equal(wp2, wpack)
+    shard = pack_conv1_weight(sd["map_classifier.0.weight"][:, C:2 * C], 1, C, with_coord=False)
+    assert torch.equal(unpack_conv1_weight(shard, 1, C, with_coord=False), sd["map_classifier.0.weight"][:, C:2 * C].bfloat16())
+    with pytest.raises(KeyError):
+        conv1_from_state_dict({}, V, C)
+    with pytest.raises(ValueError):
+        unpack_conv1_weight(wpack, V + 1, C)
+
+
+def test_plan_load_refuses_bad_files(tmp_path):
+    """mvwarp_plan_load must fail cleanly (error code + message, no CUDA call) on missing, foreign and truncated files."""
+    import ctypes as C
+    from mvdet_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.mvwarp_plan_load(str(tmp_path / "missing.mvwplan").encode(), 0, C.byref(h)) == _lib.EINVAL
+    assert b"cannot open" in lib.mvwarp_last_error()
+    junk = tmp_path / "junk.mvwplan"
+    junk.write_bytes(b"not a plan" * 100)
+    assert lib.mvwarp_plan_load(str(junk).encode(), 0, C.byref(h)) == _lib.EINVAL
+    assert b"not a plan file" in lib.mvwarp_last_error()
+    short = tmp_path / "short.mvwplan"
+    short.write_bytes(b"MVWPLAN1" + b"\0" * 16)
+    assert lib.mvwarp_plan_load(str(short).encode(), 0, C.byref(h)) == _lib.EINVAL
+    assert not h.value
+    assert lib.mvwarp_plan_save(None, b"/tmp/x") == _lib.EINVAL
+    assert lib.mvwarp_plan_matrices(None, None) == _lib.EINVAL

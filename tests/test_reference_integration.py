@@ -73,6 +73,7 @@ def reference_model(monkeypatch):
     from multiview_detector.models.persp_trans_detector import PerspTransDetector
     torch.manual_seed(0)
     model = PerspTransDetector(_fake_dataset(), arch="resnet18").eval()
+    model._calls = calls
     return model, calls
 
 
@@ -113,3 +114,29 @@ def test_reference_forward_through_the_seams(reference_model):
         assert world.shape == (B, 512 * ds.num_cam + 2, 24, 72)
         map_new = F.interpolate(model.map_classifier(world), model.reducedgrid_shape, mode="bilinear")
     assert torch.equal(map_new, map_ref)
+
+
+@pytest.mark.parametrize("variant,cls,shape,contig", [
+    ("image_proj_variant", "ImageProjVariant", (2, 3, 54, 96), True),       # warps the RGB image itself: C = 3
+    ("res_proj_variant", "ResProjVariant", (2, 1, 54, 96), False),          # warps img_res[:, 1].unsqueeze(1): C = 1, a strided slice
+    ("no_joint_conv_variant", "NoJointConvVariant", (2, 512, 54, 96), True),
+])
+def test_ablation_variants_call_the_same_seam(reference_model, variant, cls, shape, contig):
+    """the three ablation models reach the warp through the alias kornia.warp_perspective
+    (image_proj_variant.py:69, res_proj_variant.py:72, no_joint_conv_variant.py:68) with C = 3 / 1 / 512; pin what they
+    pass, so the GPU tests of the seam (tests/test_gpu_parity.py::test_ablation_variant_shapes) use the same calls."""
+    import importlib
+    _, calls = reference_model                      # fixture installs the stubs and the cuda->cpu redirection
+    mod = importlib.import_module("multiview_detector.models." + variant)
+    ds = _fake_dataset()
+    torch.manual_seed(0)
+    model = getattr(mod, cls)(ds, arch="resnet18").eval()
+    del calls[:]
+    imgs = torch.randn(2, ds.num_cam, 3, 144, 256, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        map_res, _ = model(imgs)
+    assert map_res.shape == (2, 1, 24, 72)
+    assert len(calls) == ds.num_cam
+    for got_shape, dtype, is_contig, mshape, mdtype, dsize, args, kwargs in calls:
+        assert got_shape == shape and dtype == torch.float32 and is_contig == contig
+        assert mshape == (2, 3, 3) and mdtype == torch.float32 and dsize == [24, 72] and not args and not kwargs
