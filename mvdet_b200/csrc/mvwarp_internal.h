@@ -71,11 +71,12 @@ struct DevCsr {
   uint32_t* heavy = nullptr;
   uint32_t* heavy_base_dev = nullptr;
   std::vector<uint32_t> task_base, heavy_base;  // host copies, [V+1]
+  uint32_t max_row = 0;                         // longest row (host copy)
 };
 
 // Byte offsets of one CSR's arrays inside the plan's single device allocation (also the layout of a saved plan).
 struct CsrLayout {
-  uint64_t rows_per_view = 0;
+  uint64_t rows_per_view = 0, max_row = 0;
   uint64_t row_ptr = 0, row_id = 0, entries = 0, view_base = 0, tasks = 0, heavy = 0, heavy_base = 0;
 };
 struct PlanLayout {

@@ -608,6 +608,121 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, MINB)
   csr_gather_body<T, false, FULLC, DENSE, true>(p, task_lo, task_hi, heavy_lo, n_heavy, view_lo, heavy_base, part);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// forward of fused up-sample plans, tile version (channels-last).
+//
+// The forward table has short rows (<= 16 low-res taps per grid cell, 5.4 on average at the Wildtrack shape) and no
+// heavy ones, so the warp-task machinery of the backward is overhead here: a task's row pointers, ids and entries are
+// three dependent global round trips in front of ~5 cells of work.  This kernel works like fwd_cl_kernel instead:
+// a CTA owns TBL_ROWS consecutive rows of the tile-major row order (= one 8x8 cell tile on grids that are multiples
+// of 8), phase 1 brings the rows' pointers, cell ids and ALL their entries into shared memory with coalesced loads
+// (entries of consecutive rows are contiguous), phase 2 runs one warp per cell: lanes across channels, four entries
+// x UNROLL 128-bit gathers in flight per lane, fp32 FMAs in entry order (same summation order, hence the same bits,
+// as the task kernel), streaming store into the view's channel slice of the concat row.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TBL_ROWS = 64, TBL_MAX_ENT = TBL_ROWS * 16, TBL_NE = 4;
+
+template <typename T, int UNROLL, int ALIGN, bool FULLC>
+__device__ __forceinline__ void table_cell(const T* __restrict__ gs, const int64_t* __restrict__ soff, const float* __restrict__ sw,
+                                           int n, T* __restrict__ o, int nvec, int lane) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  const T* gl = gs + lane * EPV;
+  T* ol = o + lane * EPV;
+  for (int c0 = 0; c0 < nvec; c0 += 32 * UNROLL) {
+    float acc[UNROLL][EPV];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) acc[u][e] = 0.f;
+    for (int e0 = 0; e0 < n; e0 += TBL_NE) {   // n is warp-uniform
+      uint4 val[TBL_NE][UNROLL];
+      float w[TBL_NE];
+#pragma unroll
+      for (int i = 0; i < TBL_NE; ++i) {
+        const bool on = e0 + i < n;
+        const int k = on ? e0 + i : e0;
+        const T* row = gl + soff[k];               // shared-memory broadcast
+        w[i] = sw[k];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const int c = c0 + 32 * u;
+          val[i][u] = (on && (FULLC || c + lane < nvec)) ? ldg16(row + c * EPV) : make_uint4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TBL_NE; ++i) {
+        if (e0 + i < n) {
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) {
+            float f[EPV];
+            VecTraits<T>::unpack(val[i][u], f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) acc[u][e] = __fmaf_rn(w[i], f[e], acc[u][e]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int c = c0 + 32 * u;
+      if (FULLC || c + lane < nvec) stcs16<ALIGN>(ol + c * EPV, VecTraits<T>::pack(acc[u]));
+    }
+  }
+}
+
+template <typename T, int UNROLL, int MINB, bool FULLC>
+__global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_table_tile_kernel(const KParams p) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  __shared__ uint32_t s_rp[TBL_ROWS + 1];
+  __shared__ uint32_t s_id[TBL_ROWS];
+  __shared__ int64_t s_off[TBL_MAX_ENT];
+  __shared__ float s_w[TBL_MAX_ENT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vl = blockIdx.x, v = p.view0 + vl, b = blockIdx.z;   // view fastest: the V slices of a concat row are written together
+  const uint32_t row0 = blockIdx.y * TBL_ROWS;
+  const int nrows = min((uint32_t)TBL_ROWS, p.rows_per_view - row0);
+  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (p.rows_per_view + 1) + row0;
+  if (threadIdx.x <= nrows) s_rp[threadIdx.x] = __ldg(rp + threadIdx.x);
+  if (threadIdx.x < nrows) {
+    const uint32_t id = __ldg(p.row_id + (size_t)v * p.rows_per_view + row0 + threadIdx.x);
+    s_id[threadIdx.x] = id;
+    if (p.coord_chan >= 0 && vl == 0) write_coord<T>(p, b, id);
+  }
+  __syncthreads();
+  const uint32_t e_begin = s_rp[0], e_end = s_rp[nrows];
+  const uint2* __restrict__ en = reinterpret_cast<const uint2*>(p.entries + __ldg(p.view_base + v)) + e_begin;
+  const bool dense = p.gsrc.H == (int64_t)p.gsrc.width * p.gsrc.W;
+  for (uint32_t k = threadIdx.x; k < e_end - e_begin; k += blockDim.x) {
+    const uint2 e = __ldg(en + k);
+    int64_t off;
+    if (dense) {
+      off = (int64_t)e.x * p.gsrc.W;
+    } else {
+      const int cy = e.x / p.gsrc.width, cx = e.x - cy * p.gsrc.width;
+      off = (int64_t)cy * p.gsrc.H + (int64_t)cx * p.gsrc.W;
+    }
+    s_off[k] = off;
+    s_w[k] = __uint_as_float(e.y);
+  }
+  __syncthreads();
+
+  const T* __restrict__ gs = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.gsrc.B + (int64_t)vl * p.gsrc.V + p.gsrc.chan0;
+  T* __restrict__ gd = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.gdst.B + (int64_t)vl * p.gdst.V + p.gdst.chan0;
+  const int nvec = p.C / EPV;
+  // round i: the 8 warps take 8 consecutive rows (horizontally adjacent cells of the tile), like fwd_cl_kernel
+  for (int i = warp; i < nrows; i += FWD_WARPS) {
+    const uint32_t a = s_rp[i] - e_begin;
+    const int n = (int)(s_rp[i + 1] - s_rp[i]);
+    const uint32_t id = s_id[i];
+    const int yd = id / p.gdst.width, xd = id - yd * p.gdst.width;
+    T* o = gd + (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
+    const unsigned oal = (unsigned)(reinterpret_cast<uintptr_t>(o) & 15u);  // warp-uniform
+    if (oal == 0) table_cell<T, UNROLL, 16, FULLC>(gs, s_off + a, s_w + a, n, o, nvec, lane);
+    else if ((oal & 7u) == 0) table_cell<T, UNROLL, 8, FULLC>(gs, s_off + a, s_w + a, n, o, nvec, lane);
+    else table_cell<T, UNROLL, 4, FULLC>(gs, s_off + a, s_w + a, n, o, nvec, lane);
+  }
+}
+
 // CSR gather, arbitrary strides: thread per CSR row (tile-major order), a chunk of GEN_CH channels per thread
 constexpr int GEN_CH = 16;
 template <typename T, bool COORD>
@@ -745,7 +860,21 @@ static int launch_gather_t(const LaunchArgs& a, KParams& p, const DevCsr& csr, b
     if (fullc && dense) KERNEL<T, __VA_ARGS__, true, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev); \
     else KERNEL<T, __VA_ARGS__, false, false><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev);             \
   } while (0)
-    if (FORWARD) {
+    if (FORWARD && sizeof(T) == 4 && csr.max_row <= 16 && h_hi == h_lo && tuning_variant("MVWARP_TBL_VARIANT", 0) != 1) {
+      // short rows only (always true for fused up-sample plans: <= 16 low-res taps per cell): tile kernel.  fp32 only:
+      // measured at the Wildtrack shape, fp32 0.230 -> 0.209 ms against the task kernel, bf16 0.160 -> 0.165 ms (spills)
+      const uint32_t nblk = (csr.rows_per_view + TBL_ROWS - 1) / TBL_ROWS;
+      if (nblk > 65535) { set_error("warp_views_fwd (table): more than 65535 row blocks per view"); return MVWARP_EUNSUPPORTED; }
+      dim3 tgrid(a.nviews, nblk, a.B), tblock(FWD_WARPS * 32);
+      const bool tfull = (a.C / EPV) % 64 == 0;
+#define MVW_TBL(U, M)                                                                     \
+  do {                                                                                    \
+    if (tfull) fwd_table_tile_kernel<T, U, M, true><<<tgrid, tblock, 0, a.stream>>>(p);    \
+    else fwd_table_tile_kernel<T, U, M, false><<<tgrid, tblock, 0, a.stream>>>(p);         \
+  } while (0)
+      MVW_TBL(2, 4);
+#undef MVW_TBL
+    } else if (FORWARD) {
       if (sizeof(T) == 2) MVW_GATHER(fwd_table_cl_kernel, 4);
       else MVW_GATHER(fwd_table_cl_kernel, 3);
     } else {

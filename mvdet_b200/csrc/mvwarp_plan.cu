@@ -322,6 +322,7 @@ static void bind_pointers(mvwarp_plan* p) {
   auto bind = [&](DevCsr& d, const CsrLayout& o) {
     if (o.rows_per_view == 0) return;
     d.rows_per_view = (uint32_t)o.rows_per_view;
+    d.max_row = (uint32_t)o.max_row;
     d.row_ptr = (uint32_t*)(base + o.row_ptr); d.row_id = (uint32_t*)(base + o.row_id);
     d.entries = (CsrEntry*)(base + o.entries); d.view_base = (uint64_t*)(base + o.view_base);
     d.tasks = (Task*)(base + o.tasks); d.heavy = (uint32_t*)(base + o.heavy);
@@ -382,6 +383,7 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int hl,
       CsrLayout o{};
       if (c.rows_per_view == 0) return o;
       o.rows_per_view = c.rows_per_view;
+      o.max_row = c.max_row;
       o.row_ptr = carve(c.row_ptr.size() * sizeof(uint32_t));
       o.row_id = carve(c.row_id.size() * sizeof(uint32_t));
       o.entries = carve(c.entries.size() * sizeof(CsrEntry));
