@@ -174,6 +174,30 @@ int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int nviews, cons
                           const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0, int nrows,
                           void* stream);
 
+/* The same with a choice of output dtype (MVWARP_F32 or MVWARP_BF16): bf16 feeds mvwarp_conv3x3_fwd below. */
+int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
+                             const int64_t feat_strides[5], const void* wpack, const float* bias, void* out, int out_dtype,
+                             const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0, int nrows,
+                             void* stream);
+
+/* ---- the rest of map_classifier (persp_trans_detector.py:53-54, applied at :81) -------------
+ * mvwarp_conv3x3_fwd: out = [relu](conv2d(x, W, bias, padding = dilation, dilation = dilation)) for a 3x3 kernel with
+ * 512 output channels -- map_classifier[2] = Conv2d(512, 512, 3, padding=2, dilation=2) + ReLU -- as a tcgen05 implicit
+ * GEMM whose A operand is fetched by TMA tensor copies (one [8 rows][16 cells][64 channels] box per tap and channel
+ * block, zero padding = the TMA unit's out-of-bounds fill).
+ *   x:     bf16, logical [B, Cin, H, W] channels-last (stride C == 1), Cin % 64 == 0; x_strides = (B, C, H, W) in elements.
+ *   wpack: the reference weight [512, Cin, 3, 3] packed by mvdet_b200.map_head.pack_conv3x3_weight (= pack_conv1_weight
+ *          for one "view" without the coord block): [Cin/64 * 9][512][64] bf16, rows carrying the 128-byte swizzle.
+ *   out:   [B, 512, H, W] channels-last, out_dtype MVWARP_F32 or MVWARP_BF16.  fp32 accumulation in TMEM.
+ * mvwarp_conv3x3_head_fwd: out[b, y, x] = sum_{tap, c} w[tap][c] * x[b, c, y + (tap/3-1)*d, x + (tap%3-1)*d], zero padded
+ * -- map_classifier[4] = Conv2d(512, 1, 3, padding=4, dilation=4, bias=False); w = bf16 [9][Cin] (tap-major), out fp32
+ * [B, 1, H, W] (strides given as (B, C, H, W)).  Memory-bound: plain CUDA cores, fp32 accumulation. */
+int mvwarp_conv3x3_fwd(const void* x, const int64_t x_strides[4], const void* wpack, const float* bias, void* out,
+                       const int64_t out_strides[4], int B, int H, int W, int Cin, int dilation, int relu, int out_dtype,
+                       int device, void* stream);
+int mvwarp_conv3x3_head_fwd(const void* x, const int64_t x_strides[4], const void* w, float* out, const int64_t out_strides[4],
+                            int B, int H, int W, int Cin, int dilation, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

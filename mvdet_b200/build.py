@@ -8,7 +8,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmvwarp.so")
-SOURCES = ["mvwarp_plan.cu", "mvwarp_kernels.cu", "mvwarp_conv1.cu"]
+SOURCES = ["mvwarp_plan.cu", "mvwarp_kernels.cu", "mvwarp_conv1.cu", "mvwarp_conv2.cu"]
 HEADERS = ["mvwarp_coords.h", "mvwarp_internal.h", "mvwarp_umma.h", os.path.join("..", "..", "include", "mvwarp.h")]
 
 NVCC_FLAGS = [

@@ -135,11 +135,13 @@ def warp_conv1_trainable(img_feats: torch.Tensor, weight: torch.Tensor, bias: Op
 
 def warp_conv1(img_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Sequence[int], wpack: torch.Tensor,
                bias: Optional[torch.Tensor] = None, relu: bool = True, with_coord: bool = True,
-               out: Optional[torch.Tensor] = None, rows: Optional[Sequence[int]] = None) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, rows: Optional[Sequence[int]] = None,
+               out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """relu(conv3x3(warp_views(img_feats, proj_mats, grid_shape), W) + bias) as one fused kernel (forward only).
 
     img_feats [B,V,C,H,W] bf16 CUDA, channel-contiguous; wpack from :func:`pack_conv1_weight`; bias fp32 [512] or None.
-    Returns fp32 [B,512,Hg,Wg] (channels-last).  ``out`` re-uses a result tensor; ``rows=(y0, y1)`` computes only the grid
+    Returns [B,512,Hg,Wg] (channels-last) in ``out_dtype``: fp32, or bf16 to feed :func:`mvdet_b200.map_head.conv3x3_cl`
+    (map_classifier[2]) directly.  ``out`` re-uses a result tensor; ``rows=(y0, y1)`` computes only the grid
     rows [y0, y1) of it (y0 a multiple of 8), which is how the sharded path overlaps the reduce of one band with the GEMM
     of the next."""
     if not img_feats.is_cuda:
@@ -152,18 +154,21 @@ def warp_conv1(img_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Seq
         raise ValueError(f"wpack must be a contiguous bf16 [{nblocks}, 512, 64] tensor from pack_conv1_weight")
     plan = get_plan(proj_mats, (Hs, Ws), grid_shape, img_feats.device)
     Hg, Wg = plan.grid_hw
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("warp_conv1 writes fp32 or bf16")
     if out is None:
-        out = torch.empty((B, Hg, Wg, N_OUT), dtype=torch.float32, device=img_feats.device).permute(0, 3, 1, 2)
-    elif tuple(out.shape) != (B, N_OUT, Hg, Wg) or out.dtype != torch.float32 or out.stride(1) != 1:
-        raise ValueError("out must be a channels-last fp32 [B,512,Hg,Wg] tensor")
+        out = torch.empty((B, Hg, Wg, N_OUT), dtype=out_dtype, device=img_feats.device).permute(0, 3, 1, 2)
+    elif tuple(out.shape) != (B, N_OUT, Hg, Wg) or out.dtype != out_dtype or out.stride(1) != 1:
+        raise ValueError(f"out must be a channels-last {out_dtype} [B,512,Hg,Wg] tensor")
     row0, nrows = (int(rows[0]), int(rows[1]) - int(rows[0])) if rows is not None else (0, 0)
     bias_ptr = None
     if bias is not None:
         bias = bias.detach().to(device=img_feats.device, dtype=torch.float32).contiguous()
         bias_ptr = C.c_void_p(bias.data_ptr())
     stream = C.c_void_p(torch.cuda.current_stream(img_feats.device).cuda_stream)
-    rc = _lib.load().mvwarp_warp_conv1_fwd(plan.handle, 0, V, C.c_void_p(img_feats.data_ptr()), _lib.i64x(img_feats.stride()),
-                                           C.c_void_p(wpack.data_ptr()), bias_ptr, C.c_void_p(out.data_ptr()),
-                                           _lib.i64x(out.stride()), B, Cc, int(relu), int(with_coord), row0, nrows, stream)
+    rc = _lib.load().mvwarp_warp_conv1_fwd_ex(plan.handle, 0, V, C.c_void_p(img_feats.data_ptr()), _lib.i64x(img_feats.stride()),
+                                              C.c_void_p(wpack.data_ptr()), bias_ptr, C.c_void_p(out.data_ptr()),
+                                              _lib.BF16 if out_dtype == torch.bfloat16 else _lib.F32,
+                                              _lib.i64x(out.stride()), B, Cc, int(relu), int(with_coord), row0, nrows, stream)
     _lib.check(rc, "mvwarp_warp_conv1_fwd")
     return out

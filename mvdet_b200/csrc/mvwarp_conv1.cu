@@ -127,8 +127,9 @@ struct ConvParams {
   int64_t fB, fV, fH, fW;
   const __nv_bfloat16* wpack;  // [nviews * C/64 * 9 (+1 coord block)][512][64] bf16, rows pre-swizzled
   const float* bias;           // [512] or nullptr
-  float* out;                  // [B, Hg, Wg, 512] fp32 (logical [B,512,Hg,Wg] channels-last)
-  int64_t oB, oH, oW;
+  void* out;                   // [B, Hg, Wg, 512] fp32 or bf16 (logical [B,512,Hg,Wg] channels-last)
+  int64_t oB, oH, oW;          // in elements of the output dtype
+  int out_bf16;
   int relu, with_coord, tiles_x, tiles_y;
   int tile0, ntiles;           // this launch covers tiles [tile0, tile0 + ntiles) (a band of tile rows)
   unsigned long long* stats;   // development: per CTA {cycles waiting for A, for B, total} of the MMA thread, or nullptr
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(128) warp_conv1_kernel(const ConvParams p) {
   // epilogue: thread = tile cell = TMEM lane; 512 fp32 columns in chunks of 32
   const int gy = ty0 + my, gx = tx0 + mx;
   const bool inside = gy < p.Hg && gx < p.Wg;
-  float* orow = p.out + (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW;
+  float* orow = reinterpret_cast<float*>(p.out) + (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW;   // fp32 output only
 #pragma unroll 1
   for (int c0 = 0; c0 < CV_N; c0 += 32) {
     float vv[32];
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
     const int er = (warp & 3) * 32 + lane, ey = er / CT_W, ex = er % CT_W;
     const int gy = ty0 + ey, gx = tx0 + ex;
     const bool inside = real_tile && gy < p.Hg && gx < p.Wg;
-    float* orow = p.out + (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW;
+    const int64_t ooff = (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW;
     const int cbeg = (warp >> 2) * 256;
 #pragma unroll 1
     for (int c0 = cbeg; c0 < cbeg + 256; c0 += 32) {
@@ -546,11 +547,20 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
       tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, vv);
       if (inside) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 o = make_float4(vv[i], vv[i + 1], vv[i + 2], vv[i + 3]);
-          if (p.bias) { o.x += __ldg(p.bias + c0 + i); o.y += __ldg(p.bias + c0 + i + 1); o.z += __ldg(p.bias + c0 + i + 2); o.w += __ldg(p.bias + c0 + i + 3); }
-          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          *reinterpret_cast<float4*>(orow + c0 + i) = o;
+        for (int i = 0; i < 32; ++i) {
+          if (p.bias) vv[i] += __ldg(p.bias + c0 + i);
+          if (p.relu) vv[i] = fmaxf(vv[i], 0.f);
+        }
+        if (p.out_bf16) {   // feeds the tcgen05 conv of map_classifier[2] (mvwarp_conv2.cu), which reads bf16 boxes
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            o[i] = make_uint4(pack_bf2(vv[8 * i], vv[8 * i + 1]), pack_bf2(vv[8 * i + 2], vv[8 * i + 3]),
+                              pack_bf2(vv[8 * i + 4], vv[8 * i + 5]), pack_bf2(vv[8 * i + 6], vv[8 * i + 7]));
+        } else {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ooff + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
         }
       }
     }
@@ -566,7 +576,16 @@ extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int n
                                      const int64_t feat_strides[5], const void* wpack, const float* bias, float* out,
                                      const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0, int nrows,
                                      void* stream) {
+  return mvwarp_warp_conv1_fwd_ex(plan, view0, nviews, feats, feat_strides, wpack, bias, out, MVWARP_F32, out_strides, B, C, relu,
+                                  with_coord, row0, nrows, stream);
+}
+
+extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
+                                        const int64_t feat_strides[5], const void* wpack, const float* bias, void* out, int out_dtype,
+                                        const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0, int nrows,
+                                        void* stream) {
   using namespace mvw;
+  if (out_dtype != MVWARP_F32 && out_dtype != MVWARP_BF16) { set_error("warp_conv1_fwd: unknown output dtype"); return MVWARP_EINVAL; }
   if (!plan || !feats || !feat_strides || !wpack || !out || !out_strides) { set_error("warp_conv1_fwd: null argument"); return MVWARP_EINVAL; }
   if (B <= 0 || nviews <= 0 || view0 < 0 || view0 + nviews > plan->V) { set_error("warp_conv1_fwd: bad B / view range"); return MVWARP_EINVAL; }
   if (plan->upsampled || !plan->inline_coords) { set_error("warp_conv1_fwd: needs a plain matrix plan"); return MVWARP_EUNSUPPORTED; }
@@ -575,8 +594,9 @@ extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int n
     set_error("warp_conv1_fwd: feats must be bf16 channels-last with C % 64 == 0 and 16-byte aligned texel rows");
     return MVWARP_EUNSUPPORTED;
   }
-  if (out_strides[1] != 1 || out_strides[0] % 4 || out_strides[2] % 4 || out_strides[3] % 4 || (reinterpret_cast<uintptr_t>(out) & 15u)) {
-    set_error("warp_conv1_fwd: out must be fp32 channels-last [B,512,Hg,Wg] with 16-byte aligned cell rows");
+  const int oal = out_dtype == MVWARP_BF16 ? 8 : 4;
+  if (out_strides[1] != 1 || out_strides[0] % oal || out_strides[2] % oal || out_strides[3] % oal || (reinterpret_cast<uintptr_t>(out) & 15u)) {
+    set_error("warp_conv1_fwd: out must be channels-last [B,512,Hg,Wg] with 16-byte aligned cell rows");
     return MVWARP_EUNSUPPORTED;
   }
   int prev = -1;
@@ -588,7 +608,7 @@ extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int n
   p.view0 = view0; p.nviews = nviews; p.C = C; p.B = B;
   p.feats = (const __nv_bfloat16*)feats;
   p.fB = feat_strides[0]; p.fV = feat_strides[1]; p.fH = feat_strides[3]; p.fW = feat_strides[4];
-  p.wpack = (const __nv_bfloat16*)wpack; p.bias = bias; p.out = out;
+  p.wpack = (const __nv_bfloat16*)wpack; p.bias = bias; p.out = out; p.out_bf16 = out_dtype == MVWARP_BF16;
   p.oB = out_strides[0]; p.oH = out_strides[2]; p.oW = out_strides[3];
   p.relu = relu; p.with_coord = with_coord;
   p.tiles_x = (plan->Wg + CT_W - 1) / CT_W; p.tiles_y = (plan->Hg + CT_H - 1) / CT_H;
@@ -602,7 +622,7 @@ extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int n
   p.ntiles = ((nrows + CT_H - 1) / CT_H) * p.tiles_x;
   cudaError_t e;
   const char* variant = getenv("MVWARP_CONV1_VARIANT");   // development knob: "simple" = the unpipelined validation kernel
-  if (variant && variant[0] == 's') {
+  if (variant && variant[0] == 's' && out_dtype == MVWARP_F32) {
     const int smem = 16384 + (int)CV_B_BYTES + CP_CELLS * 128 + CP_CELLS * (int)sizeof(ConvTap) + 1024;
     e = cudaFuncSetAttribute(warp_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) {

@@ -1,0 +1,320 @@
+// mvwarp_conv2.cu -- the rest of map_classifier behind the fused warp -> conv1:
+//   map_classifier[2] = Conv2d(512, 512, 3, padding=2, dilation=2) + ReLU     conv3x3_tc_kernel  (tcgen05 / TMEM / TMA)
+//   map_classifier[4] = Conv2d(512,   1, 3, padding=4, dilation=4, bias=False) conv3x3_head_kernel (memory-bound, no tensor cores)
+// (/root/reference/multiview_detector/models/persp_trans_detector.py:53-54, applied at :81).
+//
+// conv3x3_tc_kernel is an implicit GEMM like warp_conv1_pipe_kernel (M = an 8 x 16 tile of cells, N = 512 = all of
+// TMEM, K = 9 taps x Cin in blocks of 64), but here the A operand already exists in memory as a channels-last bf16
+// activation tensor, so nothing has to be produced: the K block of tap (dy, dx) and channel block cb is the BOX
+// [8 rows][16 cells][64 channels] of that tensor displaced by ((dy-1)*d, (dx-1)*d), which one TMA tensor copy
+// (cp.async.bulk.tensor.4d, SWIZZLE_128B) drops into shared memory in exactly the K-major layout the tensor core
+// reads; cells outside the image are the convolution's zero padding and come from the TMA unit's out-of-bounds fill.
+// Three single-thread roles (A boxes, packed weight blocks, MMA issue) and eight epilogue warps.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "mvwarp_internal.h"
+#include "mvwarp_umma.h"
+
+namespace mvw {
+using namespace umma;
+
+constexpr int C2_TH = 8, C2_TW = 16;              // cell tile = 128 GEMM rows
+constexpr int C2_N = 512, C2_KB = 64;
+constexpr uint32_t C2_A_BYTES = 128 * C2_KB * 2;  // 16 KB per A stage
+constexpr uint32_t C2_B_BYTES = C2_N * C2_KB * 2; // 64 KB per B stage
+constexpr int C2_PA = 4, C2_PB = 2;
+constexpr int C2_EPI = 256, C2_THREADS = C2_EPI + 96;   // 8 epilogue warps + MMA warp + weight warp + box warp
+
+struct Conv2Params {
+  const __nv_bfloat16* wpack;   // [Cin/64 * 9][512][64] bf16, rows pre-swizzled (pack_conv1_weight with one "view", no coord block)
+  const float* bias;            // [512] or nullptr
+  void* out;                    // [B, H, W, 512] bf16 or fp32 (logical [B,512,H,W] channels-last)
+  int64_t oB, oH, oW;           // in elements of the output dtype
+  int H, W, Cin, dilation, relu, out_bf16;
+  int tiles_x, tiles_y, ntiles;
+};
+
+// TMA tensor copy global -> shared, 4-D tile mode, completion on an mbarrier.  Coordinates innermost first and signed:
+// parts of the box outside the tensor are filled with zeros.
+__device__ __forceinline__ void tma_box_4d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+__device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const unsigned*>(&h);
+}
+
+template <int CL>
+__global__ void __launch_bounds__(C2_THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Conv2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                                // C2_PA x 16 KB
+  uint8_t* sB = smem + C2_PA * C2_A_BYTES;           // C2_PB x 64 KB
+  __shared__ __align__(8) uint64_t a_full[C2_PA], a_empty[C2_PA], b_full[C2_PB], b_empty[C2_PB], acc_full;
+  __shared__ uint32_t tmem_holder;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool real_tile = (int)blockIdx.x < p.ntiles;   // grid padded to a multiple of CL: a padding CTA redoes the last tile, stores nothing
+  const int tile = real_tile ? blockIdx.x : p.ntiles - 1;
+  const int tx0 = (tile % p.tiles_x) * C2_TW, ty0 = (tile / p.tiles_x) * C2_TH, b = blockIdx.z;
+  const int ncb = p.Cin / C2_KB;
+  const int NK = ncb * 9;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
+
+  if (warp == 0) tmem_alloc(&tmem_holder, C2_N);
+  if (tid == 0) {
+    for (int i = 0; i < C2_PA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C2_PB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL); }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  if (CL > 1) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+
+  if (warp == 10) {
+    // ===== A boxes: one TMA tensor copy per K block =====
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_x);
+      for (int kb = 0; kb < NK; ++kb) {
+        const int s = kb % C2_PA, cb = kb / 9, tap = kb % 9;
+        if (kb >= C2_PA) mbar_wait(&a_empty[s], ((kb / C2_PA) - 1) & 1);
+        mbar_expect_tx(&a_full[s], C2_A_BYTES);
+        tma_box_4d(sA + (size_t)s * C2_A_BYTES, &tmap_x, cb * C2_KB, tx0 + (tap % 3 - 1) * p.dilation, ty0 + (tap / 3 - 1) * p.dilation, b,
+                   &a_full[s]);
+      }
+    }
+  } else if (warp == 9) {
+    // ===== weight blocks: one bulk copy per K block (a 1/CL slice multicast to the cluster) =====
+    if (lane == 0) {
+      for (int kb = 0; kb < NK; ++kb) {
+        const int s = kb % C2_PB;
+        if (kb >= C2_PB) mbar_wait(&b_empty[s], ((kb / C2_PB) - 1) & 1);
+        mbar_expect_tx(&b_full[s], C2_B_BYTES);
+        if (CL == 1) {
+          bulk_g2s(sB + (size_t)s * C2_B_BYTES, p.wpack + (size_t)kb * (C2_N * C2_KB), C2_B_BYTES, &b_full[s]);
+        } else {
+          constexpr uint32_t SLICE = C2_B_BYTES / CL;
+          bulk_g2s_multicast(sB + (size_t)s * C2_B_BYTES + crank * SLICE,
+                             reinterpret_cast<const uint8_t*>(p.wpack + (size_t)kb * (C2_N * C2_KB)) + crank * SLICE, SLICE, &b_full[s], CMASK);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_f32(128, 256);
+      for (int kb = 0; kb < NK; ++kb) {
+        const int sa = kb % C2_PA, sb = kb % C2_PB;
+        mbar_wait(&a_full[sa], (kb / C2_PA) & 1);
+        mbar_wait(&b_full[sb], (kb / C2_PB) & 1);
+        tc_fence_after();
+        const uint32_t bbase = smem_u32(sB + (size_t)sb * C2_B_BYTES);
+        const uint64_t da = smem_desc_sw128(smem_u32(sA + (size_t)sa * C2_A_BYTES)), db0 = smem_desc_sw128(bbase),
+                       db1 = smem_desc_sw128(bbase + 256 * 128);
+#pragma unroll
+        for (int k = 0; k < C2_KB / 16; ++k) {
+          mma_bf16(tmem, da + 2 * k, db0 + 2 * k, idesc, kb > 0 || k > 0);
+          mma_bf16(tmem + 256, da + 2 * k, db1 + 2 * k, idesc, kb > 0 || k > 0);
+        }
+        mma_commit(&a_empty[sa]);
+        if (CL == 1) mma_commit(&b_empty[sb]);
+        else mma_commit_multicast(&b_empty[sb], CMASK);
+      }
+      mma_commit(&acc_full);
+    }
+  } else {
+    // ===== epilogue: thread = tile cell = TMEM lane (quarter warp % 4); warps 0-3 take channels 0-255, warps 4-7 256-511 =====
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const int er = (warp & 3) * 32 + lane, ey = er / C2_TW, ex = er % C2_TW;
+    const int gy = ty0 + ey, gx = tx0 + ex;
+    const bool inside = real_tile && gy < p.H && gx < p.W;
+    const int64_t ooff = (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW;
+    const int cbeg = (warp >> 2) * 256;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + 256; c0 += 32) {
+      float vv[32];
+      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, vv);
+      if (inside) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (p.bias) vv[i] += __ldg(p.bias + c0 + i);
+          if (p.relu) vv[i] = fmaxf(vv[i], 0.f);
+        }
+        if (p.out_bf16) {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            o[i] = make_uint4(pack_bf16x2(vv[8 * i], vv[8 * i + 1]), pack_bf16x2(vv[8 * i + 2], vv[8 * i + 3]),
+                              pack_bf16x2(vv[8 * i + 4], vv[8 * i + 5]), pack_bf16x2(vv[8 * i + 6], vv[8 * i + 7]));
+        } else {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ooff + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  if (CL > 1) cluster_sync(); else __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, C2_N);
+}
+
+// -----------------------------------------------------------------------------------------------------
+// map_classifier[4]: 512 -> 1 channel, 3x3, dilation d, no bias.  0.4 GFLOP per Wildtrack frame against 44 MB of
+// activations: memory-bound, so no tensor cores -- one warp per output cell, lanes across channels (128-bit loads of
+// the nine tap rows, the 9 x Cin weights staged in shared memory as fp32), warp-shuffle reduction, fp32 out.
+// -----------------------------------------------------------------------------------------------------
+constexpr int HD_WARPS = 8;
+
+__global__ void __launch_bounds__(HD_WARPS * 32) conv3x3_head_kernel(const __nv_bfloat16* __restrict__ x, int64_t xB, int64_t xH, int64_t xW,
+                                                                     const __nv_bfloat16* __restrict__ w /*[9][Cin]*/, float* __restrict__ out,
+                                                                     int64_t oB, int64_t oH, int64_t oW, int B, int H, int W, int Cin,
+                                                                     int dilation) {
+  extern __shared__ float sw[];   // [9][Cin]
+  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) sw[i] = __bfloat162float(w[i]);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ncell = (int64_t)B * H * W;
+  for (int64_t cell = (int64_t)blockIdx.x * HD_WARPS + warp; cell < ncell; cell += (int64_t)gridDim.x * HD_WARPS) {
+    const int b = (int)(cell / ((int64_t)H * W));
+    const int r = (int)(cell - (int64_t)b * H * W), y = r / W, xq = r - y * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + (tap / 3 - 1) * dilation, xx = xq + (tap % 3 - 1) * dilation;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;   // warp-uniform
+      const __nv_bfloat16* row = x + (int64_t)b * xB + (int64_t)yy * xH + (int64_t)xx * xW;
+      const float* wt = sw + tap * Cin;
+      for (int c = lane * 8; c < Cin; c += 256) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + c));
+        const unsigned q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc = __fmaf_rn(__uint_as_float(q[i] << 16), wt[c + 2 * i], acc);
+          acc = __fmaf_rn(__uint_as_float(q[i] & 0xffff0000u), wt[c + 2 * i + 1], acc);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[(int64_t)b * oB + (int64_t)y * oH + (int64_t)xq * oW] = acc;
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+}  // namespace mvw
+
+using namespace mvw;
+
+extern "C" int mvwarp_conv3x3_fwd(const void* x, const int64_t x_strides[4], const void* wpack, const float* bias, void* out,
+                                  const int64_t out_strides[4], int B, int H, int W, int Cin, int dilation, int relu, int out_dtype,
+                                  int device, void* stream) {
+  if (!x || !x_strides || !wpack || !out || !out_strides) { set_error("conv3x3_fwd: null argument"); return MVWARP_EINVAL; }
+  if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || dilation <= 0 || B > 65535) { set_error("conv3x3_fwd: bad B / H / W / Cin / dilation"); return MVWARP_EINVAL; }
+  if (out_dtype != MVWARP_F32 && out_dtype != MVWARP_BF16) { set_error("conv3x3_fwd: unknown output dtype"); return MVWARP_EINVAL; }
+  if (Cin % C2_KB || x_strides[1] != 1 || (reinterpret_cast<uintptr_t>(x) & 15u) || x_strides[0] % 8 || x_strides[2] % 8 || x_strides[3] % 8) {
+    set_error("conv3x3_fwd: x must be bf16 channels-last [B,Cin,H,W] with Cin % 64 == 0 and 16-byte aligned cell rows");
+    return MVWARP_EUNSUPPORTED;
+  }
+  const int oal = out_dtype == MVWARP_BF16 ? 8 : 4;
+  if (out_strides[1] != 1 || out_strides[0] % oal || out_strides[2] % oal || out_strides[3] % oal || (reinterpret_cast<uintptr_t>(out) & 15u)) {
+    set_error("conv3x3_fwd: out must be channels-last [B,512,H,W] with 16-byte aligned cell rows");
+    return MVWARP_EUNSUPPORTED;
+  }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("conv3x3_fwd: the driver does not export cuTensorMapEncodeTiled"); return MVWARP_EUNSUPPORTED; }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != device && cudaSetDevice(device) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+  auto restore = [&]() { if (prev >= 0 && prev != device) cudaSetDevice(prev); };
+
+  // x as a 4-D tensor, innermost first: (channel, x, y, batch); box = 64 channels x 16 cells x 8 rows x 1 frame
+  CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {(cuuint64_t)x_strides[3] * 2, (cuuint64_t)x_strides[2] * 2, (cuuint64_t)x_strides[0] * 2};
+  const cuuint32_t box[4] = {C2_KB, C2_TW, C2_TH, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    restore();
+    set_error("conv3x3_fwd: cuTensorMapEncodeTiled failed (code " + std::to_string((int)cr) + ")");
+    return MVWARP_ECUDA;
+  }
+  Conv2Params p{};
+  p.wpack = (const __nv_bfloat16*)wpack; p.bias = bias; p.out = out;
+  p.oB = out_strides[0]; p.oH = out_strides[2]; p.oW = out_strides[3];
+  p.H = H; p.W = W; p.Cin = Cin; p.dilation = dilation; p.relu = relu; p.out_bf16 = out_dtype == MVWARP_BF16;
+  p.tiles_x = (W + C2_TW - 1) / C2_TW; p.tiles_y = (H + C2_TH - 1) / C2_TH; p.ntiles = p.tiles_x * p.tiles_y;
+  const int smem = C2_PA * (int)C2_A_BYTES + C2_PB * (int)C2_B_BYTES + 1024;
+  const char* variant = getenv("MVWARP_CONV2_CLUSTER");   // development knob: 1 = no cluster
+  const int cl = (variant && variant[0] == '1') ? 1 : 2;
+  auto launch = [&](auto kernel, int cluster) -> cudaError_t {
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((p.ntiles + cluster - 1) / cluster * cluster, 1, B);
+    cfg.blockDim = dim3(C2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, tmap, p);
+  };
+  const cudaError_t e = cl == 1 ? launch(conv3x3_tc_kernel<1>, 1) : launch(conv3x3_tc_kernel<2>, 2);
+  restore();
+  return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "conv3x3_fwd launch");
+}
+
+extern "C" int mvwarp_conv3x3_head_fwd(const void* x, const int64_t x_strides[4], const void* w, float* out, const int64_t out_strides[4],
+                                       int B, int H, int W, int Cin, int dilation, int device, void* stream) {
+  if (!x || !x_strides || !w || !out || !out_strides) { set_error("conv3x3_head_fwd: null argument"); return MVWARP_EINVAL; }
+  if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || dilation <= 0) { set_error("conv3x3_head_fwd: bad B / H / W / Cin / dilation"); return MVWARP_EINVAL; }
+  if (Cin % 8 || x_strides[1] != 1 || (reinterpret_cast<uintptr_t>(x) & 15u) || x_strides[0] % 8 || x_strides[2] % 8 || x_strides[3] % 8 ||
+      9 * Cin * 4 > 200 * 1024) {
+    set_error("conv3x3_head_fwd: x must be bf16 channels-last [B,Cin,H,W] with Cin % 8 == 0 (Cin <= 5688) and 16-byte aligned cell rows");
+    return MVWARP_EUNSUPPORTED;
+  }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != device && cudaSetDevice(device) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+  const int smem = 9 * Cin * (int)sizeof(float);
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024) e = cudaFuncSetAttribute(conv3x3_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) {
+    const int64_t ncell = (int64_t)B * H * W;
+    const int grid = (int)std::min<int64_t>((ncell + HD_WARPS - 1) / HD_WARPS, 148 * 8);
+    conv3x3_head_kernel<<<grid, HD_WARPS * 32, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, x_strides[0], x_strides[2], x_strides[3],
+                                                                            (const __nv_bfloat16*)w, out, out_strides[0], out_strides[2],
+                                                                            out_strides[3], B, H, W, Cin, dilation);
+    e = cudaGetLastError();
+  }
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "conv3x3_head_fwd launch");
+}

@@ -118,3 +118,73 @@ def test_fused_conv1_trainable_gradients():
     assert rel_errors(gx.float(), gxr)[1] <= 5e-2
     assert rel_errors(gw, gwr)[1] <= 5e-2
     assert rel_errors(gb, gbr)[1] <= 5e-2
+
+
+# ---- the rest of map_classifier ---------------------------------------------------------
+@pytest.mark.parametrize("B,Cin,H,W,d,relu,odt", [(1, 64, 8, 16, 1, False, torch.float32), (2, 128, 24, 72, 2, True, torch.bfloat16),
+                                                  (1, 512, 30, 45, 2, True, torch.float32), (1, 64, 19, 33, 4, False, torch.float32)])
+def test_tcgen05_tma_conv3x3_matches_conv2d(B, Cin, H, W, d, relu, odt):
+    """conv3x3_cl (A operand by TMA boxes, zero padding by out-of-bounds fill) against F.conv2d in fp32 on the same
+    bf16-rounded operands; partial tiles in both directions, dilation 1 / 2 / 4."""
+    import torch.nn.functional as F
+    from mvdet_b200 import map_head as MH
+    from tests.util import rel_errors
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, Cin, H, W, generator=g).bfloat16()
+    w = (torch.randn(512, Cin, 3, 3, generator=g) * 0.05)
+    bias = torch.randn(512, generator=g)
+    ref = F.conv2d(x.float(), w.bfloat16().float(), bias, padding=d, dilation=d)
+    if relu:
+        ref = F.relu(ref)
+    out = MH.conv3x3_cl(x.cuda().contiguous(memory_format=torch.channels_last), MH.pack_conv3x3_weight(w).cuda(), bias, dilation=d,
+                        relu=relu, out_dtype=odt)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape and out.dtype == odt and out.stride(1) == 1
+    emax, el2 = rel_errors(out.float(), ref)
+    tol = 1e-4 if odt == torch.float32 else 6e-3      # bf16 output: one rounding of 2^-9 relative on each value
+    assert emax <= tol and el2 <= tol, (emax, el2)
+
+
+def test_conv3x3_head_matches_conv2d():
+    import torch.nn.functional as F
+    from mvdet_b200 import map_head as MH
+    from tests.util import rel_errors
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 512, 21, 35, generator=g).bfloat16()
+    w = torch.randn(1, 512, 3, 3, generator=g) * 0.05
+    ref = F.conv2d(x.float(), w.bfloat16().float(), None, padding=4, dilation=4)
+    out = MH.conv3x3_head(x.cuda().contiguous(memory_format=torch.channels_last), MH.pack_head_weight(w).cuda(), dilation=4)
+    assert out.shape == ref.shape
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= 1e-5 and el2 <= 1e-5, (emax, el2)
+
+
+def test_map_head_matches_the_reference_module():
+    """MapHead (fused warp->conv1 -> TMA conv -> head) against the reference's map_classifier built as a torch module
+    (persp_trans_detector.py:51-54) on the oracle's warp, with the same bf16 roundings of the activations."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from mvdet_b200.map_head import MapHead
+    from oracle import kornia_warp as K
+    from tests.util import small_rig, to_channels_last_5d, rel_errors
+    V, Cc = 2, 64
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=37)
+    torch.manual_seed(0)
+    ref_head = nn.Sequential(nn.Conv2d(Cc * V + 2, 512, 3, padding=1), nn.ReLU(),
+                             nn.Conv2d(512, 512, 3, padding=2, dilation=2), nn.ReLU(),
+                             nn.Conv2d(512, 1, 3, padding=4, dilation=4, bias=False))
+    sd = {"map_classifier." + k: v for k, v in ref_head.state_dict().items()}
+    x = torch.randn(2, V, Cc, *src_hw, generator=torch.Generator().manual_seed(1)).bfloat16()
+    bf = lambda t: t.bfloat16().float()
+    with torch.no_grad():
+        X = bf(K.warp_views_oracle(x.float(), pm, grid_hw))
+        a1 = bf(F.relu(F.conv2d(X, bf(ref_head[0].weight), ref_head[0].bias, padding=1)))
+        a2 = bf(F.relu(F.conv2d(a1, bf(ref_head[2].weight), ref_head[2].bias, padding=2, dilation=2)))
+        ref = F.conv2d(a2, bf(ref_head[4].weight), None, padding=4, dilation=4)
+    head = MapHead(sd, V, Cc, device="cuda:0")
+    out = head(to_channels_last_5d(x).cuda(), pm, grid_hw)
+    assert out.shape == ref.shape == (2, 1, *grid_hw)
+    # the two paths round the same activations to bf16 after sums taken in different orders: values within half an ulp of a
+    # rounding boundary flip, each flip is 2^-8 relative on one activation -> a few 1e-3 on the final map
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= 1e-2 and el2 <= 5e-3, (emax, el2)
