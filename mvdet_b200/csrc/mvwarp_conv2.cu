@@ -176,40 +176,85 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv3x3_tc_kernel(const __grid_
 // activations: memory-bound, so no tensor cores -- one warp per output cell, lanes across channels (128-bit loads of
 // the nine tap rows, the 9 x Cin weights staged in shared memory as fp32), warp-shuffle reduction, fp32 out.
 // -----------------------------------------------------------------------------------------------------
-constexpr int HD_WARPS = 8;
+constexpr int HD_WARPS = 8, HD_CELLS = 16;   // cells per warp: a column run (x fixed, rows `dilation` apart)
 
-__global__ void __launch_bounds__(HD_WARPS * 32) conv3x3_head_kernel(const __nv_bfloat16* __restrict__ x, int64_t xB, int64_t xH, int64_t xW,
-                                                                     const __nv_bfloat16* __restrict__ w /*[9][Cin]*/, float* __restrict__ out,
-                                                                     int64_t oB, int64_t oH, int64_t oW, int B, int H, int W, int Cin,
-                                                                     int dilation) {
-  extern __shared__ float sw[];   // [9][Cin]
-  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) sw[i] = __bfloat162float(w[i]);
-  __syncthreads();
+// A warp walks DOWN a column in steps of the dilation: cells (x, ph + d*j), j = j0 .. j0+15.  The three tap rows of cell j
+// (y-d, y, y+d) are then the rows of cells j-1, j, j+1, so a four-slot register window slides down the column: each step
+// loads ONE new tap row (3 taps x NTRIP 128-bit loads per lane, issued one step ahead) instead of three, and the other
+// two come from registers.  Lane l owns channels [8l, 8l+8) + 256 t, t < NTRIP = ceil(Cin / 256); its 9 x 8 x NTRIP
+// weights stay in registers as packed bf16 pairs.  Neighbouring warps take neighbouring columns, whose x +- d taps
+// overlap in L1.  (First version: warp per cell, nine rows per cell, weights read from shared memory: 5x slower.)
+template <int NTRIP>
+__global__ void __launch_bounds__(HD_WARPS * 32, 1) conv3x3_head_kernel(const __nv_bfloat16* __restrict__ x, int64_t xB, int64_t xH, int64_t xW,
+                                                                        const __nv_bfloat16* __restrict__ w /*[9][Cin]*/, float* __restrict__ out,
+                                                                        int64_t oB, int64_t oH, int64_t oW, int B, int H, int W, int Cin,
+                                                                        int dilation, int nblk) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ncell = (int64_t)B * H * W;
-  for (int64_t cell = (int64_t)blockIdx.x * HD_WARPS + warp; cell < ncell; cell += (int64_t)gridDim.x * HD_WARPS) {
-    const int b = (int)(cell / ((int64_t)H * W));
-    const int r = (int)(cell - (int64_t)b * H * W), y = r / W, xq = r - y * W;
-    float acc = 0.f;
+  // warp -> (batch, phase, run of the phase's rows, column); column fastest
+  int64_t wid = (int64_t)blockIdx.x * HD_WARPS + warp;
+  const int xq = (int)(wid % W); wid /= W;
+  const int jb = (int)(wid % nblk); wid /= nblk;
+  const int ph = (int)(wid % dilation);
+  const int64_t b = wid / dilation;
+  if (b >= B || ph >= H) return;
+  const int rows = (H - ph + dilation - 1) / dilation;   // cells of this phase in a column
+  const int j0 = jb * HD_CELLS, nj = min(HD_CELLS, rows - j0);
+  if (nj <= 0) return;
+
+  uint4 wt[NTRIP][9];   // packed bf16 pairs
+  bool act[NTRIP];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int yy = y + (tap / 3 - 1) * dilation, xx = xq + (tap % 3 - 1) * dilation;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;   // warp-uniform
-      const __nv_bfloat16* row = x + (int64_t)b * xB + (int64_t)yy * xH + (int64_t)xx * xW;
-      const float* wt = sw + tap * Cin;
-      for (int c = lane * 8; c < Cin; c += 256) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + c));
-        const unsigned q[4] = {v.x, v.y, v.z, v.w};
+  for (int t = 0; t < NTRIP; ++t) {
+    const int c = lane * 8 + 256 * t;
+    act[t] = c < Cin;   // Cin % 8 == 0: a lane's eight channels are all inside or all outside
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc = __fmaf_rn(__uint_as_float(q[i] << 16), wt[c + 2 * i], acc);
-          acc = __fmaf_rn(__uint_as_float(q[i] & 0xffff0000u), wt[c + 2 * i + 1], acc);
-        }
+    for (int tap = 0; tap < 9; ++tap)
+      wt[t][tap] = act[t] ? __ldg(reinterpret_cast<const uint4*>(w + (size_t)tap * Cin + c)) : make_uint4(0, 0, 0, 0);
+  }
+  const __nv_bfloat16* xb = x + b * xB + lane * 8;
+  uint4 win[4][3][NTRIP];   // [slot][dx][trip]
+  auto load_row = [&](uint4 (&dst)[3][NTRIP], int yy) {
+#pragma unroll
+    for (int dxi = 0; dxi < 3; ++dxi) {
+      const int xx = xq + (dxi - 1) * dilation;
+      const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;   // warp-uniform; outside = the conv's zero padding
+#pragma unroll
+      for (int t = 0; t < NTRIP; ++t)
+        dst[dxi][t] = (in && act[t]) ? __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)yy * xH + (int64_t)xx * xW + 256 * t)) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  const int y0 = ph + dilation * j0;
+  load_row(win[0], y0 - dilation);
+  load_row(win[1], y0);
+  load_row(win[2], y0 + dilation);
+  for (int jj = 0; jj < nj; jj += 4) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {   // jj % 4 == 0: the slot numbers below are compile-time constants
+      const int j = jj + r;
+      if (j < nj) {
+        const int y = y0 + dilation * j;
+        if (j + 1 < nj) load_row(win[(r + 3) & 3], y + 2 * dilation);   // bottom row of the NEXT cell, one step ahead
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent FMA chains (one chain of 144 would cost 4 cycles per FMA)
+#pragma unroll
+        for (int dyi = 0; dyi < 3; ++dyi)
+#pragma unroll
+          for (int dxi = 0; dxi < 3; ++dxi)
+#pragma unroll
+            for (int t = 0; t < NTRIP; ++t) {
+              const uint4 v = win[(r + dyi) & 3][dxi][t], q = wt[t][dyi * 3 + dxi];
+              const unsigned vu[4] = {v.x, v.y, v.z, v.w}, qu[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                a4[i] = __fmaf_rn(__uint_as_float(vu[i] << 16), __uint_as_float(qu[i] << 16), a4[i]);
+                a4[i] = __fmaf_rn(__uint_as_float(vu[i] & 0xffff0000u), __uint_as_float(qu[i] & 0xffff0000u), a4[i]);
+              }
+            }
+        float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[b * oB + (int64_t)y * oH + (int64_t)xq * oW] = acc;
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) out[(int64_t)b * oB + (int64_t)y * oH + (int64_t)xq * oW] = acc;
   }
 }
 
@@ -296,25 +341,27 @@ extern "C" int mvwarp_conv3x3_head_fwd(const void* x, const int64_t x_strides[4]
                                        int B, int H, int W, int Cin, int dilation, int device, void* stream) {
   if (!x || !x_strides || !w || !out || !out_strides) { set_error("conv3x3_head_fwd: null argument"); return MVWARP_EINVAL; }
   if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || dilation <= 0) { set_error("conv3x3_head_fwd: bad B / H / W / Cin / dilation"); return MVWARP_EINVAL; }
-  if (Cin % 8 || x_strides[1] != 1 || (reinterpret_cast<uintptr_t>(x) & 15u) || x_strides[0] % 8 || x_strides[2] % 8 || x_strides[3] % 8 ||
-      9 * Cin * 4 > 200 * 1024) {
-    set_error("conv3x3_head_fwd: x must be bf16 channels-last [B,Cin,H,W] with Cin % 8 == 0 (Cin <= 5688) and 16-byte aligned cell rows");
+  if (Cin % 8 || Cin > 512 || x_strides[1] != 1 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15u) || x_strides[0] % 8 ||
+      x_strides[2] % 8 || x_strides[3] % 8) {
+    set_error("conv3x3_head_fwd: x must be bf16 channels-last [B,Cin,H,W] with Cin % 8 == 0, Cin <= 512 and 16-byte aligned cell rows");
     return MVWARP_EUNSUPPORTED;
   }
+  const int nblk = ((H + dilation - 1) / dilation + HD_CELLS - 1) / HD_CELLS;   // column runs per phase
+  const int64_t nwarps = (int64_t)B * dilation * nblk * W;
+  if ((nwarps + HD_WARPS - 1) / HD_WARPS > 0x7fffffff) { set_error("conv3x3_head_fwd: too many cells"); return MVWARP_EUNSUPPORTED; }
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != device && cudaSetDevice(device) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
-  const int smem = 9 * Cin * (int)sizeof(float);
-  cudaError_t e = cudaSuccess;
-  if (smem > 48 * 1024) e = cudaFuncSetAttribute(conv3x3_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) {
-    const int64_t ncell = (int64_t)B * H * W;
-    const int grid = (int)std::min<int64_t>((ncell + HD_WARPS - 1) / HD_WARPS, 148 * 8);
-    conv3x3_head_kernel<<<grid, HD_WARPS * 32, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, x_strides[0], x_strides[2], x_strides[3],
-                                                                            (const __nv_bfloat16*)w, out, out_strides[0], out_strides[2],
-                                                                            out_strides[3], B, H, W, Cin, dilation);
-    e = cudaGetLastError();
-  }
+  const int grid = (int)((nwarps + HD_WARPS - 1) / HD_WARPS);
+  if (Cin <= 256)
+    conv3x3_head_kernel<1><<<grid, HD_WARPS * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, x_strides[0], x_strides[2], x_strides[3],
+                                                                             (const __nv_bfloat16*)w, out, out_strides[0], out_strides[2],
+                                                                             out_strides[3], B, H, W, Cin, dilation, nblk);
+  else
+    conv3x3_head_kernel<2><<<grid, HD_WARPS * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, x_strides[0], x_strides[2], x_strides[3],
+                                                                             (const __nv_bfloat16*)w, out, out_strides[0], out_strides[2],
+                                                                             out_strides[3], B, H, W, Cin, dilation, nblk);
+  const cudaError_t e = cudaGetLastError();
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "conv3x3_head_fwd launch");
 }
