@@ -174,11 +174,17 @@ int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int nviews, cons
                           const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0, int nrows,
                           void* stream);
 
-/* The same with a choice of output dtype (MVWARP_F32 or MVWARP_BF16): bf16 feeds mvwarp_conv3x3_fwd below. */
+/* The same with a choice of output dtype (MVWARP_F32 or MVWARP_BF16; bf16 feeds mvwarp_conv3x3_fwd below) and an optional
+ * scratch buffer.  The launch has one CTA per (frame, 8x16 cell tile); when that count is not a multiple of the SM count the
+ * last partial wave would keep a few SMs busy for a whole tile time (Wildtrack B=1: 345 tiles on 148 SMs = 2.33 waves cost
+ * 3).  With scratch (device memory, 16-byte aligned, >= mvwarp_warp_conv1_scratch_bytes(...) bytes, owned by the caller)
+ * the leftover tiles are split along K (by views) over the idle SMs, write fp32 partial sums to scratch, and a second
+ * small kernel adds them in a fixed order (deterministic) with bias / ReLU.  scratch == NULL: no split. */
 int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
                              const int64_t feat_strides[5], const void* wpack, const float* bias, void* out, int out_dtype,
                              const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0, int nrows,
-                             void* stream);
+                             void* scratch, int64_t scratch_bytes, void* stream);
+int64_t mvwarp_warp_conv1_scratch_bytes(const mvwarp_plan_t* plan, int nviews, int B, int row0, int nrows);
 
 /* ---- the rest of map_classifier (persp_trans_detector.py:53-54, applied at :81) -------------
  * mvwarp_conv3x3_fwd: out = [relu](conv2d(x, W, bias, padding = dilation, dilation = dilation)) for a 3x3 kernel with

@@ -166,9 +166,13 @@ def warp_conv1(img_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Seq
         bias = bias.detach().to(device=img_feats.device, dtype=torch.float32).contiguous()
         bias_ptr = C.c_void_p(bias.data_ptr())
     stream = C.c_void_p(torch.cuda.current_stream(img_feats.device).cuda_stream)
+    # scratch for the K-split of the last partial wave of tiles (include/mvwarp.h); comes from torch's caching allocator
+    nbytes = int(_lib.load().mvwarp_warp_conv1_scratch_bytes(plan.handle, V, B, row0, nrows))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=img_feats.device) if nbytes else None
     rc = _lib.load().mvwarp_warp_conv1_fwd_ex(plan.handle, 0, V, C.c_void_p(img_feats.data_ptr()), _lib.i64x(img_feats.stride()),
                                               C.c_void_p(wpack.data_ptr()), bias_ptr, C.c_void_p(out.data_ptr()),
                                               _lib.BF16 if out_dtype == torch.bfloat16 else _lib.F32,
-                                              _lib.i64x(out.stride()), B, Cc, int(relu), int(with_coord), row0, nrows, stream)
+                                              _lib.i64x(out.stride()), B, Cc, int(relu), int(with_coord), row0, nrows,
+                                              C.c_void_p(scratch.data_ptr()) if scratch is not None else None, nbytes, stream)
     _lib.check(rc, "mvwarp_warp_conv1_fwd")
     return out

@@ -131,7 +131,13 @@ struct ConvParams {
   int64_t oB, oH, oW;          // in elements of the output dtype
   int out_bf16;
   int relu, with_coord, tiles_x, tiles_y;
-  int tile0, ntiles;           // this launch covers tiles [tile0, tile0 + ntiles) (a band of tile rows)
+  int tile0, ntiles;           // this launch covers tiles [tile0, tile0 + ntiles) (a band of tile rows) of every frame
+  // work items = (frame, tile) pairs, one CTA each -- except the last partial wave: when nitems is not a multiple of the SM
+  // count, the n_tail = nitems - n_full leftover items would occupy a few SMs for a whole tile time while the rest idle
+  // (345 tiles on 148 SMs = 2.33 waves cost 3).  Those items are split along K (by views) into `split` CTAs each, which
+  // write raw fp32 partial sums to `scratch`; conv1_tail_reduce_kernel adds them in a fixed order (+ bias, ReLU).
+  int nitems, n_full, split;
+  float* scratch;              // [n_tail * split][128][512] fp32, or nullptr (split == 1)
   unsigned long long* stats;   // development: per CTA {cycles waiting for A, for B, total} of the MMA thread, or nullptr
 };
 
@@ -336,11 +342,23 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
   __shared__ __align__(8) uint64_t a_full[PA], a_empty[PA], b_full[PB], b_empty[PB], acc_full;
   __shared__ uint32_t tmem_holder;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool real_tile = (int)blockIdx.x < p.ntiles;        // the grid is padded to a multiple of CL: a padding CTA
-  const int tile = p.tile0 + (real_tile ? blockIdx.x : p.ntiles - 1);  // recomputes the last tile (it must feed the multicast), stores nothing
-  const int tx0 = (tile % p.tiles_x) * CT_W, ty0 = (tile / p.tiles_x) * CT_H, b = blockIdx.z;
+  // work item of this CTA (see ConvParams): whole items first, then the K-split parts of the tail items
+  int item = blockIdx.x, part = 0, nparts = 1;
+  if ((int)blockIdx.x >= p.n_full && p.split > 1) {
+    const int q = blockIdx.x - p.n_full;
+    item = p.n_full + q / p.split; part = q % p.split; nparts = p.split;
+  }
+  const bool real_tile = item < p.nitems;                   // with clusters the grid is padded to a multiple of CL: a padding CTA
+  if (!real_tile) item = p.nitems - 1;                      // recomputes the last item (it must feed the multicast), stores nothing
+  const int b = item / p.ntiles, tile = p.tile0 + item % p.ntiles;
+  const int tx0 = (tile % p.tiles_x) * CT_W, ty0 = (tile / p.tiles_x) * CT_H;
   const int ncb = p.C / CV_KB;
-  const int NK = p.nviews * ncb * 9 + (p.with_coord ? 1 : 0);
+  const int vlo = (part * p.nviews) / nparts, vhi = ((part + 1) * p.nviews) / nparts;   // this CTA's views (local indices)
+  const bool coord_here = p.with_coord && part == nparts - 1;
+  const bool partial = nparts > 1;
+  const int NK = (vhi - vlo) * ncb * 9 + (coord_here ? 1 : 0);
+  const int kb_main = (vhi - vlo) * ncb * 9;                // K blocks before the coord block
+  const int wblk0 = vlo * ncb * 9, wblk_coord = p.nviews * ncb * 9;   // indices into the packed weight
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
   constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
@@ -361,14 +379,15 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
     if (lane == 0) {
       for (int kb = 0; kb < NK; ++kb) {
         const int s = kb % PB;
+        const int wblk = kb < kb_main ? wblk0 + kb : wblk_coord;
         if (kb >= PB) mbar_wait(&b_empty[s], ((kb / PB) - 1) & 1);
         mbar_expect_tx(&b_full[s], CV_B_BYTES);   // the whole block lands here: my slice and the peers' multicasts
         if (CL == 1) {
-          bulk_g2s(sB + (size_t)s * CV_B_BYTES, p.wpack + (size_t)kb * (CV_N * CV_KB), CV_B_BYTES, &b_full[s]);
+          bulk_g2s(sB + (size_t)s * CV_B_BYTES, p.wpack + (size_t)wblk * (CV_N * CV_KB), CV_B_BYTES, &b_full[s]);
         } else {
           constexpr uint32_t SLICE = CV_B_BYTES / CL;
           bulk_g2s_multicast(sB + (size_t)s * CV_B_BYTES + crank * SLICE,
-                             reinterpret_cast<const uint8_t*>(p.wpack + (size_t)kb * (CV_N * CV_KB)) + crank * SLICE, SLICE, &b_full[s], CMASK);
+                             reinterpret_cast<const uint8_t*>(p.wpack + (size_t)wblk * (CV_N * CV_KB)) + crank * SLICE, SLICE, &b_full[s], CMASK);
         }
       }
     }
@@ -401,7 +420,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
       }
       mma_commit(&acc_full);
       if (p.stats) {
-        unsigned long long* st = p.stats + 3 * (size_t)(blockIdx.x + gridDim.x * blockIdx.z);
+        unsigned long long* st = p.stats + 3 * (size_t)blockIdx.x;
         st[0] = (unsigned long long)wa; st[1] = (unsigned long long)wb; st[2] = (unsigned long long)(clock64() - t_start);
       }
     }
@@ -481,11 +500,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
       }
     };
 
-    const int nblk = p.nviews * ncb;   // (view, channel-block) pairs
-    compute_taps(0, sT);
+    const int nblk = vhi * ncb;        // (view, channel-block) pairs [vlo * ncb, vhi * ncb)
+    compute_taps(vlo, sT + (vlo & 1) * CP_CELLS);
     producers_sync();
-    issue_gathers(0, 0, sT);
-    for (int blk = 0; blk < nblk; ++blk) {
+    issue_gathers(vlo, 0, sT + (vlo & 1) * CP_CELLS);
+    for (int blk = vlo * ncb; blk < nblk; ++blk) {
       const int vl = blk / ncb;
       const ConvTap* taps = sT + (vl & 1) * CP_CELLS;
       blend_patch(taps);                 // consumes the gathers issued one block earlier
@@ -508,7 +527,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
       }
       producers_sync();                  // every thread has finished reading the patch: it may be overwritten
     }
-    if (p.with_coord) {  // the two coord_map channels: all 9 taps x 2 channels in one K block (k = tap*2 + ch), rest zero
+    if (coord_here) {  // the two coord_map channels: all 9 taps x 2 channels in one K block (k = tap*2 + ch), rest zero
       unsigned short vals[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) vals[k] = 0;
@@ -545,7 +564,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
     for (int c0 = cbeg; c0 < cbeg + 256; c0 += 32) {
       float vv[32];
       tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, vv);
-      if (inside) {
+      if (partial) {   // K-split tail item: raw partial sums, combined by conv1_tail_reduce_kernel
+        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)(blockIdx.x - p.n_full) * 128 + er) * CV_N + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+      } else if (inside) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (p.bias) vv[i] += __ldg(p.bias + c0 + i);
@@ -570,20 +593,71 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
   if (warp == 0) tmem_dealloc(tmem, CV_N);
 }
 
+// out[item's cells] = [relu](bias + sum over the item's K-split parts, in part order) for the tail items of a launch.
+__global__ void __launch_bounds__(256) conv1_tail_reduce_kernel(const ConvParams p) {
+  const int item = p.n_full + blockIdx.x;
+  const int b = item / p.ntiles, tile = p.tile0 + item % p.ntiles;
+  const int tx0 = (tile % p.tiles_x) * CT_W, ty0 = (tile / p.tiles_x) * CT_H;
+  const float* base = p.scratch + (size_t)blockIdx.x * p.split * 128 * CV_N;
+  for (int i = threadIdx.x; i < 128 * CV_N / 4; i += blockDim.x) {
+    const int row = i / (CV_N / 4), c = (i % (CV_N / 4)) * 4;
+    const int gy = ty0 + row / CT_W, gx = tx0 + row % CT_W;
+    if (gy >= p.Hg || gx >= p.Wg) continue;
+    float4 a = *reinterpret_cast<const float4*>(base + (size_t)row * CV_N + c);
+    for (int s = 1; s < p.split; ++s) {
+      const float4 q = *reinterpret_cast<const float4*>(base + ((size_t)s * 128 + row) * CV_N + c);
+      a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+    }
+    if (p.bias) { a.x += __ldg(p.bias + c); a.y += __ldg(p.bias + c + 1); a.z += __ldg(p.bias + c + 2); a.w += __ldg(p.bias + c + 3); }
+    if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    const int64_t ooff = (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW + c;
+    if (p.out_bf16) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff) = make_uint2(pack_bf2(a.x, a.y), pack_bf2(a.z, a.w));
+    else *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ooff) = a;
+  }
+}
+
+// Tail decomposition of a launch with `nitems` work items of `nviews` views on `num_sms` SMs: how many leftover items and
+// into how many K parts each is split (1 = no split).
+static void tail_split(int nitems, int nviews, int num_sms, int& n_tail, int& split) {
+  n_tail = nitems % num_sms;
+  split = 1;
+  if (!n_tail) return;
+  // cost of the last wave in tile times: the parts run in ceil(n_tail * s / SMs) rounds of 1/s tile each, plus a small
+  // fixed cost per part (scratch epilogue + reduce); s = 1 costs one whole round
+  double best = 1.0;
+  for (int s = 2; s <= std::min(nviews, 8); ++s) {
+    const double cost = (double)(((int64_t)n_tail * s + num_sms - 1) / num_sms) / s + 0.02 * s;
+    if (cost < best - 1e-9) { best = cost; split = s; }
+  }
+  if (split == 1) n_tail = 0;
+}
+
 }  // namespace mvw
+
+extern "C" int64_t mvwarp_warp_conv1_scratch_bytes(const mvwarp_plan_t* plan, int nviews, int B, int row0, int nrows) {
+  using namespace mvw;
+  if (!plan || nviews <= 0 || B <= 0) return 0;
+  if (nrows <= 0) { row0 = 0; nrows = plan->Hg; }
+  const int tiles_x = (plan->Wg + CT_W - 1) / CT_W;
+  const int64_t nitems = (int64_t)((nrows + CT_H - 1) / CT_H) * tiles_x * B;
+  if (nitems > 0x7fffffff) return 0;
+  int n_tail, split;
+  tail_split((int)nitems, nviews, plan->num_sms, n_tail, split);
+  return (int64_t)n_tail * split * 128 * CV_N * (int64_t)sizeof(float);
+}
 
 extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
                                      const int64_t feat_strides[5], const void* wpack, const float* bias, float* out,
                                      const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0, int nrows,
                                      void* stream) {
   return mvwarp_warp_conv1_fwd_ex(plan, view0, nviews, feats, feat_strides, wpack, bias, out, MVWARP_F32, out_strides, B, C, relu,
-                                  with_coord, row0, nrows, stream);
+                                  with_coord, row0, nrows, nullptr, 0, stream);
 }
 
 extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
                                         const int64_t feat_strides[5], const void* wpack, const float* bias, void* out, int out_dtype,
                                         const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0, int nrows,
-                                        void* stream) {
+                                        void* scratch, int64_t scratch_bytes, void* stream) {
   using namespace mvw;
   if (out_dtype != MVWARP_F32 && out_dtype != MVWARP_BF16) { set_error("warp_conv1_fwd: unknown output dtype"); return MVWARP_EINVAL; }
   if (!plan || !feats || !feat_strides || !wpack || !out || !out_strides) { set_error("warp_conv1_fwd: null argument"); return MVWARP_EINVAL; }
@@ -620,6 +694,12 @@ extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, in
   }
   p.tile0 = (row0 / CT_H) * p.tiles_x;
   p.ntiles = ((nrows + CT_H - 1) / CT_H) * p.tiles_x;
+  if ((int64_t)p.ntiles * B > 0x7fffffff) {
+    if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
+    set_error("warp_conv1_fwd: too many tiles");
+    return MVWARP_EUNSUPPORTED;
+  }
+  p.nitems = p.ntiles * B; p.n_full = p.nitems; p.split = 1; p.scratch = nullptr;
   cudaError_t e;
   const char* variant = getenv("MVWARP_CONV1_VARIANT");   // development knob: "simple" = the unpipelined validation kernel
   if (variant && variant[0] == 's' && out_dtype == MVWARP_F32) {
@@ -636,7 +716,8 @@ extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, in
       cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (err != cudaSuccess) return err;
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((p.ntiles + cluster - 1) / cluster * cluster, 1, B);
+      const int n_tail = p.nitems - p.n_full;
+      cfg.gridDim = dim3(p.split > 1 ? p.n_full + n_tail * p.split : (p.nitems + cluster - 1) / cluster * cluster, 1, 1);
       cfg.blockDim = dim3(PIPE_THREADS);
       cfg.dynamicSmemBytes = smem;
       cfg.stream = (cudaStream_t)stream;
@@ -647,7 +728,14 @@ extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, in
       return cudaLaunchKernelEx(&cfg, kernel, p);
     };
     unsigned long long* d_stats = nullptr;
-    const size_t nst = (size_t)3 * ((p.ntiles + 3) / 4 * 4) * B;
+    if (cl == 1 && scratch && !getenv("MVWARP_CONV1_NOSPLIT")) {   // K-split of the last partial wave (see ConvParams)
+      int n_tail, split;
+      tail_split(p.nitems, nviews, plan->num_sms, n_tail, split);
+      if (split > 1 && scratch_bytes >= (int64_t)n_tail * split * 128 * CV_N * (int64_t)sizeof(float) && !(reinterpret_cast<uintptr_t>(scratch) & 15u)) {
+        p.split = split; p.n_full = p.nitems - n_tail; p.scratch = reinterpret_cast<float*>(scratch);
+      }
+    }
+    const size_t nst = (size_t)3 * ((size_t)p.nitems * 8 + 8);
     if (getenv("MVWARP_CONV1_STATS")) {   // development only: synchronous, prints where the MMA thread waits
       cudaMalloc(&d_stats, nst * sizeof(unsigned long long));
       cudaMemset(d_stats, 0, nst * sizeof(unsigned long long));
@@ -656,6 +744,10 @@ extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, in
     if (cl == 1) e = launch(warp_conv1_pipe_kernel<1>, 1);
     else if (cl == 4) e = launch(warp_conv1_pipe_kernel<4>, 4);
     else e = launch(warp_conv1_pipe_kernel<2>, 2);
+    if (e == cudaSuccess && p.split > 1) {
+      conv1_tail_reduce_kernel<<<p.nitems - p.n_full, 256, 0, (cudaStream_t)stream>>>(p);
+      e = cudaGetLastError();
+    }
     if (d_stats) {
       std::vector<unsigned long long> h(nst);
       cudaMemcpy(h.data(), d_stats, nst * sizeof(unsigned long long), cudaMemcpyDeviceToHost);

@@ -316,8 +316,11 @@ extern "C" int mvwarp_conv3x3_fwd(const void* x, const int64_t x_strides[4], con
   p.H = H; p.W = W; p.Cin = Cin; p.dilation = dilation; p.relu = relu; p.out_bf16 = out_dtype == MVWARP_BF16;
   p.tiles_x = (W + C2_TW - 1) / C2_TW; p.tiles_y = (H + C2_TH - 1) / C2_TH; p.ntiles = p.tiles_x * p.tiles_y;
   const int smem = C2_PA * (int)C2_A_BYTES + C2_PB * (int)C2_B_BYTES + 1024;
-  const char* variant = getenv("MVWARP_CONV2_CLUSTER");   // development knob: 1 = no cluster
-  const int cl = (variant && variant[0] == '1') ? 1 : 2;
+  // Cluster of 2 with multicast weight blocks: measured equal to no cluster (0.190 vs 0.185 ms at the Wildtrack shape);
+  // a K-split of the last partial wave (as in the fused conv1) does not pay here either (0.200 ms): the CTAs of a thin
+  // last wave already run faster because the weight stream from L2 is shared by fewer SMs.
+  const char* variant = getenv("MVWARP_CONV2_CLUSTER");   // development knob: 2 = cluster of two
+  const int cl = (variant && variant[0] == '2') ? 2 : 1;
   auto launch = [&](auto kernel, int cluster) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return err;
