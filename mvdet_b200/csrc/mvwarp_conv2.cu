@@ -10,6 +10,8 @@
 // (cp.async.bulk.tensor.4d, SWIZZLE_128B) drops into shared memory in exactly the K-major layout the tensor core
 // reads; cells outside the image are the convolution's zero padding and come from the TMA unit's out-of-bounds fill.
 // Three single-thread roles (A boxes, packed weight blocks, MMA issue) and eight epilogue warps.
+// Two kernels: conv3x3_tc2_kernel (default) runs CTA PAIRS with cta_group::2 MMAs of M = 256, each CTA streaming half of
+// every weight block; conv3x3_tc_kernel is the single-CTA version it grew out of (kept behind MVWARP_CONV2_1CTA=1).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -172,6 +174,144 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv3x3_tc_kernel(const __grid_
 }
 
 // -----------------------------------------------------------------------------------------------------
+// CTA-pair version (cta_group::2): the two CTAs of a cluster take two neighbouring cell tiles and run ONE MMA of
+// M = 256 per step.  Each CTA fetches its own A boxes and only HALF of every weight block (the N rows [128r, 128r+128) and
+// [256+128r, 256+128r+128) of the 512, r = rank in the pair) -- the weight stream from L2, which bounds the single-CTA kernel
+// (64 KB per 0.55 us of tensor work per SM), is halved.  All TMA copies of the pair (tensor maps for A and for the packed
+// weights, .cta_group::2) complete on the LEADER's full barriers, the leader's MMA thread issues for both CTAs, and its
+// commits arrive on the empty barriers of both (multicast).  Each CTA drains its own 128 x 512 accumulator from its own TMEM.
+// -----------------------------------------------------------------------------------------------------
+constexpr int T2_PA = 4, T2_PB = 4;
+constexpr uint32_t T2_B_BYTES = C2_B_BYTES / 2;   // 32 KB of weights per CTA per K block
+
+__device__ __forceinline__ void tma_box_4d_2cta(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void tma_box_2d_2cta(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_dst),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar_cluster)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(C2_THREADS, 1) conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                                                                   const Conv2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                                // T2_PA x 16 KB
+  uint8_t* sB = smem + T2_PA * C2_A_BYTES;           // T2_PB x 32 KB
+  __shared__ __align__(8) uint64_t a_full[T2_PA], a_empty[T2_PA], b_full[T2_PB], b_empty[T2_PB], acc_full;
+  __shared__ uint32_t tmem_holder;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();           // 0 = leader
+  const int nitems = p.ntiles * (int)gridDim.z;
+  (void)nitems;
+  const bool real_tile = (int)blockIdx.x < p.ntiles;   // grid.x padded to an even count: the padding CTA redoes the last tile, stores nothing
+  const int tile = real_tile ? blockIdx.x : p.ntiles - 1;
+  const int tx0 = (tile % p.tiles_x) * C2_TW, ty0 = (tile / p.tiles_x) * C2_TH, b = blockIdx.z;
+  const int NK = p.Cin / C2_KB * 9;
+
+  if (warp == 0) tmem_alloc_2cta(&tmem_holder, C2_N);
+  if (tid == 0) {
+    for (int i = 0; i < T2_PA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < T2_PB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+
+  if (warp == 10) {
+    // ===== A boxes (own tile), completing on the leader's barrier =====
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_x);
+      for (int kb = 0; kb < NK; ++kb) {
+        const int s = kb % T2_PA, cb = kb / 9, tap = kb % 9;
+        if (kb >= T2_PA) mbar_wait(&a_empty[s], ((kb / T2_PA) - 1) & 1);
+        if (rank == 0) mbar_expect_tx(&a_full[s], 2 * C2_A_BYTES);   // both CTAs' boxes
+        tma_box_4d_2cta(smem_u32(sA + (size_t)s * C2_A_BYTES), &tmap_x, cb * C2_KB, tx0 + (tap % 3 - 1) * p.dilation,
+                        ty0 + (tap / 3 - 1) * p.dilation, b, map_to_cta(smem_u32(&a_full[s]), 0));
+      }
+    }
+  } else if (warp == 9) {
+    // ===== this CTA's half of every weight block: two boxes of 128 rows =====
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_w);
+      for (int kb = 0; kb < NK; ++kb) {
+        const int s = kb % T2_PB;
+        if (kb >= T2_PB) mbar_wait(&b_empty[s], ((kb / T2_PB) - 1) & 1);
+        if (rank == 0) mbar_expect_tx(&b_full[s], 2 * T2_B_BYTES);
+        const uint32_t dst = smem_u32(sB + (size_t)s * T2_B_BYTES), bar = map_to_cta(smem_u32(&b_full[s]), 0);
+        tma_box_2d_2cta(dst, &tmap_w, 0, kb * C2_N + 128 * (int)rank, bar);
+        tma_box_2d_2cta(dst + T2_B_BYTES / 2, &tmap_w, 0, kb * C2_N + 256 + 128 * (int)rank, bar);
+      }
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer: the leader, for both CTAs =====
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = idesc_bf16_f32(256, 256);
+      for (int kb = 0; kb < NK; ++kb) {
+        const int sa = kb % T2_PA, sb = kb % T2_PB;
+        mbar_wait(&a_full[sa], (kb / T2_PA) & 1);
+        mbar_wait(&b_full[sb], (kb / T2_PB) & 1);
+        tc_fence_after();
+        const uint32_t bbase = smem_u32(sB + (size_t)sb * T2_B_BYTES);
+        const uint64_t da = smem_desc_sw128(smem_u32(sA + (size_t)sa * C2_A_BYTES)), db0 = smem_desc_sw128(bbase),
+                       db1 = smem_desc_sw128(bbase + T2_B_BYTES / 2);
+#pragma unroll
+        for (int k = 0; k < C2_KB / 16; ++k) {
+          mma_bf16_2cta(tmem, da + 2 * k, db0 + 2 * k, idesc, kb > 0 || k > 0);
+          mma_bf16_2cta(tmem + 256, da + 2 * k, db1 + 2 * k, idesc, kb > 0 || k > 0);
+        }
+        mma_commit_2cta(&a_empty[sa], 3);
+        mma_commit_2cta(&b_empty[sb], 3);
+      }
+      mma_commit_2cta(&acc_full, 3);
+    }
+  } else {
+    // ===== epilogue (each CTA its own tile) =====
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const int er = (warp & 3) * 32 + lane, ey = er / C2_TW, ex = er % C2_TW;
+    const int gy = ty0 + ey, gx = tx0 + ex;
+    const bool inside = real_tile && gy < p.H && gx < p.W;
+    const int64_t ooff = (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW;
+    const int cbeg = (warp >> 2) * 256;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + 256; c0 += 32) {
+      float vv[32];
+      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, vv);
+      if (inside) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (p.bias) vv[i] += __ldg(p.bias + c0 + i);
+          if (p.relu) vv[i] = fmaxf(vv[i], 0.f);
+        }
+        if (p.out_bf16) {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            o[i] = make_uint4(pack_bf16x2(vv[8 * i], vv[8 * i + 1]), pack_bf16x2(vv[8 * i + 2], vv[8 * i + 3]),
+                              pack_bf16x2(vv[8 * i + 4], vv[8 * i + 5]), pack_bf16x2(vv[8 * i + 6], vv[8 * i + 7]));
+        } else {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ooff + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 0) tmem_dealloc_2cta(tmem, C2_N);
+}
+
+// -----------------------------------------------------------------------------------------------------
 // map_classifier[4]: 512 -> 1 channel, 3x3, dilation d, no bias.  0.4 GFLOP per Wildtrack frame against 44 MB of
 // activations: memory-bound, so no tensor cores -- one warp per output cell, lanes across channels (128-bit loads of
 // the nine tap rows, the 9 x Cin weights staged in shared memory as fp32), warp-shuffle reduction, fp32 out.
@@ -310,6 +450,21 @@ extern "C" int mvwarp_conv3x3_fwd(const void* x, const int64_t x_strides[4], con
     set_error("conv3x3_fwd: cuTensorMapEncodeTiled failed (code " + std::to_string((int)cr) + ")");
     return MVWARP_ECUDA;
   }
+  // the packed weight as a 2-D tensor (64 x [blocks * 512] rows of 128 bytes), boxes of 128 rows, no swizzle (rows are pre-swizzled)
+  CUtensorMap tmap_w;
+  {
+    const cuuint64_t wdim[2] = {(cuuint64_t)C2_KB, (cuuint64_t)(Cin / C2_KB) * 9 * C2_N};
+    const cuuint64_t wstr[1] = {(cuuint64_t)C2_KB * 2};
+    const cuuint32_t wbox[2] = {C2_KB, 128};
+    const cuuint32_t west[2] = {1, 1};
+    const CUresult wr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpack), wdim, wstr, wbox, west, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (wr != CUDA_SUCCESS || (reinterpret_cast<uintptr_t>(wpack) & 15u)) {
+      restore();
+      set_error("conv3x3_fwd: cuTensorMapEncodeTiled(weights) failed (code " + std::to_string((int)wr) + ")");
+      return MVWARP_ECUDA;
+    }
+  }
   Conv2Params p{};
   p.wpack = (const __nv_bfloat16*)wpack; p.bias = bias; p.out = out;
   p.oB = out_strides[0]; p.oH = out_strides[2]; p.oW = out_strides[3];
@@ -335,7 +490,26 @@ extern "C" int mvwarp_conv3x3_fwd(const void* x, const int64_t x_strides[4], con
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, tmap, p);
   };
-  const cudaError_t e = cl == 1 ? launch(conv3x3_tc_kernel<1>, 1) : launch(conv3x3_tc_kernel<2>, 2);
+  cudaError_t e;
+  const char* one = getenv("MVWARP_CONV2_1CTA");   // development knob: the single-CTA kernel (0.203 vs 0.182 ms at Wildtrack B=1, 0.701 vs 0.672 at B=4)
+  if (!(one && one[0] == '1')) {                   // default: CTA pairs (cta_group::2)
+    const int smem2 = T2_PA * (int)C2_A_BYTES + T2_PB * (int)T2_B_BYTES + 1024;
+    e = cudaFuncSetAttribute(conv3x3_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    if (e == cudaSuccess) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((p.ntiles + 1) / 2 * 2, 1, B);
+      cfg.blockDim = dim3(C2_THREADS);
+      cfg.dynamicSmemBytes = smem2;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel, tmap, tmap_w, p);
+    }
+  } else {
+    e = cl == 1 ? launch(conv3x3_tc_kernel<1>, 1) : launch(conv3x3_tc_kernel<2>, 2);
+  }
   restore();
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "conv3x3_fwd launch");
 }
