@@ -1,9 +1,12 @@
 // mvwarp_conv1.cu -- tensor-core side of the path (north_star (c)): tcgen05 / TMEM GEMM building blocks for the
 // fused warp -> map_classifier[0] implicit GEMM (/root/reference/multiview_detector/models/persp_trans_detector.py:51,81).
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "mvwarp_internal.h"
@@ -136,8 +139,11 @@ struct ConvParams {
   // count, the n_tail = nitems - n_full leftover items would occupy a few SMs for a whole tile time while the rest idle
   // (345 tiles on 148 SMs = 2.33 waves cost 3).  Those items are split along K (by views) into `split` CTAs each, which
   // write raw fp32 partial sums to `scratch`; conv1_tail_reduce_kernel adds them in a fixed order (+ bias, ReLU).
-  int nitems, n_full, split;
+  int nitems, n_full, split, pair_mode;
   float* scratch;              // [n_tail * split][128][512] fp32, or nullptr (split == 1)
+  // CTA-pair mode (PAIR kernels): CTAs 2i, 2i+1 of the launch form a cluster; whole items first, pair i takes items 2i, 2i+1
+  // (n_full even), then for tail pair j and K part q cluster n_full/2 + j*split + q takes items n_full + 2j (+1), part q:
+  // the two CTAs of a pair always walk the same weight blocks.  Scratch slot of (tail item n_full + 2j + r, part q) = (j*split + q)*2 + r.
   unsigned long long* stats;   // development: per CTA {cycles waiting for A, for B, total} of the MMA thread, or nullptr
 };
 
@@ -332,21 +338,58 @@ constexpr int PATCH_TASKS = CP_CELLS * 8, PATCH_ROUNDS = (PATCH_TASKS + NPROD - 
 
 __device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int CL>
-__global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const ConvParams p) {
+// PAIR: CTA-pair mode (cta_group::2).  The two CTAs of a cluster work on two cell tiles and run ONE MMA of M = 256 per step,
+// issued by the even CTA; each CTA keeps only HALF of every weight block (N rows [128r, 128r+128) and [256+128r, ...)) in
+// shared memory.  The single-CTA kernel moves 16 (A stage write) + 16 (patch read) + 16 (A read) + 64 (weights in) + 64 (weights
+// read) = 176 KB through shared memory per K block against 128 B per clock = 0.72 us, more than the 0.55 us the tensor core
+// needs: shared-memory bandwidth, not the tensor pipe, bounds it.  Halving the weight traffic (112 KB, 0.46 us) lifts that.
+// Weight halves arrive as TMA tensor boxes (.cta_group::2) that complete on the leader's barrier; the peer's producer warps
+// publish their A stages with one remote arrive per warp; the leader's commits reach both CTAs' empty barriers by multicast.
+#ifndef MVW_PA2
+#define MVW_PA2 5
+#define MVW_PB2 3
+#endif
+constexpr int PA2 = MVW_PA2, PB2 = MVW_PB2;           // ring depths in pair mode (16 KB A stages, 32 KB weight stages)
+constexpr uint32_t CV_B2_BYTES = CV_B_BYTES / 2;
+
+__device__ __forceinline__ void tma_wbox_2cta(uint32_t smem_dst, const CUtensorMap* tmap, int row, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_dst),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(row), "r"(bar_cluster)
+               : "memory");
+}
+
+template <int CL, bool PAIR>
+__global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
+  static_assert(!PAIR || CL == 1, "pair mode does not multicast the weights");
+  // rings: 3 x 16 KB of A + 2 x 64 KB of weights, or in pair mode 5 x 16 KB + 3 x 32 KB (the same 176 KB): the A ring is
+  // deeper there because a stage's round trip now crosses SMs (remote arrive -> leader's MMA -> multicast commit)
+  constexpr int NPA = PAIR ? PA2 : PA, NPB = PAIR ? PB2 : PB;
+  constexpr uint32_t BSTAGE = PAIR ? CV_B2_BYTES : CV_B_BYTES;
+  static_assert(NPA * 16384 + NPB * BSTAGE == PA * 16384 + PB * CV_B_BYTES, "both modes use the same shared-memory budget");
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem;                                          // PA x 16 KB
-  uint8_t* sB = smem + PA * 16384;                             // PB x 64 KB
-  uint8_t* sP = sB + PB * CV_B_BYTES;                          // patch: 180 cells x 128 B (plain layout)
+  uint8_t* sA = smem;                                          // NPA x 16 KB
+  uint8_t* sB = smem + NPA * 16384;                            // NPB x BSTAGE
+  uint8_t* sP = sB + NPB * BSTAGE;                             // patch: 180 cells x 128 B (plain layout)
   ConvTap* sT = reinterpret_cast<ConvTap*>(sP + CP_CELLS * 128);  // taps of the halo cells: 2 buffers (current / next view)
-  __shared__ __align__(8) uint64_t a_full[PA], a_empty[PA], b_full[PB], b_empty[PB], acc_full;
+  __shared__ __align__(8) uint64_t a_full[PA2], a_empty[PA2], b_full[PB2], b_empty[PB2], acc_full;
   __shared__ uint32_t tmem_holder;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t prank = PAIR ? cluster_ctarank() : 0;      // rank in the CTA pair (0 = leader)
   // work item of this CTA (see ConvParams): whole items first, then the K-split parts of the tail items
-  int item = blockIdx.x, part = 0, nparts = 1;
-  if ((int)blockIdx.x >= p.n_full && p.split > 1) {
+  int item = blockIdx.x, part = 0, nparts = 1, slot = 0;
+  if (PAIR) {
+    const int cpair = blockIdx.x >> 1, nfp = p.n_full >> 1;
+    if (cpair >= nfp) {
+      const int q = cpair - nfp, j = q / p.split;
+      part = q % p.split; nparts = p.split;
+      item = p.n_full + 2 * j + (int)prank;
+      slot = q * 2 + (int)prank;
+    }
+  } else if ((int)blockIdx.x >= p.n_full && p.split > 1) {
     const int q = blockIdx.x - p.n_full;
     item = p.n_full + q / p.split; part = q % p.split; nparts = p.split;
+    slot = q;
   }
   const bool real_tile = item < p.nitems;                   // with clusters the grid is padded to a multiple of CL: a padding CTA
   if (!real_tile) item = p.nitems - 1;                      // recomputes the last item (it must feed the multicast), stores nothing
@@ -362,15 +405,18 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
   constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
-  if (warp == 0) tmem_alloc(&tmem_holder, CV_N);
+  if (warp == 0) { if (PAIR) tmem_alloc_2cta(&tmem_holder, CV_N); else tmem_alloc(&tmem_holder, CV_N); }
   if (tid == 0) {
-    for (int i = 0; i < PA; ++i) { mbar_init(&a_full[i], NPROD); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < PB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL); }
+    // pair mode: one arrival per producer warp on the CTA's own barrier; the peer's relay thread forwards each completed
+    // stage to the leader's barrier with ONE remote arrive (a cluster-scope release per producer warp and stage made the
+    // peer's producers, and with them the pair, 35 % slower)
+    for (int i = 0; i < NPA; ++i) { mbar_init(&a_full[i], PAIR ? NPROD / 32 + (prank == 0 ? 1 : 0) : NPROD); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NPB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], PAIR ? 1 : CL); }
     mbar_init(&acc_full, 1);
     fence_barrier_init();
   }
   tc_fence_before();
-  if (CL > 1) cluster_sync(); else __syncthreads();       // every CTA's barriers exist before any remote arrival
+  if (CL > 1 || PAIR) cluster_sync(); else __syncthreads();   // every CTA's barriers exist before any remote arrival
   tc_fence_after();
   const uint32_t tmem = tmem_holder;
 
@@ -378,9 +424,16 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
     // ===== weight streamer =====
     if (lane == 0) {
       for (int kb = 0; kb < NK; ++kb) {
-        const int s = kb % PB;
+        const int s = kb % NPB;
         const int wblk = kb < kb_main ? wblk0 + kb : wblk_coord;
-        if (kb >= PB) mbar_wait(&b_empty[s], ((kb / PB) - 1) & 1);
+        if (kb >= NPB) mbar_wait(&b_empty[s], ((kb / NPB) - 1) & 1);
+        if (PAIR) {   // my half of the block: two boxes of 128 rows, completing on the leader's barrier
+          if (prank == 0) mbar_expect_tx(&b_full[s], CV_B_BYTES);
+          const uint32_t dst = smem_u32(sB + (size_t)s * BSTAGE), bar = map_to_cta(smem_u32(&b_full[s]), 0);
+          tma_wbox_2cta(dst, &tmap_w, wblk * CV_N + 128 * (int)prank, bar);
+          tma_wbox_2cta(dst + BSTAGE / 2, &tmap_w, wblk * CV_N + 256 + 128 * (int)prank, bar);
+          continue;
+        }
         mbar_expect_tx(&b_full[s], CV_B_BYTES);   // the whole block lands here: my slice and the peers' multicasts
         if (CL == 1) {
           bulk_g2s(sB + (size_t)s * CV_B_BYTES, p.wpack + (size_t)wblk * (CV_N * CV_KB), CV_B_BYTES, &b_full[s]);
@@ -393,35 +446,54 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
     }
   } else if (warp == 8) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = idesc_bf16_f32(128, 256);
+    if (lane == 0 && prank == 0) {   // pair mode: the leader issues for both CTAs
+      const uint32_t idesc = PAIR ? idesc_bf16_f32(256, 256) : idesc_bf16_f32(128, 256);
       long long wa = 0, wb = 0;
       const long long t_start = clock64();
       for (int kb = 0; kb < NK; ++kb) {
-        const int sa = kb % PA, sb = kb % PB;
+        const int sa = kb % NPA, sb = kb % NPB;
         const long long t0 = clock64();
-        mbar_wait(&a_full[sa], (kb / PA) & 1);
+        if (PAIR) mbar_wait_cluster(&a_full[sa], (kb / NPA) & 1);   // arrivals from the peer's producer warps
+        else mbar_wait(&a_full[sa], (kb / NPA) & 1);
         const long long t1 = clock64();
-        mbar_wait(&b_full[sb], (kb / PB) & 1);
+        mbar_wait(&b_full[sb], (kb / NPB) & 1);
         const long long t2 = clock64();
         wa += t1 - t0; wb += t2 - t1;
         tc_fence_after();
-        const uint32_t bbase = smem_u32(sB + (size_t)sb * CV_B_BYTES);
+        const uint32_t bbase = smem_u32(sB + (size_t)sb * BSTAGE);
         const uint64_t da = smem_desc_sw128(smem_u32(sA + sa * 16384)), db0 = smem_desc_sw128(bbase),
-                       db1 = smem_desc_sw128(bbase + 256 * 128);
+                       db1 = smem_desc_sw128(bbase + BSTAGE / 2);
 #pragma unroll
         for (int k = 0; k < CV_KB / 16; ++k) {
-          mma_bf16(tmem, da + 2 * k, db0 + 2 * k, idesc, kb > 0 || k > 0);
-          mma_bf16(tmem + 256, da + 2 * k, db1 + 2 * k, idesc, kb > 0 || k > 0);
+          if (PAIR) {
+            mma_bf16_2cta(tmem, da + 2 * k, db0 + 2 * k, idesc, kb > 0 || k > 0);
+            mma_bf16_2cta(tmem + 256, da + 2 * k, db1 + 2 * k, idesc, kb > 0 || k > 0);
+          } else {
+            mma_bf16(tmem, da + 2 * k, db0 + 2 * k, idesc, kb > 0 || k > 0);
+            mma_bf16(tmem + 256, da + 2 * k, db1 + 2 * k, idesc, kb > 0 || k > 0);
+          }
         }
-        mma_commit(&a_empty[sa]);
-        if (CL == 1) mma_commit(&b_empty[sb]);
-        else mma_commit_multicast(&b_empty[sb], CMASK);   // every CTA of the cluster writes into this stage of mine
+        if (PAIR) {
+          mma_commit_2cta(&a_empty[sa], 3);
+          mma_commit_2cta(&b_empty[sb], 3);
+        } else {
+          mma_commit(&a_empty[sa]);
+          if (CL == 1) mma_commit(&b_empty[sb]);
+          else mma_commit_multicast(&b_empty[sb], CMASK);   // every CTA of the cluster writes into this stage of mine
+        }
       }
-      mma_commit(&acc_full);
+      if (PAIR) mma_commit_2cta(&acc_full, 3);
+      else mma_commit(&acc_full);
       if (p.stats) {
         unsigned long long* st = p.stats + 3 * (size_t)blockIdx.x;
         st[0] = (unsigned long long)wa; st[1] = (unsigned long long)wb; st[2] = (unsigned long long)(clock64() - t_start);
+      }
+    } else if (PAIR && lane == 0) {
+      // ===== relay (peer CTA): forward "my A stage is complete" to the leader's barrier =====
+      for (int kb = 0; kb < NK; ++kb) {
+        const int sa = kb % NPA;
+        mbar_wait(&a_full[sa], (kb / NPA) & 1);
+        mbar_arrive_cluster(map_to_cta(smem_u32(&a_full[sa]), 0));
       }
     }
   } else {
@@ -430,13 +502,18 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
     const int my = m / CT_W, mx = m % CT_W;
     int kb = 0;
     auto acquire_stage = [&]() -> uint8_t* {
-      const int sa = kb % PA;
-      if (kb >= PA) mbar_wait(&a_empty[sa], ((kb / PA) - 1) & 1);
+      const int sa = kb % NPA;
+      if (kb >= NPA) mbar_wait(&a_empty[sa], ((kb / NPA) - 1) & 1);
       return sA + sa * 16384;
     };
     auto publish_stage = [&]() {
       fence_proxy_async();
-      mbar_arrive(&a_full[kb % PA]);
+      if (PAIR) {   // one arrival per warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[kb % NPA]);
+      } else {
+        mbar_arrive(&a_full[kb % NPA]);
+      }
       ++kb;
     };
     auto compute_taps = [&](int vl, ConvTap* dst) {  // taps of the halo patch for one view (outside the grid = conv zero padding)
@@ -565,7 +642,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
       float vv[32];
       tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, vv);
       if (partial) {   // K-split tail item: raw partial sums, combined by conv1_tail_reduce_kernel
-        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)(blockIdx.x - p.n_full) * 128 + er) * CV_N + c0);
+        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)slot * 128 + er) * CV_N + c0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
       } else if (inside) {
@@ -589,8 +666,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
     }
   }
   tc_fence_before();
-  if (CL > 1) cluster_sync(); else __syncthreads();       // nobody leaves while a peer may still multicast into it
-  if (warp == 0) tmem_dealloc(tmem, CV_N);
+  if (CL > 1 || PAIR) cluster_sync(); else __syncthreads();   // nobody leaves while a peer may still write into it / read from it
+  if (warp == 0) { if (PAIR) tmem_dealloc_2cta(tmem, CV_N); else tmem_dealloc(tmem, CV_N); }
 }
 
 // out[item's cells] = [relu](bias + sum over the item's K-split parts, in part order) for the tail items of a launch.
@@ -598,7 +675,11 @@ __global__ void __launch_bounds__(256) conv1_tail_reduce_kernel(const ConvParams
   const int item = p.n_full + blockIdx.x;
   const int b = item / p.ntiles, tile = p.tile0 + item % p.ntiles;
   const int tx0 = (tile % p.tiles_x) * CT_W, ty0 = (tile / p.tiles_x) * CT_H;
-  const float* base = p.scratch + (size_t)blockIdx.x * p.split * 128 * CV_N;
+  // slot of (tail item t, part s): single-CTA launches t * split + s; pair launches ((t/2) * split + s) * 2 + t % 2
+  const bool pair = p.pair_mode != 0;
+  const size_t slot0 = pair ? (size_t)(blockIdx.x >> 1) * p.split * 2 + (blockIdx.x & 1) : (size_t)blockIdx.x * p.split;
+  const size_t slot_step = pair ? 2 : 1;
+  const float* base = p.scratch + slot0 * 128 * CV_N;
   // grid.y = 8 slices of 16 cells: 49 tail items alone would leave two thirds of the SMs idle (55 us instead of ~10)
   for (int i = threadIdx.x; i < 16 * CV_N / 4; i += blockDim.x) {
     const int row = blockIdx.y * 16 + i / (CV_N / 4), c = (i % (CV_N / 4)) * 4;
@@ -606,7 +687,7 @@ __global__ void __launch_bounds__(256) conv1_tail_reduce_kernel(const ConvParams
     if (gy >= p.Hg || gx >= p.Wg) continue;
     float4 a = *reinterpret_cast<const float4*>(base + (size_t)row * CV_N + c);
     for (int s = 1; s < p.split; ++s) {
-      const float4 q = *reinterpret_cast<const float4*>(base + ((size_t)s * 128 + row) * CV_N + c);
+      const float4 q = *reinterpret_cast<const float4*>(base + ((size_t)s * slot_step * 128 + row) * CV_N + c);
       a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
     }
     if (p.bias) { a.x += __ldg(p.bias + c); a.y += __ldg(p.bias + c + 1); a.z += __ldg(p.bias + c + 2); a.w += __ldg(p.bias + c + 3); }
@@ -633,6 +714,33 @@ static void tail_split(int nitems, int nviews, int num_sms, int& n_tail, int& sp
   if (split == 1) n_tail = 0;
 }
 
+// Work decomposition of a launch (ConvParams): n_full whole items, `split` K parts for each of the rest, scratch slots needed.
+// pair: CTA-pair kernels -- the unit is a pair of items on a pair of SMs, n_full is even.
+struct Decomp {
+  int n_full, split;
+  int64_t slots;
+};
+static Decomp decompose(int nitems, int nviews, int num_sms, bool pair) {
+  Decomp d{nitems, 1, 0};
+  if (!pair) {
+    int n_tail, split;
+    tail_split(nitems, nviews, num_sms, n_tail, split);
+    d.split = split; d.n_full = nitems - n_tail; d.slots = (int64_t)n_tail * split;
+    return d;
+  }
+  const int npairs = (nitems + 1) / 2;
+  int tail_pairs, split;
+  tail_split(npairs, nviews, std::max(1, num_sms / 2), tail_pairs, split);
+  if (split > 1) { d.split = split; d.n_full = 2 * (npairs - tail_pairs); d.slots = (int64_t)tail_pairs * split * 2; }
+  else { d.n_full = nitems / 2 * 2; }   // an odd last item runs as a "tail pair" of one part with a padding partner
+  return d;
+}
+
+static bool pair_mode_wanted() {
+  const char* e = getenv("MVWARP_CONV1_PAIR");   // development knob: 0 = single-CTA kernel
+  return !(e && e[0] == '0') && !getenv("MVWARP_CONV1_VARIANT");
+}
+
 }  // namespace mvw
 
 extern "C" int64_t mvwarp_warp_conv1_scratch_bytes(const mvwarp_plan_t* plan, int nviews, int B, int row0, int nrows) {
@@ -642,9 +750,8 @@ extern "C" int64_t mvwarp_warp_conv1_scratch_bytes(const mvwarp_plan_t* plan, in
   const int tiles_x = (plan->Wg + CT_W - 1) / CT_W;
   const int64_t nitems = (int64_t)((nrows + CT_H - 1) / CT_H) * tiles_x * B;
   if (nitems > 0x7fffffff) return 0;
-  int n_tail, split;
-  tail_split((int)nitems, nviews, plan->num_sms, n_tail, split);
-  return (int64_t)n_tail * split * 128 * CV_N * (int64_t)sizeof(float);
+  const Decomp d = decompose((int)nitems, nviews, plan->num_sms, pair_mode_wanted());
+  return d.slots * 128 * CV_N * (int64_t)sizeof(float);
 }
 
 extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
@@ -713,12 +820,29 @@ extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, in
   } else {
     const int smem = PA * 16384 + PB * (int)CV_B_BYTES + CP_CELLS * 128 + 2 * CP_CELLS * (int)sizeof(ConvTap) + 1024;
     const int cl = (variant && variant[0] >= '1' && variant[0] <= '4') ? variant[0] - '0' : 1;
+    const bool pair = pair_mode_wanted() && cl == 1;
+    CUtensorMap tmap_w;
+    memset(&tmap_w, 0, sizeof(tmap_w));
+    if (pair) {
+      const uint64_t nblocks = (uint64_t)nviews * (C / CV_KB) * 9 + (with_coord ? 1 : 0);
+      const int wrc = make_weight_tensor_map(&tmap_w, wpack, nblocks);
+      if (wrc) { if (prev >= 0 && prev != plan->device) cudaSetDevice(prev); return wrc; }
+    }
+    p.pair_mode = pair ? 1 : 0;
+    if (pair) p.n_full = p.nitems / 2 * 2;
+    if (cl == 1 && scratch && !getenv("MVWARP_CONV1_NOSPLIT")) {   // K-split of the last partial wave (see ConvParams)
+      const Decomp d = decompose(p.nitems, nviews, plan->num_sms, pair);
+      if (d.split > 1 && scratch_bytes >= d.slots * 128 * CV_N * (int64_t)sizeof(float) && !(reinterpret_cast<uintptr_t>(scratch) & 15u)) {
+        p.split = d.split; p.n_full = d.n_full; p.scratch = reinterpret_cast<float*>(scratch);
+      }
+    }
     auto launch = [&](auto kernel, int cluster) -> cudaError_t {
       cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (err != cudaSuccess) return err;
       cudaLaunchConfig_t cfg{};
       const int n_tail = p.nitems - p.n_full;
-      cfg.gridDim = dim3(p.split > 1 ? p.n_full + n_tail * p.split : (p.nitems + cluster - 1) / cluster * cluster, 1, 1);
+      if (p.pair_mode) cfg.gridDim = dim3(p.n_full + (n_tail + 1) / 2 * 2 * p.split, 1, 1);   // clusters: n_full / 2 whole pairs + tail pairs x parts
+      else cfg.gridDim = dim3(p.split > 1 ? p.n_full + n_tail * p.split : (p.nitems + cluster - 1) / cluster * cluster, 1, 1);
       cfg.blockDim = dim3(PIPE_THREADS);
       cfg.dynamicSmemBytes = smem;
       cfg.stream = (cudaStream_t)stream;
@@ -726,25 +850,19 @@ extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, in
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      return cudaLaunchKernelEx(&cfg, kernel, p);
+      return cudaLaunchKernelEx(&cfg, kernel, tmap_w, p);
     };
     unsigned long long* d_stats = nullptr;
-    if (cl == 1 && scratch && !getenv("MVWARP_CONV1_NOSPLIT")) {   // K-split of the last partial wave (see ConvParams)
-      int n_tail, split;
-      tail_split(p.nitems, nviews, plan->num_sms, n_tail, split);
-      if (split > 1 && scratch_bytes >= (int64_t)n_tail * split * 128 * CV_N * (int64_t)sizeof(float) && !(reinterpret_cast<uintptr_t>(scratch) & 15u)) {
-        p.split = split; p.n_full = p.nitems - n_tail; p.scratch = reinterpret_cast<float*>(scratch);
-      }
-    }
     const size_t nst = (size_t)3 * ((size_t)p.nitems * 8 + 8);
     if (getenv("MVWARP_CONV1_STATS")) {   // development only: synchronous, prints where the MMA thread waits
       cudaMalloc(&d_stats, nst * sizeof(unsigned long long));
       cudaMemset(d_stats, 0, nst * sizeof(unsigned long long));
       p.stats = d_stats;
     }
-    if (cl == 1) e = launch(warp_conv1_pipe_kernel<1>, 1);
-    else if (cl == 4) e = launch(warp_conv1_pipe_kernel<4>, 4);
-    else e = launch(warp_conv1_pipe_kernel<2>, 2);
+    if (pair) e = launch(warp_conv1_pipe_kernel<1, true>, 2);
+    else if (cl == 1) e = launch(warp_conv1_pipe_kernel<1, false>, 1);
+    else if (cl == 4) e = launch(warp_conv1_pipe_kernel<4, false>, 4);
+    else e = launch(warp_conv1_pipe_kernel<2, false>, 2);
     if (e == cudaSuccess && p.split > 1) {
       conv1_tail_reduce_kernel<<<dim3(p.nitems - p.n_full, 8), 256, 0, (cudaStream_t)stream>>>(p);
       e = cudaGetLastError();

@@ -411,6 +411,21 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+int make_weight_tensor_map(void* tmap_out, const void* wpack, uint64_t nblocks) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("the driver does not export cuTensorMapEncodeTiled"); return MVWARP_EUNSUPPORTED; }
+  if (reinterpret_cast<uintptr_t>(wpack) & 15u) { set_error("packed weights must be 16-byte aligned"); return MVWARP_EUNSUPPORTED; }
+  const cuuint64_t wdim[2] = {(cuuint64_t)C2_KB, (cuuint64_t)nblocks * C2_N};
+  const cuuint64_t wstr[1] = {(cuuint64_t)C2_KB * 2};
+  const cuuint32_t wbox[2] = {C2_KB, 128};
+  const cuuint32_t west[2] = {1, 1};
+  const CUresult wr = enc(reinterpret_cast<CUtensorMap*>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpack), wdim, wstr, wbox,
+                          west, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (wr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed (code " + std::to_string((int)wr) + ")"); return MVWARP_ECUDA; }
+  return MVWARP_OK;
+}
+
 }  // namespace mvw
 
 using namespace mvw;
@@ -450,20 +465,10 @@ extern "C" int mvwarp_conv3x3_fwd(const void* x, const int64_t x_strides[4], con
     set_error("conv3x3_fwd: cuTensorMapEncodeTiled failed (code " + std::to_string((int)cr) + ")");
     return MVWARP_ECUDA;
   }
-  // the packed weight as a 2-D tensor (64 x [blocks * 512] rows of 128 bytes), boxes of 128 rows, no swizzle (rows are pre-swizzled)
-  CUtensorMap tmap_w;
+  CUtensorMap tmap_w;   // the packed weight as a 2-D tensor of 128-byte rows, boxes of 128 rows
   {
-    const cuuint64_t wdim[2] = {(cuuint64_t)C2_KB, (cuuint64_t)(Cin / C2_KB) * 9 * C2_N};
-    const cuuint64_t wstr[1] = {(cuuint64_t)C2_KB * 2};
-    const cuuint32_t wbox[2] = {C2_KB, 128};
-    const cuuint32_t west[2] = {1, 1};
-    const CUresult wr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpack), wdim, wstr, wbox, west, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (wr != CUDA_SUCCESS || (reinterpret_cast<uintptr_t>(wpack) & 15u)) {
-      restore();
-      set_error("conv3x3_fwd: cuTensorMapEncodeTiled(weights) failed (code " + std::to_string((int)wr) + ")");
-      return MVWARP_ECUDA;
-    }
+    const int wrc = make_weight_tensor_map(&tmap_w, wpack, (uint64_t)(Cin / C2_KB) * 9);
+    if (wrc) { restore(); return wrc; }
   }
   Conv2Params p{};
   p.wpack = (const __nv_bfloat16*)wpack; p.bias = bias; p.out = out;

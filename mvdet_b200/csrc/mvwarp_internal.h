@@ -120,6 +120,10 @@ struct LaunchArgs {
   cudaStream_t stream;
 };
 
+// CUtensorMap (passed as void*: 128 bytes, 64-byte aligned) over packed weight blocks [nblocks][512][64] bf16 seen as a 2-D
+// tensor of 128-byte rows, box = 128 rows, no swizzle (the rows are pre-swizzled).  Implemented in mvwarp_conv2.cu.
+int make_weight_tensor_map(void* tmap_out, const void* wpack, uint64_t nblocks);
+
 int launch_fwd(const LaunchArgs& a);
 int launch_bwd(const LaunchArgs& a);
 int launch_device_grid(const mvwarp_plan* plan, float* d_grid_out, cudaStream_t stream);

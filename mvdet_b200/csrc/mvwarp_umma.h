@@ -135,6 +135,21 @@ __device__ __forceinline__ void mma_commit_2cta(uint64_t* bar, uint16_t cta_mask
                "h"(cta_mask)
                : "memory");
 }
+// wait with cluster-scope acquire (the arrivals come from the peer CTA's threads) / arrive on a barrier of another CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 // shared::cluster address of this CTA-local shared address in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;
