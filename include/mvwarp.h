@@ -157,6 +157,11 @@ int mvwarp_warp_views_bwd(const mvwarp_plan_t* plan, int view0, int nviews,
  * Validation hook for the descriptor / swizzle / TMEM conventions the fused warp -> conv1 kernel relies on
  * (M % 128 == 0, K % 64 == 0, device pointers). */
 int mvwarp_debug_gemm(const void* A, const void* B, void* D, int M, int N, int K, void* stream);
+/* The same with a probe layout of the A tile in shared memory: 8-row groups sbo_bytes apart (1024 = canonical), the tile shifted by
+ * start_cells * 128 bytes, chunks swizzled by absolute address bits, descriptor stride offset = sbo_bytes (+ the base-offset
+ * field if use_base_offset).  Development hook: which non-canonical operand layouts does the tensor core read correctly? */
+int mvwarp_debug_gemm_layout(const void* A, const void* B, void* D, int M, int N, int K, int sbo_bytes, int start_cells,
+                             int use_base_offset, void* stream);
 
 /* mvwarp_warp_conv1_fwd (north_star (c)): the warp fused into map_classifier[0] = Conv2d(V*C+2, 512, 3, padding=1)
  * (persp_trans_detector.py:51,81) as a tcgen05 implicit GEMM; the warped tensor is never materialised.

@@ -61,6 +61,7 @@ SIGNATURES = {
                                      C.c_int, _P]),
     "mvwarp_conv3x3_head_fwd": (C.c_int, [_P, _I64P, _P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mvwarp_debug_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "mvwarp_debug_gemm_layout": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mvwarp_warp_views_bwd": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, C.c_int, _P, _I64P,
                                         C.c_int, C.c_int, C.c_int, _P]),
 }

@@ -23,11 +23,17 @@ using namespace umma;
 // -----------------------------------------------------------------------------------------------------
 constexpr int GT_M = 128, GT_N = 256, GT_K = 64;
 
+// Layout probe (mvwarp_debug_gemm_layout): the A tile's 8-row groups are placed `sbo` bytes apart (1024 = the canonical layout),
+// the whole tile starts `start_cells` * 128 bytes into its buffer, every 16-byte chunk is swizzled by the ABSOLUTE address bits
+// (chunk ^ ((row address >> 7) & 7)), and the descriptor gets stride-byte-offset = sbo and, if `use_base_offset`, the
+// base-offset field (start >> 7) & 7.  Answers: can the nine conv taps be read straight out of a halo patch whose rows are not
+// 1024 bytes apart (tile 16 rows x 8 cells, patch pitch 10 cells = 1280 bytes) instead of being copied into canonical stages?
 __global__ void __launch_bounds__(128) gemm_tcgen05_test_kernel(const __nv_bfloat16* __restrict__ A,
-                                                               const __nv_bfloat16* __restrict__ B, float* __restrict__ D, int K) {
+                                                               const __nv_bfloat16* __restrict__ B, float* __restrict__ D, int K,
+                                                               int sbo, int start_cells, int use_base_offset) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem;                       // 128 x 128 B = 16 KB
-  uint8_t* sB = smem + GT_M * 128;          // 256 x 128 B = 32 KB
+  uint8_t* sA = smem;                       // up to 32 KB for the A probe layouts
+  uint8_t* sB = smem + 32768;               // 256 x 128 B = 32 KB
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_holder;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -48,8 +54,10 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_test_kernel(const __nv_bfloa
   for (int kb = 0; kb < K / GT_K; ++kb) {
     // stage A (row tid) and B (rows tid, tid+128): 8 chunks of 16 bytes per row, swizzled
     const uint4* ga = reinterpret_cast<const uint4*>(A + (size_t)(m0 + tid) * K + kb * GT_K);
+    const uint32_t a_row = (uint32_t)(start_cells * 128 + (tid >> 3) * sbo + (tid & 7) * 128);   // byte offset of row tid
+    const uint32_t a_phase = ((smem_u32(sA) + a_row) >> 7) & 7;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sA + sw128_offset(tid, c)) = __ldg(ga + c);
+    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sA + a_row + ((c ^ a_phase) << 4)) = __ldg(ga + c);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int r = tid + 128 * h;
@@ -61,7 +69,11 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_test_kernel(const __nv_bfloa
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint64_t da = smem_desc_sw128(smem_u32(sA)), db = smem_desc_sw128(smem_u32(sB));
+      const uint32_t a_start = smem_u32(sA) + start_cells * 128;
+      uint64_t da = smem_desc_sw128(a_start);
+      da = (da & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32);
+      if (use_base_offset) da |= (uint64_t)((a_start >> 7) & 7) << 49;
+      const uint64_t db = smem_desc_sw128(smem_u32(sB));
 #pragma unroll
       for (int k = 0; k < GT_K / 16; ++k)  // 16 bf16 = 32 bytes per step: advance the start address by 2 (x16 B)
         mma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, kb > 0 || k > 0);
@@ -91,14 +103,24 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_test_kernel(const __nv_bfloa
 using namespace mvw;
 
 extern "C" int mvwarp_debug_gemm(const void* A, const void* B, void* D, int M, int N, int K, void* stream) {
+  return mvwarp_debug_gemm_layout(A, B, D, M, N, K, 1024, 0, 0, stream);
+}
+
+extern "C" int mvwarp_debug_gemm_layout(const void* A, const void* B, void* D, int M, int N, int K, int sbo_bytes, int start_cells,
+                                        int use_base_offset, void* stream) {
   if (!A || !B || !D || N != GT_N || M <= 0 || M % GT_M || K <= 0 || K % GT_K) {
     set_error("debug_gemm: needs N == 256, M % 128 == 0, K % 64 == 0");
     return MVWARP_EINVAL;
   }
-  const int smem = (GT_M + GT_N) * 128 + 1024;
+  if (sbo_bytes < 1024 || sbo_bytes % 128 || start_cells < 0 || start_cells * 128 + 15 * sbo_bytes + 1024 > 32768) {
+    set_error("debug_gemm_layout: the probe layout must fit 32 KB (sbo >= 1024, multiple of 128)");
+    return MVWARP_EINVAL;
+  }
+  const int smem = 32768 + GT_N * 128 + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm test)");
-  gemm_tcgen05_test_kernel<<<M / GT_M, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, (float*)D, K);
+  gemm_tcgen05_test_kernel<<<M / GT_M, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, (float*)D, K, sbo_bytes,
+                                                                           start_cells, use_base_offset);
   e = cudaGetLastError();
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "debug_gemm launch");
 }
@@ -670,6 +692,293 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
   if (warp == 0) { if (PAIR) tmem_dealloc_2cta(tmem, CV_N); else tmem_dealloc(tmem, CV_N); }
 }
 
+// -----------------------------------------------------------------------------------------------------
+// Direct version (the default): CTA pairs as above, and the nine conv taps are no longer COPIED out of the halo patch --
+// the tensor core reads them in place.  The swizzle of a K-major operand is a function of the absolute shared-memory
+// address (probed: scripts/probe_umma_layout.py), so a descriptor may start at any 128-byte row of a buffer whose rows were
+// written with that rule, and the stride between its 8-row groups is free.  With the GEMM rows ordered x-major (row m = cell
+// (mx = m / 8, my = m % 8) of a tile 16 cells wide and 8 high) and the patch stored x-major too ([18][10] cells of 128 bytes),
+// the 8-row group g of tap (dy, dx) is the 8 consecutive patch cells (g + dx, dy .. dy+7): start = patch + ((dx * 10 + dy) * 128,
+// group stride = 10 * 128 = 1280 bytes.  So a patch (one view x 64 channels) is produced once and consumed by nine K blocks
+// straight away; the A stages and their 2 x 16 KB of shared-memory traffic per K block are gone (82 KB per K block in total
+// against the 112 KB of the copying pair kernel), and the ring is a ring of PATCHES.
+// -----------------------------------------------------------------------------------------------------
+constexpr int DT_X = 16, DT_Y = 8;                                             // tile: 16 cells in x, 8 in y
+constexpr int DP_X = DT_X + 2, DP_Y = DT_Y + 2, DP_CELLS = DP_X * DP_Y;        // halo patch 18 x 10 = 180 cells, x-major
+constexpr int DPATCH_BYTES = (DP_CELLS * 128 + 1023) / 1024 * 1024;           // 23 KB: every patch buffer starts 1024-aligned
+constexpr int NPATCH = 3, DPB = 4;                                             // patch ring, weight ring (32 KB stages)
+constexpr int D_SBO = DP_Y * 128;                                              // 1280 bytes between the 8-row groups of a tap
+constexpr int DP_TASKS = DP_CELLS * 8, DP_ROUNDS = (DP_TASKS + NPROD - 1) / NPROD;
+
+__global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sPatch = smem;                                        // NPATCH x 23 KB
+  uint8_t* sC = smem + NPATCH * DPATCH_BYTES;                    // 16 KB: canonical A stage of the coord_map K block
+  uint8_t* sB = sC + 16384;                                      // DPB x 32 KB
+  ConvTap* sT = reinterpret_cast<ConvTap*>(sB + DPB * CV_B2_BYTES);   // taps of the halo cells: 2 buffers (current / next view)
+  __shared__ __align__(8) uint64_t p_full[NPATCH], p_empty[NPATCH], c_full, b_full[DPB], b_empty[DPB], acc_full;
+  __shared__ uint32_t tmem_holder;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t prank = cluster_ctarank();
+  int item = blockIdx.x, part = 0, nparts = 1, slot = 0;
+  {
+    const int cpair = blockIdx.x >> 1, nfp = p.n_full >> 1;
+    if (cpair >= nfp) {
+      const int q = cpair - nfp, j = q / p.split;
+      part = q % p.split; nparts = p.split;
+      item = p.n_full + 2 * j + (int)prank;
+      slot = q * 2 + (int)prank;
+    }
+  }
+  const bool real_tile = item < p.nitems;
+  if (!real_tile) item = p.nitems - 1;
+  const int b = item / p.ntiles, tile = p.tile0 + item % p.ntiles;
+  const int tx0 = (tile % p.tiles_x) * DT_X, ty0 = (tile / p.tiles_x) * DT_Y;
+  const int ncb = p.C / CV_KB;
+  const int vlo = (part * p.nviews) / nparts, vhi = ((part + 1) * p.nviews) / nparts;
+  const bool coord_here = p.with_coord && part == nparts - 1;
+  const bool partial = nparts > 1;
+  const int npatch = (vhi - vlo) * ncb;                       // patches = (view, channel block) pairs of this CTA
+  const int NK = npatch * 9 + (coord_here ? 1 : 0);
+  const int wblk0 = vlo * ncb * 9, wblk_coord = p.nviews * ncb * 9;
+
+  if (warp == 0) tmem_alloc_2cta(&tmem_holder, CV_N);
+  if (tid == 0) {
+    const uint32_t nprod = NPROD / 32 + (prank == 0 ? 1 : 0);   // producer warps (+ the peer's relay on the leader)
+    for (int i = 0; i < NPATCH; ++i) { mbar_init(&p_full[i], nprod); mbar_init(&p_empty[i], 1); }
+    mbar_init(&c_full, nprod);
+    for (int i = 0; i < DPB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+
+  if (warp == 9) {
+    // ===== my half of every weight block: two TMA boxes of 128 rows, completing on the leader's barrier =====
+    if (lane == 0) {
+      for (int kb = 0; kb < NK; ++kb) {
+        const int s = kb % DPB;
+        const int wblk = kb < npatch * 9 ? wblk0 + kb : wblk_coord;
+        if (kb >= DPB) mbar_wait(&b_empty[s], ((kb / DPB) - 1) & 1);
+        if (prank == 0) mbar_expect_tx(&b_full[s], CV_B_BYTES);
+        const uint32_t dst = smem_u32(sB + (size_t)s * CV_B2_BYTES), bar = map_to_cta(smem_u32(&b_full[s]), 0);
+        tma_wbox_2cta(dst, &tmap_w, wblk * CV_N + 128 * (int)prank, bar);
+        tma_wbox_2cta(dst + CV_B2_BYTES / 2, &tmap_w, wblk * CV_N + 256 + 128 * (int)prank, bar);
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0 && prank == 0) {
+      // ===== MMA issuer (leader, for both CTAs) =====
+      const uint32_t idesc = idesc_bf16_f32(256, 256);
+      long long wa = 0, wb = 0;
+      const long long t_start = clock64();
+      int kb = 0;
+      auto mma_block = [&](uint64_t da) {   // one K block against weight stage kb % DPB
+        const int sb = kb % DPB;
+        const long long t1 = clock64();
+        mbar_wait(&b_full[sb], (kb / DPB) & 1);
+        wb += clock64() - t1;
+        tc_fence_after();
+        const uint32_t bbase = smem_u32(sB + (size_t)sb * CV_B2_BYTES);
+        const uint64_t db0 = smem_desc_sw128(bbase), db1 = smem_desc_sw128(bbase + CV_B2_BYTES / 2);
+#pragma unroll
+        for (int k = 0; k < CV_KB / 16; ++k) {
+          mma_bf16_2cta(tmem, da + 2 * k, db0 + 2 * k, idesc, kb > 0 || k > 0);
+          mma_bf16_2cta(tmem + 256, da + 2 * k, db1 + 2 * k, idesc, kb > 0 || k > 0);
+        }
+        mma_commit_2cta(&b_empty[sb], 3);
+        ++kb;
+      };
+      for (int pk = 0; pk < npatch; ++pk) {
+        const int i = pk % NPATCH;
+        const long long t0 = clock64();
+        mbar_wait_cluster(&p_full[i], (pk / NPATCH) & 1);
+        wa += clock64() - t0;
+        const uint32_t pbase = smem_u32(sPatch + (size_t)i * DPATCH_BYTES);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap)   // tap = ky * 3 + kx: the patch cell of tile cell (0, 0) is (x = kx, y = ky)
+          mma_block(smem_desc_sw128_sbo(pbase + (uint32_t)(((tap % 3) * DP_Y + tap / 3) * 128), D_SBO));
+        mma_commit_2cta(&p_empty[i], 3);
+      }
+      if (coord_here) {
+        const long long t0 = clock64();
+        mbar_wait_cluster(&c_full, 0);
+        wa += clock64() - t0;
+        mma_block(smem_desc_sw128(smem_u32(sC)));
+      }
+      mma_commit_2cta(&acc_full, 3);
+      if (p.stats) {
+        unsigned long long* st = p.stats + 3 * (size_t)blockIdx.x;
+        st[0] = (unsigned long long)wa; st[1] = (unsigned long long)wb; st[2] = (unsigned long long)(clock64() - t_start);
+      }
+    } else if (lane == 0) {
+      // ===== relay (peer): forward "my patch is complete" to the leader's barrier with one remote arrive =====
+      for (int pk = 0; pk < npatch; ++pk) {
+        const int i = pk % NPATCH;
+        mbar_wait(&p_full[i], (pk / NPATCH) & 1);
+        mbar_arrive_cluster(map_to_cta(smem_u32(&p_full[i]), 0));
+      }
+      if (coord_here) {
+        mbar_wait(&c_full, 0);
+        mbar_arrive_cluster(map_to_cta(smem_u32(&c_full), 0));
+      }
+    }
+  } else {
+    // ===== producers (256 threads), then epilogue =====
+    auto compute_taps = [&](int vl, ConvTap* dst) {   // patch cell i = (px = i / 10, py = i % 10) <-> grid cell (tx0 + px - 1, ty0 + py - 1)
+      const int v = p.view0 + vl;
+      for (int i = tid; i < DP_CELLS; i += NPROD) {
+        const int gx = tx0 + i / DP_Y - 1, gy = ty0 + i % DP_Y - 1;
+        ConvTap t;
+        t.mask = 0; t.x0 = t.y0 = 0; t.pad = 0;
+        t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
+        if (gy >= 0 && gy < p.Hg && gx >= 0 && gx < p.Wg) {
+          float Tm[9];
+#pragma unroll
+          for (int q = 0; q < 9; ++q) Tm[q] = __ldg(p.T + 9 * v + q);
+          float sx, sy;
+          norm_src_coord(Tm, gx, gy, p.Hg, p.Wg, sx, sy);
+          const Taps tp = make_taps(sx, sy, p.Hs, p.Ws);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) t.w[k] = tp.w[k];
+          t.x0 = tp.x0; t.y0 = tp.y0; t.mask = tp.mask;
+        }
+        dst[i] = t;
+      }
+    };
+    uint4 tv[DP_ROUNDS][4];   // gathers in flight for the next patch
+    auto issue_gathers = [&](int vl, int cb, const ConvTap* taps) {
+      const __nv_bfloat16* fv = p.feats + (int64_t)b * p.fB + (int64_t)vl * p.fV + cb * CV_KB;
+#pragma unroll
+      for (int j = 0; j < DP_ROUNDS; ++j) {
+        const int task = tid + j * NPROD;
+        const int cell = task >> 3, ch = task & 7;
+        if (task < DP_TASKS) {
+          const ConvTap t = taps[cell];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int xx = t.x0 + (k & 1), yy = t.y0 + (k >> 1);
+            tv[j][k] = (t.mask >> k & 1) ? __ldg(reinterpret_cast<const uint4*>(fv + (int64_t)yy * p.fH + (int64_t)xx * p.fW + ch * 8))
+                                         : make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+    };
+    auto blend_patch = [&](const ConvTap* taps, uint8_t* patch) {   // patch buffers are 1024-aligned: swizzle phase = cell & 7
+#pragma unroll
+      for (int j = 0; j < DP_ROUNDS; ++j) {
+        const int task = tid + j * NPROD;
+        const int cell = task >> 3, ch = task & 7;
+        if (task < DP_TASKS) {
+          const ConvTap t = taps[cell];
+          const unsigned* a = &tv[j][0].x; const unsigned* bq = &tv[j][1].x; const unsigned* c = &tv[j][2].x; const unsigned* d = &tv[j][3].x;
+          unsigned o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float lo = __fmaf_rn(bf_lo(d[q]), t.w[3], __fmaf_rn(bf_lo(c[q]), t.w[2], __fmaf_rn(bf_lo(bq[q]), t.w[1], __fmul_rn(bf_lo(a[q]), t.w[0]))));
+            const float hi = __fmaf_rn(bf_hi(d[q]), t.w[3], __fmaf_rn(bf_hi(c[q]), t.w[2], __fmaf_rn(bf_hi(bq[q]), t.w[1], __fmul_rn(bf_hi(a[q]), t.w[0]))));
+            o[q] = pack_bf2(lo, hi);
+          }
+          *reinterpret_cast<uint4*>(patch + cell * 128 + ((ch ^ (cell & 7)) << 4)) = t.mask ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0, 0, 0, 0);
+        }
+      }
+    };
+    auto publish = [&](uint64_t* bar) {   // all of this warp's writes -> async proxy, then one arrival per warp
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+
+    if (npatch > 0) {
+      compute_taps(vlo, sT + (vlo & 1) * DP_CELLS);
+      producers_sync();
+      issue_gathers(vlo, 0, sT + (vlo & 1) * DP_CELLS);
+    }
+    for (int pk = 0; pk < npatch; ++pk) {
+      const int blk = vlo * ncb + pk, vl = blk / ncb;
+      const int i = pk % NPATCH;
+      if (pk >= NPATCH) mbar_wait(&p_empty[i], ((pk / NPATCH) - 1) & 1);   // the nine K blocks that read this buffer are done
+      blend_patch(sT + (vl & 1) * DP_CELLS, sPatch + (size_t)i * DPATCH_BYTES);    // consumes the gathers issued one patch earlier
+      publish(&p_full[i]);
+      if (pk + 1 < npatch) {             // the next patch's gathers fly while the tensor core works on this one
+        const int nvl = (blk + 1) / ncb, ncbi = (blk + 1) % ncb;
+        if (ncbi == 0) {                 // next patch opens a new view: its taps go to the other buffer
+          producers_sync();              // everybody is done reading the buffer of the view before this one
+          compute_taps(nvl, sT + (nvl & 1) * DP_CELLS);
+          producers_sync();
+        }
+        issue_gathers(nvl, ncbi, sT + (nvl & 1) * DP_CELLS);
+      }
+    }
+    if (coord_here) {  // the two coord_map channels: all 9 taps x 2 channels in one K block (k = tap*2 + ch), canonical layout
+      const int m = tid & 127, half = tid >> 7, mx = m / DT_Y, my = m % DT_Y;
+      unsigned short vals[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) vals[k] = 0;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int gy = ty0 + my + tap / 3 - 1, gx = tx0 + mx + tap % 3 - 1;
+        if (gy >= 0 && gy < p.Hg && gx >= 0 && gx < p.Wg) {
+          vals[tap * 2] = __bfloat16_as_ushort(__float2bfloat16_rn(__ldg(p.coord_x + gx)));
+          vals[tap * 2 + 1] = __bfloat16_as_ushort(__float2bfloat16_rn(__ldg(p.coord_y + gy)));
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = 4 * half + cc;     // chunks 0..3 carry k = 0..31 (18 used), chunks 4..7 are zero
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (half == 0) {
+          r.x = vals[cc * 8 + 0] | ((unsigned)vals[cc * 8 + 1] << 16); r.y = vals[cc * 8 + 2] | ((unsigned)vals[cc * 8 + 3] << 16);
+          r.z = vals[cc * 8 + 4] | ((unsigned)vals[cc * 8 + 5] << 16); r.w = vals[cc * 8 + 6] | ((unsigned)vals[cc * 8 + 7] << 16);
+        }
+        *reinterpret_cast<uint4*>(sC + sw128_offset(m, c)) = r;
+      }
+      publish(&c_full);
+    }
+    // ----- epilogue: thread = GEMM row = TMEM lane (quarter warp % 4); warps 0-3 take columns 0-255, warps 4-7 256-511 -----
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const int er = (warp & 3) * 32 + lane, ex = er / DT_Y, ey = er % DT_Y;
+    const int gy = ty0 + ey, gx = tx0 + ex;
+    const bool inside = real_tile && gy < p.Hg && gx < p.Wg;
+    const int64_t ooff = (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW;
+    const int cbeg = (warp >> 2) * 256;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + 256; c0 += 32) {
+      float vv[32];
+      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, vv);
+      if (partial) {
+        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)slot * 128 + er) * CV_N + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+      } else if (inside) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (p.bias) vv[i] += __ldg(p.bias + c0 + i);
+          if (p.relu) vv[i] = fmaxf(vv[i], 0.f);
+        }
+        if (p.out_bf16) {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            o[i] = make_uint4(pack_bf2(vv[8 * i], vv[8 * i + 1]), pack_bf2(vv[8 * i + 2], vv[8 * i + 3]),
+                              pack_bf2(vv[8 * i + 4], vv[8 * i + 5]), pack_bf2(vv[8 * i + 6], vv[8 * i + 7]));
+        } else {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ooff + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 0) tmem_dealloc_2cta(tmem, CV_N);
+}
+
 // out[item's cells] = [relu](bias + sum over the item's K-split parts, in part order) for the tail items of a launch.
 __global__ void __launch_bounds__(256) conv1_tail_reduce_kernel(const ConvParams p) {
   const int item = p.n_full + blockIdx.x;
@@ -683,7 +992,8 @@ __global__ void __launch_bounds__(256) conv1_tail_reduce_kernel(const ConvParams
   // grid.y = 8 slices of 16 cells: 49 tail items alone would leave two thirds of the SMs idle (55 us instead of ~10)
   for (int i = threadIdx.x; i < 16 * CV_N / 4; i += blockDim.x) {
     const int row = blockIdx.y * 16 + i / (CV_N / 4), c = (i % (CV_N / 4)) * 4;
-    const int gy = ty0 + row / CT_W, gx = tx0 + row % CT_W;
+    // GEMM row -> tile cell: y-major 8 x 16 in the copying kernels, x-major (16 wide, 8 high) in the direct kernel; the tile is 16 x 8 cells either way
+    const int gy = ty0 + (p.pair_mode == 2 ? row % DT_Y : row / CT_W), gx = tx0 + (p.pair_mode == 2 ? row / DT_Y : row % CT_W);
     if (gy >= p.Hg || gx >= p.Wg) continue;
     float4 a = *reinterpret_cast<const float4*>(base + (size_t)row * CV_N + c);
     for (int s = 1; s < p.split; ++s) {
@@ -736,9 +1046,11 @@ static Decomp decompose(int nitems, int nviews, int num_sms, bool pair) {
   return d;
 }
 
-static bool pair_mode_wanted() {
-  const char* e = getenv("MVWARP_CONV1_PAIR");   // development knob: 0 = single-CTA kernel
-  return !(e && e[0] == '0') && !getenv("MVWARP_CONV1_VARIANT");
+// 0 = single-CTA kernel, 1 = CTA pairs with copied tap stages, 2 = CTA pairs reading the taps in place (default)
+static int pair_mode_wanted() {
+  const char* e = getenv("MVWARP_CONV1_PAIR");   // development knob
+  if (getenv("MVWARP_CONV1_VARIANT")) return 0;
+  return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2;
 }
 
 }  // namespace mvw
@@ -750,7 +1062,7 @@ extern "C" int64_t mvwarp_warp_conv1_scratch_bytes(const mvwarp_plan_t* plan, in
   const int tiles_x = (plan->Wg + CT_W - 1) / CT_W;
   const int64_t nitems = (int64_t)((nrows + CT_H - 1) / CT_H) * tiles_x * B;
   if (nitems > 0x7fffffff) return 0;
-  const Decomp d = decompose((int)nitems, nviews, plan->num_sms, pair_mode_wanted());
+  const Decomp d = decompose((int)nitems, nviews, plan->num_sms, pair_mode_wanted() != 0);
   return d.slots * 128 * CV_N * (int64_t)sizeof(float);
 }
 
@@ -820,7 +1132,8 @@ extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, in
   } else {
     const int smem = PA * 16384 + PB * (int)CV_B_BYTES + CP_CELLS * 128 + 2 * CP_CELLS * (int)sizeof(ConvTap) + 1024;
     const int cl = (variant && variant[0] >= '1' && variant[0] <= '4') ? variant[0] - '0' : 1;
-    const bool pair = pair_mode_wanted() && cl == 1;
+    const int pmode = cl == 1 ? pair_mode_wanted() : 0;
+    const bool pair = pmode != 0;
     CUtensorMap tmap_w;
     memset(&tmap_w, 0, sizeof(tmap_w));
     if (pair) {
@@ -828,7 +1141,7 @@ extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, in
       const int wrc = make_weight_tensor_map(&tmap_w, wpack, nblocks);
       if (wrc) { if (prev >= 0 && prev != plan->device) cudaSetDevice(prev); return wrc; }
     }
-    p.pair_mode = pair ? 1 : 0;
+    p.pair_mode = pmode;
     if (pair) p.n_full = p.nitems / 2 * 2;
     if (cl == 1 && scratch && !getenv("MVWARP_CONV1_NOSPLIT")) {   // K-split of the last partial wave (see ConvParams)
       const Decomp d = decompose(p.nitems, nviews, plan->num_sms, pair);
@@ -859,7 +1172,22 @@ extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, in
       cudaMemset(d_stats, 0, nst * sizeof(unsigned long long));
       p.stats = d_stats;
     }
-    if (pair) e = launch(warp_conv1_pipe_kernel<1, true>, 2);
+    if (pmode == 2) {
+      const int smem_d = NPATCH * DPATCH_BYTES + 16384 + DPB * (int)CV_B2_BYTES + 2 * DP_CELLS * (int)sizeof(ConvTap) + 1024;
+      e = cudaFuncSetAttribute(warp_conv1_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
+      if (e == cudaSuccess) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(p.n_full + (p.nitems - p.n_full + 1) / 2 * 2 * p.split, 1, 1);
+        cfg.blockDim = dim3(PIPE_THREADS);
+        cfg.dynamicSmemBytes = smem_d;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, warp_conv1_direct_kernel, tmap_w, p);
+      }
+    } else if (pair) e = launch(warp_conv1_pipe_kernel<1, true>, 2);
     else if (cl == 1) e = launch(warp_conv1_pipe_kernel<1, false>, 1);
     else if (cl == 4) e = launch(warp_conv1_pipe_kernel<4, false>, 4);
     else e = launch(warp_conv1_pipe_kernel<2, false>, 2);

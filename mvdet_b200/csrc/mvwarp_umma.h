@@ -72,6 +72,19 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same with an arbitrary stride between the 8-row groups (multiple of 16 bytes).  Probed on B200 (scripts/probe_umma_layout.py):
+// the 128-byte swizzle is applied to the ABSOLUTE shared-memory address bits (chunk ^= (address >> 7) & 7), so an operand whose
+// rows were written with that rule is read correctly from any 128-byte-aligned start address and with any group stride, with the
+// descriptor's base-offset field left at 0.
+__device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) { return (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4)); }
 
 // kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A and B bf16 (bits 7-9, 10-12 = 1), both K-major
