@@ -180,6 +180,10 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv3x3_tc_kernel(const __grid_
 // (64 KB per 0.55 us of tensor work per SM), is halved.  All TMA copies of the pair (tensor maps for A and for the packed
 // weights, .cta_group::2) complete on the LEADER's full barriers, the leader's MMA thread issues for both CTAs, and its
 // commits arrive on the empty barriers of both (multicast).  Each CTA drains its own 128 x 512 accumulator from its own TMEM.
+// Tried and dropped: fetching the tile's halo patch ONCE per channel block (one x-major TMA box through a tensor map with the
+// dimensions listed as (C, y, x, batch)) and reading the nine taps in place like warp_conv1_direct_kernel does -- correct, but
+// 0.200 vs 0.193 ms at Wildtrack B=1 and 0.716 vs 0.685 ms at B=4: with only 72 K blocks per tile this kernel is bound by the
+// per-tile prologue and the un-overlapped epilogue (all 512 TMEM columns hold the accumulator), not by its A side.
 // -----------------------------------------------------------------------------------------------------
 constexpr int T2_PA = 4, T2_PB = 4;
 constexpr uint32_t T2_B_BYTES = C2_B_BYTES / 2;   // 32 KB of weights per CTA per K block
