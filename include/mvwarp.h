@@ -164,7 +164,9 @@ int mvwarp_debug_gemm_layout(const void* A, const void* B, void* D, int M, int N
                              int use_base_offset, void* stream);
 
 /* mvwarp_warp_conv1_fwd (north_star (c)): the warp fused into map_classifier[0] = Conv2d(V*C+2, 512, 3, padding=1)
- * (persp_trans_detector.py:51,81) as a tcgen05 implicit GEMM; the warped tensor is never materialised.
+ * (persp_trans_detector.py:51,81) as a tcgen05 implicit GEMM; the warped tensor is never materialised.  Runs in CTA pairs
+ * (cta_group::2, M = 256 per MMA, half of every weight block per SM) whose nine conv taps the tensor core reads in place from
+ * the warped halo patch; needs a device with thread-block clusters and TMA (sm_100a).
  *   out[b, n, y, x] = (bias ? bias[n] : 0) + sum_{dy,dx} sum_{ch} W[n, ch, dy, dx] * X[b, ch, y+dy-1, x+dx-1]   (+ ReLU if relu)
  * with X = the warp of views [view0, view0+nviews) (+ the two coord_map channels if with_coord), zero padded.
  * feats: bf16, logical [B, nviews, C, Hs, Ws], channel-contiguous, C % 64 == 0.  out: fp32 [B, 512, Hg, Wg] channels-last.

@@ -1,5 +1,13 @@
-// mvwarp_conv1.cu -- tensor-core side of the path (north_star (c)): tcgen05 / TMEM GEMM building blocks for the
-// fused warp -> map_classifier[0] implicit GEMM (/root/reference/multiview_detector/models/persp_trans_detector.py:51,81).
+// mvwarp_conv1.cu -- tensor-core side of the path (north_star (c)): the fused warp -> map_classifier[0] implicit GEMM on
+// tcgen05 / TMEM (/root/reference/multiview_detector/models/persp_trans_detector.py:51,81).  Kernels, in the order they were
+// developed (each kept because the next one is measured against it; profiles/README.md has the numbers):
+//   gemm_tcgen05_test_kernel   validation GEMM that pins the descriptor / swizzle / TMEM conventions (and the layout probe)
+//   warp_conv1_kernel          correctness-first fused kernel, no pipelining            (MVWARP_CONV1_VARIANT=s)
+//   warp_conv1_pipe_kernel     warp-specialised mbarrier pipeline, tap stages copied out of the halo patch; optionally a
+//                              cluster with multicast weights (<CL>, MVWARP_CONV1_VARIANT=2|4) or CTA pairs with
+//                              cta_group::2 MMAs (<1, true>, MVWARP_CONV1_PAIR=1); single CTAs: MVWARP_CONV1_PAIR=0
+//   warp_conv1_direct_kernel   THE DEFAULT: CTA pairs, taps read in place from the halo patch (no tap copies)
+//   conv1_tail_reduce_kernel   adds the K-split partial sums of the last partial wave of tiles
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>

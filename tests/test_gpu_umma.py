@@ -188,3 +188,52 @@ def test_map_head_matches_the_reference_module():
     # rounding boundary flip, each flip is 2^-8 relative on one activation -> a few 1e-3 on the final map
     emax, el2 = rel_errors(out, ref)
     assert emax <= 1e-2 and el2 <= 5e-3, (emax, el2)
+
+
+def test_operand_swizzle_follows_absolute_address():
+    """The property warp_conv1_direct_kernel rests on: an A operand written with chunk ^= (address >> 7) & 7 is
+    read correctly from any 128-byte-aligned start and with any stride between its 8-row groups, base-offset field 0."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    M, K = 128, 128
+    A = torch.randn(M, K, generator=g).bfloat16().cuda()
+    B = torch.randn(256, K, generator=g).bfloat16().cuda()
+    ref = A.float() @ B.float().T
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for sbo, start in [(1024, 0), (1024, 3), (1280, 0), (1280, 1), (1280, 11), (1280, 21), (1536, 5)]:
+        D = torch.full((M, 256), float("nan"), device="cuda")
+        _lib.check(lib.mvwarp_debug_gemm_layout(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(D.data_ptr()), M, 256, K,
+                                                sbo, start, 0, stream), "mvwarp_debug_gemm_layout")
+        torch.cuda.synchronize()
+        assert float((D - ref).abs().max() / ref.abs().max()) <= 1e-5, (sbo, start)
+    D = torch.empty(M, 256, device="cuda")
+    assert lib.mvwarp_debug_gemm_layout(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(D.data_ptr()), M, 256, K, 1000, 0, 0,
+                                        stream) == _lib.EINVAL
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_fused_conv1_kernel_generations_agree(mode, monkeypatch):
+    """Single-CTA kernel (0), CTA pairs with copied tap stages (1) and the default direct kernel (2) against the same reference,
+    on a shape with an odd tile count (padding CTA in pair mode), partial tiles, the coord block and a K-split tail; bf16 output too."""
+    from mvdet_b200 import conv1
+    from tests.util import small_rig, to_channels_last_5d, rel_errors
+    monkeypatch.setenv("MVWARP_CONV1_PAIR", mode)
+    V, Cc = 3, 64
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=41, grid=(24, 72))     # 3 x 5 tiles = 15 per frame
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, V, Cc, *src_hw, generator=g).bfloat16()
+    weight = torch.randn(512, V * Cc + 2, 3, 3, generator=g) * 0.05
+    bias = torch.randn(512, generator=g)
+    ref = _conv1_reference(x, pm, grid_hw, weight, bias, relu=True)
+    wpack = conv1.pack_conv1_weight(weight, V, Cc).cuda()
+    xd = to_channels_last_5d(x).cuda()
+    out = conv1.warp_conv1(xd, pm, grid_hw, wpack, bias, relu=True)
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= 1e-4 and el2 <= 1e-4, (mode, emax, el2)
+    out16 = conv1.warp_conv1(xd, pm, grid_hw, wpack, bias, relu=True, out_dtype=torch.bfloat16)
+    assert out16.dtype == torch.bfloat16 and torch.equal(out16, out.bfloat16())
+    again = conv1.warp_conv1(xd, pm, grid_hw, wpack, bias, relu=True)
+    assert torch.equal(again, out)                                         # deterministic (fixed K-split reduce order)
+    rows = conv1.warp_conv1(xd, pm, grid_hw, wpack, bias, relu=True, rows=(8, 24))
+    emax, _ = rel_errors(rows[:, :, 8:24], ref[:, :, 8:24])
+    assert emax <= 1e-4

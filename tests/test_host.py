@@ -260,3 +260,24 @@ def test_plan_load_refuses_bad_files(tmp_path):
     assert not h.value
     assert lib.mvwarp_plan_save(None, b"/tmp/x") == _lib.EINVAL
     assert lib.mvwarp_plan_matrices(None, None) == _lib.EINVAL
+
+
+def test_map_head_weight_packing():
+    """map_head.pack_conv3x3_weight / pack_head_weight: layouts of map_classifier[2] / [4] (persp_trans_detector.py:53-54)."""
+    from mvdet_b200.map_head import pack_conv3x3_weight, pack_head_weight
+    g = torch.Generator().manual_seed(2)
+    w2 = torch.randn(512, 128, 3, 3, generator=g)
+    p2 = pack_conv3x3_weight(w2)
+    assert p2.shape == (2 * 9, 512, 64) and p2.dtype == torch.bfloat16
+    wb = w2.bfloat16()
+    for (cb, tap, n, k) in [(0, 0, 0, 0), (1, 7, 300, 41), (0, 4, 511, 63)]:
+        pos = (k // 8) ^ (n & 7)
+        assert p2[cb * 9 + tap, n, pos * 8 + k % 8] == wb[n, cb * 64 + k, tap // 3, tap % 3]
+    w3 = torch.randn(1, 512, 3, 3, generator=g)
+    p3 = pack_head_weight(w3)
+    assert p3.shape == (9, 512) and p3.dtype == torch.bfloat16
+    assert p3[5, 17] == w3.bfloat16()[0, 17, 1, 2]
+    with pytest.raises(ValueError):
+        pack_conv3x3_weight(torch.randn(512, 100, 3, 3))
+    with pytest.raises(ValueError):
+        pack_head_weight(torch.randn(2, 512, 3, 3))
