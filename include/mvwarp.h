@@ -193,6 +193,23 @@ int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, int nviews, c
                              void* scratch, int64_t scratch_bytes, void* stream);
 int64_t mvwarp_warp_conv1_scratch_bytes(const mvwarp_plan_t* plan, int nviews, int B, int row0, int nrows);
 
+/* mvwarp_warp_conv1_fwd_p2p: the view-sharded fused conv1 with the reduce-scatter of its partial sums fused into the GEMM's
+ * epilogue ("each rank computes its per-view conv1 partial sum, partials are combined with a reduce over NVLink").
+ * Rank r of nranks (<= 8, one process per GPU) owns the grid rows [band_row0[r], band_row0[r+1]).  peer_inbox[r] is rank r's
+ * inbox as mapped into THIS process (symmetric / IPC memory; fp32 [nranks][B][band_rows_max][Wg][512]): the epilogue of every
+ * tile stores this rank's raw partial sums (no bias, no ReLU) for the tile's cells into slot my_rank of the owner's inbox --
+ * peer-to-peer stores over NVLink / NVSwitch that ride along with the tensor-core work, no extra kernel, no collective call.
+ * After a cross-rank barrier every rank adds the nranks slots of its own inbox (+ bias, ReLU): mvdet_b200.sharding.
+ * Replaces: conv1 partial + torch.distributed.all_reduce in the view-sharded map_classifier[0] (persp_trans_detector.py:51,81). */
+/* mvwarp_inbox_reduce: the owner's side of that exchange.  out[b][i] = [relu](bias[i % 512] + sum_s inbox[s][b][i]) for the nslots
+ * slots (added in slot order: deterministic), i < n_per_b (a multiple of 512: whole cells); slot_pitch / b_pitch in elements;
+ * out contiguous [B][n_per_b], MVWARP_F32 or MVWARP_BF16.  One pass over the data. */
+int mvwarp_inbox_reduce(const float* inbox, int nslots, int64_t slot_pitch, int64_t b_pitch, int B, int64_t n_per_b,
+                        const float* bias, int relu, void* out, int out_dtype, int device, void* stream);
+int mvwarp_warp_conv1_fwd_p2p(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats, const int64_t feat_strides[5],
+                              const void* wpack, int B, int C, int with_coord, int nranks, int my_rank, const uint64_t* peer_inbox,
+                              const int32_t* band_row0, int band_rows_max, void* stream);
+
 /* ---- the rest of map_classifier (persp_trans_detector.py:53-54, applied at :81) -------------
  * mvwarp_conv3x3_fwd: out = [relu](conv2d(x, W, bias, padding = dilation, dilation = dilation)) for a 3x3 kernel with
  * 512 output channels -- map_classifier[2] = Conv2d(512, 512, 3, padding=2, dilation=2) + ReLU -- as a tcgen05 implicit

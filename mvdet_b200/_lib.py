@@ -56,6 +56,9 @@ SIGNATURES = {
                                         C.c_int, C.c_int, C.c_int, _P]),
     "mvwarp_warp_conv1_fwd_ex": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, _P, _P, _P, C.c_int, _I64P, C.c_int, C.c_int, C.c_int,
                                            C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P]),
+    "mvwarp_warp_conv1_fwd_p2p": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.c_int, _P]),
+    "mvwarp_inbox_reduce": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int64, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
     "mvwarp_warp_conv1_scratch_bytes": (C.c_int64, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mvwarp_conv3x3_fwd": (C.c_int, [_P, _I64P, _P, _P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, _P]),

@@ -175,6 +175,18 @@ struct ConvParams {
   // (n_full even), then for tail pair j and K part q cluster n_full/2 + j*split + q takes items n_full + 2j (+1), part q:
   // the two CTAs of a pair always walk the same weight blocks.  Scratch slot of (tail item n_full + 2j + r, part q) = (j*split + q)*2 + r.
   unsigned long long* stats;   // development: per CTA {cycles waiting for A, for B, total} of the MMA thread, or nullptr
+  // Fused reduce-scatter over NVLink peer memory (view-sharded conv1, direct kernel only).  Rank r of p2p_n owns the grid rows
+  // [p2p_row0[r], p2p_row0[r+1]); instead of storing its partial sums locally, the epilogue of every tile writes them -- raw
+  // fp32, no bias / ReLU -- straight into the OWNER's inbox (a symmetric-memory buffer mapped into this process):
+  //   inbox[owner][p2p_src][b][y - row0[owner]][x][512].  The stores ride along with the GEMM tile by tile, so the exchange costs
+  // no extra kernel and no SMs; afterwards every rank sums the p2p_n slots of its own inbox (mvdet_b200.sharding).
+  int p2p_n, p2p_src;
+  int p2p_tile_shift;          // tiles are visited starting at the band AFTER this rank's own, so that at any moment the ranks store
+                               // into different owners' inboxes (all ranks walking the map in the same order made every rank hit the
+                               // same owner at once: 32 ms instead of 8 on 8 GPUs)
+  int p2p_row0[9];
+  unsigned long long p2p_inbox[8];
+  long long p2p_src_pitch, p2p_b_pitch;   // elements between source slots / batch elements of an inbox
 };
 
 struct ConvTap {
@@ -740,7 +752,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
   }
   const bool real_tile = item < p.nitems;
   if (!real_tile) item = p.nitems - 1;
-  const int b = item / p.ntiles, tile = p.tile0 + item % p.ntiles;
+  const int b = item / p.ntiles, tile = p.tile0 + (item % p.ntiles + p.p2p_tile_shift) % p.ntiles;
   const int tx0 = (tile % p.tiles_x) * DT_X, ty0 = (tile / p.tiles_x) * DT_Y;
   const int ncb = p.C / CV_KB;
   const int vlo = (part * p.nviews) / nparts, vhi = ((part + 1) * p.nviews) / nparts;
@@ -953,6 +965,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
     const int gy = ty0 + ey, gx = tx0 + ex;
     const bool inside = real_tile && gy < p.Hg && gx < p.Wg;
     const int64_t ooff = (int64_t)b * p.oB + (int64_t)gy * p.oH + (int64_t)gx * p.oW;
+    float* p2p_dst = nullptr;
+    if (p.p2p_n > 0 && inside) {
+      int o = 0;
+      while (o + 1 < p.p2p_n && gy >= p.p2p_row0[o + 1]) ++o;
+      p2p_dst = reinterpret_cast<float*>(p.p2p_inbox[o]) + (int64_t)p.p2p_src * p.p2p_src_pitch + (int64_t)b * p.p2p_b_pitch +
+                ((int64_t)(gy - p.p2p_row0[o]) * p.Wg + gx) * CV_N;
+    }
     const int cbeg = (warp >> 2) * 256;
 #pragma unroll 1
     for (int c0 = cbeg; c0 < cbeg + 256; c0 += 32) {
@@ -962,6 +981,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
         float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)slot * 128 + er) * CV_N + c0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+      } else if (p.p2p_n > 0) {
+        if (inside) {   // raw partial sums into the inbox of the rank that owns this grid row (peer memory over NVLink)
+          float4* o = reinterpret_cast<float4*>(p2p_dst + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+        }
       } else if (inside) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -1082,10 +1107,103 @@ extern "C" int mvwarp_warp_conv1_fwd(const mvwarp_plan_t* plan, int view0, int n
                                   with_coord, row0, nrows, nullptr, 0, stream);
 }
 
+namespace mvw {
+// out[b][i] = [relu](bias[i % 512] + sum over slots s (in slot order) of inbox[s][b][i]),  i < n_per_b = rows * Wg * 512:
+// the owner's side of the fused reduce-scatter.  One pass: nslots reads and one write per element, 128-bit accesses.
+template <typename TO>
+__global__ void __launch_bounds__(256) inbox_reduce_kernel(const float* __restrict__ inbox, int nslots, int64_t slot_pitch, int64_t b_pitch,
+                                                           int64_t n_per_b, const float* __restrict__ bias, int relu, TO* __restrict__ out) {
+  const int b = blockIdx.y;
+  const float* src = inbox + (int64_t)b * b_pitch;
+  TO* dst = out + (int64_t)b * n_per_b;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n_per_b; i += (int64_t)gridDim.x * blockDim.x * 4) {
+    float4 a = __ldcs(reinterpret_cast<const float4*>(src + i));
+    for (int s = 1; s < nslots; ++s) {
+      const float4 q = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)s * slot_pitch + i));
+      a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+    }
+    if (bias) {
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + (i & 511)));
+      a.x += bq.x; a.y += bq.y; a.z += bq.z; a.w += bq.w;
+    }
+    if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    if (sizeof(TO) == 4) *reinterpret_cast<float4*>(dst + i) = a;
+    else *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf2(a.x, a.y), pack_bf2(a.z, a.w));
+  }
+}
+}  // namespace mvw
+
+extern "C" int mvwarp_inbox_reduce(const float* inbox, int nslots, int64_t slot_pitch, int64_t b_pitch, int B, int64_t n_per_b,
+                                   const float* bias, int relu, void* out, int out_dtype, int device, void* stream) {
+  using namespace mvw;
+  if (!inbox || !out || nslots < 1 || B < 1 || B > 65535 || n_per_b < 0 || n_per_b % 512 || slot_pitch % 4 || b_pitch % 4 ||
+      ((reinterpret_cast<uintptr_t>(inbox) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15u) ||
+      (out_dtype != MVWARP_F32 && out_dtype != MVWARP_BF16)) {
+    set_error("inbox_reduce: bad argument (elements per batch item must be a multiple of 512, pointers 16-byte aligned)");
+    return MVWARP_EINVAL;
+  }
+  if (n_per_b == 0) return MVWARP_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != device && cudaSetDevice(device) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+  const int64_t want = (n_per_b / 4 + 255) / 256;
+  dim3 grid((unsigned)std::min<int64_t>(want, 148 * 16), B);
+  if (out_dtype == MVWARP_F32)
+    inbox_reduce_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(inbox, nslots, slot_pitch, b_pitch, n_per_b, bias, relu, (float*)out);
+  else
+    inbox_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(inbox, nslots, slot_pitch, b_pitch, n_per_b, bias, relu,
+                                                                                 (__nv_bfloat16*)out);
+  const cudaError_t e = cudaGetLastError();
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "inbox_reduce launch");
+}
+
+namespace {
+struct P2PArgs {
+  int n = 0, src = 0, band_rows_max = 0;
+  const uint64_t* inbox = nullptr;
+  const int32_t* row0 = nullptr;
+};
+int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats, const int64_t feat_strides[5], const void* wpack,
+                 const float* bias, void* out, int out_dtype, const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0,
+                 int nrows, void* scratch, int64_t scratch_bytes, const P2PArgs& p2p, void* stream);
+}  // namespace
+
 extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
                                         const int64_t feat_strides[5], const void* wpack, const float* bias, void* out, int out_dtype,
                                         const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0, int nrows,
                                         void* scratch, int64_t scratch_bytes, void* stream) {
+  return conv1_launch(plan, view0, nviews, feats, feat_strides, wpack, bias, out, out_dtype, out_strides, B, C, relu, with_coord, row0, nrows,
+                      scratch, scratch_bytes, P2PArgs{}, stream);
+}
+
+extern "C" int mvwarp_warp_conv1_fwd_p2p(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats,
+                                         const int64_t feat_strides[5], const void* wpack, int B, int C, int with_coord, int nranks,
+                                         int my_rank, const uint64_t* peer_inbox, const int32_t* band_row0, int band_rows_max, void* stream) {
+  using namespace mvw;
+  if (!plan || !peer_inbox || !band_row0 || nranks < 1 || nranks > 8 || my_rank < 0 || my_rank >= nranks || band_rows_max <= 0) {
+    set_error("warp_conv1_fwd_p2p: bad rank / inbox arguments (1..8 ranks)");
+    return MVWARP_EINVAL;
+  }
+  if (band_row0[0] != 0 || band_row0[nranks] != plan->Hg) { set_error("warp_conv1_fwd_p2p: the row bands must cover [0, Hg)"); return MVWARP_EINVAL; }
+  for (int r = 0; r < nranks; ++r) {
+    if (band_row0[r + 1] < band_row0[r] || band_row0[r + 1] - band_row0[r] > band_rows_max || (peer_inbox[r] & 15u) || !peer_inbox[r]) {
+      set_error("warp_conv1_fwd_p2p: bad row band or inbox pointer");
+      return MVWARP_EINVAL;
+    }
+  }
+  P2PArgs a;
+  a.n = nranks; a.src = my_rank; a.band_rows_max = band_rows_max; a.inbox = peer_inbox; a.row0 = band_row0;
+  // `out` is unused in this mode; the shared argument checks want a non-null, 16-byte aligned pointer and channels-last strides
+  const int64_t os[4] = {(int64_t)plan->Hg * plan->Wg * 512, 1, (int64_t)plan->Wg * 512, 512};
+  return conv1_launch(plan, view0, nviews, feats, feat_strides, wpack, nullptr, reinterpret_cast<void*>(uintptr_t(16)), MVWARP_F32, os, B, C, 0,
+                      with_coord, 0, 0, nullptr, 0, a, stream);
+}
+
+namespace {
+int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* feats, const int64_t feat_strides[5], const void* wpack,
+                 const float* bias, void* out, int out_dtype, const int64_t out_strides[4], int B, int C, int relu, int with_coord, int row0,
+                 int nrows, void* scratch, int64_t scratch_bytes, const P2PArgs& p2p, void* stream) {
   using namespace mvw;
   if (out_dtype != MVWARP_F32 && out_dtype != MVWARP_BF16) { set_error("warp_conv1_fwd: unknown output dtype"); return MVWARP_EINVAL; }
   if (!plan || !feats || !feat_strides || !wpack || !out || !out_strides) { set_error("warp_conv1_fwd: null argument"); return MVWARP_EINVAL; }
@@ -1150,6 +1268,19 @@ extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, in
       if (wrc) { if (prev >= 0 && prev != plan->device) cudaSetDevice(prev); return wrc; }
     }
     p.pair_mode = pmode;
+    if (p2p.n > 0) {
+      if (pmode != 2) {
+        if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
+        set_error("warp_conv1_fwd_p2p: only the direct kernel writes to peer inboxes (unset MVWARP_CONV1_PAIR / _VARIANT)");
+        return MVWARP_EUNSUPPORTED;
+      }
+      p.p2p_n = p2p.n; p.p2p_src = p2p.src;
+      for (int r = 0; r <= p2p.n; ++r) p.p2p_row0[r] = p2p.row0[r];
+      for (int r = 0; r < p2p.n; ++r) p.p2p_inbox[r] = p2p.inbox[r];
+      p.p2p_tile_shift = (p2p.row0[(p2p.src + 1) % p2p.n] / CT_H) * p.tiles_x % p.ntiles;   // first tile of the next rank's band
+      p.p2p_b_pitch = (long long)p2p.band_rows_max * plan->Wg * CV_N;
+      p.p2p_src_pitch = p.p2p_b_pitch * B;
+    }
     if (pair) p.n_full = p.nitems / 2 * 2;
     if (cl == 1 && scratch && !getenv("MVWARP_CONV1_NOSPLIT")) {   // K-split of the last partial wave (see ConvParams)
       const Decomp d = decompose(p.nitems, nviews, plan->num_sms, pair);
@@ -1215,3 +1346,4 @@ extern "C" int mvwarp_warp_conv1_fwd_ex(const mvwarp_plan_t* plan, int view0, in
   if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "warp_conv1_fwd launch");
 }
+}  // namespace

@@ -187,3 +187,150 @@ def conv1_fused_allreduce(local_feats: torch.Tensor, proj_mats: torch.Tensor, gr
         main.wait_stream(side)
         phys.record_stream(side)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# Fused GEMM + reduce-scatter over NVLink peer memory (no collective call on the data path)
+# ------------------------------------------------------------------------------------------------------
+def row_bands(grid_rows: int, world_size: int) -> List[int]:
+    """Band edges ``[r0, r1, ..., Hg]``: rank r owns the grid rows ``[edges[r], edges[r+1])``.  Bands are whole tile rows
+    (8 grid rows) of the fused kernel, balanced like :func:`view_partition`."""
+    tile_rows = (int(grid_rows) + 7) // 8
+    edges, acc = [0], 0
+    for _, n in view_partition(tile_rows, world_size):
+        acc += n
+        edges.append(min(int(grid_rows), 8 * acc))
+    return edges
+
+
+class Conv1Inbox:
+    """Symmetric-memory inboxes for :func:`conv1_fused_reduce_scatter`: on every rank one fp32 buffer
+    ``[world, B, band_rows_max, Wg, 512]`` (slot s = the partial sums rank s computed for MY rows), mapped into every
+    process of the group so that the fused kernel's epilogue can store into its peers' inboxes directly."""
+
+    def __init__(self, grid_shape: Sequence[int], batch: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("the fused reduce-scatter addresses at most 8 peers (one NVSwitch box)")
+        self.Hg, self.Wg, self.B = int(grid_shape[0]), int(grid_shape[1]), int(batch)
+        self.edges = row_bands(self.Hg, self.world)
+        self.band_rows_max = max(b - a for a, b in zip(self.edges[:-1], self.edges[1:]))
+        self.buf = symm.empty((self.world, self.B, self.band_rows_max, self.Wg, 512), dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.buf, group)
+        self.buf.zero_()                       # slots of ranks without cameras are never written: they must read as zero
+        self.handle.barrier(channel=0)
+        # every rank's inbox as mapped into this process (get_buffer accounts for the tensor's offset inside the allocation)
+        self.peers = [self.handle.get_buffer(r, tuple(self.buf.shape), torch.float32) for r in range(self.world)]
+        self.peer_ptrs = [int(t.data_ptr()) for t in self.peers]
+        self.side_stream = torch.cuda.Stream(device)
+        if self.peer_ptrs[self.rank] != self.buf.data_ptr():
+            raise RuntimeError("symmetric memory: my own inbox is mapped at an unexpected address")
+
+    @property
+    def my_rows(self) -> Tuple[int, int]:
+        return self.edges[self.rank], self.edges[self.rank + 1]
+
+
+def _reduce_my_inbox(inbox: "Conv1Inbox", bias: Optional[torch.Tensor], relu: bool, out_dtype: torch.dtype) -> torch.Tensor:
+    """Sum the slots of this rank's inbox over its own rows (+ bias, ReLU) in one pass: [B, 512, rows, Wg] channels-last."""
+    import ctypes as C
+    from . import _lib
+    y0, y1 = inbox.my_rows
+    rows = y1 - y0
+    dev = inbox.buf.device
+    band = torch.empty((inbox.B, rows, inbox.Wg, 512), dtype=out_dtype, device=dev)
+    bias_ptr = None
+    if bias is not None:
+        bias = bias.detach().to(device=dev, dtype=torch.float32).contiguous()
+        bias_ptr = C.c_void_p(bias.data_ptr())
+    b_pitch = inbox.band_rows_max * inbox.Wg * 512
+    rc = _lib.load().mvwarp_inbox_reduce(C.c_void_p(inbox.buf.data_ptr()), inbox.world, b_pitch * inbox.B, b_pitch, inbox.B,
+                                         rows * inbox.Wg * 512, bias_ptr, int(relu), C.c_void_p(band.data_ptr()),
+                                         _lib.BF16 if out_dtype == torch.bfloat16 else _lib.F32, dev.index,
+                                         C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "mvwarp_inbox_reduce")
+    return band.permute(0, 3, 1, 2)
+
+
+def conv1_fused_reduce_scatter(local_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Sequence[int],
+                               wpack_local: torch.Tensor, bias: Optional[torch.Tensor], shard: ViewShard, inbox: Conv1Inbox,
+                               relu: bool = True, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """This rank's row band ``[B, 512, rows, Wg]`` of ``relu(conv1(concat of all ranks' warps) + bias)``.
+
+    The fused warp -> conv1 kernel computes this rank's partial sums for the WHOLE map, and its epilogue stores each tile
+    straight into the inbox of the rank that owns the tile's rows (peer-to-peer stores over NVLink / NVSwitch riding along with
+    the tensor-core work: ``mvwarp_warp_conv1_fwd_p2p``) -- the reduce-scatter costs no kernel, no SMs and no collective call.
+    After one barrier every rank sums the slots of its own inbox in rank order (deterministic), adds the bias, applies the ReLU.
+    A second barrier keeps the next call from overwriting an inbox that is still being read."""
+    import ctypes as C
+    from . import _lib
+    from .plan import get_plan
+    B, nv, Cc, Hs, Ws = local_feats.shape
+    if B != inbox.B or (int(grid_shape[0]), int(grid_shape[1])) != (inbox.Hg, inbox.Wg):
+        raise ValueError("the inbox was sized for another batch / grid")
+    if shard.count:
+        if local_feats.dtype != torch.bfloat16 or local_feats.stride(2) != 1:
+            raise ValueError("conv1_fused_reduce_scatter needs bf16 channel-contiguous features")
+        mats = proj_mats[shard.first_view:shard.first_view + shard.count]
+        plan = get_plan(mats, (Hs, Ws), grid_shape, local_feats.device)
+        ptrs = (C.c_uint64 * inbox.world)(*inbox.peer_ptrs)
+        rows = (C.c_int32 * (inbox.world + 1))(*inbox.edges)
+        stream = C.c_void_p(torch.cuda.current_stream(local_feats.device).cuda_stream)
+        rc = _lib.load().mvwarp_warp_conv1_fwd_p2p(plan.handle, 0, nv, C.c_void_p(local_feats.data_ptr()), _lib.i64x(local_feats.stride()),
+                                                   C.c_void_p(wpack_local.data_ptr()), B, Cc, int(shard.owns_coord_map), inbox.world,
+                                                   inbox.rank, ptrs, rows, inbox.band_rows_max, stream)
+        _lib.check(rc, "mvwarp_warp_conv1_fwd_p2p")
+    inbox.handle.barrier(channel=0)            # every rank's stores into my inbox have landed
+    band = _reduce_my_inbox(inbox, bias, relu, out_dtype)          # slots added in rank order (deterministic)
+    inbox.handle.barrier(channel=1)            # my inbox has been read: peers may start the next step
+    return band
+
+
+def conv1_fused_reduce_scatter_ce(local_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Sequence[int],
+                                  wpack_local: torch.Tensor, bias: Optional[torch.Tensor], shard: ViewShard, inbox: Conv1Inbox,
+                                  relu: bool = True, workspace: Optional[torch.Tensor] = None,
+                                  out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """Same result as :func:`conv1_fused_reduce_scatter`, with the exchange on the COPY ENGINES instead of in the epilogue.
+
+    The fused kernel runs band by band -- the bands are the ranks' row bands, visited in the rotated order r+1, r+2, ..., r --
+    and writes its partial sums locally at full speed; as soon as band j is done, a side stream pushes it into slot r of owner
+    j's inbox with peer-to-peer ``cudaMemcpyAsync`` (copy engines over NVLink: no SMs, so the tensor cores are not disturbed,
+    and thanks to the rotation every owner receives from exactly one sender at a time).  The rank's own band comes last and is
+    written straight into its own inbox slot, so the last remote copy hides behind it; what remains exposed is one barrier
+    and the sum over the slots."""
+    from .conv1 import warp_conv1
+    B, nv, Cc, Hs, Ws = local_feats.shape
+    Hg, Wg = inbox.Hg, inbox.Wg
+    dev = local_feats.device
+    R, r = inbox.world, inbox.rank
+    if workspace is None:
+        workspace = torch.empty((B, Hg, Wg, 512), dtype=torch.float32, device=dev)
+    main = torch.cuda.current_stream(dev)
+    side = inbox.side_stream
+    mats = proj_mats[shard.first_view:shard.first_view + shard.count]
+    peers = inbox.peers
+    for k in range(R):
+        j = (r + 1 + k) % R
+        y0, y1 = inbox.edges[j], inbox.edges[j + 1]
+        if y1 <= y0 or not shard.count:
+            continue
+        if j == r:        # my own band: the kernel writes into my inbox slot directly (the slot is [B, band_rows_max, Wg, 512])
+            # warp_conv1 addresses rows of a whole [B,512,Hg,Wg] map: hand it a view whose row y0 is the slot's row 0
+            base = inbox.buf[r]                                           # [B, band_rows_max, Wg, 512]
+            whole = torch.as_strided(base, (B, Hg, Wg, 512), base.stride(), storage_offset=base.storage_offset() - y0 * Wg * 512)
+            warp_conv1(local_feats, mats, grid_shape, wpack_local, None, relu=False, with_coord=shard.owns_coord_map,
+                       out=whole.permute(0, 3, 1, 2), rows=(y0, y1))
+        else:
+            warp_conv1(local_feats, mats, grid_shape, wpack_local, None, relu=False, with_coord=shard.owns_coord_map,
+                       out=workspace.permute(0, 3, 1, 2), rows=(y0, y1))
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                peers[j][r, :, :y1 - y0].copy_(workspace[:, y0:y1], non_blocking=True)
+    main.wait_stream(side)
+    workspace.record_stream(side)
+    inbox.handle.barrier(channel=0)
+    band = _reduce_my_inbox(inbox, bias, relu, out_dtype)
+    inbox.handle.barrier(channel=1)
+    return band

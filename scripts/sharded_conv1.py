@@ -61,6 +61,7 @@ def main():
     feats = torch.randn(B, shard.count, Hs, Ws, C, device=dev, dtype=torch.bfloat16).permute(0, 1, 4, 2, 3)
     weight = (torch.randn(Cout, V * C + 2, 3, 3, device=dev, dtype=torch.bfloat16) * 0.02).contiguous(memory_format=torch.channels_last)
     bias = torch.randn(Cout, device=dev, dtype=torch.bfloat16)
+    dist.broadcast(bias, src=world - 1)      # one model: every rank holds the same bias (the weight slices are disjoint anyway)
     wpack = S.pack_conv1_weight_shard(weight.float(), shard, C)
     bias32 = bias.float()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -107,6 +108,48 @@ def main():
             res_pipe_err = float((full - seq).abs().max() / seq.abs().max())
             del seq
         del full
+    # fused GEMM + reduce-scatter over NVLink peer memory: each rank ends with its row band of relu(conv1); no collective call
+    inbox = S.Conv1Inbox((Hg, Wg), B, dev)
+    rtimes, gtimes = [], []
+    for it in range(4):
+        dist.barrier(); torch.cuda.synchronize()
+        pe = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        pe[0].record()
+        band = S.conv1_fused_reduce_scatter(feats, pm, (Hg, Wg), wpack, bias32, shard, inbox)
+        pe[1].record()
+        # optional: every rank gets the whole map (bf16, what map_classifier[2] reads): all-gather of the bands, padded to equal size
+        mine = torch.zeros((B, inbox.band_rows_max, Wg, 512), dtype=torch.bfloat16, device=dev)
+        mine[:, :band.shape[2]] = band.permute(0, 2, 3, 1)
+        gathered = torch.empty((world,) + tuple(mine.shape), dtype=torch.bfloat16, device=dev)
+        dist.all_gather_into_tensor(gathered, mine)
+        pe[2].record(); torch.cuda.synchronize()
+        rtimes.append(pe[0].elapsed_time(pe[1])); gtimes.append(pe[1].elapsed_time(pe[2]))
+        if it == 0:
+            seq = S.reduce_partials(S.conv1_partial_fused(feats, pm, (Hg, Wg), wpack, bias32, shard), relu=True)
+            y0, y1 = inbox.my_rows
+            res_p2p_err = float((band - seq[:, :, y0:y1]).abs().max() / seq.abs().max())
+            del seq
+        del band, mine, gathered
+    # the same exchange on the copy engines (band-wise kernel launches in rotated owner order, P2P cudaMemcpyAsync on a side stream)
+    ctimes = []
+    work = torch.empty((B, Hg, Wg, 512), dtype=torch.float32, device=dev)
+    for it in range(4):
+        dist.barrier(); torch.cuda.synchronize()
+        pe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        pe[0].record()
+        band = S.conv1_fused_reduce_scatter_ce(feats, pm, (Hg, Wg), wpack, bias32, shard, inbox, workspace=work)
+        pe[1].record(); torch.cuda.synchronize()
+        ctimes.append(pe[0].elapsed_time(pe[1]))
+        if it == 0:
+            seq = S.reduce_partials(S.conv1_partial_fused(feats, pm, (Hg, Wg), wpack, bias32, shard), relu=True)
+            y0, y1 = inbox.my_rows
+            res_ce_err = float((band - seq[:, :, y0:y1]).abs().max() / seq.abs().max())
+            del seq
+        del band
+    del work
+    rt = torch.tensor([sum(rtimes[1:]) / len(rtimes[1:]), sum(gtimes[1:]) / len(gtimes[1:]), res_p2p_err,
+                       sum(ctimes[1:]) / len(ctimes[1:]), res_ce_err], device=dev)
+    dist.all_reduce(rt, op=dist.ReduceOp.MAX)
     pt = torch.tensor([sum(ptimes[1:]) / len(ptimes[1:])], device=dev)
     dist.all_reduce(pt, op=dist.ReduceOp.MAX)
     ft = torch.tensor([sum(ftimes[1:]) / len(ftimes[1:])], device=dev)
@@ -119,6 +162,9 @@ def main():
                     "warp_ms": float(t[0]), "conv1_partial_ms": float(t[1]), "allreduce_relu_ms": float(t[2]),
                     "conv1_partial_tflops": flops / (float(t[1]) * 1e-3) / 1e12,
                     "fused_pipelined_with_allreduce_ms": float(pt[0]), "pipelined_vs_sequential_max_rel_diff": res_pipe_err,
+                    "fused_reduce_scatter_p2p_ms": float(rt[0]), "p2p_allgather_bf16_ms": float(rt[1]),
+                    "p2p_vs_allreduce_max_rel_diff": float(rt[2]),
+                    "fused_reduce_scatter_copy_engine_ms": float(rt[3]), "copy_engine_vs_allreduce_max_rel_diff": float(rt[4]),
                     "fused_warp_conv1_partial_ms": float(ft[0]), "fused_tflops": flops / (float(ft[0]) * 1e-3) / 1e12,
                     "allreduce_bytes": B * Cout * Hg * Wg * 4,
                     "allreduce_busbw_gbs": 2 * (world - 1) / world * B * Cout * Hg * Wg * 4 / (float(t[2]) * 1e-3) / 1e9})

@@ -237,3 +237,40 @@ def test_fused_conv1_kernel_generations_agree(mode, monkeypatch):
     rows = conv1.warp_conv1(xd, pm, grid_hw, wpack, bias, relu=True, rows=(8, 24))
     emax, _ = rel_errors(rows[:, :, 8:24], ref[:, :, 8:24])
     assert emax <= 1e-4
+
+
+def test_fused_conv1_p2p_epilogue_single_rank():
+    """mvwarp_warp_conv1_fwd_p2p with this process as two of three 'ranks' of the row ownership (the inbox pointers all point into
+    one local buffer): the raw partial sums land in the right slot / band / cell, and slot sums reproduce the ordinary output."""
+    from mvdet_b200 import conv1
+    from mvdet_b200.plan import get_plan
+    from mvdet_b200.sharding import row_bands
+    from tests.util import small_rig, to_channels_last_5d, rel_errors
+    V, Cc, B = 2, 64, 2
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=43)                   # 24 x 72 grid: 3 tile rows
+    Hg, Wg = grid_hw
+    g = torch.Generator().manual_seed(0)
+    x = to_channels_last_5d(torch.randn(B, V, Cc, *src_hw, generator=g).bfloat16()).cuda()
+    weight = torch.randn(512, V * Cc + 2, 3, 3, generator=g) * 0.05
+    wpack = conv1.pack_conv1_weight(weight, V, Cc).cuda()
+    ref = conv1.warp_conv1(x, pm, grid_hw, wpack, None, relu=False)       # [B,512,Hg,Wg] fp32, no bias
+    world = 3
+    edges = row_bands(Hg, world)
+    assert edges == [0, 8, 16, 24]
+    band_max = 8
+    inboxes = torch.full((world, world, B, band_max, Wg, 512), float("nan"), device="cuda")   # [owner][src][b][y][x][c]
+    plan = get_plan(pm, src_hw, grid_hw, "cuda:0")
+    lib = _lib.load()
+    ptrs = (C.c_uint64 * world)(*[inboxes[o].data_ptr() for o in range(world)])
+    rows = (C.c_int32 * (world + 1))(*edges)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    src = 1
+    _lib.check(lib.mvwarp_warp_conv1_fwd_p2p(plan.handle, 0, V, C.c_void_p(x.data_ptr()), _lib.i64x(x.stride()), C.c_void_p(wpack.data_ptr()),
+                                             B, Cc, 1, world, src, ptrs, rows, band_max, stream), "mvwarp_warp_conv1_fwd_p2p")
+    torch.cuda.synchronize()
+    for o in range(world):
+        got = inboxes[o, src, :, :edges[o + 1] - edges[o]].permute(0, 3, 1, 2)      # [B,512,rows,Wg]
+        emax, _ = rel_errors(got, ref[:, :, edges[o]:edges[o + 1]])
+        assert emax <= 1e-5, (o, emax)
+        others = inboxes[o, [s for s in range(world) if s != src]]
+        assert bool(others.isnan().all())                                           # nothing written outside slot `src`
