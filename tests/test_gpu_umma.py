@@ -274,3 +274,22 @@ def test_fused_conv1_p2p_epilogue_single_rank():
         assert emax <= 1e-5, (o, emax)
         others = inboxes[o, [s for s in range(world) if s != src]]
         assert bool(others.isnan().all())                                           # nothing written outside slot `src`
+
+
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_inbox_reduce_matches_torch(odt):
+    """mvwarp_inbox_reduce: slots added in slot order + bias + ReLU in one pass, over the first `rows` rows of every batch element."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    nslots, B, band_max, rows, Wg = 3, 2, 8, 5, 9
+    inbox = torch.randn(nslots, B, band_max, Wg, 512, generator=g).cuda()
+    bias = torch.randn(512, generator=g).cuda()
+    out = torch.empty(B, rows, Wg, 512, dtype=odt, device="cuda")
+    b_pitch = band_max * Wg * 512
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.mvwarp_inbox_reduce(C.c_void_p(inbox.data_ptr()), nslots, b_pitch * B, b_pitch, B, rows * Wg * 512, C.c_void_p(bias.data_ptr()), 1,
+                                       C.c_void_p(out.data_ptr()), _lib.BF16 if odt == torch.bfloat16 else _lib.F32, 0, stream), "mvwarp_inbox_reduce")
+    ref = ((inbox[0, :, :rows] + inbox[1, :, :rows]) + inbox[2, :, :rows] + bias).relu()
+    assert torch.equal(out, ref.to(odt))
+    assert lib.mvwarp_inbox_reduce(C.c_void_p(inbox.data_ptr()), nslots, b_pitch * B, b_pitch, B, 100, None, 0, C.c_void_p(out.data_ptr()),
+                                   _lib.F32, 0, stream) == _lib.EINVAL

@@ -83,3 +83,20 @@ def test_sharded_warp_and_conv1_reduce_gloo(world, V):
         assert ret["gather_equal"] is True            # rank-order concat of the slices == the reference concat
         assert ret["conv_err"] <= 1e-5                # sum of per-shard conv1 partials == unsharded conv1
         assert ret["slice"][0] == 0
+
+
+def test_row_bands_are_whole_tile_rows_and_cover_the_grid():
+    """Row ownership of the fused reduce-scatter (sharding.row_bands): bands of whole 8-row tile rows, balanced, covering [0, Hg)."""
+    from mvdet_b200.sharding import row_bands
+    assert row_bands(480, 8) == [0, 64, 128, 192, 256, 312, 368, 424, 480]      # 60 tile rows: 8,8,8,8,7,7,7,7
+    assert row_bands(120, 8) == [0, 16, 32, 48, 64, 80, 96, 112, 120]           # 15 tile rows
+    assert row_bands(24, 3) == [0, 8, 16, 24]
+    assert row_bands(20, 4) == [0, 8, 16, 20, 20]                               # 3 tile rows on 4 ranks: the last owns nothing
+    for Hg in (1, 7, 8, 9, 120, 160, 480, 1000):
+        for world in (1, 2, 3, 8):
+            e = row_bands(Hg, world)
+            assert len(e) == world + 1 and e[0] == 0 and e[-1] == Hg
+            assert all(b >= a for a, b in zip(e[:-1], e[1:]))
+            assert all(a % 8 == 0 for a in e[:-1] if a < Hg)
+            sizes = [(b - a + 7) // 8 for a, b in zip(e[:-1], e[1:])]
+            assert max(sizes) - min(sizes) <= 1
