@@ -293,3 +293,21 @@ def test_inbox_reduce_matches_torch(odt):
     assert torch.equal(out, ref.to(odt))
     assert lib.mvwarp_inbox_reduce(C.c_void_p(inbox.data_ptr()), nslots, b_pitch * B, b_pitch, B, 100, None, 0, C.c_void_p(out.data_ptr()),
                                    _lib.F32, 0, stream) == _lib.EINVAL
+
+
+def test_fused_conv1_ragged_grid_and_many_views():
+    """Default (direct) kernel on a grid that is no multiple of the 16 x 8 tile in either direction (20 x 60) with 5 views
+    (K-split parts of unequal view counts) and B = 3 (odd item count: a padding CTA in the last pair)."""
+    from mvdet_b200 import conv1
+    from tests.util import small_rig, to_channels_last_5d, rel_errors
+    V, Cc, B = 5, 64, 3
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=47, grid=(20, 60))
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, V, Cc, *src_hw, generator=g).bfloat16()
+    weight = torch.randn(512, V * Cc + 2, 3, 3, generator=g) * 0.05
+    bias = torch.randn(512, generator=g)
+    ref = _conv1_reference(x, pm, grid_hw, weight, bias, relu=True)
+    out = conv1.warp_conv1(to_channels_last_5d(x).cuda(), pm, grid_hw, conv1.pack_conv1_weight(weight, V, Cc).cuda(), bias, relu=True)
+    assert out.shape == (B, 512, 20, 60)
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= 1e-4 and el2 <= 1e-4, (emax, el2)
