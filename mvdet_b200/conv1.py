@@ -120,6 +120,9 @@ class _WarpConv1Fn(torch.autograd.Function):
         x = ops.warp_views_with_plan(feats, plan)
         w = weight.detach().to(x.dtype).contiguous(memory_format=torch.channels_last)
         g16 = g.to(x.dtype).contiguous(memory_format=torch.channels_last)
+        # cuDNN for both gradients: the data gradient on the library's own TMA convolution (7 launches with the transposed, tap-flipped
+        # weight into a 16-byte aligned [B,Hg,Wg,V*512] buffer) was measured at 37.5 vs 38.8 ms per B=8 step and 4.76 vs 4.58 ms at B=1 --
+        # not worth a second code path (profiles/r01_logs/train_step*.txt)
         gx, gw, _ = torch.ops.aten.convolution_backward(g16, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [need_x, need_w, False])
         g_feats = None
         if need_x:

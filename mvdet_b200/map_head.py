@@ -46,16 +46,20 @@ def _check_cl_bf16(x: torch.Tensor, who: str):
 
 
 def conv3x3_cl(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor] = None, dilation: int = 1,
-               relu: bool = False, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+               relu: bool = False, out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``[relu](conv2d(x, W, bias, padding=dilation, dilation=dilation))`` with 512 output channels on tcgen05 + TMA.
-    x bf16 channels-last [B,Cin,H,W]; wpack from :func:`pack_conv3x3_weight`.  Returns channels-last [B,512,H,W]."""
+    x bf16 channels-last [B,Cin,H,W]; wpack from :func:`pack_conv3x3_weight`.  Returns channels-last [B,512,H,W]; ``out`` may be
+    a channel slice of a wider channels-last tensor (16-byte aligned cell rows)."""
     _check_cl_bf16(x, "conv3x3_cl")
     B, Cin, H, W = x.shape
     if wpack.dtype != torch.bfloat16 or tuple(wpack.shape) != ((Cin // KB) * 9, N_OUT, KB) or not wpack.is_contiguous() or Cin % KB:
         raise ValueError(f"wpack must be a contiguous bf16 [{(Cin // KB) * 9}, 512, 64] tensor from pack_conv3x3_weight")
     if out_dtype not in (torch.float32, torch.bfloat16):
         raise ValueError("conv3x3_cl writes fp32 or bf16")
-    out = torch.empty((B, H, W, N_OUT), dtype=out_dtype, device=x.device).permute(0, 3, 1, 2)
+    if out is None:
+        out = torch.empty((B, H, W, N_OUT), dtype=out_dtype, device=x.device).permute(0, 3, 1, 2)
+    elif tuple(out.shape) != (B, N_OUT, H, W) or out.dtype != out_dtype or out.stride(1) != 1:
+        raise ValueError(f"out must be a channel-contiguous {out_dtype} [B,512,H,W] tensor")
     bias_ptr = None
     if bias is not None:
         bias = bias.detach().to(device=x.device, dtype=torch.float32).contiguous()

@@ -87,13 +87,13 @@ def test_fused_conv1_rejects_what_it_cannot_run():
         conv1.pack_conv1_weight(torch.randn(512, 50, 3, 3), 1, 48)   # C % 64 != 0
 
 
-def test_fused_conv1_trainable_gradients():
+@pytest.mark.parametrize("V,Cc", [(2, 64), (1, 512)])
+def test_fused_conv1_trainable_gradients(V, Cc):
     """warp_conv1_trainable: fused forward, unfused backward -- gradients against autograd through the oracle."""
     import torch.nn.functional as F
     from mvdet_b200 import conv1
     from oracle import kornia_warp as K
     from tests.util import small_rig, to_channels_last_5d, rel_errors
-    V, Cc = 2, 64
     pm, src_hw, grid_hw = small_rig(num_cam=V, seed=35)
     g = torch.Generator().manual_seed(0)
     x = torch.randn(1, V, Cc, *src_hw, generator=g).bfloat16()
