@@ -183,7 +183,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv3x3_tc_kernel(const __grid_
 // Tried and dropped: fetching the tile's halo patch ONCE per channel block (one x-major TMA box through a tensor map with the
 // dimensions listed as (C, y, x, batch)) and reading the nine taps in place like warp_conv1_direct_kernel does -- correct, but
 // 0.200 vs 0.193 ms at Wildtrack B=1 and 0.716 vs 0.685 ms at B=4: with only 72 K blocks per tile this kernel is bound by the
-// per-tile prologue and the un-overlapped epilogue (all 512 TMEM columns hold the accumulator), not by its A side.
+// per-tile prologue and the un-overlapped epilogue (all 512 TMEM columns hold the accumulator), not by its A side.  Staging the
+// bf16 tile in shared memory for coalesced 512-byte store runs (instead of 16 bytes per lane, 1 KB apart) changed nothing either
+// (0.183 / 0.694 ms): what a short tile loses is the pipeline fill and the two cluster barriers, not the stores.
 // -----------------------------------------------------------------------------------------------------
 constexpr int T2_PA = 4, T2_PB = 4;
 constexpr uint32_t T2_B_BYTES = C2_B_BYTES / 2;   // 32 KB of weights per CTA per K block
