@@ -45,6 +45,10 @@ def parse_args():
                          "F.interpolate(-> 270x480) into the warp; NOT the headline workload")
     ap.add_argument("--out-pitch", type=int, default=0,
                     help="experiment: channel pitch of the channels-last output / grad_out (0 = dense V*C+2)")
+    ap.add_argument("--distinct-cameras", action="store_true",
+                    help="N > 1: give rank r cameras [7r, 7r+7) of one 7N-camera ring (every rank then has a different "
+                         "homography set, hence different U / nnz and a different amount of work) instead of N copies of the "
+                         "N=1 ring (equal work per GPU: the weak-scaling default)")
     ap.add_argument("--ref-channels", type=int, default=64,
                     help="reference arm: channels per step (a bounded 1/8-frame sample by default)")
     return ap.parse_args()
@@ -186,6 +190,13 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def parallelism_note(args, spec, world):
+    how = (f"cameras [{spec.num_cam}r, {spec.num_cam}r+{spec.num_cam}) of one {spec.num_cam * world}-camera ring (work differs per rank)"
+           if getattr(args, "distinct_cameras", False) and world > 1 else
+           f"ring r of {world} identical {spec.num_cam}-camera rings (the N=1 work on every GPU)")
+    return f"view-sharded: each of {world} ranks warps its own {spec.num_cam} cameras - {how}; no data-path collective"
+
+
 def workload_config(args, spec, world):
     Hs, Ws = spec.feat_shape
     Hg, Wg = spec.grid_shape
@@ -196,7 +207,7 @@ def workload_config(args, spec, world):
                         f"{args.dtype}, {args.mode}",
             "rig": spec.name, "batch_per_gpu": args.batch, "views_per_gpu": spec.num_cam, "channels": args.channels,
             "layout": "channels_last" if args.layout == "cl" else "NCHW contiguous", "mode": args.mode,
-            "parallelism": f"view-sharded: each of {world} ranks warps its own {spec.num_cam} cameras (no data-path collective)",
+            "parallelism": parallelism_note(args, spec, world),
             "l2": "output (>= 0.3 GB per step) larger than the 126 MB L2; the low-res features (206 MB fp32) are not",
             "note": "extra configuration, not BASELINE.json's metric: frames are the same, the op reads the trunk output directly"}
     return {
@@ -205,7 +216,7 @@ def workload_config(args, spec, world):
         "rig": spec.name, "batch_per_gpu": args.batch, "views_per_gpu": spec.num_cam, "channels": args.channels,
         "layout": "channels_last (NHWC physical, logical [B,V,C,H,W])" if args.layout == "cl" else "NCHW contiguous",
         "mode": args.mode,
-        "parallelism": f"view-sharded: each of {world} ranks warps its own {spec.num_cam} cameras (no data-path collective)",
+        "parallelism": parallelism_note(args, spec, world),
         "l2": "inputs (>= 1.2 GB per step) larger than the 126 MB L2; no flush needed",
     }
 
@@ -230,12 +241,18 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     base = RIGS[args.rig]
-    # rank r owns cameras [r*V, (r+1)*V) of a (world*V)-camera rig generated by the same recipe
-    spec = RigSpec(base.name, base.num_cam * world, base.img_shape, base.worldgrid_shape, base.img_reduce,
-                   base.grid_reduce, base.channels, base.seed)
     V, Cc, B = base.num_cam, args.channels, args.batch
-    pm_all = synthetic_rig(spec)
-    pm = pm_all[rank * V:(rank + 1) * V]
+    if args.distinct_cameras and world > 1:
+        # rank r owns cameras [r*V, (r+1)*V) of ONE (world*V)-camera ring generated by the same recipe: the ranks' homographies
+        # (and so their unique-texel counts, CSR sizes and kernel times) all differ from the N=1 rig's and from each other
+        spec = RigSpec(base.name, base.num_cam * world, base.img_shape, base.worldgrid_shape, base.img_reduce,
+                       base.grid_reduce, base.channels, base.seed)
+        pm = synthetic_rig(spec)[rank * V:(rank + 1) * V]
+    else:
+        # weak scaling = the N=1 work on every GPU: a (world*V)-camera installation made of `world` copies of the N=1 ring,
+        # rank r warping ring r (its own features, its own channel slice; no data-path collective)
+        spec = base
+        pm = synthetic_rig(base)
     Hs, Ws = base.feat_shape
     Hg, Wg = base.grid_shape
     if args.fuse_upsample:
@@ -418,7 +435,7 @@ def run_e2e(args, plan, feats_dev, grad_out_dev, dev, world, dist):
     ev_in = [torch.cuda.Event() for _ in range(NBUF)]
     ev_comp = [torch.cuda.Event() for _ in range(NBUF)]     # compute of the step using buffer i is done
     ev_out = [torch.cuda.Event() for _ in range(NBUF)]      # its results are on the host
-    steps = max(4, min(args.steps, 8))
+    steps = max(4, min(args.steps, 32))   # a stream of frames: pipeline fill + drain cost one step's worth of copies in total
 
     def one(k):
         i = k % NBUF

@@ -152,7 +152,7 @@ int mvwarp_warp_views_bwd(const mvwarp_plan_t* plan, int view0, int nviews,
                           void* grad_feats, const int64_t feat_strides[5],
                           int B, int C, int dtype, void* stream);
 
-/* ---- tensor-core building blocks (north_star (c), work in progress) ---------------------------------------
+/* ---- tensor-core building blocks (north_star (c)): validation hooks -----------------------------------------
  * mvwarp_debug_gemm: D[M,256] (fp32) = A[M,K] (bf16, row-major) x B[256,K]^T (bf16, row-major) on tcgen05 / TMEM.
  * Validation hook for the descriptor / swizzle / TMEM conventions the fused warp -> conv1 kernel relies on
  * (M % 128 == 0, K % 64 == 0, device pointers). */
