@@ -54,6 +54,8 @@ def _out_strides_cl(B: int, ctot: int, Hg: int, Wg: int):
 def _launch_fwd(plan: WarpPlan, feats: torch.Tensor, out: torch.Tensor, view0: int, out_chan0: int, coord_chan: int):
     """feats [B,nv,C,Hs,Ws] (any strides) -> out [B,Ctot,Hg,Wg] (any strides)."""
     B, nv, Cc = feats.shape[:3]
+    if B == 0:                       # empty batch: nothing to launch (grid_sample / cat return empty tensors too)
+        return
     rc = _lib.load().mvwarp_warp_views_fwd(
         plan.handle, view0, nv, C.c_void_p(feats.data_ptr()), _lib.i64x(feats.stride()),
         C.c_void_p(out.data_ptr()), _lib.i64x(out.stride()), out_chan0, coord_chan,
@@ -63,6 +65,8 @@ def _launch_fwd(plan: WarpPlan, feats: torch.Tensor, out: torch.Tensor, view0: i
 
 def _launch_bwd(plan: WarpPlan, grad_out: torch.Tensor, grad_feats: torch.Tensor, view0: int, out_chan0: int):
     B, nv, Cc = grad_feats.shape[:3]
+    if B == 0:
+        return
     rc = _lib.load().mvwarp_warp_views_bwd(
         plan.handle, view0, nv, C.c_void_p(grad_out.data_ptr()), _lib.i64x(grad_out.stride()), out_chan0,
         C.c_void_p(grad_feats.data_ptr()), _lib.i64x(grad_feats.stride()),
@@ -240,6 +244,8 @@ def warp_perspective(src: torch.Tensor, M: torch.Tensor, dsize: Sequence[int], m
         raise NotImplementedError("mvwarp.warp_perspective needs one homography per call (a camera rig is "
                                   "batch-invariant); use one call per distinct M")
     _check_feats(src)
+    if src.shape[0] == 0:
+        return src.new_empty((0, src.shape[1], int(dsize[0]), int(dsize[1])))
     plan = get_plan(Mc[:1], src.shape[-2:], dsize, src.device)
     feats5 = src.unsqueeze(1)
     cl = src.dim() == 4 and src.stride(1) == 1 and src.shape[1] > 1

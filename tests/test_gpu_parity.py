@@ -238,6 +238,21 @@ def test_errors_and_no_cpu_fallback():
         ops.warp_perspective(x.to(DEV)[0], pm[0], grid_hw)
 
 
+def test_empty_batch_returns_empty_tensors():
+    """B = 0: no launch, empty tensors of the right shapes, backward too.  (kornia 0.6.11's transform_points divides by the batch
+    size, so the reference path raises ZeroDivisionError here; returning empty tensors is a harmless superset.)"""
+    pm, src_hw, grid_hw = small_rig()
+    x = to_channels_last_5d(_feats(1, 3, 4, src_hw)).to(DEV)[:0].requires_grad_(True)
+    with pytest.raises(ZeroDivisionError):
+        K.warp_views_oracle(torch.zeros(0, 3, 4, *src_hw), pm, grid_hw)
+    out = mv.warp_views(x, pm, grid_hw)
+    assert tuple(out.shape) == (0, 3 * 4 + 2, *grid_hw)
+    (gx,) = torch.autograd.grad(out, x, torch.zeros_like(out))
+    assert tuple(gx.shape) == tuple(x.shape)
+    y = ops.warp_perspective(torch.zeros(0, 4, *src_hw, device=DEV), pm[:1].float().expand(0, 3, 3).to(DEV), grid_hw)
+    assert tuple(y.shape) == (0, 4, *grid_hw)
+
+
 def test_rig32_slice_forward_backward():
     """The 32-camera full-resolution rig (480x1440 grid, CSR rows up to 1360 taps), 4 of its views, small C."""
     spec = RIG32
