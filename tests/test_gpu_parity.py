@@ -437,3 +437,65 @@ def test_plan_disk_cache(tmp_path):
     p3 = P.get_plan(pm, src_hw, grid_hw, DEV, cache_dir=str(tmp_path))
     assert p3.stats == p1.stats and files[0].stat().st_size > 1000
     P.clear_plan_cache()
+
+
+# ---- shipped wiring (mvdet_b200.integration) on a duck-typed detector -------------------------------------------
+class _TinyDetector(torch.nn.Module):
+    """Same attribute names and forward as PerspTransDetector (persp_trans_detector.py:14-87), small enough for a test.
+    Its own forward is the reference's loop: per-camera warp_perspective (seam 1), list append, cat with coord_map."""
+
+    def __init__(self, pm, src_hw, grid_hw, C=8):
+        super().__init__()
+        from mvdet_b200.geometry import create_coord_map
+        self.num_cam = pm.shape[0]
+        self.base_pt1 = torch.nn.Conv2d(3, C, 3, padding=1)
+        self.base_pt2 = torch.nn.Sequential(torch.nn.ReLU(), torch.nn.Conv2d(C, C, 1))
+        self.img_classifier = torch.nn.Conv2d(C, 2, 1)
+        self.map_classifier = torch.nn.Sequential(torch.nn.Conv2d(C * self.num_cam + 2, 4, 3, padding=1), torch.nn.ReLU(),
+                                                  torch.nn.Conv2d(4, 1, 3, padding=2, dilation=2))
+        self.proj_mats = [pm[v] for v in range(self.num_cam)]
+        self.upsample_shape, self.reducedgrid_shape = list(src_hw), list(grid_hw)
+        self.coord_map = create_coord_map(grid_hw)
+
+    def forward(self, imgs, visualize=False):
+        import torch.nn.functional as F
+        B = imgs.shape[0]
+        world_features, imgs_result = [], []
+        for cam in range(self.num_cam):
+            f = self.base_pt2(self.base_pt1(imgs[:, cam].to(DEV)))
+            f = F.interpolate(f, self.upsample_shape, mode="bilinear")
+            imgs_result.append(self.img_classifier(f))
+            proj_mat = self.proj_mats[cam].repeat([B, 1, 1]).float().to(DEV)
+            world_features.append(ops.warp_perspective(f, proj_mat, self.reducedgrid_shape))
+        world = torch.cat(world_features + [self.coord_map.repeat([B, 1, 1, 1]).to(DEV)], dim=1)
+        return F.interpolate(self.map_classifier(world), self.reducedgrid_shape, mode="bilinear"), imgs_result
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_patch_detector_matches_the_per_camera_loop(channels_last):
+    """Seam 2 as shipped code against seam 1 on the GPU: one warp_views call == V warp_perspective calls + cat + coord_map,
+    forward (same bits in NCHW; to rounding when the model switches to channels-last convolutions) and parameter gradients."""
+    import copy
+    from mvdet_b200 import integration
+    pm, src_hw, grid_hw = small_rig()
+    torch.manual_seed(0)
+    ref = _TinyDetector(pm, src_hw, grid_hw).to(DEV)
+    new = integration.patch_detector(copy.deepcopy(ref), channels_last=channels_last)
+    imgs = torch.randn(2, 3, 3, 18, 32, generator=torch.Generator().manual_seed(1))
+    map_ref, img_ref = ref(imgs)
+    map_new, img_new = new(imgs)
+    assert map_new.shape == map_ref.shape == (2, 1, *grid_hw)
+    if channels_last:
+        emax, _ = rel_errors(map_new, map_ref)
+        assert emax <= 1e-4, emax
+    else:
+        assert torch.equal(map_new, map_ref)
+        assert all(torch.equal(a, b) for a, b in zip(img_new, img_ref))
+    map_ref.square().sum().backward()
+    map_new.square().sum().backward()
+    for (name, a), (_, b) in zip(new.named_parameters(), ref.named_parameters()):
+        if b.grad is None:
+            assert a.grad is None, name
+            continue
+        emax, _ = rel_errors(a.grad, b.grad)
+        assert emax <= 1e-4, (name, emax)

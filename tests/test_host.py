@@ -281,3 +281,40 @@ def test_map_head_weight_packing():
         pack_conv3x3_weight(torch.randn(512, 100, 3, 3))
     with pytest.raises(ValueError):
         pack_head_weight(torch.randn(2, 512, 3, 3))
+
+
+def test_install_kornia_shim_without_kornia(monkeypatch):
+    """Seam 1 as shipped code: with no kornia installed the shim registers stub modules, so the reference's `import kornia`
+    and both spellings of the call (persp_trans_detector.py:69, image_proj_variant.py:69) reach the given function."""
+    import importlib
+    import sys
+    from mvdet_b200 import integration
+    if importlib.util.find_spec("kornia") is not None:
+        pytest.skip("kornia is installed here; the stub branch is not taken")
+    for name in ("kornia", "kornia.geometry", "kornia.geometry.transform"):
+        monkeypatch.delitem(sys.modules, name, raising=False)
+    marker = lambda src, M, dsize, *a, **k: ("warped", tuple(dsize))
+    try:
+        mod = integration.install_kornia_shim(warp=marker)
+        import kornia
+        import kornia.geometry.transform as kgt
+        assert kornia is mod and kgt.warp_perspective is marker and kornia.warp_perspective is marker
+        assert kornia.geometry.transform.warp_perspective(None, None, [3, 4]) == ("warped", (3, 4))
+        integration.install_kornia_shim(warp=len)          # idempotent: re-pointing re-uses the registered modules
+        assert sys.modules["kornia"] is mod and kornia.warp_perspective is len
+    finally:
+        for name in ("kornia", "kornia.geometry", "kornia.geometry.transform"):
+            sys.modules.pop(name, None)
+
+
+def test_install_kornia_shim_defaults_to_the_cuda_seam(monkeypatch):
+    import sys
+    from mvdet_b200 import integration, ops
+    for name in ("kornia", "kornia.geometry", "kornia.geometry.transform"):
+        monkeypatch.delitem(sys.modules, name, raising=False)
+    try:
+        mod = integration.install_kornia_shim()
+        assert mod.geometry.transform.warp_perspective is ops.warp_perspective
+    finally:
+        for name in ("kornia", "kornia.geometry", "kornia.geometry.transform"):
+            sys.modules.pop(name, None)

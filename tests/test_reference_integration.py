@@ -140,3 +140,62 @@ def test_ablation_variants_call_the_same_seam(reference_model, variant, cls, sha
     for got_shape, dtype, is_contig, mshape, mdtype, dsize, args, kwargs in calls:
         assert got_shape == shape and dtype == torch.float32 and is_contig == contig
         assert mshape == (2, 3, 3) and mdtype == torch.float32 and dsize == [24, 72] and not args and not kwargs
+
+
+def test_patch_detector_reproduces_the_reference_forward(reference_model):
+    """mvdet_b200.integration.patch_detector (seam 2 as shipped code): the patched forward, with the oracle standing in for the
+    CUDA op, returns exactly what the unmodified reference forward returns -- map_result and every img_res, bit for bit."""
+    from mvdet_b200 import integration
+    from oracle import kornia_warp as K
+    model, calls = reference_model
+    ds = _fake_dataset()
+    imgs = torch.randn(2, ds.num_cam, 3, 144, 256, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        map_ref, img_ref = model(imgs)
+    n_ref_calls = len(calls)
+    assert n_ref_calls == ds.num_cam
+    seen = []
+
+    def warp_fn(img_feats, proj_mats, grid_shape):
+        seen.append((tuple(img_feats.shape), proj_mats.dtype, tuple(proj_mats.shape), list(grid_shape)))
+        return K.warp_views_oracle(img_feats, proj_mats, grid_shape)
+
+    patched = integration.patch_detector(model, channels_last=False, warp_fn=warp_fn)
+    assert patched is model
+    with torch.no_grad():
+        map_new, img_new = model(imgs)
+    assert len(calls) == n_ref_calls                       # the per-camera kornia call is gone ...
+    assert seen == [((2, ds.num_cam, 512, 54, 96), torch.float64, (ds.num_cam, 3, 3), [24, 72])]   # ... one warp_views call instead
+    assert torch.equal(map_new, map_ref)
+    assert len(img_new) == len(img_ref) and all(torch.equal(a, b) for a, b in zip(img_new, img_ref))
+    with torch.no_grad():
+        map_again, _ = model.reference_forward(imgs)       # the original forward stays reachable
+    assert torch.equal(map_again, map_ref) and len(calls) == 2 * n_ref_calls
+    with pytest.raises(NotImplementedError):
+        model(imgs, visualize=True)
+    with pytest.raises(AssertionError):
+        model(imgs[:, :2])
+    with pytest.raises(TypeError):
+        integration.patch_detector(torch.nn.Linear(2, 2))
+
+
+def test_patch_detector_channels_last_keeps_the_result(reference_model):
+    """channels_last=True only changes memory formats: same map_result to rounding (CPU convolutions take other kernels)."""
+    from mvdet_b200 import integration
+    from oracle import kornia_warp as K
+    model, _ = reference_model
+    ds = _fake_dataset()
+    imgs = torch.randn(1, ds.num_cam, 3, 144, 256, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        map_ref, _ = model(imgs)
+    layouts = []
+
+    def warp_fn(img_feats, proj_mats, grid_shape):
+        layouts.append(img_feats.stride(2) == 1)
+        return K.warp_views_oracle(img_feats, proj_mats, grid_shape)
+
+    integration.patch_detector(model, channels_last=True, warp_fn=warp_fn)
+    with torch.no_grad():
+        map_new, _ = model(imgs.contiguous())
+    assert layouts == [True]                               # trunk + F.interpolate + torch.stack hand over channel-contiguous features
+    assert float((map_new - map_ref).abs().max()) <= 1e-4 * float(map_ref.abs().max())
