@@ -14,8 +14,8 @@ def small_rig(num_cam=3, seed=5, src=(54, 96), grid=(24, 72)) -> tuple:
 
 def rel_errors(a: torch.Tensor, o: torch.Tensor):
     """(max-relative, l2-relative) error of a against oracle o (SURVEY.md 8d definitions)."""
-    a = a.double().cpu()
-    o = o.double().cpu()
+    a = a.detach().double().cpu()
+    o = o.detach().double().cpu()
     denom_max = o.abs().max().clamp_min(1e-30)
     denom_l2 = o.norm().clamp_min(1e-30)
     return float((a - o).abs().max() / denom_max), float((a - o).norm() / denom_l2)
