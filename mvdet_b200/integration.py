@@ -45,53 +45,86 @@ def install_kornia_shim(warp: Optional[Callable] = None) -> types.ModuleType:
     return kornia
 
 
-def _device_of(module: torch.nn.Module) -> torch.device:
-    return next(module.parameters()).device
+def _onto(t: torch.Tensor, module: torch.nn.Module) -> torch.Tensor:
+    """``t`` on the device of ``module``'s parameters -- the reference's ``.to('cuda:0')`` hops (:63-66, 81) without the hard-coded name."""
+    p = next(module.parameters(), None)
+    return t if p is None else t.to(p.device)
 
 
-def warped_forward(model, imgs: torch.Tensor, visualize: bool = False, warp_fn: Optional[Callable] = None):
+def _split_img_classifier(img_classifier):
+    """(first 1x1 convolution, the rest) of the reference's img_classifier = Conv2d(512,64,1), ReLU, Conv2d(64,2,1) (:48-49)."""
+    first = img_classifier[0] if isinstance(img_classifier, torch.nn.Sequential) and len(img_classifier) > 0 else None
+    ok = (isinstance(first, torch.nn.Conv2d) and first.kernel_size == (1, 1) and first.stride == (1, 1) and
+          first.padding == (0, 0) and first.groups == 1)
+    if not ok:
+        raise TypeError("fuse_upsample needs img_classifier to start with a 1x1 Conv2d (the reference's does, "
+                        "persp_trans_detector.py:48): a 1x1 convolution commutes with the bilinear up-sample")
+    return first, img_classifier[1:]
+
+
+def warped_forward(model, imgs: torch.Tensor, visualize: bool = False, warp_fn: Optional[Callable] = None,
+                   fuse_upsample: bool = False):
     """``PerspTransDetector.forward`` (persp_trans_detector.py:57-87) with lines 68-69, 75, 77 replaced by one ``warp_views`` call.
 
     Returns ``(map_result, imgs_result)`` like the reference.  Sub-modules run where the reference put them (each on the device of
     its own parameters; the reference pins all of them to ``cuda:0``); the warp and ``map_classifier`` run on ``map_classifier``'s
-    device.  ``visualize`` is the reference's matplotlib debugging switch and is not supported here."""
+    device.  ``visualize`` is the reference's matplotlib debugging switch and is not supported here.
+
+    ``fuse_upsample=True`` additionally removes the 512-channel ``F.interpolate`` of line 65 (a 1.86 GB tensor per Wildtrack frame that
+    the reference writes, reads twice and back-propagates through): the warp reads the trunk's low-res output through
+    :func:`mvdet_b200.ops.warp_views_upsampled` (up-sample composed into the plan), and ``img_classifier`` up-samples AFTER its first
+    1x1 convolution -- 64 channels instead of 512; exact in real arithmetic because a 1x1 convolution (bias included: bilinear
+    weights sum to one) commutes with the per-channel linear interpolation.  Results agree with the reference order to rounding
+    (1e-5 relative in the tests), not bit for bit.  ``warp_fn`` then has the signature of ``warp_views_upsampled``."""
     if visualize:
         raise NotImplementedError("visualize=True is the reference's matplotlib debugging path; call the original forward for it")
     if warp_fn is None:
-        from .ops import warp_views as warp_fn
+        if fuse_upsample:
+            from .ops import warp_views_upsampled as warp_fn
+        else:
+            from .ops import warp_views as warp_fn
     B, N = imgs.shape[:2]
     if N != model.num_cam:
         raise AssertionError(f"imgs carries {N} views, the model has {model.num_cam}")          # the reference asserts (:59)
-    d1, d2 = _device_of(model.base_pt1), _device_of(model.base_pt2)
-    dh, dm = _device_of(model.img_classifier), _device_of(model.map_classifier)
+    head_first, head_rest = _split_img_classifier(model.img_classifier) if fuse_upsample else (None, None)
     feats, imgs_result = [], []
     for cam in range(model.num_cam):                                                            # :62
-        f = model.base_pt1(imgs[:, cam].to(d1))                                                 # :63
-        f = model.base_pt2(f.to(d2))                                                            # :64
-        f = F.interpolate(f, model.upsample_shape, mode="bilinear")                             # :65
-        imgs_result.append(model.img_classifier(f.to(dh)))                                      # :66-67
-        feats.append(f.to(dm))
-    img_feats = torch.stack(feats, dim=1)                                                       # [B,V,C,Hs,Ws]; keeps channels-last
+        f = model.base_pt1(_onto(imgs[:, cam], model.base_pt1))                                 # :63
+        f = model.base_pt2(_onto(f, model.base_pt2))                                            # :64
+        if fuse_upsample:
+            h = F.interpolate(head_first(_onto(f, head_first)), model.upsample_shape, mode="bilinear")   # :65-66 reordered: 1x1 conv, then up-sample
+            imgs_result.append(head_rest(h))
+        else:
+            f = F.interpolate(f, model.upsample_shape, mode="bilinear")                         # :65
+            imgs_result.append(model.img_classifier(_onto(f, model.img_classifier)))            # :66-67
+        feats.append(_onto(f, model.map_classifier))
+    img_feats = torch.stack(feats, dim=1)                                                       # [B,V,C,H,W]; keeps channels-last
     proj_mats = torch.stack([m for m in model.proj_mats])                                       # float64 CPU (:29-30); op applies .float() (:68)
-    world_features = warp_fn(img_feats, proj_mats, model.reducedgrid_shape)                     # :68-69, 75, 77
+    if fuse_upsample:
+        world_features = warp_fn(img_feats, model.upsample_shape, proj_mats, model.reducedgrid_shape)   # :65 (for the warp) + :68-69, 75, 77
+    else:
+        world_features = warp_fn(img_feats, proj_mats, model.reducedgrid_shape)                 # :68-69, 75, 77
     map_result = model.map_classifier(world_features)                                           # :81
     map_result = F.interpolate(map_result, model.reducedgrid_shape, mode="bilinear")            # :82
     return map_result, imgs_result
 
 
-def patch_detector(model, channels_last: bool = True, warp_fn: Optional[Callable] = None):
+def patch_detector(model, channels_last: bool = True, warp_fn: Optional[Callable] = None, fuse_upsample: bool = False):
     """Give ``model`` (a ``PerspTransDetector``) the :func:`warped_forward`; returns the same object.
 
     ``channels_last=True`` also converts the model's parameters to ``torch.channels_last`` so that the trunk, ``F.interpolate`` and
     ``torch.stack`` hand the warp channel-contiguous features (the fast kernels; NCHW is accepted but ~3x slower) and cuDNN
     consumes the channels-last result directly.  Feed ``imgs.contiguous(memory_format=torch.channels_last)`` per camera for the
-    full effect.  The original forward stays reachable as ``model.reference_forward``."""
+    full effect.  ``fuse_upsample``: see :func:`warped_forward`.  The original forward stays reachable as ``model.reference_forward``."""
     missing = [a for a in _ATTRS if not hasattr(model, a)]
     if missing:
         raise TypeError(f"patch_detector needs a PerspTransDetector-like model; missing attributes: {missing}")
+    if fuse_upsample:
+        _split_img_classifier(model.img_classifier)
     if channels_last:
         model.to(memory_format=torch.channels_last)
     if not hasattr(model, "reference_forward"):
         model.reference_forward = model.forward
-    model.forward = types.MethodType(lambda self, imgs, visualize=False: warped_forward(self, imgs, visualize, warp_fn), model)
+    model.forward = types.MethodType(
+        lambda self, imgs, visualize=False: warped_forward(self, imgs, visualize, warp_fn, fuse_upsample), model)
     return model

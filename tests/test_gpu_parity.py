@@ -450,7 +450,7 @@ class _TinyDetector(torch.nn.Module):
         self.num_cam = pm.shape[0]
         self.base_pt1 = torch.nn.Conv2d(3, C, 3, padding=1)
         self.base_pt2 = torch.nn.Sequential(torch.nn.ReLU(), torch.nn.Conv2d(C, C, 1))
-        self.img_classifier = torch.nn.Conv2d(C, 2, 1)
+        self.img_classifier = torch.nn.Sequential(torch.nn.Conv2d(C, 4, 1), torch.nn.ReLU(), torch.nn.Conv2d(4, 2, 1, bias=False))
         self.map_classifier = torch.nn.Sequential(torch.nn.Conv2d(C * self.num_cam + 2, 4, 3, padding=1), torch.nn.ReLU(),
                                                   torch.nn.Conv2d(4, 1, 3, padding=2, dilation=2))
         self.proj_mats = [pm[v] for v in range(self.num_cam)]
@@ -498,5 +498,27 @@ def test_patch_detector_matches_the_per_camera_loop(channels_last, monkeypatch):
         if b.grad is None:
             assert a.grad is None, name
             continue
+        emax, _ = rel_errors(a.grad, b.grad)
+        assert emax <= 1e-4, (name, emax)
+
+
+def test_patch_detector_fused_upsample_on_gpu(monkeypatch):
+    """fuse_upsample=True on the GPU: warp_views_upsampled on the trunk's low-res output + img_classifier up-sampling after its 1x1
+    convolution, against the reference order (interpolate 8 channels, per-camera warp, cat): forward and parameter gradients."""
+    import copy
+    from mvdet_b200 import integration
+    pm, src_hw, grid_hw = small_rig()
+    torch.manual_seed(0)
+    ref = _TinyDetector(pm, src_hw, grid_hw).to(DEV)
+    new = integration.patch_detector(copy.deepcopy(ref), channels_last=True, fuse_upsample=True)
+    imgs = torch.randn(2, 3, 3, 18, 32, generator=torch.Generator().manual_seed(1))
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    map_ref, img_ref = ref(imgs)
+    map_new, img_new = new(imgs)
+    assert rel_errors(map_new, map_ref)[0] <= 1e-4
+    assert all(rel_errors(a, b)[0] <= 1e-4 for a, b in zip(img_new, img_ref))
+    (map_ref.square().sum() + sum(r.square().sum() for r in img_ref)).backward()
+    (map_new.square().sum() + sum(r.square().sum() for r in img_new)).backward()
+    for (name, a), (_, b) in zip(new.named_parameters(), ref.named_parameters()):
         emax, _ = rel_errors(a.grad, b.grad)
         assert emax <= 1e-4, (name, emax)

@@ -199,3 +199,33 @@ def test_patch_detector_channels_last_keeps_the_result(reference_model):
         map_new, _ = model(imgs.contiguous())
     assert layouts == [True]                               # trunk + F.interpolate + torch.stack hand over channel-contiguous features
     assert float((map_new - map_ref).abs().max()) <= 1e-4 * float(map_ref.abs().max())
+
+
+def test_patch_detector_fused_upsample_agrees_to_rounding(reference_model):
+    """fuse_upsample=True: the warp reads the trunk's low-res output (two-step oracle standing in for warp_views_upsampled) and
+    img_classifier up-samples after its first 1x1 convolution -- the same map_result / img_res as the reference order to rounding."""
+    from mvdet_b200 import integration
+    from oracle import kornia_warp as K
+    model, calls = reference_model
+    ds = _fake_dataset()
+    imgs = torch.randn(2, ds.num_cam, 3, 144, 256, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        map_ref, img_ref = model(imgs)
+    seen = []
+
+    def warp_up(img_feats_low, upsample_shape, proj_mats, grid_shape):
+        seen.append((tuple(img_feats_low.shape), list(upsample_shape)))
+        V = img_feats_low.shape[1]
+        up = torch.stack([F.interpolate(img_feats_low[:, v], upsample_shape, mode="bilinear") for v in range(V)], dim=1)  # :65
+        return K.warp_views_oracle(up, proj_mats, grid_shape)
+
+    integration.patch_detector(model, channels_last=False, warp_fn=warp_up, fuse_upsample=True)
+    with torch.no_grad():
+        map_new, img_new = model(imgs)
+    assert seen == [((2, ds.num_cam, 512, 18, 32), [54, 96])]          # the 512-channel up-sample is gone from the model's forward
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert rel(map_new, map_ref) <= 1e-5
+    assert all(rel(a, b) <= 1e-5 for a, b in zip(img_new, img_ref))
+    model.img_classifier = torch.nn.Sequential(torch.nn.Conv2d(512, 2, 3, padding=1))
+    with pytest.raises(TypeError):
+        integration.patch_detector(model, fuse_upsample=True)          # a 3x3 first layer does not commute with the up-sample
