@@ -311,3 +311,44 @@ def test_fused_conv1_ragged_grid_and_many_views():
     assert out.shape == (B, 512, 20, 60)
     emax, el2 = rel_errors(out, ref)
     assert emax <= 1e-4 and el2 <= 1e-4, (emax, el2)
+
+
+def test_patch_detector_fused_head_inference():
+    """integration.patch_detector(model, fused_head=True): under no_grad the warp + map_classifier run as MapHead's three kernels and
+    agree with the model's own un-fused forward to bf16 rounding; with autograd on the un-fused path runs and gradients flow."""
+    import torch.nn as nn
+    from mvdet_b200 import integration
+    from tests.util import small_rig, rel_errors
+    V, Cc = 2, 64
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=37)
+
+    class Det(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.num_cam = V
+            self.base_pt1, self.base_pt2 = nn.Conv2d(3, Cc, 3, padding=1), nn.Sequential(nn.ReLU(), nn.Conv2d(Cc, Cc, 1))
+            self.img_classifier = nn.Sequential(nn.Conv2d(Cc, 8, 1), nn.ReLU(), nn.Conv2d(8, 2, 1, bias=False))
+            self.map_classifier = nn.Sequential(nn.Conv2d(Cc * V + 2, 512, 3, padding=1), nn.ReLU(),
+                                                nn.Conv2d(512, 512, 3, padding=2, dilation=2), nn.ReLU(),
+                                                nn.Conv2d(512, 1, 3, padding=4, dilation=4, bias=False))
+            self.proj_mats = [pm[v] for v in range(V)]
+            self.upsample_shape, self.reducedgrid_shape = list(src_hw), list(grid_hw)
+
+        def forward(self, imgs, visualize=False):
+            raise RuntimeError("replaced by patch_detector")
+
+    torch.manual_seed(0)
+    model = integration.patch_detector(Det().cuda().eval(), fused_head=True)
+    assert model.fused_map_head is not None
+    imgs = torch.randn(2, V, 3, 18, 32, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        fused, res_f = model(imgs)
+    plain, res_p = model(imgs)                              # autograd on: the un-fused path (cuDNN, fp32 / TF32)
+    assert fused.shape == plain.shape == (2, 1, *grid_hw) and not fused.requires_grad and plain.requires_grad
+    emax, el2 = rel_errors(fused, plain)
+    assert emax <= 3e-2 and el2 <= 2e-2, (emax, el2)        # bf16 activations + weights against fp32
+    assert all(torch.equal(a, b) for a, b in zip(res_f, res_p))
+    plain.square().sum().backward()
+    assert model.map_classifier[0].weight.grad is not None and model.base_pt1.weight.grad is not None
+    with pytest.raises(ValueError):
+        integration.patch_detector(Det().cuda(), fused_head=True, fuse_upsample=True)
