@@ -63,7 +63,7 @@ def _split_img_classifier(img_classifier):
 
 
 def warped_forward(model, imgs: torch.Tensor, visualize: bool = False, warp_fn: Optional[Callable] = None,
-                   fuse_upsample: bool = False, fused_head=None):
+                   fuse_upsample: bool = False, fused_head=None, fused_conv1: bool = False):
     """``PerspTransDetector.forward`` (persp_trans_detector.py:57-87) with lines 68-69, 75, 77 replaced by one ``warp_views`` call.
 
     Returns ``(map_result, imgs_result)`` like the reference.  Sub-modules run where the reference put them (each on the device of
@@ -79,7 +79,10 @@ def warped_forward(model, imgs: torch.Tensor, visualize: bool = False, warp_fn: 
 
     ``fused_head`` (a :class:`mvdet_b200.map_head.MapHead`; see :func:`patch_detector`) replaces the warp AND ``map_classifier``
     (:68-81) by three fused kernels whenever autograd is off: fused warp -> conv1 on tcgen05, dilated conv by TMA, 512 -> 1 head,
-    bf16 activations with fp32 accumulation.  With autograd on the un-fused path runs (the fused kernels are forward-only)."""
+    bf16 activations with fp32 accumulation.  With autograd on the un-fused path runs (the fused kernels are forward-only) --
+    unless ``fused_conv1`` is set: then ``map_classifier[0]`` + ReLU run as :func:`mvdet_b200.conv1.warp_conv1_trainable` (fused
+    tcgen05 forward on bf16 features; backward = re-materialised warp + cuDNN's convolution backward + the deterministic CSR warp
+    backward; BASELINE.json configs[2]) and the rest of ``map_classifier`` follows in torch."""
     if visualize:
         raise NotImplementedError("visualize=True is the reference's matplotlib debugging path; call the original forward for it")
     if warp_fn is None:
@@ -110,6 +113,15 @@ def warped_forward(model, imgs: torch.Tensor, visualize: bool = False, warp_fn: 
             x = x.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
         map_result = fused_head(x, proj_mats, model.reducedgrid_shape)                          # :68-81
         return F.interpolate(map_result, model.reducedgrid_shape, mode="bilinear"), imgs_result # :82
+    if fused_conv1:
+        from .conv1 import warp_conv1_trainable
+        x = img_feats.to(torch.bfloat16)
+        if x.stride(2) != 1:
+            x = x.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+        conv = model.map_classifier[0]
+        a1 = warp_conv1_trainable(x, conv.weight, conv.bias, proj_mats, model.reducedgrid_shape, relu=True)   # :68-77 + map_classifier[0:2]
+        map_result = model.map_classifier[2:](a1)                                               # :81, the rest
+        return F.interpolate(map_result, model.reducedgrid_shape, mode="bilinear"), imgs_result # :82
     if fuse_upsample:
         world_features = warp_fn(img_feats, model.upsample_shape, proj_mats, model.reducedgrid_shape)   # :65 (for the warp) + :68-69, 75, 77
     else:
@@ -120,7 +132,7 @@ def warped_forward(model, imgs: torch.Tensor, visualize: bool = False, warp_fn: 
 
 
 def patch_detector(model, channels_last: bool = True, warp_fn: Optional[Callable] = None, fuse_upsample: bool = False,
-                   fused_head: bool = False):
+                   fused_head: bool = False, fused_conv1: bool = False):
     """Give ``model`` (a ``PerspTransDetector``) the :func:`warped_forward`; returns the same object.
 
     ``channels_last=True`` also converts the model's parameters to ``torch.channels_last`` so that the trunk, ``F.interpolate`` and
@@ -129,13 +141,21 @@ def patch_detector(model, channels_last: bool = True, warp_fn: Optional[Callable
     full effect.  ``fuse_upsample``: see :func:`warped_forward`.  ``fused_head=True`` packs ``map_classifier``'s CURRENT weights into a
     :class:`mvdet_b200.map_head.MapHead` (stored as ``model.fused_map_head``; patch again after loading another checkpoint) and uses
     it under ``torch.no_grad()`` -- inference: 1.14 ms per Wildtrack frame for the warp + ``map_classifier`` against 2.01 ms un-fused.
-    It needs the up-sampled features, so it excludes ``fuse_upsample``.  The original forward stays reachable as
+    It needs the up-sampled features, so it excludes ``fuse_upsample``.  ``fused_conv1=True`` (training; also excludes ``fuse_upsample``)
+    runs ``map_classifier[0]`` + ReLU as the fused warp -> conv1 kernel with gradients, see :func:`warped_forward`.  The original forward stays reachable as
     ``model.reference_forward``."""
     missing = [a for a in _ATTRS if not hasattr(model, a)]
     if missing:
         raise TypeError(f"patch_detector needs a PerspTransDetector-like model; missing attributes: {missing}")
-    if fuse_upsample and fused_head:
-        raise ValueError("fused_head needs the up-sampled features (the fused conv1 kernel warps them itself); it excludes fuse_upsample")
+    if fuse_upsample and (fused_head or fused_conv1):
+        raise ValueError("fused_head / fused_conv1 need the up-sampled features (the fused conv1 kernel warps them itself); "
+                         "they exclude fuse_upsample")
+    if fused_conv1:
+        mc = model.map_classifier
+        ok = (isinstance(mc, torch.nn.Sequential) and len(mc) >= 2 and isinstance(mc[0], torch.nn.Conv2d) and
+              isinstance(mc[1], torch.nn.ReLU) and mc[0].kernel_size == (3, 3) and mc[0].padding == (1, 1) and mc[0].out_channels == 512)
+        if not ok:
+            raise TypeError("fused_conv1 needs map_classifier to start with Conv2d(V*C+2, 512, 3, padding=1), ReLU (persp_trans_detector.py:51)")
     if fuse_upsample:
         _split_img_classifier(model.img_classifier)
     head = None
@@ -153,5 +173,5 @@ def patch_detector(model, channels_last: bool = True, warp_fn: Optional[Callable
     if not hasattr(model, "reference_forward"):
         model.reference_forward = model.forward
     model.forward = types.MethodType(
-        lambda self, imgs, visualize=False: warped_forward(self, imgs, visualize, warp_fn, fuse_upsample, head), model)
+        lambda self, imgs, visualize=False: warped_forward(self, imgs, visualize, warp_fn, fuse_upsample, head, fused_conv1), model)
     return model

@@ -352,3 +352,14 @@ def test_patch_detector_fused_head_inference():
     assert model.map_classifier[0].weight.grad is not None and model.base_pt1.weight.grad is not None
     with pytest.raises(ValueError):
         integration.patch_detector(Det().cuda(), fused_head=True, fuse_upsample=True)
+
+    # fused_conv1: the training path through warp_conv1_trainable agrees with the un-fused autograd path to bf16 rounding
+    for p_ in model.parameters():
+        p_.grad = None
+    g_plain = torch.autograd.grad(model(imgs)[0].square().sum(), [model.map_classifier[0].weight, model.base_pt1.weight])
+    trained = integration.patch_detector(model, fused_conv1=True)
+    out_f, _ = trained(imgs)
+    assert out_f.requires_grad and rel_errors(out_f, plain)[1] <= 2e-2
+    g_fused = torch.autograd.grad(out_f.square().sum(), [model.map_classifier[0].weight, model.base_pt1.weight])
+    for a, b in zip(g_fused, g_plain):
+        assert rel_errors(a, b)[1] <= 6e-2, rel_errors(a, b)
