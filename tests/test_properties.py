@@ -99,3 +99,31 @@ def test_inverse_csr_is_the_transpose_of_the_forward_taps(seed, hs, ws, hg, wg):
         # entries with zero weight are legal (a tap exactly on a texel), but no entry may exist where the forward has none
         assert bool(((mine != 0) <= (A.abs() > 0) | (mine.abs() <= 2e-6)).all())
     assert total == stt["nnz"]
+
+
+@settings(max_examples=15, deadline=None, derandomize=True)
+@given(seed=st.integers(0, 10_000), hl=st.integers(1, 6), wl=st.integers(1, 7), fy=st.sampled_from([1, 2, 3, 2.5, 1.4]),
+       fx=st.sampled_from([1, 2, 3, 1.75]), hg=st.integers(2, 7), wg=st.integers(2, 9))
+def test_composed_upsample_map_equals_the_two_step_matrix(seed, hl, wl, fy, fx, hg, wg):
+    """Fused up-sample plans for ANY low-res size and (also non-integer, also 1:1) up-sample ratio: the composed map on the
+    low-res image against the dense matrix of  grid_sample(F.interpolate(., bilinear, align_corners=False))  in float64."""
+    import torch.nn.functional as F
+    hs, ws = max(2, int(round(hl * fy))), max(2, int(round(wl * fx)))
+    spec = RigSpec("rnd", 1, img_shape=(1080, 1920), worldgrid_shape=(480, 1440), img_reduce=4, grid_reduce=4, seed=seed)
+    pm = synthetic_rig(spec)
+    g = P.host_grid(P.src_norm_trans_dst_norm(pm, (hs, ws), (hg, wg)), (hg, wg))
+    stt, tex_of, row_ptr, cells, weights = P.host_csr(g, (hs, ws), with_map=True, lowres_hw=(hl, wl))
+    nlow = hl * wl
+    eye = torch.eye(nlow, dtype=torch.float64).reshape(1, nlow, hl, wl)
+    # ATen computes the up-sample's source index and lambdas in the tensor's dtype; the plan mirrors the fp32 formulas, so build the
+    # reference up-sample in fp32 (exact on a one-hot basis: each value is a product of two fp32 lambdas) and warp it in float64
+    up = F.interpolate(eye.float(), (hs, ws), mode="bilinear").double()
+    A = F.grid_sample(up, g[0][None].double(), mode="bilinear", padding_mode="zeros", align_corners=True)[0].reshape(nlow, hg * wg).T
+    mine = torch.zeros_like(A)
+    rp = row_ptr[0].long()
+    assert torch.equal(torch.sort(tex_of[0].long()).values, torch.arange(nlow))
+    for r in range(nlow):
+        seg = slice(int(rp[r]), int(rp[r + 1]))
+        mine[:, int(tex_of[0][r])].index_add_(0, cells[seg].long(), weights[seg].double())
+    assert int(rp[-1]) == stt["nnz"]
+    assert float((mine - A).abs().max()) <= 2e-6, float((mine - A).abs().max())
