@@ -1207,7 +1207,7 @@ int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* f
   using namespace mvw;
   if (out_dtype != MVWARP_F32 && out_dtype != MVWARP_BF16) { set_error("warp_conv1_fwd: unknown output dtype"); return MVWARP_EINVAL; }
   if (!plan || !feats || !feat_strides || !wpack || !out || !out_strides) { set_error("warp_conv1_fwd: null argument"); return MVWARP_EINVAL; }
-  if (B <= 0 || nviews <= 0 || view0 < 0 || view0 + nviews > plan->V) { set_error("warp_conv1_fwd: bad B / view range"); return MVWARP_EINVAL; }
+  if (B <= 0 || nviews <= 0 || view0 < 0 || view0 > plan->V || nviews > plan->V - view0) { set_error("warp_conv1_fwd: bad B / view range"); return MVWARP_EINVAL; }
   if (plan->upsampled || !plan->inline_coords) { set_error("warp_conv1_fwd: needs a plain matrix plan"); return MVWARP_EUNSUPPORTED; }
   if (C <= 0 || C % CV_KB || feat_strides[2] != 1 || (reinterpret_cast<uintptr_t>(feats) & 15u) || feat_strides[0] % 8 ||
       feat_strides[1] % 8 || feat_strides[3] % 8 || feat_strides[4] % 8) {

@@ -441,6 +441,9 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int hl,
   } catch (const std::exception& ex) {
     set_error(std::string("plan_create: ") + ex.what());
     return MVWARP_EINVAL;
+  } catch (...) {
+    set_error("plan_create: unknown C++ exception");
+    return MVWARP_EINVAL;
   }
 }
 
@@ -496,6 +499,12 @@ int mvwarp_host_csr_upsampled(const float* grid_host, int V, int hl, int wl, int
   } catch (const std::bad_alloc&) {
     set_error("host_csr: host allocation failed");
     return MVWARP_ENOMEM;
+  } catch (const std::exception& ex) {  // the header's promise: nothing is ever thrown across the boundary
+    set_error(std::string("host_csr: ") + ex.what());
+    return MVWARP_EINVAL;
+  } catch (...) {
+    set_error("host_csr: unknown C++ exception");
+    return MVWARP_EINVAL;
   }
 }
 
@@ -600,6 +609,12 @@ int mvwarp_plan_save(const mvwarp_plan_t* plan, const char* path) {
   } catch (const std::bad_alloc&) {
     set_error("plan_save: host allocation failed");
     return MVWARP_ENOMEM;
+  } catch (const std::exception& ex) {  // the header's promise: nothing is ever thrown across the boundary
+    set_error(std::string("plan_save: ") + ex.what());
+    return MVWARP_EINVAL;
+  } catch (...) {
+    set_error("plan_save: unknown C++ exception");
+    return MVWARP_EINVAL;
   }
 }
 
@@ -681,6 +696,12 @@ int mvwarp_plan_load(const char* path, int device, mvwarp_plan_t** plan_out) {
   } catch (const std::bad_alloc&) {
     set_error("plan_load: host allocation failed");
     return MVWARP_ENOMEM;
+  } catch (const std::exception& ex) {  // the header's promise: nothing is ever thrown across the boundary
+    set_error(std::string("plan_load: ") + ex.what());
+    return MVWARP_EINVAL;
+  } catch (...) {
+    set_error("plan_load: unknown C++ exception");
+    return MVWARP_EINVAL;
   }
 }
 
@@ -728,7 +749,7 @@ int mvwarp_plan_device_grid(const mvwarp_plan_t* plan, float* grid_host_out, voi
 static int check_call(const mvwarp_plan_t* plan, int view0, int nviews, const void* a, const void* b,
                       const int64_t* fs, const int64_t* os, int B, int C, int dtype, const char* who) {
   if (!plan || !a || !b || !fs || !os) { set_error(std::string(who) + ": null argument"); return MVWARP_EINVAL; }
-  if (B <= 0 || C <= 0 || nviews <= 0 || view0 < 0 || view0 + nviews > plan->V) {
+  if (B <= 0 || C <= 0 || nviews <= 0 || view0 < 0 || view0 > plan->V || nviews > plan->V - view0) {
     set_error(std::string(who) + ": bad B/C/view range");
     return MVWARP_EINVAL;
   }

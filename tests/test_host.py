@@ -46,6 +46,40 @@ def test_bad_arguments_return_error_codes_not_crashes():
         _lib.check(_lib.EINVAL, "demo")
 
 
+def test_every_entry_point_rejects_null_arguments_without_a_gpu():
+    """include/mvwarp.h: "returns a negative MVWARP_E* code on failure, and never throws or aborts across the boundary" -- every
+    compute entry point, called with null pointers / impossible sizes on a box with no GPU, must come back with EINVAL and a message."""
+    lib = _lib.load()
+    i5, i4 = _lib.i64x([1] * 5), _lib.i64x([1] * 4)
+    st, h = _lib.Stats(), ctypes.c_void_p()
+    nine = ctypes.cast((ctypes.c_float * 9)(), ctypes.POINTER(ctypes.c_float))
+    calls = {
+        "warp_views_fwd": lambda: lib.mvwarp_warp_views_fwd(None, 0, 1, None, i5, None, i4, 0, -1, 1, 4, 0, None),
+        "warp_views_bwd": lambda: lib.mvwarp_warp_views_bwd(None, 0, 1, None, i4, 0, None, i5, 1, 4, 0, None),
+        "plan_stats": lambda: lib.mvwarp_plan_stats(None, ctypes.byref(st)),
+        "plan_save": lambda: lib.mvwarp_plan_save(None, b"/tmp/x"),
+        "plan_load": lambda: lib.mvwarp_plan_load(b"/nonexistent/x.mvwplan", 0, ctypes.byref(h)),
+        "plan_matrices": lambda: lib.mvwarp_plan_matrices(None, None),
+        "plan_device_grid": lambda: lib.mvwarp_plan_device_grid(None, None, None),
+        "warp_conv1_fwd": lambda: lib.mvwarp_warp_conv1_fwd(None, 0, 1, None, i5, None, None, None, i4, 1, 64, 1, 1, 0, 0, None),
+        "warp_conv1_fwd_ex": lambda: lib.mvwarp_warp_conv1_fwd_ex(None, 0, 1, None, i5, None, None, None, 0, i4, 1, 64, 1, 1, 0, 0,
+                                                                  None, 0, None),
+        "conv3x3_fwd": lambda: lib.mvwarp_conv3x3_fwd(None, i4, None, None, None, i4, 1, 8, 8, 64, 1, 1, 0, 0, None),
+        "conv3x3_head_fwd": lambda: lib.mvwarp_conv3x3_head_fwd(None, i4, None, None, i4, 1, 8, 8, 64, 1, 0, None),
+        "inbox_reduce": lambda: lib.mvwarp_inbox_reduce(None, 2, 0, 0, 1, 512, None, 0, None, 0, 0, None),
+        "warp_conv1_fwd_p2p": lambda: lib.mvwarp_warp_conv1_fwd_p2p(None, 0, 1, None, i5, None, 1, 64, 1, 2, 0, None, None, 8, None),
+        "debug_gemm": lambda: lib.mvwarp_debug_gemm(None, None, None, 128, 256, 64, None),
+        "debug_gemm_layout": lambda: lib.mvwarp_debug_gemm_layout(None, None, None, 128, 256, 64, 1024, 0, 0, None),
+        "plan_create": lambda: lib.mvwarp_plan_create(nine, 1, 0, 4, 4, 4, 0, ctypes.byref(h)),
+        "plan_create_upsampled": lambda: lib.mvwarp_plan_create_upsampled(nine, 1, 0, 0, 4, 4, 4, 4, 0, ctypes.byref(h)),
+        "plan_create_from_grid": lambda: lib.mvwarp_plan_create_from_grid(None, 1, 4, 4, 4, 4, 0, ctypes.byref(h)),
+    }
+    for name, call in calls.items():
+        assert call() == _lib.EINVAL, name
+        assert len(lib.mvwarp_last_error()) > 0, name
+    assert lib.mvwarp_warp_conv1_scratch_bytes(None, 1, 1, 0, 0) == 0
+
+
 def test_matrix_chain_matches_oracle_bits():
     for spec in (WILDTRACK, MULTIVIEWX):
         pm = synthetic_rig(spec)
