@@ -191,6 +191,8 @@ def run_reference(args):
 
 
 def parallelism_note(args, spec, world):
+    if world == 1:
+        return f"one GPU warps all {spec.num_cam} cameras (views shard across GPUs with no data-path collective: --gpus N)"
     how = (f"cameras [{spec.num_cam}r, {spec.num_cam}r+{spec.num_cam}) of one {spec.num_cam * world}-camera ring (work differs per rank)"
            if getattr(args, "distinct_cameras", False) and world > 1 else
            f"ring r of {world} identical {spec.num_cam}-camera rings (the N=1 work on every GPU)")
