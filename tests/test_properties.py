@@ -18,9 +18,9 @@ SETTINGS = dict(max_examples=25, deadline=None, derandomize=True)
 @pytest.fixture(autouse=True)
 def _single_threaded_oracle():
     """The oracle is the kornia chain on ONE CPU thread -- the reference forces OMP_NUM_THREADS=1 (main.py:3).  That matters in one
-    corner these tests found: with 8 MKL threads and a bmm batch of B*Hg = 2, MKL splits each tiny GEMM across threads and the
-    columns past the last multiple of 48 (Wg = 98..106, 148, 152, 196 ...) come out 1 ulp different; every other shape
-    (Hg = 1, 3..160 x Wg = 45..399 swept) is thread-count independent."""
+    corner these tests found: when MKL has >= ~3 threads per bmm batch item (B*Hg = 2 at 6-8 threads, <= 5 at 16) it splits each
+    tiny GEMM across threads and the columns just past a multiple of 48 (Wg = 97..106, 148, 152, 196 ...) come out 1 ulp
+    different; B*Hg = 1 and B*Hg >= 6 (swept to 480, 3-16 threads) are thread-count independent -- every real grid."""
     n = torch.get_num_threads()
     torch.set_num_threads(1)
     yield
