@@ -522,3 +522,37 @@ def test_patch_detector_fused_upsample_on_gpu(monkeypatch):
     for (name, a), (_, b) in zip(new.named_parameters(), ref.named_parameters()):
         emax, _ = rel_errors(a.grad, b.grad)
         assert emax <= 1e-4, (name, emax)
+
+
+def test_forward_and_backward_are_cuda_graph_capturable():
+    """The launches take the current stream, allocate only through torch and never synchronise once the plan is cached, so a
+    forward + backward can be captured in a CUDA graph and replayed on new inputs (launch-bound B=1 loops)."""
+    pm, src_hw, grid_hw = small_rig()
+    plan = P.get_plan(pm, src_hw, grid_hw, DEV)
+    x = to_channels_last_5d(_feats(1, 3, 8, src_hw)).to(DEV)
+    go = torch.randn(1, 3 * 8 + 2, *grid_hw, generator=torch.Generator().manual_seed(2)).to(DEV).contiguous(memory_format=torch.channels_last)
+    out = torch.empty_like(go)
+    gx = torch.empty_like(x)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                           # warm-up outside the capture
+        ops.warp_views_fwd_into(plan, x, out, 0, 0, 3 * 8)
+        ops.warp_views_bwd_into(plan, go, gx, 0, 0)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ops.warp_views_fwd_into(plan, x, out, 0, 0, 3 * 8)
+        ops.warp_views_bwd_into(plan, go, gx, 0, 0)
+    x2 = to_channels_last_5d(_feats(1, 3, 8, src_hw) * 3.0 + 1.0).to(DEV)
+    go2 = go * -2.0
+    x.copy_(x2)
+    go.copy_(go2)
+    out.zero_()
+    gx.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    ref_out = torch.empty_like(out)
+    ref_gx = torch.empty_like(gx)
+    ops.warp_views_fwd_into(plan, x2, ref_out, 0, 0, 3 * 8)
+    ops.warp_views_bwd_into(plan, go2, ref_gx, 0, 0)
+    assert torch.equal(out, ref_out) and torch.equal(gx, ref_gx)
