@@ -556,3 +556,30 @@ def test_forward_and_backward_are_cuda_graph_capturable():
     ops.warp_views_fwd_into(plan, x2, ref_out, 0, 0, 3 * 8)
     ops.warp_views_bwd_into(plan, go2, ref_gx, 0, 0)
     assert torch.equal(out, ref_out) and torch.equal(gx, ref_gx)
+
+
+def test_realistic_upsampled_features_at_the_wildtrack_shape():
+    """SURVEY.md 8(d)'s "realistic" inputs: features that are a 3x bilinear up-sample of a low-res map (persp_trans_detector.py:65)
+    instead of white noise, two Wildtrack cameras at full size: forward bit-identical, gradient within 1e-5, bf16 inside its bound."""
+    import torch.nn.functional as F
+    spec = WILDTRACK
+    pm = synthetic_rig(spec)[[1, 4]]
+    Hs, Ws = spec.feat_shape
+    V, C = 2, 32
+    low = torch.randn(V, C, Hs // 3, Ws // 3, generator=torch.Generator().manual_seed(7))
+    x = F.interpolate(low, (Hs, Ws), mode="bilinear")[None]             # [1,V,C,Hs,Ws]
+    xo = x.clone().requires_grad_(True)
+    ref = K.warp_views_oracle(xo, pm, spec.grid_shape)
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (gref,) = torch.autograd.grad(ref, xo, go)
+    xd = to_channels_last_5d(x).to(DEV).requires_grad_(True)
+    out = mv.warp_views(xd, pm, spec.grid_shape)
+    assert bit_equal_fraction(out, ref) == 1.0
+    (gx,) = torch.autograd.grad(out, xd, go.to(DEV).contiguous(memory_format=torch.channels_last))
+    emax, el2 = rel_errors(gx, gref)
+    assert emax <= TOL and el2 <= TOL, (emax, el2)
+    xb = x.bfloat16()
+    refb = K.warp_views_oracle(xb.float(), pm, spec.grid_shape)
+    outb = mv.warp_views(to_channels_last_5d(xb).to(DEV), pm, spec.grid_shape)
+    bound = 2.0 ** -8 * refb.abs() + 1e-6 * refb.abs().max()
+    assert bool(((outb.float().cpu() - refb).abs() <= bound).all())
