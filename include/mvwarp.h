@@ -152,7 +152,9 @@ int mvwarp_warp_views_bwd(const mvwarp_plan_t* plan, int view0, int nviews,
                           void* grad_feats, const int64_t feat_strides[5],
                           int B, int C, int dtype, void* stream);
 
-/* ---- tensor-core building blocks (north_star (c)): validation hooks -----------------------------------------
+#ifdef MVWARP_DEV
+/* ---- tensor-core building blocks (north_star (c)): validation hooks, DEVELOPMENT BUILD ONLY ------------------
+ * (mvdet_b200/libmvwarp_dev.so, compiled with -DMVWARP_DEV; the product library does not export them)
  * mvwarp_debug_gemm: D[M,256] (fp32) = A[M,K] (bf16, row-major) x B[256,K]^T (bf16, row-major) on tcgen05 / TMEM.
  * Validation hook for the descriptor / swizzle / TMEM conventions the fused warp -> conv1 kernel relies on
  * (M % 128 == 0, K % 64 == 0, device pointers). */
@@ -162,6 +164,7 @@ int mvwarp_debug_gemm(const void* A, const void* B, void* D, int M, int N, int K
  * field if use_base_offset).  Development hook: which non-canonical operand layouts does the tensor core read correctly? */
 int mvwarp_debug_gemm_layout(const void* A, const void* B, void* D, int M, int N, int K, int sbo_bytes, int start_cells,
                              int use_base_offset, void* stream);
+#endif /* MVWARP_DEV */
 
 /* mvwarp_warp_conv1_fwd (north_star (c)): the warp fused into map_classifier[0] = Conv2d(V*C+2, 512, 3, padding=1)
  * (persp_trans_detector.py:51,81) as a tcgen05 implicit GEMM; the warped tensor is never materialised.  Runs in CTA pairs

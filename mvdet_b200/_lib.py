@@ -63,13 +63,18 @@ SIGNATURES = {
     "mvwarp_conv3x3_fwd": (C.c_int, [_P, _I64P, _P, _P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, _P]),
     "mvwarp_conv3x3_head_fwd": (C.c_int, [_P, _I64P, _P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
-    "mvwarp_debug_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
-    "mvwarp_debug_gemm_layout": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mvwarp_warp_views_bwd": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, C.c_int, _P, _I64P,
                                         C.c_int, C.c_int, C.c_int, _P]),
 }
 
+# exported by the development build only (mvdet_b200/libmvwarp_dev.so, -DMVWARP_DEV; include/mvwarp.h #ifdef MVWARP_DEV)
+DEV_SIGNATURES = {
+    "mvwarp_debug_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "mvwarp_debug_gemm_layout": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+}
+
 _lib = None
+_dev_lib = None
 _lock = threading.Lock()
 
 
@@ -100,6 +105,24 @@ def load():
             raise MvwarpError(f"libmvwarp.so ABI version {lib.mvwarp_version()} != 1: rebuild")
         _lib = lib
     return _lib
+
+
+def load_dev():
+    """The development build (superseded kernel generations, MVWARP_* tuning knobs, mvwarp_debug_* hooks) as a SEPARATE ctypes
+    handle.  Used by tests and scripts only; nothing in the package calls it."""
+    global _dev_lib
+    if _dev_lib is not None:
+        return _dev_lib
+    from .build import DEV_LIB_PATH, build_library
+    with _lock:
+        if _dev_lib is None:
+            path = os.environ.get("MVWARP_DEV_LIB") or (DEV_LIB_PATH if os.path.exists(DEV_LIB_PATH) else build_library(dev=True))
+            lib = C.CDLL(path)
+            for name, (res, args) in {**SIGNATURES, **DEV_SIGNATURES}.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _dev_lib = lib
+    return _dev_lib
 
 
 def check(rc: int, what: str):

@@ -23,6 +23,7 @@
 namespace mvw {
 using namespace umma;
 
+#ifdef MVWARP_DEV  // development build only: validation GEMM + layout probe
 // -----------------------------------------------------------------------------------------------------
 // Stage-1 validation kernel: D[M, 256] = A[M, K] * B[256, K]^T, bf16 in, fp32 out, K % 64 == 0, M % 128 == 0.
 // One CTA per 128-row tile, operands staged by all threads into 128-byte-swizzled K-major shared memory,
@@ -106,10 +107,12 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_test_kernel(const __nv_bfloa
   if (warp == 0) tmem_dealloc(tmem, GT_N);
 }
 
+#endif  // MVWARP_DEV
 }  // namespace mvw
 
 using namespace mvw;
 
+#ifdef MVWARP_DEV  // validation hooks: exported by the development build only (mvdet_b200/libmvwarp_dev.so)
 extern "C" int mvwarp_debug_gemm(const void* A, const void* B, void* D, int M, int N, int K, void* stream) {
   return mvwarp_debug_gemm_layout(A, B, D, M, N, K, 1024, 0, 0, stream);
 }
@@ -133,6 +136,7 @@ extern "C" int mvwarp_debug_gemm_layout(const void* A, const void* B, void* D, i
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "debug_gemm launch");
 }
 
+#endif  // MVWARP_DEV
 // =====================================================================================================
 // Fused warp -> conv1 (north_star (c)):  out1[b, n, y, x] = bias[n] + sum_{dy,dx,ch} W[n, ch, dy, dx] * X[b, ch, y+dy-1, x+dx-1]
 // with X = warp_views(feats) (never materialised), zero padding, optional ReLU.
@@ -203,6 +207,7 @@ __device__ __forceinline__ unsigned pack_bf2(float a, float b) {
   return *reinterpret_cast<const unsigned*>(&h);
 }
 
+#ifdef MVWARP_DEV  // superseded kernel generation, kept in the development build for comparison runs
 // Step A: correctness-first version -- one stage, every thread takes part in every phase.
 __global__ void __launch_bounds__(128) warp_conv1_kernel(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -359,6 +364,7 @@ __global__ void __launch_bounds__(128) warp_conv1_kernel(const ConvParams p) {
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, CV_N);
 }
+#endif  // MVWARP_DEV
 
 
 // -----------------------------------------------------------------------------------------------------
@@ -401,6 +407,7 @@ __device__ __forceinline__ void tma_wbox_2cta(uint32_t smem_dst, const CUtensorM
                : "memory");
 }
 
+#ifdef MVWARP_DEV  // superseded kernel generations (single CTA / cluster multicast / copying CTA pairs)
 template <int CL, bool PAIR>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
   static_assert(!PAIR || CL == 1, "pair mode does not multicast the weights");
@@ -711,6 +718,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_pipe_kernel(const 
   if (CL > 1 || PAIR) cluster_sync(); else __syncthreads();   // nobody leaves while a peer may still write into it / read from it
   if (warp == 0) { if (PAIR) tmem_dealloc_2cta(tmem, CV_N); else tmem_dealloc(tmem, CV_N); }
 }
+#endif  // MVWARP_DEV
 
 // -----------------------------------------------------------------------------------------------------
 // Direct version (the default): CTA pairs as above, and the nine conv taps are no longer COPIED out of the halo patch --
@@ -1079,12 +1087,34 @@ static Decomp decompose(int nitems, int nviews, int num_sms, bool pair) {
   return d;
 }
 
-// 0 = single-CTA kernel, 1 = CTA pairs with copied tap stages, 2 = CTA pairs reading the taps in place (default)
-static int pair_mode_wanted() {
-  const char* e = getenv("MVWARP_CONV1_PAIR");   // development knob
-  if (getenv("MVWARP_CONV1_VARIANT")) return 0;
-  return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2;
+// Development knobs, read ONCE (first launch) and only by the development build; the product library has no knobs.
+struct Conv1Knobs {
+  int pair_mode = 2;      // 0 = single-CTA kernel, 1 = CTA pairs with copied tap stages, 2 = CTA pairs reading the taps in place (default)
+  int cluster = 1;        // MVWARP_CONV1_VARIANT=2|4: cluster multicast of the weight blocks (single-CTA kernel)
+  bool simple = false;    // MVWARP_CONV1_VARIANT=s: the unpipelined validation kernel
+  bool nosplit = false;   // MVWARP_CONV1_NOSPLIT: no K split of the last partial wave
+  bool stats = false;     // MVWARP_CONV1_STATS: synchronous, prints where the MMA thread waits
+};
+static const Conv1Knobs& conv1_knobs() {
+  static const Conv1Knobs k = [] {
+    Conv1Knobs r;
+#ifdef MVWARP_DEV
+    const char* e = getenv("MVWARP_CONV1_PAIR");
+    const char* v = getenv("MVWARP_CONV1_VARIANT");
+    if (e && e[0] >= '0' && e[0] <= '2') r.pair_mode = e[0] - '0';
+    if (v) {
+      r.pair_mode = 0;
+      if (v[0] == 's') r.simple = true;
+      else if (v[0] >= '1' && v[0] <= '4') r.cluster = v[0] - '0';
+    }
+    r.nosplit = getenv("MVWARP_CONV1_NOSPLIT") != nullptr;
+    r.stats = getenv("MVWARP_CONV1_STATS") != nullptr;
+#endif
+    return r;
+  }();
+  return k;
 }
+static int pair_mode_wanted() { return conv1_knobs().pair_mode; }
 
 }  // namespace mvw
 
@@ -1247,18 +1277,20 @@ int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* f
   }
   p.nitems = p.ntiles * B; p.n_full = p.nitems; p.split = 1; p.scratch = nullptr;
   cudaError_t e;
-  const char* variant = getenv("MVWARP_CONV1_VARIANT");   // development knob: "simple" = the unpipelined validation kernel
-  if (variant && variant[0] == 's' && out_dtype == MVWARP_F32) {
+  const Conv1Knobs& knobs = conv1_knobs();
+#ifdef MVWARP_DEV
+  if (knobs.simple && out_dtype == MVWARP_F32) {
     const int smem = 16384 + (int)CV_B_BYTES + CP_CELLS * 128 + CP_CELLS * (int)sizeof(ConvTap) + 1024;
     e = cudaFuncSetAttribute(warp_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) {
       warp_conv1_kernel<<<dim3(p.ntiles, 1, B), 128, smem, (cudaStream_t)stream>>>(p);
       e = cudaGetLastError();
     }
-  } else {
-    const int smem = PA * 16384 + PB * (int)CV_B_BYTES + CP_CELLS * 128 + 2 * CP_CELLS * (int)sizeof(ConvTap) + 1024;
-    const int cl = (variant && variant[0] >= '1' && variant[0] <= '4') ? variant[0] - '0' : 1;
-    const int pmode = cl == 1 ? pair_mode_wanted() : 0;
+  } else
+#endif
+  {
+    const int cl = knobs.cluster;
+    const int pmode = cl == 1 ? knobs.pair_mode : 0;
     const bool pair = pmode != 0;
     CUtensorMap tmap_w;
     memset(&tmap_w, 0, sizeof(tmap_w));
@@ -1282,12 +1314,14 @@ int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* f
       p.p2p_src_pitch = p.p2p_b_pitch * B;
     }
     if (pair) p.n_full = p.nitems / 2 * 2;
-    if (cl == 1 && scratch && !getenv("MVWARP_CONV1_NOSPLIT")) {   // K-split of the last partial wave (see ConvParams)
+    if (cl == 1 && scratch && !knobs.nosplit) {   // K-split of the last partial wave (see ConvParams)
       const Decomp d = decompose(p.nitems, nviews, plan->num_sms, pair);
       if (d.split > 1 && scratch_bytes >= d.slots * 128 * CV_N * (int64_t)sizeof(float) && !(reinterpret_cast<uintptr_t>(scratch) & 15u)) {
         p.split = d.split; p.n_full = d.n_full; p.scratch = reinterpret_cast<float*>(scratch);
       }
     }
+#ifdef MVWARP_DEV
+    const int smem = PA * 16384 + PB * (int)CV_B_BYTES + CP_CELLS * 128 + 2 * CP_CELLS * (int)sizeof(ConvTap) + 1024;
     auto launch = [&](auto kernel, int cluster) -> cudaError_t {
       cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (err != cudaSuccess) return err;
@@ -1304,9 +1338,10 @@ int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* f
       cfg.attrs = attr; cfg.numAttrs = 1;
       return cudaLaunchKernelEx(&cfg, kernel, tmap_w, p);
     };
+#endif
     unsigned long long* d_stats = nullptr;
     const size_t nst = (size_t)3 * ((size_t)p.nitems * 8 + 8);
-    if (getenv("MVWARP_CONV1_STATS")) {   // development only: synchronous, prints where the MMA thread waits
+    if (knobs.stats) {   // development only: synchronous, prints where the MMA thread waits
       cudaMalloc(&d_stats, nst * sizeof(unsigned long long));
       cudaMemset(d_stats, 0, nst * sizeof(unsigned long long));
       p.stats = d_stats;
@@ -1326,10 +1361,15 @@ int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* f
         cfg.attrs = attr; cfg.numAttrs = 1;
         e = cudaLaunchKernelEx(&cfg, warp_conv1_direct_kernel, tmap_w, p);
       }
-    } else if (pair) e = launch(warp_conv1_pipe_kernel<1, true>, 2);
+    }
+#ifdef MVWARP_DEV
+    else if (pair) e = launch(warp_conv1_pipe_kernel<1, true>, 2);
     else if (cl == 1) e = launch(warp_conv1_pipe_kernel<1, false>, 1);
     else if (cl == 4) e = launch(warp_conv1_pipe_kernel<4, false>, 4);
     else e = launch(warp_conv1_pipe_kernel<2, false>, 2);
+#else
+    else { set_error("warp_conv1_fwd: this build carries the direct kernel only"); e = cudaErrorNotSupported; }
+#endif
     if (e == cudaSuccess && p.split > 1) {
       conv1_tail_reduce_kernel<<<dim3(p.nitems - p.n_full, 8), 256, 0, (cudaStream_t)stream>>>(p);
       e = cudaGetLastError();

@@ -56,6 +56,7 @@ __device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
   return *reinterpret_cast<const unsigned*>(&h);
 }
 
+#ifdef MVWARP_DEV  // single-CTA generation of the TMA convolution (development build only)
 template <int CL>
 __global__ void __launch_bounds__(C2_THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Conv2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv3x3_tc_kernel(const __grid_
   if (CL > 1) cluster_sync(); else __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, C2_N);
 }
+#endif  // MVWARP_DEV
 
 // -----------------------------------------------------------------------------------------------------
 // CTA-pair version (cta_group::2): the two CTAs of a cluster take two neighbouring cell tiles and run ONE MMA of
@@ -485,8 +487,11 @@ extern "C" int mvwarp_conv3x3_fwd(const void* x, const int64_t x_strides[4], con
   // Cluster of 2 with multicast weight blocks: measured equal to no cluster (0.190 vs 0.185 ms at the Wildtrack shape);
   // a K-split of the last partial wave (as in the fused conv1) does not pay here either (0.200 ms): the CTAs of a thin
   // last wave already run faster because the weight stream from L2 is shared by fewer SMs.
-  const char* variant = getenv("MVWARP_CONV2_CLUSTER");   // development knob: 2 = cluster of two
-  const int cl = (variant && variant[0] == '2') ? 2 : 1;
+#ifdef MVWARP_DEV
+  // development knobs, read once: MVWARP_CONV2_CLUSTER=2 (cluster of two, single-CTA kernel), MVWARP_CONV2_1CTA=1 (the single-CTA
+  // kernel: 0.203 vs 0.182 ms at Wildtrack B=1, 0.701 vs 0.672 at B=4)
+  static const int cl = [] { const char* v = getenv("MVWARP_CONV2_CLUSTER"); return (v && v[0] == '2') ? 2 : 1; }();
+  static const bool one_cta = [] { const char* v = getenv("MVWARP_CONV2_1CTA"); return v && v[0] == '1'; }();
   auto launch = [&](auto kernel, int cluster) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return err;
@@ -501,9 +506,12 @@ extern "C" int mvwarp_conv3x3_fwd(const void* x, const int64_t x_strides[4], con
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, tmap, p);
   };
+#else
+  constexpr bool one_cta = false;
+  (void)smem;
+#endif
   cudaError_t e;
-  const char* one = getenv("MVWARP_CONV2_1CTA");   // development knob: the single-CTA kernel (0.203 vs 0.182 ms at Wildtrack B=1, 0.701 vs 0.672 at B=4)
-  if (!(one && one[0] == '1')) {                   // default: CTA pairs (cta_group::2)
+  if (!one_cta) {                                  // default: CTA pairs (cta_group::2)
     const int smem2 = T2_PA * (int)C2_A_BYTES + T2_PB * (int)T2_B_BYTES + 1024;
     e = cudaFuncSetAttribute(conv3x3_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
     if (e == cudaSuccess) {
@@ -518,9 +526,12 @@ extern "C" int mvwarp_conv3x3_fwd(const void* x, const int64_t x_strides[4], con
       cfg.attrs = attr; cfg.numAttrs = 1;
       e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel, tmap, tmap_w, p);
     }
-  } else {
+  }
+#ifdef MVWARP_DEV
+  else {
     e = cl == 1 ? launch(conv3x3_tc_kernel<1>, 1) : launch(conv3x3_tc_kernel<2>, 2);
   }
+#endif
   restore();
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "conv3x3_fwd launch");
 }

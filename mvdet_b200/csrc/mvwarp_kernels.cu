@@ -883,9 +883,18 @@ static Side concat_side(const LaunchArgs& a, int width) {
   return Side{a.os[0], (int64_t)a.C * a.os[1], a.os[2], a.os[3], a.os[1], (int64_t)a.out_chan0 * a.os[1], width};
 }
 
-static int tuning_variant(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
+// Tuning knobs exist in the development build only (-DMVWARP_DEV) and are read once; the product library takes the defaults.
+struct WarpKnobs { int fwd = 0, bwd = 0, tbl = 0, nchw = 0; };
+static const WarpKnobs& warp_knobs() {
+  static const WarpKnobs k = [] {
+    WarpKnobs r;
+#ifdef MVWARP_DEV
+    auto get = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
+    r.fwd = get("MVWARP_FWD_VARIANT"); r.bwd = get("MVWARP_BWD_VARIANT"); r.tbl = get("MVWARP_TBL_VARIANT"); r.nchw = get("MVWARP_NCHW_VARIANT");
+#endif
+    return r;
+  }();
+  return k;
 }
 
 // channel-contiguous feature tensor whose every texel row starts 16-byte aligned
@@ -924,7 +933,7 @@ static int launch_gather_t(const LaunchArgs& a, KParams& p, const DevCsr& csr, b
     if (fullc && dense) KERNEL<T, __VA_ARGS__, true, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev); \
     else KERNEL<T, __VA_ARGS__, false, false><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev);             \
   } while (0)
-    if (FORWARD && sizeof(T) == 4 && csr.max_row <= 16 && h_hi == h_lo && tuning_variant("MVWARP_TBL_VARIANT", 0) != 1) {
+    if (FORWARD && sizeof(T) == 4 && csr.max_row <= 16 && h_hi == h_lo && warp_knobs().tbl != 1) {
       // short rows only (always true for fused up-sample plans: <= 16 low-res taps per cell): tile kernel.  fp32 only:
       // measured at the Wildtrack shape, fp32 0.230 -> 0.209 ms against the task kernel, bf16 0.160 -> 0.165 ms (spills)
       const uint32_t nblk = (csr.rows_per_view + TBL_ROWS - 1) / TBL_ROWS;
@@ -942,7 +951,7 @@ static int launch_gather_t(const LaunchArgs& a, KParams& p, const DevCsr& csr, b
       if (sizeof(T) == 2) MVW_GATHER(fwd_table_cl_kernel, 4);
       else MVW_GATHER(fwd_table_cl_kernel, 3);
     } else {
-      switch (tuning_variant("MVWARP_BWD_VARIANT", 0)) {  // tuning knob (development only)
+      switch (warp_knobs().bwd) {  // tuning knob (development build only)
         case 1: MVW_GATHER(bwd_cl_kernel, 3, false); break;
         case 2: MVW_GATHER(bwd_cl_kernel, 4, true); break;
         case 3: MVW_GATHER(bwd_cl_kernel, 3, true); break;
@@ -995,13 +1004,13 @@ static int launch_fwd_t(const LaunchArgs& a) {
     else if (fullc) fwd_cl_kernel<T, false, U, M, true, K><<<grid, block, 0, a.stream>>>(p);    \
     else fwd_cl_kernel<T, false, U, M, false, K><<<grid, block, 0, a.stream>>>(p);              \
   } while (0)
-    switch (tuning_variant("MVWARP_FWD_VARIANT", 0)) {  // tuning knob (development only)
+    switch (warp_knobs().fwd) {  // tuning knob (development build only)
       case 1: MVW_FWD(2, 3, false); break;
       case 2: MVW_FWD(2, 4, true); break;
       default: MVW_FWD(2, 4, false); break;
     }
 #undef MVW_FWD
-  } else if (a.fs[4] == 1 && a.os[3] == 1 && tuning_variant("MVWARP_NCHW_VARIANT", 0) == 0) {
+  } else if (a.fs[4] == 1 && a.os[3] == 1 && warp_knobs().nchw == 0) {
     // x-contiguous planes (NCHW, the reference's layout): 2-D cell tiles, 64 channels per thread
     const int nchunk = (a.C + NCHW_CH - 1) / NCHW_CH;
     int rc = check_grid_dims(a, (int64_t)a.B * nchunk);

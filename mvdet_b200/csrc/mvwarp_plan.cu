@@ -89,8 +89,12 @@ static void csr_from_triplets(const std::vector<Triplet>& trip, size_t nrows, in
   for (const Triplet& t : trip) out.entries[cursor[t.row]++] = t.e;
 
   // tasks (budget / heavy threshold overridable for tuning runs only)
+#ifdef MVWARP_DEV
   static const uint32_t budget = getenv("MVWARP_TASK_BUDGET") ? (uint32_t)atoi(getenv("MVWARP_TASK_BUDGET")) : TASK_BUDGET;
   static const uint32_t heavy_len = getenv("MVWARP_HEAVY_LEN") ? (uint32_t)atoi(getenv("MVWARP_HEAVY_LEN")) : HEAVY_LEN;
+#else
+  constexpr uint32_t budget = TASK_BUDGET, heavy_len = HEAVY_LEN;
+#endif
   Task cur{0, 0, (uint16_t)view};
   uint32_t weight = 0;
   auto flush = [&]() {
@@ -532,8 +536,9 @@ int mvwarp_plan_create_upsampled(const float* T, int V, int hl, int wl, int Hs, 
 // up-sample plans only) | matrices [V*9] (inline plans only) | the device allocation, byte for byte.
 namespace {
 struct PlanFileHeader {
-  char magic[8];             // "MVWPLAN1"
+  char magic[8];             // "MVWPLAN2"
   uint32_t header_bytes;     // sizeof(PlanFileHeader): a struct change invalidates old files
+  uint32_t schema;           // plan_schema(): bumped by hand when the MEANING of an array changes, mixed with the record sizes
   uint32_t abi_version;      // MVWARP_VERSION
   uint32_t task_budget, task_max_rows, heavy_len, csr_tile;  // work decomposition baked into the tasks
   int32_t V, Hs, Ws, Hg, Wg, hl, wl, upsampled, inline_coords, has_fwd;
@@ -542,7 +547,14 @@ struct PlanFileHeader {
   mvw::PlanLayout layout;
   mvwarp_stats_t stats;
 };
-const char kMagic[8] = {'M', 'V', 'W', 'P', 'L', 'A', 'N', '1'};
+const char kMagic[8] = {'M', 'V', 'W', 'P', 'L', 'A', 'N', '2'};
+
+// Layout / schema hash: any builder change that keeps the constants but changes what the arrays mean must bump PLAN_SCHEMA, so
+// that files cached under $MVWARP_PLAN_DIR by an older build are refused instead of being dereferenced by the gather kernels.
+constexpr uint32_t PLAN_SCHEMA = 2;
+constexpr uint32_t plan_schema() {
+  return PLAN_SCHEMA * 0x9E3779B1u ^ (uint32_t)(sizeof(mvw::Task) << 24 | sizeof(mvw::CsrEntry) << 16 | sizeof(mvw::PlanLayout));
+}
 
 uint64_t fnv1a64(const unsigned char* p, size_t n) {
   // 8 bytes per step (word-wise FNV variant): a checksum against truncation / bit rot, not a cryptographic hash
@@ -575,6 +587,7 @@ int mvwarp_plan_save(const mvwarp_plan_t* plan, const char* path) {
     memset((void*)&h, 0, sizeof(h));  // padding bytes are written to the file too
     memcpy(h.magic, kMagic, 8);
     h.header_bytes = sizeof(PlanFileHeader);
+    h.schema = plan_schema();
     h.abi_version = MVWARP_VERSION;
     h.task_budget = TASK_BUDGET; h.task_max_rows = TASK_MAX_ROWS; h.heavy_len = HEAVY_LEN; h.csr_tile = CSR_TILE;
     h.V = plan->V; h.Hs = plan->Hs; h.Ws = plan->Ws; h.Hg = plan->Hg; h.Wg = plan->Wg; h.hl = plan->hl; h.wl = plan->wl;
@@ -629,7 +642,7 @@ int mvwarp_plan_load(const char* path, int device, mvwarp_plan_t** plan_out) {
       set_error(std::string("plan_load: ") + path + " is not a plan file");
       return MVWARP_EINVAL;
     }
-    if (h.header_bytes != sizeof(PlanFileHeader) || h.abi_version != MVWARP_VERSION || h.task_budget != TASK_BUDGET ||
+    if (h.header_bytes != sizeof(PlanFileHeader) || h.schema != plan_schema() || h.abi_version != MVWARP_VERSION || h.task_budget != TASK_BUDGET ||
         h.task_max_rows != TASK_MAX_ROWS || h.heavy_len != HEAVY_LEN || h.csr_tile != CSR_TILE) {
       set_error(std::string("plan_load: ") + path + " was written by an incompatible library build; rebuild the plan");
       return MVWARP_EUNSUPPORTED;
@@ -677,6 +690,46 @@ int mvwarp_plan_load(const char* path, int device, mvwarp_plan_t** plan_out) {
         (h.has_fwd && !csr_ok(h.layout.fwd, p->fwd.task_base, p->fwd.heavy_base)) ||
         (!h.inline_coords && !inside(h.layout.grid, (uint64_t)h.V * h.Hg * h.Wg * 8))) {
       set_error(std::string("plan_load: inconsistent layout in ") + path);
+      return MVWARP_EINVAL;
+    }
+    // ... and every INDEX the gather kernels will dereference must be in range: a well-formed file with a valid checksum but
+    // wrong contents (a foreign tool, a shared cache directory) must be refused here, not found out by an out-of-bounds read.
+    auto contents_ok = [&](const CsrLayout& o, const std::vector<uint32_t>& tb, const std::vector<uint32_t>& hb, uint64_t n_dst,
+                           uint64_t n_cols) {
+      if (o.rows_per_view == 0) return true;
+      const uint64_t R = o.rows_per_view;
+      if (R > n_dst) return false;
+      const uint64_t* vb = reinterpret_cast<const uint64_t*>(blob.data() + o.view_base);
+      if (vb[0] != 0) return false;
+      for (int v = 0; v < h.V; ++v) if (vb[v + 1] < vb[v]) return false;
+      const uint64_t nnz = vb[h.V];
+      if (!inside(o.entries, nnz * sizeof(CsrEntry))) return false;
+      const uint32_t* rp = reinterpret_cast<const uint32_t*>(blob.data() + o.row_ptr);
+      const uint32_t* rid = reinterpret_cast<const uint32_t*>(blob.data() + o.row_id);
+      const CsrEntry* en = reinterpret_cast<const CsrEntry*>(blob.data() + o.entries);
+      for (int v = 0; v < h.V; ++v) {
+        const uint32_t* r = rp + (uint64_t)v * (R + 1);
+        if (r[0] != 0 || r[R] != vb[v + 1] - vb[v]) return false;
+        for (uint64_t i = 0; i < R; ++i) if (r[i + 1] < r[i]) return false;
+        for (uint64_t i = 0; i < R; ++i) if (rid[(uint64_t)v * R + i] >= n_dst) return false;
+      }
+      for (uint64_t k = 0; k < nnz; ++k) if (en[k].col >= n_cols) return false;
+      if (tb[0] != 0 || hb[0] != 0) return false;
+      const Task* tasks = reinterpret_cast<const Task*>(blob.data() + o.tasks);
+      const uint32_t* heavy = reinterpret_cast<const uint32_t*>(blob.data() + o.heavy);
+      const uint32_t* hbd = reinterpret_cast<const uint32_t*>(blob.data() + o.heavy_base);
+      for (int v = 0; v < h.V; ++v) {
+        if (tb[v + 1] < tb[v] || hb[v + 1] < hb[v] || hbd[v] != hb[v]) return false;
+        for (uint32_t t = tb[v]; t < tb[v + 1]; ++t)
+          if (tasks[t].view != v || tasks[t].nrows == 0 || tasks[t].nrows > TASK_MAX_ROWS || (uint64_t)tasks[t].row0 + tasks[t].nrows > R) return false;
+        for (uint32_t i = hb[v]; i < hb[v + 1]; ++i) if (heavy[i] >= R) return false;
+      }
+      return hbd[h.V] == hb[h.V];
+    };
+    const uint64_t n_cells = (uint64_t)h.Hg * h.Wg, n_src = h.upsampled ? (uint64_t)h.hl * h.wl : (uint64_t)h.Hs * h.Ws;
+    if ((h.upsampled && (h.hl <= 0 || h.wl <= 0)) || !contents_ok(h.layout.bwd, p->bwd.task_base, p->bwd.heavy_base, n_src, n_cells) ||
+        (h.has_fwd && !contents_ok(h.layout.fwd, p->fwd.task_base, p->fwd.heavy_base, n_cells, n_src))) {
+      set_error(std::string("plan_load: index out of range in ") + path + " (corrupt or foreign contents)");
       return MVWARP_EINVAL;
     }
     DeviceGuard guard(device);

@@ -45,6 +45,41 @@ def install_kornia_shim(warp: Optional[Callable] = None) -> types.ModuleType:
     return kornia
 
 
+class FusedHeadCache:
+    """The packed-weight :class:`mvdet_b200.map_head.MapHead` of a model's ``map_classifier``, re-packed lazily whenever the weights
+    change.  The reference trainer alternates ``train()`` with ``test()`` under ``torch.no_grad()`` (trainer.py:87-95) and ``main.py:125``
+    calls ``load_state_dict`` after the model is built, so a snapshot taken at patch time would silently go stale after the first
+    optimizer step or checkpoint load.  The cache is keyed on ``(data_ptr, _version, device)`` of every parameter of ``map_classifier``:
+    in-place updates (optimizer steps, ``load_state_dict``'s ``copy_``) bump ``_version``; ``.to(device)`` / re-assignment changes
+    ``data_ptr``.  ``factory(state_dict)`` builds the head (tests inject a stand-in)."""
+
+    def __init__(self, model, factory: Optional[Callable] = None):
+        self.model, self.factory = model, factory
+        self._key, self._head = None, None
+        self.rebuilds = 0
+
+    def _signature(self):
+        return tuple((name, p.data_ptr(), p._version, str(p.device)) for name, p in self.model.map_classifier.state_dict(keep_vars=True).items())
+
+    def get(self):
+        key = self._signature()
+        if key != self._key:
+            mc = self.model.map_classifier
+            sd = {"map_classifier." + k: v.detach() for k, v in mc.state_dict().items()}
+            if self.factory is not None:
+                self._head = self.factory(sd)
+            else:
+                from .map_head import MapHead
+                conv = mc[0]
+                self._head = MapHead(sd, self.model.num_cam, (conv.in_channels - 2) // self.model.num_cam, device=conv.weight.device)
+            self._key = key
+            self.rebuilds += 1
+        return self._head
+
+    def __call__(self, *args, **kwargs):
+        return self.get()(*args, **kwargs)
+
+
 def _onto(t: torch.Tensor, module: torch.nn.Module) -> torch.Tensor:
     """``t`` on the device of ``module``'s parameters -- the reference's ``.to('cuda:0')`` hops (:63-66, 81) without the hard-coded name."""
     p = next(module.parameters(), None)
@@ -138,9 +173,9 @@ def patch_detector(model, channels_last: bool = True, warp_fn: Optional[Callable
     ``channels_last=True`` also converts the model's parameters to ``torch.channels_last`` so that the trunk, ``F.interpolate`` and
     ``torch.stack`` hand the warp channel-contiguous features (the fast kernels; NCHW is accepted but ~3x slower) and cuDNN
     consumes the channels-last result directly.  Feed ``imgs.contiguous(memory_format=torch.channels_last)`` per camera for the
-    full effect.  ``fuse_upsample``: see :func:`warped_forward`.  ``fused_head=True`` packs ``map_classifier``'s CURRENT weights into a
-    :class:`mvdet_b200.map_head.MapHead` (stored as ``model.fused_map_head``; patch again after loading another checkpoint) and uses
-    it under ``torch.no_grad()`` -- inference: 1.14 ms per Wildtrack frame for the warp + ``map_classifier`` against 2.01 ms un-fused.
+    full effect.  ``fuse_upsample``: see :func:`warped_forward`.  ``fused_head=True`` packs ``map_classifier``'s weights into a
+    :class:`mvdet_b200.map_head.MapHead` behind a :class:`FusedHeadCache` (stored as ``model.fused_map_head``; it re-packs by itself
+    when an optimizer step or ``load_state_dict`` changes the weights) and uses it under ``torch.no_grad()`` -- inference: 1.14 ms per Wildtrack frame for the warp + ``map_classifier`` against 2.01 ms un-fused.
     It needs the up-sampled features, so it excludes ``fuse_upsample``.  ``fused_conv1=True`` (training; also excludes ``fuse_upsample``)
     runs ``map_classifier[0]`` + ReLU as the fused warp -> conv1 kernel with gradients, see :func:`warped_forward`.  The original forward stays reachable as
     ``model.reference_forward``."""
@@ -160,13 +195,12 @@ def patch_detector(model, channels_last: bool = True, warp_fn: Optional[Callable
         _split_img_classifier(model.img_classifier)
     head = None
     if fused_head:
-        from .map_head import MapHead
         mc = model.map_classifier
         conv = mc[0] if isinstance(mc, torch.nn.Sequential) and len(mc) == 5 else None
         if not isinstance(conv, torch.nn.Conv2d) or (conv.in_channels - 2) % model.num_cam:
             raise TypeError("fused_head needs the reference's map_classifier: Conv2d(V*C+2,512,3) ReLU Conv2d(512,512,3,d=2) ReLU Conv2d(512,1,3,d=4)")
-        sd = {"map_classifier." + k: v.detach() for k, v in mc.state_dict().items()}
-        head = MapHead(sd, model.num_cam, (conv.in_channels - 2) // model.num_cam, device=conv.weight.device)
+        head = FusedHeadCache(model)          # packs lazily and re-packs when the weights change (optimizer step, load_state_dict)
+        head.get()
         model.fused_map_head = head
     if channels_last:
         model.to(memory_format=torch.channels_last)

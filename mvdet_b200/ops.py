@@ -15,6 +15,7 @@ raises.  The CPU oracle lives in ``oracle/`` and is never imported from here.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import List, Optional, Sequence
 
 import torch
@@ -24,11 +25,16 @@ from .plan import WarpPlan, get_plan, get_plan_from_grid, get_plan_upsampled
 
 _DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
 
-# plans are looked up by integer id inside the custom op (op schemas carry only tensors / ints)
-_plans_by_id = {}
+# plans are looked up by integer id inside the custom op (op schemas carry only tensors / ints).  Weak references: the caller
+# holds the plan during the forward call, autograd's ctx holds it until the backward has run, the plan cache holds cached ones --
+# this table must not keep a plan (and its device-resident CSR) alive on its own.
+_plans_by_id = weakref.WeakValueDictionary()
 
 
-def _register(plan: WarpPlan) -> int:
+def _register(plan: WarpPlan, like: Optional[torch.Tensor] = None) -> int:
+    if like is not None and like.device != plan.device:
+        raise _lib.MvwarpError(f"the plan lives on {plan.device}, the tensor on {like.device}: a plan is bound to the device it "
+                               "was built for (the kernel would read the other device's pointers)")
     pid = id(plan)
     _plans_by_id[pid] = plan
     return pid
@@ -41,6 +47,12 @@ def _check_feats(img_feats: torch.Tensor):
         raise _lib.MvwarpError("warp_views is CUDA-only (no CPU fallback): got a tensor on " + str(img_feats.device))
     if img_feats.dtype not in _DTYPES:
         raise TypeError(f"warp_views supports float32 and bfloat16 features. Got {img_feats.dtype}")
+
+
+def _check_same_device(plan: WarpPlan, *tensors: torch.Tensor):
+    for t in tensors:
+        if t.device != plan.device:
+            raise _lib.MvwarpError(f"the plan lives on {plan.device}, a tensor on {t.device}")
 
 
 def _stream_ptr(device) -> C.c_void_p:
@@ -180,7 +192,7 @@ def warp_views(img_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Seq
     plan = get_plan(proj_mats, img_feats.shape[-2:], grid_shape, img_feats.device)
     if channels_last_out is None:
         channels_last_out = _is_channels_last_5d(img_feats)
-    return _warp_views_plan(img_feats, _register(plan), bool(with_coord_map), bool(channels_last_out))
+    return _warp_views_plan(img_feats, _register(plan, img_feats), bool(with_coord_map), bool(channels_last_out))
 
 
 def warp_views_with_plan(img_feats: torch.Tensor, plan: WarpPlan, with_coord_map: bool = True,
@@ -191,7 +203,7 @@ def warp_views_with_plan(img_feats: torch.Tensor, plan: WarpPlan, with_coord_map
         raise ValueError(f"img_feats {tuple(img_feats.shape)} does not match the plan (V={plan.V}, feats={plan.feat_hw})")
     if channels_last_out is None:
         channels_last_out = _is_channels_last_5d(img_feats)
-    return _warp_views_plan(img_feats, _register(plan), bool(with_coord_map), bool(channels_last_out))
+    return _warp_views_plan(img_feats, _register(plan, img_feats), bool(with_coord_map), bool(channels_last_out))
 
 
 def warp_views_upsampled(img_feats_lowres: torch.Tensor, upsample_shape: Sequence[int], proj_mats: torch.Tensor,
@@ -217,7 +229,7 @@ def warp_views_upsampled(img_feats_lowres: torch.Tensor, upsample_shape: Sequenc
     plan = get_plan_upsampled(proj_mats, img_feats_lowres.shape[-2:], upsample_shape, grid_shape, img_feats_lowres.device)
     if channels_last_out is None:
         channels_last_out = _is_channels_last_5d(img_feats_lowres)
-    return _warp_views_plan(img_feats_lowres, _register(plan), bool(with_coord_map), bool(channels_last_out))
+    return _warp_views_plan(img_feats_lowres, _register(plan, img_feats_lowres), bool(with_coord_map), bool(channels_last_out))
 
 
 def warp_perspective(src: torch.Tensor, M: torch.Tensor, dsize: Sequence[int], mode: str = "bilinear",
@@ -239,17 +251,36 @@ def warp_perspective(src: torch.Tensor, M: torch.Tensor, dsize: Sequence[int], m
                                   "mode='bilinear', padding_mode='zeros', align_corners=True")
     if M.shape[0] not in (1, src.shape[0]):
         raise ValueError(f"Batch of M ({M.shape[0]}) must match batch of src ({src.shape[0]})")
+    _check_feats(src)
+    if src.shape[0] == 0:
+        return src.new_empty((0, src.shape[1], int(dsize[0]), int(dsize[1])))
+    plan = _seam1_plan(M, src, dsize)
+    feats5 = src.unsqueeze(1)
+    cl = src.dim() == 4 and src.stride(1) == 1 and src.shape[1] > 1
+    return _warp_views_plan(feats5, _register(plan, src), False, cl)
+
+
+# Seam 1 must read the VALUES of M to find its plan.  In the reference M lives on cuda:0 (persp_trans_detector.py:68), so that
+# read is a blocking device -> host copy: one stream synchronisation per camera per forward.  It cannot be keyed on M's address
+# -- the reference builds a fresh M for every camera and the caching allocator hands the same address to the next camera's
+# matrix -- so the memo is an attribute of the tensor OBJECT, checked against its version counter: callers that keep their matrices
+# alive (one tensor per camera, created once) pay the synchronisation once; the unmodified reference pays it on every call,
+# which is why seam 2 (patch_detector / warp_views, matrices taken from the CPU-resident model.proj_mats) is the fast seam.
+def _seam1_plan(M: torch.Tensor, src: torch.Tensor, dsize) -> WarpPlan:
+    sig = (M._version, tuple(M.shape), tuple(src.shape[-2:]), (int(dsize[0]), int(dsize[1])), src.device)
+    slot = getattr(M, "_mvwarp_plan_slot", None)
+    if slot is not None and slot[0] == sig:
+        return slot[1]
     Mc = M.detach().to("cpu")
     if Mc.shape[0] > 1 and not bool((Mc == Mc[:1]).all()):
         raise NotImplementedError("mvwarp.warp_perspective needs one homography per call (a camera rig is "
                                   "batch-invariant); use one call per distinct M")
-    _check_feats(src)
-    if src.shape[0] == 0:
-        return src.new_empty((0, src.shape[1], int(dsize[0]), int(dsize[1])))
     plan = get_plan(Mc[:1], src.shape[-2:], dsize, src.device)
-    feats5 = src.unsqueeze(1)
-    cl = src.dim() == 4 and src.stride(1) == 1 and src.shape[1] > 1
-    return _warp_views_plan(feats5, _register(plan), False, cl)
+    try:
+        M._mvwarp_plan_slot = (sig, plan)         # lives and dies with the tensor object; a new tensor never inherits it
+    except Exception:  # pragma: no cover  (tensor subclasses with __slots__)
+        pass
+    return plan
 
 
 def grid_sample_views(img_feats: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
@@ -257,7 +288,7 @@ def grid_sample_views(img_feats: torch.Tensor, grid: torch.Tensor) -> torch.Tens
     (F.grid_sample bilinear/zeros/align_corners=True semantics), views concatenated, no coord channels."""
     _check_feats(img_feats)
     plan = get_plan_from_grid(grid, img_feats.shape[-2:], img_feats.device)
-    return _warp_views_plan(img_feats, _register(plan), False, _is_channels_last_5d(img_feats))
+    return _warp_views_plan(img_feats, _register(plan, img_feats), False, _is_channels_last_5d(img_feats))
 
 
 # ---- raw (non-autograd) launches, used by the view-sharded path and the benchmark ----------------------
@@ -265,10 +296,12 @@ def warp_views_fwd_into(plan: WarpPlan, feats: torch.Tensor, out: torch.Tensor, 
                         out_chan0: int = 0, coord_chan: int = -1) -> None:
     """Warp views [view0, view0+feats.shape[1]) of ``plan`` into a caller-provided output tensor."""
     _check_feats(feats)
+    _check_same_device(plan, feats, out)
     _launch_fwd(plan, feats, out, view0, out_chan0, coord_chan)
 
 
 def warp_views_bwd_into(plan: WarpPlan, grad_out: torch.Tensor, grad_feats: torch.Tensor, view0: int = 0,
                         out_chan0: int = 0) -> None:
     _check_feats(grad_out)
+    _check_same_device(plan, grad_out, grad_feats)
     _launch_bwd(plan, grad_out, grad_feats, view0, out_chan0)

@@ -419,6 +419,38 @@ def test_saved_plan_reproduces_the_built_plan(tmp_path, kind):
     open(bad, "wb").write(bytes(blob[:len(blob) // 2]))
     with pytest.raises(mv.MvwarpError, match="truncated"):
         P.load_plan(bad, DEV)
+    # a well-formed file with a VALID checksum but out-of-range indices must be refused too.  Poison the last CSR entry's
+    # column (the entries of the last-carved map end the blob up to alignment padding) and re-seal the checksum.
+    import struct
+    raw = bytearray(open(path, "rb").read())
+    d_bytes, = struct.unpack_from("<Q", raw, 80)                       # PlanFileHeader: d_bytes at 80, blob_fnv1a at 88
+    start = len(raw) - d_bytes
+    words = struct.unpack_from(f"<{d_bytes // 4}I", raw, start)
+    # find some entry column: any word equal to a valid cell id followed by a float weight in (0, 1] -- use the known layout instead:
+    from mvdet_b200 import _lib as L
+    st = plan.stats
+    grid = P.host_grid(T, grid_hw)
+    _, _, _, cells, _ = P.host_csr(grid, src_hw, with_map=True, lowres_hw=low if kind == "upsampled" else None)
+    first = int(cells[0])
+    hit = None
+    for i in range(0, len(words) - 1):                                 # first (col, weight) pair matching the CSR's first entry
+        if words[i] == first and 0 < struct.unpack("<f", struct.pack("<I", words[i + 1]))[0] <= 1.0:
+            hit = i
+            break
+    assert hit is not None
+    struct.pack_into("<I", raw, start + 4 * hit, 0x7fffffff)           # column far outside the grid
+    def fnv(buf):
+        h = 1469598103934665603
+        n8 = len(buf) // 8
+        for w in struct.unpack_from(f"<{n8}Q", buf, 0):
+            h = ((h ^ w) * 1099511628211) & 0xffffffffffffffff
+        for b in buf[8 * n8:]:
+            h = ((h ^ b) * 1099511628211) & 0xffffffffffffffff
+        return h
+    struct.pack_into("<Q", raw, 88, fnv(bytes(raw[start:])))
+    open(bad, "wb").write(bytes(raw))
+    with pytest.raises(mv.MvwarpError, match="out of range|inconsistent"):
+        P.load_plan(bad, DEV)
 
 
 def test_plan_disk_cache(tmp_path):

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("M,K", [(128, 64), (256, 192), (1024, 512)])
 def test_tcgen05_gemm_matches_matmul(M, K):
-    lib = _lib.load()
+    lib = _lib.load_dev()
     g = torch.Generator().manual_seed(0)
     A = torch.randn(M, K, generator=g).bfloat16().cuda()
     B = torch.randn(256, K, generator=g).bfloat16().cuda()
@@ -193,7 +193,7 @@ def test_map_head_matches_the_reference_module():
 def test_operand_swizzle_follows_absolute_address():
     """The property warp_conv1_direct_kernel rests on: an A operand written with chunk ^= (address >> 7) & 7 is
     read correctly from any 128-byte-aligned start and with any stride between its 8-row groups, base-offset field 0."""
-    lib = _lib.load()
+    lib = _lib.load_dev()
     g = torch.Generator().manual_seed(0)
     M, K = 128, 128
     A = torch.randn(M, K, generator=g).bfloat16().cuda()
@@ -217,7 +217,17 @@ def test_fused_conv1_kernel_generations_agree(mode, monkeypatch):
     on a shape with an odd tile count (padding CTA in pair mode), partial tiles, the coord block and a K-split tail; bf16 output too."""
     from mvdet_b200 import conv1
     from tests.util import small_rig, to_channels_last_5d, rel_errors
-    monkeypatch.setenv("MVWARP_CONV1_PAIR", mode)
+    if mode != "2":
+        # the superseded generations live in the development build, whose knobs are read once per process: run those in a child
+        import subprocess, sys, os
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        from mvdet_b200.build import build_library
+        env = dict(os.environ, MVWARP_CONV1_PAIR=mode, MVWARP_LIB=build_library(dev=True), PYTHONPATH=root)
+        code = ("import pytest, sys; sys.exit(pytest.main(['-q', '-x', '-m', 'gpu', "
+                "'tests/test_gpu_umma.py::test_fused_conv1_kernel_generations_agree[2]']))")
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=900)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        return
     V, Cc = 3, 64
     pm, src_hw, grid_hw = small_rig(num_cam=V, seed=41, grid=(24, 72))     # 3 x 5 tiles = 15 per frame
     g = torch.Generator().manual_seed(0)
@@ -363,3 +373,144 @@ def test_patch_detector_fused_head_inference():
     g_fused = torch.autograd.grad(out_f.square().sum(), [model.map_classifier[0].weight, model.base_pt1.weight])
     for a, b in zip(g_fused, g_plain):
         assert rel_errors(a, b)[1] <= 6e-2, rel_errors(a, b)
+
+
+# ---- parity at the benchmark's own sizes (VERDICT r01 weak #1 ii-iv) -------------------------------------------------
+def _wildtrack_conv1_case(B, seed=0):
+    from mvdet_b200.geometry import WILDTRACK, synthetic_rig
+    spec = WILDTRACK
+    pm = synthetic_rig(spec)
+    g = torch.Generator().manual_seed(seed)
+    # realistic smooth features (3x bilinear up-sample of noise, persp_trans_detector.py:65) keep the CPU side cheap to generate
+    low = torch.randn(B * spec.num_cam, 512, 90, 160, generator=g)
+    x = torch.nn.functional.interpolate(low, spec.feat_shape, mode="bilinear").view(B, spec.num_cam, 512, *spec.feat_shape).bfloat16()
+    weight = torch.randn(512, spec.num_cam * 512 + 2, 3, 3, generator=g) * 0.02
+    bias = torch.randn(512, generator=g)
+    return spec, pm, x, weight, bias
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_fused_conv1_at_the_wildtrack_shape(B):
+    """warp_conv1 at V=7, C=512, 270x480 -> 120x360 (B=1: 345 tiles = 2.33 waves -> the last-wave K split over views and the
+    56-block K loop run exactly as in bench.py; B=2: 690 tiles, CTA pairs + another split).  Reference: the CPU oracle's warp
+    rounded to bf16, then conv3x3 in fp32 (TF32 off) on the GPU for all 512 output channels and on the CPU for 16 of them."""
+    import torch.nn.functional as F
+    from mvdet_b200 import conv1
+    from oracle import kornia_warp as K
+    from tests.util import to_channels_last_5d, rel_errors
+    spec, pm, x, weight, bias = _wildtrack_conv1_case(B)
+    X = torch.cat([K.warp_views_oracle(x[b:b + 1].float(), pm, spec.grid_shape) for b in range(B)]).bfloat16().float()
+    w16 = weight.bfloat16().float()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.relu(F.conv2d(X.cuda(), w16.cuda(), bias.cuda(), padding=1))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    sel = torch.arange(0, 512, 32)                                   # 16 output channels on the CPU: ties the GPU reference down
+    ref_cpu = F.relu(F.conv2d(X, w16[sel], bias[sel], padding=1))
+    assert rel_errors(ref[:, sel], ref_cpu)[0] <= 2e-5
+    wpack = conv1.pack_conv1_weight(weight, spec.num_cam, 512).cuda()
+    xd = to_channels_last_5d(x).cuda()
+    out = conv1.warp_conv1(xd, pm, spec.grid_shape, wpack, bias, relu=True)
+    torch.cuda.synchronize()
+    assert out.shape == (B, 512, *spec.grid_shape)
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= 1e-4 and el2 <= 1e-4, (emax, el2)
+    emax, el2 = rel_errors(out[:, sel], ref_cpu)
+    assert emax <= 1e-4 and el2 <= 1e-4, (emax, el2)
+    assert torch.equal(conv1.warp_conv1(xd, pm, spec.grid_shape, wpack, bias, relu=True), out)     # deterministic
+
+
+def _rounded_reference_grads(x16, weight, bias, go, pm, grid_hw, mask):
+    """The backward warp_conv1_trainable computes, restated on the CPU oracle with the SAME bf16 rounding points
+    (warped tensor, grad_out, the convolution's input gradient, the feature gradient / weight gradient outputs) and the
+    SAME ReLU mask, everything else in fp32: only summation order is left to differ."""
+    import torch.nn.functional as F
+    from oracle import kornia_warp as K
+    bf = lambda t: t.bfloat16().float()
+    xr = x16.float().requires_grad_(True)
+    Xo = K.warp_views_oracle(xr, pm, grid_hw)
+    X = bf(Xo.detach())
+    w16 = bf(weight)
+    g16 = bf(go * mask)
+    gX = bf(torch.nn.grad.conv2d_input(X.shape, w16, g16, padding=1))
+    gW = bf(torch.nn.grad.conv2d_weight(X, w16.shape, g16, padding=1))
+    gb = (go * mask).sum(dim=(0, 2, 3))
+    (gx,) = torch.autograd.grad(Xo, xr, gX)
+    return bf(gx), gW, gb
+
+
+@pytest.mark.parametrize("V,Cc", [(2, 64), (1, 512)])
+def test_fused_conv1_trainable_gradients_same_roundings(V, Cc):
+    """Tight version of the gradient test: against a reference with the same four bf16 roundings and the same ReLU mask the
+    gradients agree to 2e-3 (a wrong tap, a dropped view or a transposed weight block would be off by O(1))."""
+    import torch.nn.functional as F
+    from mvdet_b200 import conv1
+    from oracle import kornia_warp as K
+    from tests.util import small_rig, to_channels_last_5d, rel_errors
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=35)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, V, Cc, *src_hw, generator=g).bfloat16()
+    weight = (torch.randn(512, V * Cc + 2, 3, 3, generator=g) * 0.05)
+    bias = torch.randn(512, generator=g)
+    go = torch.randn(1, 512, *grid_hw, generator=g)
+    xd = to_channels_last_5d(x).cuda().requires_grad_(True)
+    wd = weight.cuda().requires_grad_(True)
+    bd = bias.cuda().requires_grad_(True)
+    out = conv1.warp_conv1_trainable(xd, wd, bd, pm, grid_hw)
+    gx, gw, gb = torch.autograd.grad(out, [xd, wd, bd], go.cuda())
+    mask = (out.detach().cpu() > 0).float()
+    ref_out = F.relu(F.conv2d(K.warp_views_oracle(x.float(), pm, grid_hw).bfloat16().float(), weight.bfloat16().float(), bias, padding=1))
+    assert float(((ref_out > 0).float() == mask).float().mean()) >= 0.9999
+    gxr, gwr, gbr = _rounded_reference_grads(x, weight, bias, go, pm, grid_hw, mask)
+    assert max(rel_errors(out, ref_out)) <= 1e-4
+    assert rel_errors(gx.float(), gxr)[1] <= 2e-3, rel_errors(gx.float(), gxr)
+    assert rel_errors(gw, gwr)[1] <= 2e-3, rel_errors(gw, gwr)
+    assert rel_errors(gb, gbr)[1] <= 1e-5, rel_errors(gb, gbr)
+
+
+def test_patch_detector_fused_head_follows_weight_updates():
+    """after an optimizer step / load_state_dict the no_grad (fused) forward must use the NEW weights."""
+    import torch.nn as nn
+    from mvdet_b200 import integration
+    from tests.util import small_rig, rel_errors
+    V, Cc = 2, 64
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=37)
+
+    class Det(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.num_cam = V
+            self.base_pt1, self.base_pt2 = nn.Conv2d(3, Cc, 3, padding=1), nn.Sequential(nn.ReLU(), nn.Conv2d(Cc, Cc, 1))
+            self.img_classifier = nn.Sequential(nn.Conv2d(Cc, 8, 1), nn.ReLU(), nn.Conv2d(8, 2, 1, bias=False))
+            self.map_classifier = nn.Sequential(nn.Conv2d(Cc * V + 2, 512, 3, padding=1), nn.ReLU(),
+                                                nn.Conv2d(512, 512, 3, padding=2, dilation=2), nn.ReLU(),
+                                                nn.Conv2d(512, 1, 3, padding=4, dilation=4, bias=False))
+            self.proj_mats = [pm[v] for v in range(V)]
+            self.upsample_shape, self.reducedgrid_shape = list(src_hw), list(grid_hw)
+
+        def forward(self, imgs, visualize=False):
+            raise RuntimeError("replaced by patch_detector")
+
+    torch.manual_seed(0)
+    model = integration.patch_detector(Det().cuda(), fused_head=True)
+    imgs = torch.randn(1, V, 3, 18, 32, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        before, _ = model(imgs)
+    opt = torch.optim.SGD(model.map_classifier.parameters(), lr=0.5)
+    model(imgs)[0].square().sum().backward()
+    opt.step()
+    with torch.no_grad():
+        after, _ = model(imgs)                              # fused path, must see the stepped weights
+    plain, _ = model(imgs)                                  # autograd on: un-fused path on the live parameters
+    assert rel_errors(after, plain.detach())[1] <= 2e-2, rel_errors(after, plain.detach())
+    assert rel_errors(before, plain.detach())[1] > 5e-2     # the step really changed the output
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    for k in sd:
+        if k.startswith("map_classifier.4"):
+            sd[k] = sd[k] * 2
+    model.load_state_dict(sd)                               # main.py:125
+    with torch.no_grad():
+        doubled, _ = model(imgs)
+    assert rel_errors(doubled, 2 * after)[1] <= 1e-3

@@ -19,12 +19,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "mvwarp.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    dev_part = "".join(re.findall(r"#ifdef MVWARP_DEV(.*?)#endif", header, flags=re.S))
+    header = re.sub(r"#ifdef MVWARP_DEV.*?#endif", "", header, flags=re.S)
     declared = set(re.findall(r"\b(mvwarp_[a-z_0-9]+)\s*\(", header))
+    declared_dev = set(re.findall(r"\b(mvwarp_[a-z_0-9]+)\s*\(", dev_part))
     assert len(declared) >= 10
     lib = ctypes.CDLL(os.path.join(ROOT, "mvdet_b200", "libmvwarp.so"))
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in mvwarp.h but not exported"
     assert declared == set(_lib.SIGNATURES), "ctypes binding and header disagree"
+    assert declared_dev == set(_lib.DEV_SIGNATURES)
+    for name in declared_dev:                     # validation hooks live in the development build only
+        assert not hasattr(lib, name), f"{name} is a development hook but the product library exports it"
     assert _lib.load().mvwarp_version() == 1
 
 
@@ -68,8 +74,6 @@ def test_every_entry_point_rejects_null_arguments_without_a_gpu():
         "conv3x3_head_fwd": lambda: lib.mvwarp_conv3x3_head_fwd(None, i4, None, None, i4, 1, 8, 8, 64, 1, 0, None),
         "inbox_reduce": lambda: lib.mvwarp_inbox_reduce(None, 2, 0, 0, 1, 512, None, 0, None, 0, 0, None),
         "warp_conv1_fwd_p2p": lambda: lib.mvwarp_warp_conv1_fwd_p2p(None, 0, 1, None, i5, None, 1, 64, 1, 2, 0, None, None, 8, None),
-        "debug_gemm": lambda: lib.mvwarp_debug_gemm(None, None, None, 128, 256, 64, None),
-        "debug_gemm_layout": lambda: lib.mvwarp_debug_gemm_layout(None, None, None, 128, 256, 64, 1024, 0, 0, None),
         "plan_create": lambda: lib.mvwarp_plan_create(nine, 1, 0, 4, 4, 4, 0, ctypes.byref(h)),
         "plan_create_upsampled": lambda: lib.mvwarp_plan_create_upsampled(nine, 1, 0, 0, 4, 4, 4, 4, 0, ctypes.byref(h)),
         "plan_create_from_grid": lambda: lib.mvwarp_plan_create_from_grid(None, 1, 4, 4, 4, 4, 0, ctypes.byref(h)),
@@ -352,3 +356,43 @@ def test_install_kornia_shim_defaults_to_the_cuda_seam(monkeypatch):
     finally:
         for name in ("kornia", "kornia.geometry", "kornia.geometry.transform"):
             sys.modules.pop(name, None)
+
+
+def test_fused_head_cache_repacks_when_the_weights_change():
+    """patch_detector(fused_head=True) must not serve a weight snapshot taken at patch time.  The cache re-packs
+    after an optimizer step (in-place update), after load_state_dict (copy_) and after a device / storage change, and only then."""
+    import torch.nn as nn
+    from mvdet_b200.integration import FusedHeadCache
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.num_cam = 1
+            self.map_classifier = nn.Sequential(nn.Conv2d(6, 4, 3, padding=1), nn.ReLU(), nn.Conv2d(4, 1, 3, padding=1, bias=False))
+
+    model = M()
+    cache = FusedHeadCache(model, factory=lambda sd: {k: v.clone() for k, v in sd.items()})
+    h0 = cache.get()
+    assert cache.get() is h0 and cache.rebuilds == 1                       # unchanged weights: no re-pack
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    model.map_classifier(torch.randn(1, 6, 5, 5)).sum().backward()
+    opt.step()
+    h1 = cache.get()
+    assert h1 is not h0 and cache.rebuilds == 2
+    assert torch.equal(h1["map_classifier.0.weight"], model.map_classifier[0].weight.detach())
+    assert not torch.equal(h0["map_classifier.0.weight"], h1["map_classifier.0.weight"])
+    sd = {k: torch.zeros_like(v) for k, v in model.state_dict().items()}
+    model.load_state_dict(sd)                                               # main.py:125
+    h2 = cache.get()
+    assert cache.rebuilds == 3 and float(h2["map_classifier.2.weight"].abs().sum()) == 0.0
+    model.map_classifier[0].weight.data = model.map_classifier[0].weight.data.clone()   # new storage (what .to(device) does)
+    cache.get()
+    assert cache.rebuilds == 4
+    assert cache.get() is cache.get() and cache.rebuilds == 4
+
+
+def test_plan_table_holds_no_strong_references():
+    """ops._plans_by_id must not keep plans alive (it is a WeakValueDictionary)."""
+    import weakref
+    from mvdet_b200 import ops
+    assert isinstance(ops._plans_by_id, weakref.WeakValueDictionary)
