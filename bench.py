@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--mode", default="fwdbwd", choices=["fwdbwd", "fwd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-dense", action="store_true",
+                    help="end-to-end leg: copy the WHOLE feature / feature-gradient tensors across PCIe (round-1 behaviour) instead of "
+                         "only the texels the warp can touch (mvwarp_copy_touched_texels)")
     ap.add_argument("--fuse-upsample", action="store_true",
                     help="extra configuration (SURVEY.md 8f rank 1): feed the trunk's 90x160 feature map and fuse "
                          "F.interpolate(-> 270x480) into the warp; NOT the headline workload")
@@ -640,11 +643,20 @@ def run_e2e(args, plan, pm, feats_dev, grad_out_dev, dev, world, dist):
     ev_out = [torch.cuda.Event() for _ in range(NBUF)]      # its results are on the host
     steps = max(4, min(args.steps, 32))   # a stream of frames: pipeline fill + drain cost one step's worth of copies in total
 
+    sparse = not args.e2e_dense and feats_dev.stride(2) == 1
+    if sparse and do_bwd:
+        h_gf.zero_()                                         # zeroed ONCE: rows outside the touched set are zero in every step's gradient
+
+    last = {}
+
     def one(k):
         i = k % NBUF
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_comp[i])                      # inputs of step k-2 no longer needed
-            d_feats[i].copy_(h_feats, non_blocking=True)
+            if sparse:                                       # every texel the warp can read (rig-constant set), gathered across PCIe
+                ops.copy_touched_texels(plan, h_feats, d_feats[i])
+            else:
+                d_feats[i].copy_(h_feats, non_blocking=True)
             if do_bwd:
                 d_go[i].copy_(h_go, non_blocking=True)
             ev_in[i].record(s_in)
@@ -657,6 +669,7 @@ def run_e2e(args, plan, pm, feats_dev, grad_out_dev, dev, world, dist):
             else:
                 out = ops.warp_views(x, pm, plan.grid_hw)
             gx = torch.autograd.grad(out, x, d_go[i])[0] if do_bwd else None
+            last["gx"] = gx
             d_feats[i].requires_grad_(False)
             ev_comp[i].record(s_comp)
         with torch.cuda.stream(s_out):
@@ -664,7 +677,10 @@ def run_e2e(args, plan, pm, feats_dev, grad_out_dev, dev, world, dist):
             h_out.copy_(out.detach(), non_blocking=True)
             out.record_stream(s_out)
             if do_bwd:
-                h_gf.copy_(gx, non_blocking=True)
+                if sparse:                                   # every non-zero row of the feature gradient, scattered across PCIe
+                    ops.copy_touched_texels(plan, gx, h_gf)
+                else:
+                    h_gf.copy_(gx, non_blocking=True)
                 gx.record_stream(s_out)
             ev_out[i].record(s_out)
 
@@ -683,12 +699,25 @@ def run_e2e(args, plan, pm, feats_dev, grad_out_dev, dev, world, dist):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     nbytes = lambda t: t.numel() * t.element_size()
-    h2d = nbytes(h_feats) + (nbytes(h_go) if do_bwd else 0)
-    d2h = nbytes(h_out) + (nbytes(h_gf) if do_bwd else 0)
+    feat_bytes = nbytes(h_feats)
+    if sparse:                                               # bytes actually moved: U touched texels x C channels per frame
+        feat_bytes = B * plan.stats["unique_texels"] * feats_dev.shape[2] * feats_dev.element_size()
+    h2d = feat_bytes + (nbytes(h_go) if do_bwd else 0)
+    d2h = nbytes(h_out) + (feat_bytes if do_bwd else 0)
+    if do_bwd and sparse:                                    # the host gradient must equal the dense one (untouched rows: zero)
+        check = bool(torch.equal(h_gf, last["gx"].cpu()))
+    else:
+        check = None
     return {"value": B * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "transfer": ("sparse: only the texels some grid cell samples cross PCIe (U of V*Hs*Ws = "
+                         f"{plan.stats['unique_texels']} of {plan.V * plan.feat_hw[0] * plan.feat_hw[1]}, rig-constant) -- gathered from / "
+                         "scattered into mapped pinned host memory by mvwarp_copy_touched_texels; out and grad_out are dense copies; the "
+                         "host gradient tensor is zeroed once" if sparse else "dense: whole tensors, cudaMemcpyAsync"),
+            "dense_bytes_each_way": nbytes(h_feats) + nbytes(h_out),
+            "host_gradient_equals_dense": check,
             "pcie_gbs_each_way": [h2d * steps / dt / 1e9, d2h * steps / dt / 1e9],
-            "api": "mvdet_b200.warp_views (plan-cache lookup included) + torch.autograd.grad on pinned host buffers; H2D / compute / D2H "
+            "api": "mvdet_b200.ops.copy_touched_texels + mvdet_b200.warp_views (plan-cache lookup included) + torch.autograd.grad on pinned host buffers; H2D / compute / D2H "
                    "double-buffered on three streams, all copies inside the timed region"}
 
 

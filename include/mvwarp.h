@@ -152,6 +152,39 @@ int mvwarp_warp_views_bwd(const mvwarp_plan_t* plan, int view0, int nviews,
                           void* grad_feats, const int64_t feat_strides[5],
                           int B, int C, int dtype, void* stream);
 
+/* ---- "list" variants: one tensor per camera ------------------------------------------------------
+ * The reference's trunk produces ONE feature tensor per camera inside the camera loop (persp_trans_detector.py:62-66) and appends
+ * the warped result to a Python list (:75).  These entry points take the per-camera tensors as they are: feats[v] (resp.
+ * grad_feats[v]) is the DEVICE pointer of local view v, logical [B, C, Hs, Ws] with strides feat_strides[4] = (B, C, H, W) shared
+ * by all views (same shape, same memory format); `feats` itself is a HOST array of nviews pointers (nviews <= MVWARP_MAX_LIST_VIEWS).
+ * One launch covers all views (the pointers travel in the kernel's parameter space), so no [B,V,C,H,W] stack copy -- a 1.86 GB read
+ * plus a 1.86 GB write per Wildtrack frame, more than the warp itself moves -- is ever made, and the backward writes each camera's
+ * gradient straight into its own tensor.  Everything else as mvwarp_warp_views_fwd / _bwd.
+ * Replaces persp_trans_detector.py:68-69,75,77 without torch.stack. */
+#define MVWARP_MAX_LIST_VIEWS 64
+int mvwarp_warp_views_fwd_list(const mvwarp_plan_t* plan, int view0, int nviews, const void* const* feats,
+                               const int64_t feat_strides[4], void* out, const int64_t out_strides[4], int out_chan0,
+                               int coord_chan, int B, int C, int dtype, void* stream);
+int mvwarp_warp_views_bwd_list(const mvwarp_plan_t* plan, int view0, int nviews, const void* grad_out,
+                               const int64_t out_strides[4], int out_chan0, void* const* grad_feats,
+                               const int64_t feat_strides[4], int B, int C, int dtype, void* stream);
+
+/* ---- host-resident features: move only what the warp can touch ---------------------------------------------------
+ * mvwarp_copy_touched_texels: for every batch element, every view in [view0, view0+nviews) and every feature texel (ys, xs) that
+ * at least one grid cell samples (= the non-empty rows of the plan's inverse CSR map; 26 % of the texels on the Wildtrack rig,
+ * a function of the calibration alone), copy the texel's C channel values from `src` to `dst`.  Both are logical
+ * [B, nviews, C, H, W] tensors, channel-contiguous, strides in elements as (B, V, C, H, W); H x W is the feature map the plan's
+ * kernels read (the low-res map for fused up-sample plans).  Either pointer may be device memory or PINNED HOST memory
+ * (unified addressing: the gather / scatter kernel reads or writes it across PCIe directly), so
+ *   host feats   -> device feats        sends the warp everything it will read            (0.49 GB instead of 1.86 GB per frame), and
+ *   device grads -> host grads          returns every non-zero row of the feature gradient (the host tensor is zeroed once).
+ * mvwarp_plan_touched: the list itself -- touched_base_out [V+1] offsets, touched_out [>= U] linear texel ids ys*W + xs,
+ * ascending per view (either may be NULL).
+ * Replaces the dense host -> device hops of persp_trans_detector.py:63-68 for callers whose features are host-resident. */
+int mvwarp_copy_touched_texels(const mvwarp_plan_t* plan, int view0, int nviews, const void* src, const int64_t src_strides[5],
+                               void* dst, const int64_t dst_strides[5], int B, int C, int dtype, void* stream);
+int mvwarp_plan_touched(const mvwarp_plan_t* plan, uint32_t* touched_base_out, uint32_t* touched_out, uint64_t capacity);
+
 #ifdef MVWARP_DEV
 /* ---- tensor-core building blocks (north_star (c)): validation hooks, DEVELOPMENT BUILD ONLY ------------------
  * (mvdet_b200/libmvwarp_dev.so, compiled with -DMVWARP_DEV; the product library does not export them)

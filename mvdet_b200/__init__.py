@@ -12,7 +12,7 @@ from ._lib import MvwarpError
 
 def __getattr__(name):  # ops import torch.library machinery lazily
     if name in ("warp_views", "warp_views_with_plan", "warp_views_upsampled", "warp_perspective", "grid_sample_views",
-                "warp_views_fwd_into", "warp_views_bwd_into"):
+                "warp_views_fwd_into", "warp_views_bwd_into", "warp_views_list"):
         from . import ops
         return getattr(ops, name)
     if name in ("get_plan", "get_plan_from_grid", "get_plan_upsampled", "load_plan", "WarpPlan", "src_norm_trans_dst_norm", "host_grid", "host_csr"):

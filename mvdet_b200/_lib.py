@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("MVWARP_LIB", _DEFAULT_LIB_PATH)
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 F32, BF16 = 0, 1
+MAX_LIST_VIEWS = 64      # MVWARP_MAX_LIST_VIEWS (include/mvwarp.h)
 
 
 class Stats(C.Structure):
@@ -63,6 +64,12 @@ SIGNATURES = {
     "mvwarp_conv3x3_fwd": (C.c_int, [_P, _I64P, _P, _P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, _P]),
     "mvwarp_conv3x3_head_fwd": (C.c_int, [_P, _I64P, _P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "mvwarp_warp_views_fwd_list": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), _I64P, _P, _I64P, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, _P]),
+    "mvwarp_warp_views_bwd_list": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, C.c_int, C.POINTER(_P), _I64P,
+                                             C.c_int, C.c_int, C.c_int, _P]),
+    "mvwarp_copy_touched_texels": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, _P, _I64P, C.c_int, C.c_int, C.c_int, _P]),
+    "mvwarp_plan_touched": (C.c_int, [_P, _U32P, _U32P, C.c_uint64]),
     "mvwarp_warp_views_bwd": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, C.c_int, _P, _I64P,
                                         C.c_int, C.c_int, C.c_int, _P]),
 }

@@ -82,6 +82,7 @@ struct CsrLayout {
 struct PlanLayout {
   uint64_t T = 0, grid = 0, coord_x = 0, coord_y = 0;
   CsrLayout bwd, fwd;
+  uint64_t touched = 0, touched_base = 0;   // feature texels with >= 1 tap, ascending per view; [V+1] offsets (mvwarp_copy_touched_texels)
 };
 
 }  // namespace mvw
@@ -102,6 +103,8 @@ struct mvwarp_plan {
   float* d_coord_x = nullptr;      // [Wg]  coord_map channel 0 along x
   float* d_coord_y = nullptr;      // [Hg]  coord_map channel 1 along y
   mvw::DevCsr bwd, fwd;
+  uint32_t* d_touched = nullptr;           // [U] linear texel ids (ys*W + xs of the feature map the kernels read), ascending per view
+  std::vector<uint32_t> touched_base;      // host copy, [V+1]
   mvw::PlanLayout layout;          // where everything lives inside d_base (mvwarp_plan_save / _load)
   std::vector<float> h_T;          // host copy of the matrices (inline mode), for mvwarp_plan_matrices
   mvwarp_stats_t stats{};
@@ -118,6 +121,9 @@ struct LaunchArgs {
   int64_t os[4];                  // out / grad_out strides (B,C,H,W)
   int out_chan0, coord_chan;
   cudaStream_t stream;
+  // "list" calls (mvwarp_warp_views_fwd_list / _bwd_list): one device pointer per local view for the feature side (feats in the
+  // forward, grad_feats in the backward); fs[1] (the V stride) is then unused.  nullptr: one dense [B,V,C,H,W] tensor.
+  const void* const* view_ptrs = nullptr;
 };
 
 // CUtensorMap (passed as void*: 128 bytes, 64-byte aligned) over packed weight blocks [nblocks][512][64] bf16 seen as a 2-D
@@ -127,5 +133,19 @@ int make_weight_tensor_map(void* tmap_out, const void* wpack, uint64_t nblocks);
 int launch_fwd(const LaunchArgs& a);
 int launch_bwd(const LaunchArgs& a);
 int launch_device_grid(const mvwarp_plan* plan, float* d_grid_out, cudaStream_t stream);
+
+// RAII: make `dev` current for the scope of a call (the autograd worker thread's current device is not ours to assume)
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
 
 }  // namespace mvw

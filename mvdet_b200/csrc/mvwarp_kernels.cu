@@ -19,6 +19,8 @@
 
 namespace mvw {
 
+constexpr int MAX_LIST_VIEWS = MVWARP_MAX_LIST_VIEWS;
+
 // One side of a CSR gather: element strides of a [batch][view][y][x][channel] addressing,
 //   addr = base + b*B + vl*V + chan0 + c*C + y*H + x*W,   (y, x) = (id / width, id % width).
 struct Side {
@@ -49,7 +51,19 @@ struct KParams {
   int64_t oB, oC, oH, oW;
   int out_chan0, coord_chan;
   int tiles_x, tiles_y, cchunk;
+  // "list" calls: the views' feature maps (forward) / feature gradients (backward) are SEPARATE tensors, one per camera, as the
+  // reference's trunk produces them (persp_trans_detector.py:63-66): view vl lives at vptr[vl] instead of base + vl * V-stride.
+  // Lives in the kernel's parameter space (constant bank), so one launch still covers all views -- no stack copy, no per-view launch.
+  int per_view;
+  int feats_is_src;      // CSR gathers: 1 = the feature side is the gather's source (forward table), 0 = its destination (backward)
+  uint64_t vptr[MAX_LIST_VIEWS];
 };
+
+// base of local view vl on the feature side (element pointer, batch 0)
+template <typename T>
+__device__ __forceinline__ T* feats_view(const KParams& p, const void* dense_base, int vl, int64_t vstride) {
+  return p.per_view ? reinterpret_cast<T*>(p.vptr[vl]) : reinterpret_cast<T*>(const_cast<void*>(dense_base)) + (int64_t)vl * vstride;
+}
 
 
 // ---------------------------------------------------------------------------------------------------
@@ -290,7 +304,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_cl_kernel(const KPar
   }
   __syncthreads();
 
-  const T* __restrict__ src = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.fB + (int64_t)vl * p.fV;
+  const T* __restrict__ src = feats_view<const T>(p, p.src, vl, p.fV) + (int64_t)b * p.fB;
   T* __restrict__ dst = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
   const int nvec = p.C / EPV;
 
@@ -322,7 +336,7 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const KParams p) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) Tm[i] = kInline ? __ldg(p.T + 9 * v + i) : 0.f;
   const Taps tp = cell_taps<kInline>(p, Tm, v, x, y);
-  const T* __restrict__ src = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.fB + (int64_t)vl * p.fV;
+  const T* __restrict__ src = feats_view<const T>(p, p.src, vl, p.fV) + (int64_t)b * p.fB;
   T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (int64_t)y * p.oH + (int64_t)x * p.oW;
   if (p.coord_chan >= 0 && vl == 0 && chunk == 0) {
     o[(int64_t)p.coord_chan * p.oC] = from_float<T>(__ldg(p.coord_x + x));
@@ -369,7 +383,7 @@ __global__ void __launch_bounds__(NCHW_TW * NCHW_TH) fwd_nchw_kernel(const KPara
 #pragma unroll
   for (int i = 0; i < 9; ++i) Tm[i] = kInline ? __ldg(p.T + 9 * v + i) : 0.f;
   const Taps tp = cell_taps<kInline>(p, Tm, v, x, y);
-  const T* __restrict__ src = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.fB + (int64_t)vl * p.fV;
+  const T* __restrict__ src = feats_view<const T>(p, p.src, vl, p.fV) + (int64_t)b * p.fB;
   T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (int64_t)y * p.oH + x;
   if (p.coord_chan >= 0 && vl == 0 && chunk == 0) {
     o[(int64_t)p.coord_chan * p.oC] = from_float<T>(__ldg(p.coord_x + x));
@@ -544,8 +558,10 @@ __device__ __forceinline__ void gather_task(const KParams& p, uint32_t tid, uint
   const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (p.rows_per_view + 1) + task.row0;
   const uint32_t* __restrict__ ids = p.row_id + (size_t)v * p.rows_per_view + task.row0;
   const uint2* __restrict__ en = reinterpret_cast<const uint2*>(p.entries + __ldg(p.view_base + v));
-  const T* __restrict__ gs = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.gsrc.B + (int64_t)vl * p.gsrc.V + p.gsrc.chan0;
-  T* __restrict__ gd = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.gdst.B + (int64_t)vl * p.gdst.V + p.gdst.chan0;
+  const T* __restrict__ gs = (p.feats_is_src ? feats_view<const T>(p, p.src, vl, p.gsrc.V) : reinterpret_cast<const T*>(p.src) + (int64_t)vl * p.gsrc.V) +
+                               (int64_t)b * p.gsrc.B + p.gsrc.chan0;
+  T* __restrict__ gd = (p.feats_is_src ? reinterpret_cast<T*>(p.dst) + (int64_t)vl * p.gdst.V : feats_view<T>(p, p.dst, vl, p.gdst.V)) +
+                         (int64_t)b * p.gdst.B + p.gdst.chan0;
   const int nvec = p.C / EPV;
 
   const uint32_t rpl = (lane <= nrows) ? __ldg(rp + lane) : 0u;
@@ -599,10 +615,11 @@ __device__ __forceinline__ void gather_heavy_row(const KParams& p, uint32_t hid,
   const uint32_t a = __ldg(rp), e = __ldg(rp + 1);
   const uint32_t id = __ldg(p.row_id + (size_t)v * p.rows_per_view + row);
   const uint2* __restrict__ en = reinterpret_cast<const uint2*>(p.entries + __ldg(p.view_base + v));
-  const T* __restrict__ gs = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.gsrc.B + (int64_t)vl * p.gsrc.V + p.gsrc.chan0;
+  const T* __restrict__ gs = (p.feats_is_src ? feats_view<const T>(p, p.src, vl, p.gsrc.V) : reinterpret_cast<const T*>(p.src) + (int64_t)vl * p.gsrc.V) +
+                               (int64_t)b * p.gsrc.B + p.gsrc.chan0;
   const int yd = id / p.gdst.width, xd = id - yd * p.gdst.width;
-  T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.gdst.B + (int64_t)vl * p.gdst.V + p.gdst.chan0 +
-                      (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
+  T* __restrict__ o = (p.feats_is_src ? reinterpret_cast<T*>(p.dst) + (int64_t)vl * p.gdst.V : feats_view<T>(p, p.dst, vl, p.gdst.V)) +
+                      (int64_t)b * p.gdst.B + p.gdst.chan0 + (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
   if (DSTANY && p.coord_chan >= 0 && vl == 0 && threadIdx.x == 0) write_coord<T>(p, b, id);
   const int nvec = p.C / EPV;
   const uint32_t seg = (e - a + BWD_WARPS - 1) / BWD_WARPS;
@@ -770,8 +787,10 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_table_tile_kernel(co
   }
   __syncthreads();
 
-  const T* __restrict__ gs = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.gsrc.B + (int64_t)vl * p.gsrc.V + p.gsrc.chan0;
-  T* __restrict__ gd = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.gdst.B + (int64_t)vl * p.gdst.V + p.gdst.chan0;
+  const T* __restrict__ gs = (p.feats_is_src ? feats_view<const T>(p, p.src, vl, p.gsrc.V) : reinterpret_cast<const T*>(p.src) + (int64_t)vl * p.gsrc.V) +
+                               (int64_t)b * p.gsrc.B + p.gsrc.chan0;
+  T* __restrict__ gd = (p.feats_is_src ? reinterpret_cast<T*>(p.dst) + (int64_t)vl * p.gdst.V : feats_view<T>(p, p.dst, vl, p.gdst.V)) +
+                         (int64_t)b * p.gdst.B + p.gdst.chan0;
   const int nvec = p.C / EPV;
   // round i: the 8 warps take 8 consecutive rows (horizontally adjacent cells of the tile), like fwd_cl_kernel
   for (int i = warp; i < nrows; i += FWD_WARPS) {
@@ -802,9 +821,10 @@ __device__ __forceinline__ void gather_generic_body(const KParams& p) {
   const uint32_t id = __ldg(p.row_id + (size_t)v * p.rows_per_view + row);
   if (COORD && p.coord_chan >= 0 && vl == 0 && chunk == 0) write_coord<T>(p, b, id);
   const int yd = id / p.gdst.width, xd = id - yd * p.gdst.width;
-  const T* __restrict__ gs = reinterpret_cast<const T*>(p.src) + (int64_t)b * p.gsrc.B + (int64_t)vl * p.gsrc.V + p.gsrc.chan0;
-  T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.gdst.B + (int64_t)vl * p.gdst.V + p.gdst.chan0 +
-                      (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
+  const T* __restrict__ gs = (p.feats_is_src ? feats_view<const T>(p, p.src, vl, p.gsrc.V) : reinterpret_cast<const T*>(p.src) + (int64_t)vl * p.gsrc.V) +
+                               (int64_t)b * p.gsrc.B + p.gsrc.chan0;
+  T* __restrict__ o = (p.feats_is_src ? reinterpret_cast<T*>(p.dst) + (int64_t)vl * p.gdst.V : feats_view<T>(p, p.dst, vl, p.gdst.V)) +
+                      (int64_t)b * p.gdst.B + p.gdst.chan0 + (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
   // entry-major: each (col, w) is fetched once and applied to the whole channel chunk (accumulators in registers),
   // so the CSR walk is amortised over GEN_CH channels and GEN_CH independent loads are in flight per entry
   const int c0 = chunk * p.cchunk, nc = min(p.C - c0, p.cchunk);
@@ -868,6 +888,9 @@ static KParams make_params(const LaunchArgs& a) {
   p.tiles_x = (pl->Wg + FWD_TILE_W - 1) / FWD_TILE_W;
   p.tiles_y = (pl->Hg + FWD_TILE_H - 1) / FWD_TILE_H;
   p.cchunk = GEN_CH;
+  p.per_view = a.view_ptrs != nullptr;
+  if (a.view_ptrs)
+    for (int v = 0; v < a.nviews && v < MAX_LIST_VIEWS; ++v) p.vptr[v] = reinterpret_cast<uint64_t>(a.view_ptrs[v]);
   return p;
 }
 
@@ -898,11 +921,17 @@ static const WarpKnobs& warp_knobs() {
 }
 
 // channel-contiguous feature tensor whose every texel row starts 16-byte aligned
-static bool feats_vector_ok(const void* ptr, const int64_t fs[5], int C, int epv) {
-  if (fs[2] != 1 || C % epv != 0) return false;
-  if (reinterpret_cast<uintptr_t>(ptr) & 15u) return false;
+static bool feats_vector_ok(const LaunchArgs& a, const void* ptr, int epv) {
+  const int64_t* fs = a.fs;
+  if (fs[2] != 1 || a.C % epv != 0) return false;
+  if (a.view_ptrs) {
+    for (int v = 0; v < a.nviews; ++v)
+      if (reinterpret_cast<uintptr_t>(a.view_ptrs[v]) & 15u) return false;
+  } else if (reinterpret_cast<uintptr_t>(ptr) & 15u) {
+    return false;
+  }
   for (int i : {0, 1, 3, 4})
-    if (fs[i] % epv != 0) return false;
+    if ((i != 1 || !a.view_ptrs) && fs[i] % epv != 0) return false;
   return true;
 }
 
@@ -979,11 +1008,12 @@ static int launch_fwd_t(const LaunchArgs& a) {
   KParams p = make_params(a);
   const bool inl = a.plan->inline_coords != 0;
   constexpr int EPV = VecTraits<T>::EPV;
-  const bool fast = feats_vector_ok(a.feats_or_grad_out, a.fs, a.C, EPV) && a.os[1] == 1 &&
+  const bool fast = feats_vector_ok(a, a.feats_or_grad_out, EPV) && a.os[1] == 1 &&
                     (reinterpret_cast<uintptr_t>(a.out_or_grad_feats) % sizeof(float) == 0) &&
                     (sizeof(T) == 4 || (a.os[0] % 2 == 0 && a.os[2] % 2 == 0 && a.os[3] % 2 == 0 && a.out_chan0 % 2 == 0));
   if (a.plan->upsampled) {  // fused up-sample plan: the forward is a table gather from the low-res feature map
     set_csr(p, a.plan->fwd);
+    p.feats_is_src = 1;
     p.gsrc = feats_side(a, a.plan->wl);
     p.gdst = concat_side(a, a.plan->Wg);
     return launch_gather_t<T, true>(a, p, a.plan->fwd, fast);
@@ -1036,10 +1066,11 @@ template <typename T>
 static int launch_bwd_t(const LaunchArgs& a) {
   KParams p = make_params(a);
   constexpr int EPV = VecTraits<T>::EPV;
-  const bool fast = feats_vector_ok(a.out_or_grad_feats, a.fs, a.C, EPV) && a.os[1] == 1 &&
+  const bool fast = feats_vector_ok(a, a.out_or_grad_feats, EPV) && a.os[1] == 1 &&
                     (reinterpret_cast<uintptr_t>(a.feats_or_grad_out) % sizeof(float) == 0) &&
                     (sizeof(T) == 4 || (a.os[0] % 2 == 0 && a.os[2] % 2 == 0 && a.os[3] % 2 == 0 && a.out_chan0 % 2 == 0));
   set_csr(p, a.plan->bwd);
+  p.feats_is_src = 0;
   p.gsrc = concat_side(a, a.plan->Wg);
   p.gdst = feats_side(a, a.plan->upsampled ? a.plan->wl : a.plan->Ws);
   p.coord_chan = -1;

@@ -273,18 +273,6 @@ void host_build_maps_upsampled(const float* grid, int V, int hl, int wl, int Hs,
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
-  }
-  ~DeviceGuard() {
-    int cur = -1;
-    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
-  }
-};
 
 static int check_shapes(int V, int Hs, int Ws, int Hg, int Wg) {
   if (V <= 0 || Hs <= 0 || Ws <= 0 || Hg <= 0 || Wg <= 0) {
@@ -334,6 +322,7 @@ static void bind_pointers(mvwarp_plan* p) {
   };
   bind(p->bwd, L.bwd);
   bind(p->fwd, L.fwd);
+  p->d_touched = (uint32_t*)(base + L.touched);
 }
 
 static int plan_create_impl(const float* T, const float* grid_in, int V, int hl, int wl, int Hs, int Ws, int Hg, int Wg,
@@ -404,6 +393,25 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int hl,
     L.coord_y = carve(Hg * sizeof(float));
     L.bwd = carve_csr(maps.bwd);
     L.fwd = carve_csr(maps.fwd);
+    // touched feature texels (rows of the inverse map with >= 1 entry), ascending per view: what a host-resident feature tensor
+    // has to send to the device, and the only rows of the feature gradient that are ever non-zero
+    std::vector<uint32_t> touched, touched_base((size_t)V + 1, 0);
+    {
+      const HostCsr& c = maps.bwd;
+      touched.reserve(c.nonempty_rows);
+      for (int v = 0; v < V; ++v) {
+        const uint32_t* rp = c.row_ptr.data() + (size_t)v * (c.rows_per_view + 1);
+        const uint32_t* id = c.row_id.data() + (size_t)v * c.rows_per_view;
+        const size_t first = touched.size();
+        for (size_t r = 0; r < c.rows_per_view; ++r)
+          if (rp[r + 1] > rp[r]) touched.push_back(id[r]);
+        std::sort(touched.begin() + first, touched.end());
+        touched_base[v + 1] = (uint32_t)touched.size();
+      }
+    }
+    L.touched = carve(touched.size() * sizeof(uint32_t));
+    L.touched_base = carve(touched_base.size() * sizeof(uint32_t));
+    p->touched_base = touched_base;
     p->d_bytes = off;
     e = cudaMalloc(&p->d_base, p->d_bytes);
     if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(plan)"); }
@@ -432,6 +440,8 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int hl,
     up(p->d_coord_y, cy.data(), Hg * sizeof(float));
     up_csr(p->bwd, maps.bwd);
     up_csr(p->fwd, maps.fwd);
+    up(p->d_touched, touched.data(), touched.size() * sizeof(uint32_t));
+    up((char*)p->d_base + L.touched_base, touched_base.data(), touched_base.size() * sizeof(uint32_t));
     if (e != cudaSuccess) { cudaFree(p->d_base); delete p; return cuda_fail(e, "plan upload"); }
 
     fill_stats(p->stats, maps, V, Hs, Ws, Hg, Wg, p->hl, p->wl);
@@ -727,6 +737,21 @@ int mvwarp_plan_load(const char* path, int device, mvwarp_plan_t** plan_out) {
       return hbd[h.V] == hb[h.V];
     };
     const uint64_t n_cells = (uint64_t)h.Hg * h.Wg, n_src = h.upsampled ? (uint64_t)h.hl * h.wl : (uint64_t)h.Hs * h.Ws;
+    {
+      bool tok = inside(h.layout.touched_base, ((uint64_t)h.V + 1) * 4);
+      if (tok) {
+        const uint32_t* tb = reinterpret_cast<const uint32_t*>(blob.data() + h.layout.touched_base);
+        tok = tb[0] == 0;
+        for (int v = 0; v < h.V && tok; ++v) tok = tb[v + 1] >= tb[v];
+        tok = tok && inside(h.layout.touched, (uint64_t)tb[h.V] * 4);
+        if (tok) {
+          const uint32_t* t = reinterpret_cast<const uint32_t*>(blob.data() + h.layout.touched);
+          for (uint32_t i = 0; i < tb[h.V] && tok; ++i) tok = t[i] < n_src;
+          p->touched_base.assign(tb, tb + h.V + 1);
+        }
+      }
+      if (!tok) { set_error(std::string("plan_load: bad touched-texel list in ") + path); return MVWARP_EINVAL; }
+    }
     if ((h.upsampled && (h.hl <= 0 || h.wl <= 0)) || !contents_ok(h.layout.bwd, p->bwd.task_base, p->bwd.heavy_base, n_src, n_cells) ||
         (h.has_fwd && !contents_ok(h.layout.fwd, p->fwd.task_base, p->fwd.heavy_base, n_cells, n_src))) {
       set_error(std::string("plan_load: index out of range in ") + path + " (corrupt or foreign contents)");
@@ -842,6 +867,47 @@ int mvwarp_warp_views_bwd(const mvwarp_plan_t* plan, int view0, int nviews, cons
   memcpy(a.os, out_strides, sizeof(a.os));
   a.out_chan0 = out_chan0; a.coord_chan = -1; a.stream = (cudaStream_t)stream;
   return launch_bwd(a);
+}
+
+static int list_call(const mvwarp_plan_t* plan, int view0, int nviews, const void* const* views, const void* concat,
+                     const int64_t feat_strides[4], const int64_t out_strides[4], int out_chan0, int coord_chan, int B, int C,
+                     int dtype, void* stream, bool forward) {
+  const char* who = forward ? "warp_views_fwd_list" : "warp_views_bwd_list";
+  if (!plan || !views || !concat || !feat_strides || !out_strides) { set_error(std::string(who) + ": null argument"); return MVWARP_EINVAL; }
+  if (nviews <= 0) { set_error(std::string(who) + ": bad B/C/view range"); return MVWARP_EINVAL; }
+  if (nviews > MVWARP_MAX_LIST_VIEWS) {
+    set_error(std::string(who) + ": more than MVWARP_MAX_LIST_VIEWS views in one call (split the list)");
+    return MVWARP_EUNSUPPORTED;
+  }
+  for (int v = 0; v < nviews; ++v)
+    if (!views[v]) { set_error(std::string(who) + ": null view pointer"); return MVWARP_EINVAL; }
+  const int64_t fs5[5] = {feat_strides[0], 0, feat_strides[1], feat_strides[2], feat_strides[3]};
+  int rc = check_call(plan, view0, nviews, views[0], concat, fs5, out_strides, B, C, dtype, who);
+  if (rc) return rc;
+  if (out_chan0 < 0) { set_error(std::string(who) + ": negative out_chan0"); return MVWARP_EINVAL; }
+  DeviceGuard guard(plan->device);
+  if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+  LaunchArgs a{};
+  a.plan = plan; a.view0 = view0; a.nviews = nviews; a.B = B; a.C = C; a.dtype = dtype;
+  a.feats_or_grad_out = forward ? views[0] : concat;
+  a.out_or_grad_feats = forward ? const_cast<void*>(concat) : const_cast<void*>(views[0]);
+  memcpy(a.fs, fs5, sizeof(a.fs));
+  memcpy(a.os, out_strides, sizeof(a.os));
+  a.out_chan0 = out_chan0; a.coord_chan = forward ? coord_chan : -1; a.stream = (cudaStream_t)stream;
+  a.view_ptrs = views;
+  return forward ? launch_fwd(a) : launch_bwd(a);
+}
+
+int mvwarp_warp_views_fwd_list(const mvwarp_plan_t* plan, int view0, int nviews, const void* const* feats,
+                               const int64_t feat_strides[4], void* out, const int64_t out_strides[4], int out_chan0,
+                               int coord_chan, int B, int C, int dtype, void* stream) {
+  return list_call(plan, view0, nviews, feats, out, feat_strides, out_strides, out_chan0, coord_chan, B, C, dtype, stream, true);
+}
+
+int mvwarp_warp_views_bwd_list(const mvwarp_plan_t* plan, int view0, int nviews, const void* grad_out,
+                               const int64_t out_strides[4], int out_chan0, void* const* grad_feats,
+                               const int64_t feat_strides[4], int B, int C, int dtype, void* stream) {
+  return list_call(plan, view0, nviews, grad_feats, grad_out, feat_strides, out_strides, out_chan0, -1, B, C, dtype, stream, false);
 }
 
 }  // extern "C"

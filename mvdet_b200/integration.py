@@ -120,7 +120,12 @@ def warped_forward(model, imgs: torch.Tensor, visualize: bool = False, warp_fn: 
     backward; BASELINE.json configs[2]) and the rest of ``map_classifier`` follows in torch."""
     if visualize:
         raise NotImplementedError("visualize=True is the reference's matplotlib debugging path; call the original forward for it")
+    list_fn = None
     if warp_fn is None:
+        # the CUDA op takes the per-camera tensors as they are (mvwarp_warp_views_fwd_list): no torch.stack, i.e. no 1.86 GB copy per
+        # Wildtrack frame in the forward and none in the backward.  A caller-supplied warp_fn (the CPU tests' oracle) keeps the
+        # stacked-tensor signature.
+        from .ops import warp_views_list as list_fn
         if fuse_upsample:
             from .ops import warp_views_upsampled as warp_fn
         else:
@@ -140,8 +145,23 @@ def warped_forward(model, imgs: torch.Tensor, visualize: bool = False, warp_fn: 
             f = F.interpolate(f, model.upsample_shape, mode="bilinear")                         # :65
             imgs_result.append(model.img_classifier(_onto(f, model.img_classifier)))            # :66-67
         feats.append(_onto(f, model.map_classifier))
-    img_feats = torch.stack(feats, dim=1)                                                       # [B,V,C,H,W]; keeps channels-last
     proj_mats = torch.stack([m for m in model.proj_mats])                                       # float64 CPU (:29-30); op applies .float() (:68)
+    fused_now = (fused_head is not None and not torch.is_grad_enabled()) or fused_conv1
+    if list_fn is not None and not fused_now:
+        world_features = list_fn(feats, proj_mats, model.reducedgrid_shape,
+                                 upsample_shape=model.upsample_shape if fuse_upsample else None)   # :68-69, 75, 77 (+ :65 when fused)
+        map_result = model.map_classifier(world_features)                                       # :81
+        return F.interpolate(map_result, model.reducedgrid_shape, mode="bilinear"), imgs_result # :82
+    if fused_now and warp_fn is not None and feats[0].is_cuda:
+        # the fused tcgen05 kernels read bf16 channel-contiguous [B,V,C,H,W]: convert, transpose (NCHW trunks) and stack in ONE pass
+        # per camera instead of torch.stack (fp32 read + write) followed by .to(bf16) (another read + write)
+        Bf, Cf, Hf, Wf = feats[0].shape
+        x = torch.empty((Bf, len(feats), Hf, Wf, Cf), dtype=torch.bfloat16, device=feats[0].device).permute(0, 1, 4, 2, 3)
+        for v, f in enumerate(feats):
+            x[:, v].copy_(f)
+        img_feats = x
+    else:
+        img_feats = torch.stack(feats, dim=1)                                                   # [B,V,C,H,W]; keeps channels-last
     if fused_head is not None and not torch.is_grad_enabled():
         x = img_feats.to(torch.bfloat16)
         if x.stride(2) != 1:                                                                    # NCHW trunk: one transposing copy

@@ -615,3 +615,127 @@ def test_realistic_upsampled_features_at_the_wildtrack_shape():
     outb = mv.warp_views(to_channels_last_5d(xb).to(DEV), pm, spec.grid_shape)
     bound = 2.0 ** -8 * refb.abs() + 1e-6 * refb.abs().max()
     assert bool(((outb.float().cpu() - refb).abs() <= bound).all())
+
+
+# ---- list variant: one tensor per camera, no stack copy (VERDICT r01 missing #3) -------------------------------------
+@pytest.mark.parametrize("layout", ["cl", "nchw", "mixed"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_warp_views_list_equals_warp_views(layout, dtype):
+    """warp_views_list(per-camera tensors) == warp_views(stacked tensor), bit for bit, forward and backward; channels-last and
+    NCHW cameras go through ONE launch (pointer table in the kernel parameters), mixed formats through per-view launches."""
+    pm, src_hw, grid_hw = small_rig(num_cam=4, seed=61)
+    B, V, Cc = 2, 4, 40
+    x = _feats(B, V, Cc, src_hw).to(dtype)
+    cams = []
+    for v in range(V):
+        t = x[:, v].to(DEV)
+        if layout == "cl" or (layout == "mixed" and v % 2 == 0):
+            t = t.contiguous(memory_format=torch.channels_last)
+        else:
+            t = t.contiguous()
+        cams.append(t.requires_grad_(True))
+    out = ops.warp_views_list(cams, pm, grid_hw)
+    stacked = (to_channels_last_5d(x) if layout == "cl" else x.contiguous()).to(DEV).requires_grad_(True)
+    ref = ops.warp_views(stacked, pm, grid_hw)
+    assert out.shape == ref.shape and torch.equal(out, ref)
+    assert (out.stride(1) == 1) == (layout != "nchw")
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(3)).to(dtype).to(DEV)
+    grads = torch.autograd.grad(out, cams, go)
+    (gref,) = torch.autograd.grad(ref, stacked, go)
+    for v in range(V):
+        assert grads[v].shape == cams[v].shape
+        assert torch.equal(grads[v], gref[:, v]), (layout, v)
+    # only some cameras need a gradient (frozen trunk for the others): autograd drops the rest
+    cams2 = [c.detach().requires_grad_(v == 1) for v, c in enumerate(cams)]
+    (g1,) = torch.autograd.grad(ops.warp_views_list(cams2, pm, grid_hw), [cams2[1]], go)
+    assert torch.equal(g1, gref[:, 1])
+
+
+def test_warp_views_list_upsampled_and_errors():
+    pm, src_hw, grid_hw = small_rig(num_cam=3, seed=63)
+    low = (src_hw[0] // 3, src_hw[1] // 3)
+    x = _feats(1, 3, 32, low)
+    cams = [x[:, v].to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for v in range(3)]
+    out = ops.warp_views_list(cams, pm, grid_hw, upsample_shape=src_hw)
+    xs = to_channels_last_5d(x).to(DEV).requires_grad_(True)
+    ref = ops.warp_views_upsampled(xs, src_hw, pm, grid_hw)
+    assert torch.equal(out, ref)
+    go = torch.randn_like(ref)
+    grads = torch.autograd.grad(out, cams, go)
+    (gref,) = torch.autograd.grad(ref, xs, go)
+    assert all(torch.equal(grads[v], gref[:, v]) for v in range(3))
+    with pytest.raises(ValueError):
+        ops.warp_views_list(cams[:2], pm, grid_hw)                   # 2 tensors, 3 matrices
+    with pytest.raises(ValueError):
+        ops.warp_views_list([cams[0], cams[1][:, :16], cams[2]], pm, grid_hw)
+    with pytest.raises(mv.MvwarpError):
+        ops.warp_views_list([c.detach().cpu() for c in cams], pm, grid_hw)
+
+
+def test_patched_detector_uses_no_stack_copy(monkeypatch):
+    """integration.warped_forward hands the per-camera tensors to warp_views_list: torch.stack must not be called on the features."""
+    from mvdet_b200 import integration
+    pm, src_hw, grid_hw = small_rig(num_cam=3, seed=5)
+    model = integration.patch_detector(_TinyDetector(pm, src_hw, grid_hw).to(DEV))
+    imgs = torch.randn(2, 3, 3, src_hw[0] // 3, src_hw[1] // 3, generator=torch.Generator().manual_seed(2))
+    real_stack = torch.stack
+    sizes = []
+
+    def spy(tensors, dim=0, **kw):
+        sizes.append(max(t.numel() for t in tensors))
+        return real_stack(tensors, dim=dim, **kw)
+
+    monkeypatch.setattr(torch, "stack", spy)
+    out, _ = model(imgs)
+    out.sum().backward()
+    assert max(sizes) <= 9, sizes                                    # only the 3x3 matrices get stacked
+
+
+# ---- host-resident features: only the touched texels cross the bus (VERDICT r01 next #8) -----------------------------
+@pytest.mark.parametrize("kind", ["plain", "upsampled"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_copy_touched_texels_round_trip(kind, dtype):
+    """Pinned host features -> device through the gather kernel: the warp of the sparsely staged tensor equals the warp of the dense
+    one bit for bit (every texel the warp reads was sent); device gradient -> zeroed pinned host tensor through the scatter equals
+    the dense gradient bit for bit (every non-zero row came back, the rest is zero)."""
+    pm, src_hw, grid_hw = small_rig(num_cam=3, seed=71)
+    low = (src_hw[0] // 3, src_hw[1] // 3)
+    B, V, Cc = 2, 3, 24
+    if kind == "plain":
+        plan, feat_hw = P.get_plan(pm, src_hw, grid_hw, DEV), src_hw
+    else:
+        plan, feat_hw = P.get_plan_upsampled(pm, low, src_hw, grid_hw, DEV), low
+    x = _feats(B, V, Cc, feat_hw).to(dtype)
+    h_x = torch.empty((B, V, *feat_hw, Cc), dtype=dtype).pin_memory().permute(0, 1, 4, 2, 3)
+    h_x.copy_(x)
+    d_sparse = torch.full((B, V, *feat_hw, Cc), float("nan"), dtype=dtype, device=DEV).permute(0, 1, 4, 2, 3)
+    ops.copy_touched_texels(plan, h_x, d_sparse)
+    base, ids = ops.touched_texels(plan)
+    assert int(base[-1]) == plan.stats["unique_texels"] == ids.numel()
+    mask = torch.zeros(V, feat_hw[0] * feat_hw[1], dtype=torch.bool)
+    for v in range(V):
+        seg = ids[int(base[v]):int(base[v + 1])].long()
+        assert bool((seg[1:] > seg[:-1]).all())
+        mask[v, seg] = True
+    mask = mask.view(1, V, 1, *feat_hw)
+    got = d_sparse.cpu()
+    assert bool(got.isnan().logical_not().eq(mask.expand_as(got)).all())          # exactly the touched texels were written
+    d_sparse = torch.nan_to_num(d_sparse, nan=0.0)                                # untouched texels are never read; any finite value does
+    d_dense = to_channels_last_5d(x).to(DEV).requires_grad_(True)
+    a = ops.warp_views_with_plan(d_dense, plan)
+    b = ops.warp_views_with_plan(d_sparse, plan)
+    assert torch.equal(a, b)
+    go = torch.randn(a.shape, generator=torch.Generator().manual_seed(4)).to(dtype).to(DEV)
+    (g,) = torch.autograd.grad(a, d_dense, go)
+    h_g = torch.zeros((B, V, *feat_hw, Cc), dtype=dtype).pin_memory().permute(0, 1, 4, 2, 3)
+    ops.copy_touched_texels(plan, g, h_g)
+    torch.cuda.synchronize()
+    assert torch.equal(h_g, g.cpu())
+    # view sub-range + argument checks
+    d2 = torch.zeros_like(d_sparse[:, 1:])
+    ops.copy_touched_texels(plan, h_x[:, 1:], d2, view0=1)
+    assert torch.equal(torch.nan_to_num(d2.cpu()), torch.where(mask[:, 1:].expand_as(got[:, 1:]), h_x[:, 1:], torch.zeros_like(h_x[:, 1:])))
+    with pytest.raises(mv.MvwarpError):
+        ops.copy_touched_texels(plan, x.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3), d_sparse)   # pageable host memory
+    with pytest.raises(ValueError):
+        ops.copy_touched_texels(plan, torch.empty((B, V, Cc, *feat_hw), dtype=dtype).pin_memory(), d_sparse)   # not channel-contiguous
