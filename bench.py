@@ -329,6 +329,46 @@ def run_conv1_fused(args, spec, pm, dev, rank, world, dist):
     return res
 
 
+def run_conv1_train_step(args, spec, pm, dev):
+    """BASELINE.json configs[2]: the Wildtrack TRAINING step at B=8 in bf16 -- relu(map_classifier[0](warp_views(feats))) forward
+    + backward with gradients for the features, the weight and the bias.  mvdet_b200.conv1.warp_conv1_trainable: fused tcgen05
+    forward, data gradient on the library's TMA-fed tcgen05 convolution, weight gradient on cuDNN, deterministic CSR warp backward;
+    beside it the un-fused path (warp_views + F.conv2d under autograd, i.e. cuDNN for all three convolutions)."""
+    import torch
+    import torch.nn.functional as F
+    from mvdet_b200 import conv1, ops
+    V, Cc, B = spec.num_cam, 512, 8
+    Hs, Ws = spec.feat_shape
+    Hg, Wg = spec.grid_shape
+    gen = torch.Generator(device=dev).manual_seed(300)
+    feats = torch.randn((B, V, Hs, Ws, Cc), device=dev, generator=gen).to(torch.bfloat16).permute(0, 1, 4, 2, 3).requires_grad_(True)
+    weight = (torch.randn((512, V * Cc + 2, 3, 3), device=dev, generator=gen) * 0.02).requires_grad_(True)
+    bias = torch.randn((512,), device=dev, generator=gen).requires_grad_(True)
+    go = torch.randn((B, Hg, Wg, 512), device=dev, generator=gen).permute(0, 3, 1, 2)
+    wpack = conv1.pack_conv1_weight(weight, V, Cc)
+    w16 = weight.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    b16 = bias.detach().to(torch.bfloat16).requires_grad_(True)
+    go16 = go.to(torch.bfloat16)
+
+    def fused():
+        out = conv1.warp_conv1_trainable(feats, weight, bias, pm, (Hg, Wg), wpack=wpack)
+        torch.autograd.grad(out, [feats, weight, bias], go)
+
+    def unfused():
+        out = F.relu(F.conv2d(ops.warp_views(feats, pm, (Hg, Wg)), w16, b16, padding=1))
+        torch.autograd.grad(out, [feats, w16, b16], go16)
+
+    tf = _event_times(fused, 5, 2, torch.cuda.synchronize)
+    tu = _event_times(unfused, 5, 2, torch.cuda.synchronize)
+    flops = 3 * 2.0 * B * Hg * Wg * 512 * (V * Cc + 2) * 9          # forward + data gradient + weight gradient
+    return {"workload": f"{spec.name} B={B} bf16 training step: fwd + bwd of relu(conv1(warp_views(feats))), grads for feats / weight / bias",
+            "ms": tf["median"], "ms_min": tf["min"], "frames_per_s": B / (tf["median"] * 1e-3),
+            "tflops": flops / (tf["median"] * 1e-3) / 1e12, "unfused_cudnn_ms": tu["median"],
+            "speedup_vs_unfused": tu["median"] / tf["median"],
+            "kernels": "forward: warp_conv1_direct_kernel (tcgen05); dgrad: conv3x3_tc2_kernel x V (tcgen05 + TMA); wgrad: cuDNN; "
+                       "warp backward: bwd_cl_kernel (bf16, 16-byte aligned rows)"}
+
+
 def run_sharded_conv1(args, dev, rank, world, dist):
     """BASELINE.json configs[3] / north_star's multi-GPU design, STRONG scaling: ONE 32-camera rig (512 ch x 270x480 -> the
     full-resolution 480x1440 grid), its cameras partitioned across the N ranks.  Each rank runs the fused warp -> conv1 kernel on
@@ -554,6 +594,9 @@ def run_ours(args):
     if not args.no_conv1 and not args.fuse_upsample and args.layout == "cl" and Cc % 64 == 0:
         legs["conv1_fused"] = guarded(run_conv1_fused, args, base, pm, dev, rank, world, dist if world > 1 else None)
         torch.cuda.empty_cache()
+        if world == 1 and Cc == 512:
+            legs["conv1_train_step"] = guarded(run_conv1_train_step, args, base, pm, dev)
+            torch.cuda.empty_cache()
     if not args.no_sharded_conv1 and not args.fuse_upsample and args.layout == "cl":
         legs["sharded_conv1"] = guarded(run_sharded_conv1, args, dev, rank, world, dist if world > 1 else None)
         torch.cuda.empty_cache()
@@ -638,6 +681,8 @@ def run_e2e(args, plan, pm, feats_dev, grad_out_dev, dev, world, dist):
     d_feats = [torch.empty_like(feats_dev) for _ in range(NBUF)]
     d_go = [torch.empty_like(grad_out_dev) for _ in range(NBUF)]
     s_in, s_comp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    s_in_k, s_out_k = torch.cuda.Stream(dev), torch.cuda.Stream(dev)   # the gather / scatter kernels run beside the copy engines
+    ev_in_k = [torch.cuda.Event() for _ in range(NBUF)]
     ev_in = [torch.cuda.Event() for _ in range(NBUF)]
     ev_comp = [torch.cuda.Event() for _ in range(NBUF)]     # compute of the step using buffer i is done
     ev_out = [torch.cuda.Event() for _ in range(NBUF)]      # its results are on the host
@@ -651,17 +696,22 @@ def run_e2e(args, plan, pm, feats_dev, grad_out_dev, dev, world, dist):
 
     def one(k):
         i = k % NBUF
+        if sparse:
+            with torch.cuda.stream(s_in_k):                  # every texel the warp can read (rig-constant set), gathered across PCIe by
+                s_in_k.wait_event(ev_comp[i])                # a kernel, concurrently with the copy engine's dense grad_out copy below
+                ops.copy_touched_texels(plan, h_feats, d_feats[i])
+                ev_in_k[i].record(s_in_k)
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_comp[i])                      # inputs of step k-2 no longer needed
-            if sparse:                                       # every texel the warp can read (rig-constant set), gathered across PCIe
-                ops.copy_touched_texels(plan, h_feats, d_feats[i])
-            else:
+            if not sparse:
                 d_feats[i].copy_(h_feats, non_blocking=True)
             if do_bwd:
                 d_go[i].copy_(h_go, non_blocking=True)
             ev_in[i].record(s_in)
         with torch.cuda.stream(s_comp):
             s_comp.wait_event(ev_in[i])
+            if sparse:
+                s_comp.wait_event(ev_in_k[i])
             x = d_feats[i].requires_grad_(do_bwd)
             # the public op, plan-cache lookup included (the matrices are hashed on every call)
             if plan.upsampled:
@@ -676,13 +726,15 @@ def run_e2e(args, plan, pm, feats_dev, grad_out_dev, dev, world, dist):
             s_out.wait_event(ev_comp[i])
             h_out.copy_(out.detach(), non_blocking=True)
             out.record_stream(s_out)
-            if do_bwd:
-                if sparse:                                   # every non-zero row of the feature gradient, scattered across PCIe
-                    ops.copy_touched_texels(plan, gx, h_gf)
-                else:
-                    h_gf.copy_(gx, non_blocking=True)
+            if do_bwd and not sparse:
+                h_gf.copy_(gx, non_blocking=True)
                 gx.record_stream(s_out)
             ev_out[i].record(s_out)
+        if do_bwd and sparse:
+            with torch.cuda.stream(s_out_k):                 # every non-zero row of the feature gradient, scattered across PCIe
+                s_out_k.wait_event(ev_comp[i])
+                ops.copy_touched_texels(plan, gx, h_gf)
+                gx.record_stream(s_out_k)
 
     for k in range(NBUF):                                    # warm-up: fills the pipeline, primes the allocator
         one(k)

@@ -246,6 +246,17 @@ int mvwarp_warp_conv1_fwd_p2p(const mvwarp_plan_t* plan, int view0, int nviews, 
                               const void* wpack, int B, int C, int with_coord, int nranks, int my_rank, const uint64_t* peer_inbox,
                               const int32_t* band_row0, int band_rows_max, void* stream);
 
+/* ---- backward of relu(conv1 + bias): the element-wise front end (training step, trainer.py:48) ---------------------------
+ * mvwarp_relu_bwd_cast:  g16[b,n,y,x] = bf16(grad_out[b,n,y,x] * (out[b,n,y,x] > 0))  (out == NULL: no mask) and, if bias_grad != NULL,
+ * bias_grad[n] = sum_{b,y,x} of the masked fp32 gradient in a fixed order (deterministic) -- one pass instead of three torch ops.
+ * grad_out / out: fp32 [B,C,H,W] channels-last; g16: bf16 channels-last with any (8-element aligned) strides, e.g. the interior of
+ * the zero-padded buffer the weight-gradient GEMMs read.  Strides as (B, C, H, W) in elements.  scratch: device floats,
+ * >= mvwarp_relu_bwd_scratch_floats(C, device) (only needed with bias_grad).  C must divide 2048 and be a multiple of 8. */
+int64_t mvwarp_relu_bwd_scratch_floats(int C, int device);
+int mvwarp_relu_bwd_cast(const float* grad_out, const int64_t go_strides[4], const float* out, const int64_t out_strides[4],
+                         void* g16, const int64_t g_strides[4], float* bias_grad, float* scratch, int64_t scratch_floats,
+                         int B, int H, int W, int C, int device, void* stream);
+
 /* ---- the rest of map_classifier (persp_trans_detector.py:53-54, applied at :81) -------------
  * mvwarp_conv3x3_fwd: out = [relu](conv2d(x, W, bias, padding = dilation, dilation = dilation)) for a 3x3 kernel with
  * 512 output channels -- map_classifier[2] = Conv2d(512, 512, 3, padding=2, dilation=2) + ReLU -- as a tcgen05 implicit

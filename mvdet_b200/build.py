@@ -82,4 +82,9 @@ def build_library(force: bool = False, verbose: bool = False, dev: bool = False)
 
 if __name__ == "__main__":
     import sys
-    print(build_library(force=True, verbose="-v" in sys.argv, dev="--dev" in sys.argv))
+    # python -m mvdet_b200.build [--dev | --all] [-v]
+    if "--all" in sys.argv:
+        print(build_library(force=True, verbose="-v" in sys.argv))
+        print(build_library(force=True, verbose="-v" in sys.argv, dev=True))
+    else:
+        print(build_library(force=True, verbose="-v" in sys.argv, dev="--dev" in sys.argv))

@@ -9,6 +9,7 @@ into the shared-memory image the kernel's B operand expects.  CUDA only, bf16 in
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -91,10 +92,111 @@ def conv1_to_state_dict(wpack: torch.Tensor, bias: torch.Tensor, num_views: int,
             prefix + "bias": bias.detach().to(dtype).clone()}
 
 
+def pack_conv1_dgrad_weight(weight: torch.Tensor, num_views: int, channels: int):
+    """Per-view packed weights of the DATA gradient of ``map_classifier[0]``: the gradient w.r.t. view v's warped channels is itself a
+    3x3 convolution, ``gX_v[c] = sum_{n,ky,kx} g[n](y+1-ky, x+1-kx) * W[n, v*C+c, ky, kx]``, i.e. ``conv3x3(g, W'_v, padding=1)`` with
+    ``W'_v[c, n, ky, kx] = W[n, v*C + c, 2-ky, 2-kx]`` (in/out transposed, taps flipped).  Returns a list of V packed blocks for
+    :func:`mvdet_b200.map_head.conv3x3_cl` (the TMA-fed tcgen05 convolution; needs C == 512 output channels per view)."""
+    V, Cc = int(num_views), int(channels)
+    if Cc != N_OUT:
+        raise ValueError("the tcgen05 data-gradient path needs 512 channels per view (the convolution kernel has 512 outputs)")
+    w = weight.detach()[:, :V * Cc].reshape(N_OUT, V, Cc, 3, 3)
+    out = []
+    for v in range(V):
+        wt = w[:, v].flip(-1, -2).permute(1, 0, 2, 3).contiguous()            # [c, n, ky, kx]
+        out.append(pack_conv1_weight(wt, 1, N_OUT, with_coord=False))
+    return out
+
+
+_pad_cache = {}
+
+
+def _padded_buffers(device, B: int, Hg: int, Wg: int, P: int):
+    """``(Xp [B,Hg+2,Wg+2,P], Gp [B,Hg+2,Wg+2,512])`` bf16, zeroed ONCE per shape: every step overwrites the interiors completely (the
+    warp forward writes every cell, zeros included), so the zero borders / pad channels survive and no per-step memset is needed."""
+    key = (str(device), B, Hg, Wg, P)
+    hit = _pad_cache.get("k")
+    if hit is None or hit[0] != key:
+        _pad_cache.pop("k", None)
+        Xp = torch.zeros((B, Hg + 2, Wg + 2, P), dtype=torch.bfloat16, device=device)
+        Gp = torch.zeros((B, Hg + 2, Wg + 2, N_OUT), dtype=torch.bfloat16, device=device)
+        _pad_cache["k"] = (key, Xp, Gp)
+    return _pad_cache["k"][1], _pad_cache["k"][2]
+
+
+def relu_bwd_cast(grad_out: torch.Tensor, out: Optional[torch.Tensor], g16: torch.Tensor, want_bias_grad: bool) -> Optional[torch.Tensor]:
+    """``g16 <- bf16(grad_out * (out > 0))`` and the bias gradient ``sum_{b,y,x}`` of the masked gradient in ONE pass
+    (``mvwarp_relu_bwd_cast``).  grad_out / out fp32 channels-last [B,512,H,W]; g16 a bf16 channels-last view of any strides."""
+    B, Cn, H, W = grad_out.shape
+    lib = _lib.load()
+    dev = grad_out.device
+    bias_grad = scratch = None
+    nscr = 0
+    if want_bias_grad:
+        nscr = int(lib.mvwarp_relu_bwd_scratch_floats(Cn, dev.index))
+        scratch = torch.empty(nscr, dtype=torch.float32, device=dev)
+        bias_grad = torch.empty(Cn, dtype=torch.float32, device=dev)
+    rc = lib.mvwarp_relu_bwd_cast(C.c_void_p(grad_out.data_ptr()), _lib.i64x(grad_out.stride()),
+                                  C.c_void_p(out.data_ptr()) if out is not None else None,
+                                  _lib.i64x(out.stride()) if out is not None else None,
+                                  C.c_void_p(g16.data_ptr()), _lib.i64x(g16.stride()),
+                                  C.c_void_p(bias_grad.data_ptr()) if want_bias_grad else None,
+                                  C.c_void_p(scratch.data_ptr()) if want_bias_grad else None, nscr, B, H, W, Cn, dev.index,
+                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "mvwarp_relu_bwd_cast")
+    return bias_grad
+
+
+def conv1_wgrad_gemm(plan, feats: torch.Tensor, Xp: torch.Tensor, Gp: torch.Tensor, with_coord: bool = True) -> torch.Tensor:
+    """Weight gradient of ``map_classifier[0]`` as NINE plain GEMMs on shifted views -- no im2col, no cuDNN.
+
+    ``gW[n, ch, ky, kx] = sum_{b,y,x} g[b,n,y,x] * X[b,ch,y+ky-1,x+kx-1]`` with X = warp_views(feats) zero-padded.  X goes into the
+    interior of the zero-bordered buffer ``Xp[B, Hg+2, Wg+2, P]`` (P = V*C+2 rounded up to 8 channels, so every row is 16-byte
+    aligned) -- the warp forward kernel stores straight into that view -- and ``g`` sits in the top-left corner of the zero-bordered
+    ``Gp[B, Hg+2, Wg+2, 512]`` (written there by :func:`relu_bwd_cast`).  In the flattened position index
+    ``p = (b*(Hg+2) + y)*(Wg+2) + x`` the tap (ky, kx) is then a CONSTANT shift ``ky*(Wg+2) + kx``:
+    ``gW[:, :, ky, kx] = Gp[:K].T @ Xp[shift : shift+K]``  (K = all positions minus the largest shift; the positions cut off hold
+    zeros of Gp).  Each is one cuBLAS bf16 GEMM (M = 512, N = P, K = B*(Hg+2)*(Wg+2)) with fp32 accumulation and fp32 output: a
+    plain library GEMM is all this contraction needs once the shifts are views (DESIGN.md section 6 has the traffic analysis of a
+    hand-written tcgen05 version and why it would not beat this)."""
+    from . import ops
+    B, V, Cc = feats.shape[:3]
+    Hg, Wg = plan.grid_hw
+    ctot = V * Cc + (2 if with_coord else 0)
+    P = Xp.shape[-1]
+    ops.warp_views_fwd_into(plan, feats, Xp[:, 1:Hg + 1, 1:Wg + 1, :ctot].permute(0, 3, 1, 2), 0, 0, V * Cc if with_coord else -1)
+    Xf, Gf = Xp.view(-1, P), Gp.view(-1, N_OUT)
+    K = Xf.shape[0] - (2 * (Wg + 2) + 2)
+    Gt = Gf[:K].t()                                                     # [512, K] view (column-major operand for cuBLAS)
+    taps = []
+    for ky in range(3):
+        for kx in range(3):
+            s0 = ky * (Wg + 2) + kx
+            taps.append(torch.mm(Gt, Xf[s0:s0 + K], out_dtype=torch.float32))       # bf16 x bf16 -> fp32 accumulate, fp32 out
+    gw = torch.stack(taps).view(3, 3, N_OUT, P)
+    return gw[..., :ctot].permute(2, 3, 0, 1)                           # [512, V*C+2, 3, 3] (a view)
+
+
+_dgrad_cache = {}
+
+
+def _dgrad_packs(weight: torch.Tensor, V: int, Cc: int):
+    """Packed data-gradient weights, re-packed only when the weight changes (keyed on storage address + version counter)."""
+    key = (weight.data_ptr(), weight._version, weight.device, V, Cc)
+    hit = _dgrad_cache.get("k")
+    if hit is None or hit[0] != key:
+        _dgrad_cache["k"] = (key, pack_conv1_dgrad_weight(weight, V, Cc))
+    return _dgrad_cache["k"][1]
+
+
 class _WarpConv1Fn(torch.autograd.Function):
-    """Training wrapper: fused forward; the backward re-materialises the warped tensor (0.12 ms at the Wildtrack shape)
-    and runs cuDNN's convolution backward (``aten.convolution_backward``: no second forward convolution) and ``warp_views``'
-    deterministic backward."""
+    """Training wrapper: fused tcgen05 forward.  Backward, no cuDNN anywhere:
+    * ``mvwarp_relu_bwd_cast``: ReLU mask + bf16 rounding + bias gradient in one pass, written into the zero-bordered buffer ``Gp``;
+    * DATA gradient: the library's own TMA-fed tcgen05 convolution, one launch per view with the transposed, tap-flipped weight
+      block, into a 16-byte aligned ``[B,Hg,Wg,V*C]`` buffer which the deterministic CSR warp backward reads on its aligned path;
+    * WEIGHT gradient: the warped tensor is re-materialised into the zero-bordered buffer ``Xp`` (0.12 ms per Wildtrack frame) and the
+      nine taps are nine cuBLAS GEMMs on shifted views of ``Gp`` / ``Xp`` (:func:`conv1_wgrad_gemm`).
+    ``MVWARP_CUDNN_DGRAD=1`` / ``MVWARP_CUDNN_WGRAD=1`` switch either gradient back to ``aten.convolution_backward`` (comparison runs)."""
 
     @staticmethod
     def forward(ctx, img_feats, weight, bias, proj_mats, grid_shape, wpack, relu):
@@ -106,31 +208,45 @@ class _WarpConv1Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         from . import ops
+        from .map_head import conv3x3_cl
         from .plan import get_plan
         img_feats, weight, bias, out = ctx.saved_tensors
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
-        g = grad_out
-        if ctx.relu:
-            g = g * (out > 0)
         feats = img_feats.detach()
         B, V, Cc, Hs, Ws = feats.shape
         plan = get_plan(ctx.proj_mats, (Hs, Ws), ctx.grid_shape, feats.device)
-        # re-materialise the warped tensor (bf16, channels-last; 0.12 ms per Wildtrack frame) and hand it, with the bf16 weight, straight to
-        # the convolution's backward: no second forward convolution, no autograd graph
-        x = ops.warp_views_with_plan(feats, plan)
-        w = weight.detach().to(x.dtype).contiguous(memory_format=torch.channels_last)
-        g16 = g.to(x.dtype).contiguous(memory_format=torch.channels_last)
-        # cuDNN for both gradients: the data gradient on the library's own TMA convolution (7 launches with the transposed, tap-flipped
-        # weight into a 16-byte aligned [B,Hg,Wg,V*512] buffer) was measured at 37.5 vs 38.8 ms per B=8 step and 4.76 vs 4.58 ms at B=1 --
-        # not worth a second code path (profiles/r01_logs/train_step*.txt)
-        gx, gw, _ = torch.ops.aten.convolution_backward(g16, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [need_x, need_w, False])
+        Hg, Wg = plan.grid_hw
+        ctot = V * Cc + 2
+        Xp, Gp = _padded_buffers(feats.device, B, Hg, Wg, (ctot + 7) // 8 * 8)
+        # ReLU mask + bf16 rounding + bias gradient in one pass, written straight into the padded buffer of the weight-gradient GEMMs;
+        # g16 is the [B,512,Hg,Wg] channels-last VIEW of that buffer's interior, which the data-gradient convolution reads through TMA
+        g16 = Gp[:, :Hg, :Wg].permute(0, 3, 1, 2)
+        go = grad_out
+        if go.dtype != torch.float32 or go.stride(1) != 1:
+            go = go.float().contiguous(memory_format=torch.channels_last)
+        g_b = relu_bwd_cast(go, out if ctx.relu else None, g16, need_b)
+        own_dgrad = need_x and Cc == N_OUT and os.environ.get("MVWARP_CUDNN_DGRAD") != "1"
+        gemm_wgrad = need_w and os.environ.get("MVWARP_CUDNN_WGRAD") != "1"
+        gx = gw = None
+        if gemm_wgrad:
+            gw = conv1_wgrad_gemm(plan, feats, Xp, Gp)
+        if (need_w and not gemm_wgrad) or (need_x and not own_dgrad):      # comparison paths: cuDNN's convolution backward
+            x = ops.warp_views_with_plan(feats, plan)
+            w = weight.detach().to(x.dtype).contiguous(memory_format=torch.channels_last)
+            gx, gw2, _ = torch.ops.aten.convolution_backward(g16.contiguous(memory_format=torch.channels_last), x, w, None, [1, 1], [1, 1],
+                                                             [1, 1], False, [0, 0], 1, [need_x and not own_dgrad, need_w and not gemm_wgrad, False])
+            gw = gw if gemm_wgrad else gw2
+        if own_dgrad:
+            gx_buf = torch.empty((B, Hg, Wg, V * Cc), dtype=feats.dtype, device=feats.device)    # pitch V*C: every cell row 16-byte aligned
+            gx = gx_buf.permute(0, 3, 1, 2)
+            for v, wp in enumerate(_dgrad_packs(weight, V, Cc)):
+                conv3x3_cl(g16, wp, None, dilation=1, relu=False, out_dtype=feats.dtype, out=gx[:, v * Cc:(v + 1) * Cc])
         g_feats = None
         if need_x:
             g_feats = torch.empty((B, V, Hs, Ws, Cc), dtype=feats.dtype, device=feats.device).permute(0, 1, 4, 2, 3)
             ops.warp_views_bwd_into(plan, gx, g_feats)        # deterministic CSR gather; the two coord channels of gx get no gradient
         g_w = gw.to(weight.dtype) if need_w else None
-        g_b = g.sum(dim=(0, 2, 3)).to(bias.dtype) if need_b else None
-        return g_feats, g_w, g_b, None, None, None, None
+        return g_feats, g_w, (g_b.to(bias.dtype) if need_b else None), None, None, None, None
 
 
 def warp_conv1_trainable(img_feats: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], proj_mats: torch.Tensor,

@@ -48,9 +48,20 @@ __global__ void __launch_bounds__(COPY_WARPS * 32) copy_touched_kernel(const Cop
     const char* s = p.src + (int64_t)b * p.sB + (int64_t)vl * p.sV + (int64_t)y * p.sH + (int64_t)x * p.sW;
     char* d = p.dst + (int64_t)b * p.dB + (int64_t)vl * p.dV + (int64_t)y * p.dH + (int64_t)x * p.dW;
     if (VEC == 16) {
-      for (int o = lane * 16; o < p.row_bytes; o += 32 * 16) {
-        const uint4 v = *reinterpret_cast<const uint4*>(s + o);
-        *reinterpret_cast<uint4*>(d + o) = v;
+      // four independent 16-byte loads per lane in flight (a 2 KB fp32 texel row in one trip): reads from host memory are
+      // latency-bound (~2 us per round trip over PCIe), so the bytes in flight, not the instruction count, set the bandwidth
+      for (int o0 = lane * 16; o0 < p.row_bytes; o0 += 4 * 32 * 16) {
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int o = o0 + i * 32 * 16;
+          if (o < p.row_bytes) v[i] = *reinterpret_cast<const uint4*>(s + o);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int o = o0 + i * 32 * 16;
+          if (o < p.row_bytes) *reinterpret_cast<uint4*>(d + o) = v[i];
+        }
       }
     } else {
       for (int o = lane * VEC; o < p.row_bytes; o += 32 * VEC) {
@@ -103,9 +114,9 @@ extern "C" int mvwarp_copy_touched_texels(const mvwarp_plan_t* plan, int view0, 
     for (int64_t a : all) if (a % n) return false;
     return true;
   };
-  // Enough warps to keep the bus full (2 CTAs x 8 warps x 512 B per SM = 1.2 MB in flight against a bandwidth-delay product of
+  // Enough warps to keep the bus full (4 CTAs x 8 warps x 2 KB per SM = 9 MB in flight against a bandwidth-delay product of
   // ~0.1 MB), few enough that the warp kernels of neighbouring frames keep most of every SM while a copy is in progress.
-  const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)p.nrows + COPY_WARPS - 1) / COPY_WARPS, (uint64_t)plan->num_sms * 2);
+  const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)p.nrows + COPY_WARPS - 1) / COPY_WARPS, (uint64_t)plan->num_sms * 4);
   dim3 grid(blocks, B), block(COPY_WARPS * 32);
   if (aligned(16)) copy_touched_kernel<16><<<grid, block, 0, (cudaStream_t)stream>>>(p);
   else if (aligned(4)) copy_touched_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>(p);

@@ -435,7 +435,7 @@ def _rounded_reference_grads(x16, weight, bias, go, pm, grid_hw, mask):
     w16 = bf(weight)
     g16 = bf(go * mask)
     gX = bf(torch.nn.grad.conv2d_input(X.shape, w16, g16, padding=1))
-    gW = bf(torch.nn.grad.conv2d_weight(X, w16.shape, g16, padding=1))
+    gW = torch.nn.grad.conv2d_weight(X, w16.shape, g16, padding=1)        # the GEMM weight gradient returns fp32 (cuDNN's: bf16)
     gb = (go * mask).sum(dim=(0, 2, 3))
     (gx,) = torch.autograd.grad(Xo, xr, gX)
     return bf(gx), gW, gb
