@@ -510,10 +510,25 @@ def run_ours(args):
         if do_bwd:
             grad_feats = torch.empty((B, V, Cc, Hs, Ws), device=dev, dtype=dtype)
 
-    def step():
+    # NCHW trunk + fused up-sample plan: the op transposes the small low-res map once (mvwarp_layout_transpose) and runs the
+    # channel-contiguous kernels; time that whole route (transposes included), not the raw planar kernels
+    routed = args.fuse_upsample and args.layout == "nchw"
+    cl_out = out.stride(1) == 1
+
+    def fwd():
+        if routed:
+            return ops._warp_views_plan(feats, ops._register(plan), True, cl_out)
         ops.warp_views_fwd_into(plan, feats, out, 0, 0, V * Cc)
+
+    def bwd():
+        if routed:
+            return ops._warp_views_plan_bwd(grad_out, ops._register(plan), Cc, False)
+        ops.warp_views_bwd_into(plan, grad_out, grad_feats, 0, 0)
+
+    def step():
+        fwd()
         if do_bwd:
-            ops.warp_views_bwd_into(plan, grad_out, grad_feats, 0, 0)
+            bwd()
 
     def barrier():
         if world > 1:
@@ -533,10 +548,10 @@ def run_ours(args):
     t_begin.record()
     for k in range(args.steps):
         ev[k][0].record()
-        ops.warp_views_fwd_into(plan, feats, out, 0, 0, V * Cc)
+        fwd()
         ev[k][1].record()
         if do_bwd:
-            ops.warp_views_bwd_into(plan, grad_out, grad_feats, 0, 0)
+            bwd()
         ev[k][2].record()
     t_end.record()
     barrier()
@@ -561,8 +576,8 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     fwd_bytes = B * plan.fwd_bytes(Cc, elem)
     bwd_bytes = B * plan.bwd_bytes(Cc, elem)
-    kfwd = ("fwd_table_cl_kernel" if args.layout == "cl" else "fwd_table_generic_kernel") if args.fuse_upsample else \
-           ("fwd_cl_kernel" if args.layout == "cl" else "fwd_generic_kernel")
+    kfwd = ("fwd_table_tile_kernel" if args.layout == "cl" else "transpose_tiles_kernel + fwd_table_tile_kernel") if args.fuse_upsample else \
+           ("fwd_cl_kernel" if args.layout == "cl" else "fwd_nchw_kernel")
     roof_fwd = {"kernel": kfwd, "bound": "hbm",
                 "achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "algorithmic_bytes": fwd_bytes, "ms": fwd_ms, "traffic": None}
@@ -570,7 +585,8 @@ def run_ours(args):
     roofline = roof_fwd
     extra = {}
     if do_bwd:
-        roof_bwd = {"kernel": "bwd_cl_kernel" if args.layout == "cl" else "bwd_generic_kernel", "bound": "hbm",
+        roof_bwd = {"kernel": "bwd_cl_kernel" if args.layout == "cl" else ("bwd_cl_kernel + transpose_tiles_kernel" if routed else "bwd_generic_kernel"),
+                    "bound": "hbm",
                     "achieved": bwd_bytes / (bwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                     "algorithmic_bytes": bwd_bytes, "ms": bwd_ms, "traffic": None}
         roof_bwd["frac"] = roof_bwd["achieved"] / peak
@@ -623,7 +639,7 @@ def run_ours(args):
             "config": workload_config(args, base, world),
             "roofline": roofline, **extra,
             "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": args.steps * (2 if do_bwd else 1),
+            "gpu_launches": args.steps * (2 if do_bwd else 1) * (2 if routed else 1),
             "clocks": clocks.summary(wall0, wall1),
             "plan": {k: plan.stats[k] for k in ("unique_texels", "nnz", "valid_cells", "max_row", "device_bytes")},
             "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},

@@ -169,6 +169,16 @@ int mvwarp_warp_views_bwd_list(const mvwarp_plan_t* plan, int view0, int nviews,
                                const int64_t out_strides[4], int out_chan0, void* const* grad_feats,
                                const int64_t feat_strides[4], int B, int C, int dtype, void* stream);
 
+/* ---- NCHW trunks: planar <-> channel-contiguous feature maps ------------------------------------------------------------
+ * mvwarp_layout_transpose: N images of C planes x HW texels.  to_channels_last = 1: src [N][C][HW] (the NCHW tensors the
+ * reference's trunk emits, persp_trans_detector.py:63-65) -> dst [N][HW][C]; 0: the reverse (the feature gradient on its way back
+ * to an NCHW trunk).  Each image dense; consecutive images *_image_stride elements apart (0 = back to back), so a per-camera tensor
+ * [B,C,H,W] can be written into / read from its slice of a stacked [B,V,H,W,C] buffer.  Device pointers, MVWARP_F32 / MVWARP_BF16.  Used by warp_views_list / warp_views_upsampled on
+ * the LOW-RES trunk output of fused up-sample plans, where transposing once (2 x 206 MB per Wildtrack frame) and running the
+ * channel-contiguous kernels beats gathering 4 bytes per channel and tap from planes. */
+int mvwarp_layout_transpose(const void* src, int64_t src_image_stride, void* dst, int64_t dst_image_stride, int N, int C, int HW,
+                            int dtype, int to_channels_last, int device, void* stream);
+
 /* ---- host-resident features: move only what the warp can touch ---------------------------------------------------
  * mvwarp_copy_touched_texels: for every batch element, every view in [view0, view0+nviews) and every feature texel (ys, xs) that
  * at least one grid cell samples (= the non-empty rows of the plan's inverse CSR map; 26 % of the texels on the Wildtrack rig,

@@ -70,6 +70,7 @@ SIGNATURES = {
                                              C.c_int, C.c_int, C.c_int, _P]),
     "mvwarp_relu_bwd_scratch_floats": (C.c_int64, [C.c_int, C.c_int]),
     "mvwarp_relu_bwd_cast": (C.c_int, [_P, _I64P, _P, _I64P, _P, _I64P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "mvwarp_layout_transpose": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mvwarp_copy_touched_texels": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, _P, _I64P, C.c_int, C.c_int, C.c_int, _P]),
     "mvwarp_plan_touched": (C.c_int, [_P, _U32P, _U32P, C.c_uint64]),
     "mvwarp_warp_views_bwd": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, C.c_int, _P, _I64P,

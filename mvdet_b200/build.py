@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmvwarp.so")
 DEV_LIB_PATH = os.path.join(PKG_DIR, "libmvwarp_dev.so")
 OBJ_DIR = os.path.join(PKG_DIR, "csrc", "_obj")
-SOURCES = ["mvwarp_plan.cu", "mvwarp_kernels.cu", "mvwarp_conv1.cu", "mvwarp_conv2.cu", "mvwarp_conv1_bwd.cu", "mvwarp_host_io.cu"]
+SOURCES = ["mvwarp_plan.cu", "mvwarp_kernels.cu", "mvwarp_conv1.cu", "mvwarp_conv2.cu", "mvwarp_conv1_bwd.cu", "mvwarp_host_io.cu", "mvwarp_layout.cu"]
 HEADERS = ["mvwarp_coords.h", "mvwarp_internal.h", "mvwarp_umma.h", os.path.join("..", "..", "include", "mvwarp.h")]
 
 NVCC_FLAGS = [

@@ -99,6 +99,44 @@ def _empty_feats_like(shape, like: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------------
+# NCHW trunks + fused up-sample plans: transpose the small low-res map once, then run the channel-contiguous kernels
+# ------------------------------------------------------------------------------------------------------
+def _planes_dense(t: torch.Tensor) -> bool:
+    """[..., C, H, W] with every image's C x H x W block dense NCHW (x fastest)."""
+    C_, H, W = t.shape[-3:]
+    return t.stride(-1) == 1 and t.stride(-2) == W and t.stride(-3) == H * W and C_ > 1
+
+
+def _transpose(src: torch.Tensor, src_img: int, dst: torch.Tensor, dst_img: int, N: int, Cc: int, HW: int, to_cl: bool):
+    rc = _lib.load().mvwarp_layout_transpose(C.c_void_p(src.data_ptr()), src_img, C.c_void_p(dst.data_ptr()), dst_img, N, Cc, HW,
+                                             _DTYPES[src.dtype], int(to_cl), src.device.index, _stream_ptr(src.device))
+    _lib.check(rc, "mvwarp_layout_transpose")
+
+
+def _lowres_to_cl(views, B: int, V: int, Cc: int, H: int, W: int) -> torch.Tensor:
+    """NCHW low-res maps (a stacked [B,V,C,h,w] tensor or V tensors [B,C,h,w]) -> one channel-contiguous [B,V,C,h,w] tensor."""
+    ref = views if isinstance(views, torch.Tensor) else views[0]
+    tmp = torch.empty((B, V, H, W, Cc), dtype=ref.dtype, device=ref.device)
+    if isinstance(views, torch.Tensor):
+        if views.is_contiguous():
+            _transpose(views, 0, tmp, 0, B * V, Cc, H * W, True)
+        else:
+            for b in range(B):
+                for v in range(V):
+                    _transpose(views[b, v], 0, tmp[b, v], 0, 1, Cc, H * W, True)
+    else:
+        for v, f in enumerate(views):
+            _transpose(f, f.stride(0), tmp[:, v], V * H * W * Cc, B, Cc, H * W, True)
+    return tmp.permute(0, 1, 4, 2, 3)
+
+
+def _use_transposed_route(plan: WarpPlan, t: torch.Tensor) -> bool:
+    # only where it pays: the low-res map of a fused up-sample plan is 9x smaller than the tensor the reference materialises, so two
+    # extra passes over it are cheap; a full-resolution NCHW tensor would cost more to transpose than the planar kernels lose
+    return plan.upsampled and t.stride(-3) != 1 and _planes_dense(t) and t.shape[0] > 0
+
+
+# ------------------------------------------------------------------------------------------------------
 # torch.library custom op (forward + registered backward)
 # ------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("mvwarp::warp_views_plan", mutates_args=(), device_types="cuda")
@@ -111,6 +149,8 @@ def _warp_views_plan(img_feats: torch.Tensor, plan_id: int, with_coord: bool, ch
         out = torch.empty((B, Hg, Wg, ctot), dtype=img_feats.dtype, device=img_feats.device).permute(0, 3, 1, 2)
     else:
         out = torch.empty((B, ctot, Hg, Wg), dtype=img_feats.dtype, device=img_feats.device)
+    if _use_transposed_route(plan, img_feats):
+        img_feats = _lowres_to_cl(img_feats, B, V, Cc, Hs, Ws)
     _launch_fwd(plan, img_feats, out, 0, 0, V * Cc if with_coord else -1)
     return out
 
@@ -135,6 +175,11 @@ def _warp_views_plan_bwd(grad_out: torch.Tensor, plan_id: int, C_: int, feats_ch
         grad_feats = torch.empty((B, V, Hs, Ws, C_), dtype=grad_out.dtype, device=grad_out.device).permute(0, 1, 4, 2, 3)
     else:
         grad_feats = torch.empty((B, V, C_, Hs, Ws), dtype=grad_out.dtype, device=grad_out.device)
+        if _use_transposed_route(plan, grad_feats) and B > 0:
+            tmp = torch.empty((B, V, Hs, Ws, C_), dtype=grad_out.dtype, device=grad_out.device)
+            _launch_bwd(plan, grad_out, tmp.permute(0, 1, 4, 2, 3), 0, 0)
+            _transpose(tmp, 0, grad_feats, 0, B * V, C_, Hs * Ws, False)
+            return grad_feats
     _launch_bwd(plan, grad_out, grad_feats, 0, 0)
     return grad_feats
 
@@ -220,7 +265,12 @@ def _warp_views_list(feats: Sequence[torch.Tensor], plan_id: int, with_coord: bo
         out = torch.empty((B, Hg, Wg, ctot), dtype=feats[0].dtype, device=feats[0].device).permute(0, 3, 1, 2)
     else:
         out = torch.empty((B, ctot, Hg, Wg), dtype=feats[0].dtype, device=feats[0].device)
-    _launch_fwd_list(plan, list(feats), out, V * Cc if with_coord else -1)
+    feats = list(feats)
+    if _same_layout(feats) and _use_transposed_route(plan, feats[0]):
+        Hl, Wl = plan.feat_hw
+        _launch_fwd(plan, _lowres_to_cl(feats, B, V, Cc, Hl, Wl), out, 0, 0, V * Cc if with_coord else -1)
+    else:
+        _launch_fwd_list(plan, feats, out, V * Cc if with_coord else -1)
     return out
 
 
@@ -242,6 +292,13 @@ def _warp_views_list_bwd(grad_out: torch.Tensor, plan_id: int, C_: int, feats_ch
         grads = [torch.empty((B, Hs, Ws, C_), dtype=grad_out.dtype, device=grad_out.device).permute(0, 3, 1, 2) for _ in range(plan.V)]
     else:
         grads = [torch.empty((B, C_, Hs, Ws), dtype=grad_out.dtype, device=grad_out.device) for _ in range(plan.V)]
+        if B > 0 and _use_transposed_route(plan, grads[0]):
+            V = plan.V
+            tmp = torch.empty((B, V, Hs, Ws, C_), dtype=grad_out.dtype, device=grad_out.device)
+            _launch_bwd(plan, grad_out, tmp.permute(0, 1, 4, 2, 3), 0, 0)
+            for v in range(V):
+                _transpose(tmp[:, v], V * Hs * Ws * C_, grads[v], 0, B, C_, Hs * Ws, False)
+            return grads
     _launch_bwd_list(plan, grad_out, grads)
     return grads
 

@@ -739,3 +739,46 @@ def test_copy_touched_texels_round_trip(kind, dtype):
         ops.copy_touched_texels(plan, x.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3), d_sparse)   # pageable host memory
     with pytest.raises(ValueError):
         ops.copy_touched_texels(plan, torch.empty((B, V, Cc, *feat_hw), dtype=dtype).pin_memory(), d_sparse)   # not channel-contiguous
+
+
+# ---- NCHW trunks through fused up-sample plans: one transpose of the low-res map, then the channel-contiguous kernels --------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_nchw_lowres_route_equals_channels_last(dtype):
+    """warp_views_upsampled / warp_views_list on NCHW low-res maps (what an unmodified reference trunk emits) give the same bits as
+    on channel-contiguous ones, forward and backward, and the gradient comes back in NCHW; odd sizes exercise the tile edges."""
+    pm, src_hw, grid_hw = small_rig(num_cam=3, seed=81)
+    low = (src_hw[0] // 3, src_hw[1] // 3)                               # 18 x 32
+    B, V, Cc = 2, 3, 40
+    x = _feats(B, V, Cc, low).to(dtype)
+    x_nchw = x.contiguous().to(DEV).requires_grad_(True)
+    x_cl = to_channels_last_5d(x).to(DEV).requires_grad_(True)
+    a = ops.warp_views_upsampled(x_nchw, src_hw, pm, grid_hw)
+    b = ops.warp_views_upsampled(x_cl, src_hw, pm, grid_hw)
+    assert torch.equal(a, b) and a.stride(1) != 1 and b.stride(1) == 1   # out layout follows the input
+    go = torch.randn(a.shape, generator=torch.Generator().manual_seed(9)).to(dtype).to(DEV)
+    (ga,) = torch.autograd.grad(a, x_nchw, go)
+    (gb,) = torch.autograd.grad(b, x_cl, go)
+    assert ga.is_contiguous() and torch.equal(ga, gb)
+    cams = [x[:, v].contiguous().to(DEV).requires_grad_(True) for v in range(V)]
+    c = ops.warp_views_list(cams, pm, grid_hw, upsample_shape=src_hw, channels_last_out=True)
+    assert torch.equal(c, b) and c.stride(1) == 1
+    gl = torch.autograd.grad(c, cams, go)
+    assert all(g.is_contiguous() and torch.equal(g, gb[:, v]) for v, g in enumerate(gl))
+    # non-contiguous batch / view strides take per-image transposes
+    big = torch.zeros(B, V + 1, Cc, *low, dtype=dtype, device=DEV)
+    big[:, :V] = x_nchw.detach()
+    assert torch.equal(ops.warp_views_upsampled(big[:, :V], src_hw, pm, grid_hw), a)
+
+
+def test_layout_transpose_round_trip():
+    from mvdet_b200 import _lib as L
+    import ctypes as C
+    for dtype, code in ((torch.float32, L.F32), (torch.bfloat16, L.BF16)):
+        x = torch.randn(3, 37, 19 * 23, generator=torch.Generator().manual_seed(1)).to(dtype).to(DEV)      # ragged tiles
+        y = torch.empty(3, 19 * 23, 37, dtype=dtype, device=DEV)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L.check(L.load().mvwarp_layout_transpose(C.c_void_p(x.data_ptr()), 0, C.c_void_p(y.data_ptr()), 0, 3, 37, 19 * 23, code, 1, 0, stream), "t")
+        assert torch.equal(y, x.transpose(1, 2).contiguous())
+        z = torch.empty_like(x)
+        L.check(L.load().mvwarp_layout_transpose(C.c_void_p(y.data_ptr()), 0, C.c_void_p(z.data_ptr()), 0, 3, 37, 19 * 23, code, 0, 0, stream), "t")
+        assert torch.equal(z, x)

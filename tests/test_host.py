@@ -77,6 +77,7 @@ def test_every_entry_point_rejects_null_arguments_without_a_gpu():
         "warp_views_fwd_list": lambda: lib.mvwarp_warp_views_fwd_list(None, 0, 1, None, i4, None, i4, 0, -1, 1, 4, 0, None),
         "warp_views_bwd_list": lambda: lib.mvwarp_warp_views_bwd_list(None, 0, 1, None, i4, 0, None, i4, 1, 4, 0, None),
         "relu_bwd_cast": lambda: lib.mvwarp_relu_bwd_cast(None, i4, None, i4, None, i4, None, None, 0, 1, 4, 4, 512, 0, None),
+        "layout_transpose": lambda: lib.mvwarp_layout_transpose(None, 0, None, 0, 1, 4, 4, 0, 1, 0, None),
         "copy_touched_texels": lambda: lib.mvwarp_copy_touched_texels(None, 0, 1, None, i5, None, i5, 1, 4, 0, None),
         "plan_touched": lambda: lib.mvwarp_plan_touched(None, None, None, 0),
         "plan_create": lambda: lib.mvwarp_plan_create(nine, 1, 0, 4, 4, 4, 0, ctypes.byref(h)),
