@@ -503,10 +503,12 @@ def run_ours(args):
             grad_feats = torch.empty((B, V, Hs, Ws, Cc), device=dev, dtype=dtype).permute(0, 1, 4, 2, 3)
     else:
         feats = torch.randn((B, V, Cc, Hs, Ws), device=dev, generator=gen).to(dtype)
-        out = torch.empty((B, ctot, Hg, Wg), device=dev, dtype=dtype)
+        # NCHW trunk + fused up-sample: the op's result (and so the gradient cuDNN hands back) is channels-last memory format
+        mf = torch.channels_last if args.fuse_upsample else torch.contiguous_format
+        out = torch.empty((B, ctot, Hg, Wg), device=dev, dtype=dtype).contiguous(memory_format=mf)
         grad_out = grad_feats = None
         if do_bwd or not args.no_e2e:
-            grad_out = torch.randn((B, ctot, Hg, Wg), device=dev, generator=gen).to(dtype)
+            grad_out = torch.randn((B, ctot, Hg, Wg), device=dev, generator=gen).to(dtype).contiguous(memory_format=mf)
         if do_bwd:
             grad_feats = torch.empty((B, V, Cc, Hs, Ws), device=dev, dtype=dtype)
 

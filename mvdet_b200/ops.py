@@ -398,7 +398,7 @@ def warp_views_list(feats: Sequence[torch.Tensor], proj_mats: torch.Tensor, grid
     else:
         plan = get_plan(proj_mats, feats[0].shape[-2:], grid_shape, feats[0].device)
     if channels_last_out is None:
-        channels_last_out = _is_channels_last_4d(feats[0])
+        channels_last_out = _is_channels_last_4d(feats[0]) or (_same_layout(feats) and _use_transposed_route(plan, feats[0]))
     return _warp_views_list(feats, _register(plan, feats[0]), bool(with_coord_map), bool(channels_last_out))
 
 
@@ -424,7 +424,9 @@ def warp_views_upsampled(img_feats_lowres: torch.Tensor, upsample_shape: Sequenc
         raise ValueError(f"proj_mats has {proj_mats.shape[0]} views, img_feats has {img_feats_lowres.shape[1]}")
     plan = get_plan_upsampled(proj_mats, img_feats_lowres.shape[-2:], upsample_shape, grid_shape, img_feats_lowres.device)
     if channels_last_out is None:
-        channels_last_out = _is_channels_last_5d(img_feats_lowres)
+        # NCHW low-res maps are transposed once and warped by the channel-contiguous kernels, which want a channel-contiguous result
+        # too (same logical tensor, torch.channels_last memory format: cuDNN's convolutions consume it directly)
+        channels_last_out = _is_channels_last_5d(img_feats_lowres) or _use_transposed_route(plan, img_feats_lowres)
     return _warp_views_plan(img_feats_lowres, _register(plan, img_feats_lowres), bool(with_coord_map), bool(channels_last_out))
 
 

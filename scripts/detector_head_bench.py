@@ -5,7 +5,10 @@ from a synthetic trunk output [B,7,512,90,160].  Four wirings of the same module
   torch      the reference's loop with ATen grid_sample on a precomputed grid + torch.cat (NCHW, fp32)  [no kornia overhead]
   seam2      mvdet_b200.integration.patch_detector(model)                       (channels-last, fp32)
   seam2+up   patch_detector(model, fuse_upsample=True)                           (channels-last, fp32)
+  seam2 nchw+up   patch_detector(model, fuse_upsample=True, channels_last=False): the UNMODIFIED NCHW model; the op transposes the
+                  low-res maps once and returns a channels-last result
   seam2+up bf16   the same under torch.autocast(bfloat16) for the convolutions, features in bf16
+  seam2 conv1 bf16  patch_detector(model, fused_conv1=True) under autocast: fused tcgen05 conv1 forward, backward without cuDNN
 Prints one JSON line.   usage: detector_head_bench.py [B] [iters]"""
 import copy, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -84,10 +87,13 @@ def main():
     out["torch_ms"] = round(timeit(lambda: run(ref, feats_low)), 3)
     x_cl = feats_low.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
     for name, kw, ac in (("seam2", {}, False), ("seam2_fused_upsample", {"fuse_upsample": True}, False),
-                         ("seam2_fused_upsample_bf16", {"fuse_upsample": True}, True)):
+                         ("seam2_nchw_model_fused_upsample", {"fuse_upsample": True, "channels_last": False}, False),
+                         ("seam2_fused_upsample_bf16", {"fuse_upsample": True}, True),
+                         ("seam2_fused_conv1_bf16", {"fused_conv1": True}, True)):
         model = copy.deepcopy(ref)
-        integration.patch_detector(model, channels_last=True, **kw)
-        x = x_cl.bfloat16() if ac else x_cl
+        kw = dict({"channels_last": True}, **kw)
+        integration.patch_detector(model, **kw)
+        x = feats_low if not kw["channels_last"] else (x_cl.bfloat16() if ac else x_cl)
         m = run(model, x, ac)
         out[name + "_ms"] = round(timeit(lambda: run(model, x, ac)), 3)
         out[name + "_map_rel_diff"] = float((m.float() - m_ref).abs().max() / m_ref.abs().max())

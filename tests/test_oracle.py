@@ -152,3 +152,21 @@ def test_kornia_error_conventions():
         K.warp_perspective(torch.zeros(1, 4, 4), torch.eye(3)[None], [4, 4])
     with pytest.raises(ValueError):
         K.warp_perspective(torch.zeros(1, 1, 4, 4), torch.eye(3), [4, 4])
+
+
+def test_create_meshgrid_arithmetic_matches_a_vendored_copy_of_kornia():
+    """The only piece of kornia source that exists in this image: transformers ships a copy of ``kornia.utils.grid.create_meshgrid``
+    ("Copied from kornia library : kornia/kornia/utils/grid.py:26", transformers/models/efficientloftr/modeling_efficientloftr.py).
+    Its 1-D coordinate arithmetic -- ``linspace(0, n-1, n)``, then ``(xs / (n - 1) - 0.5) * 2`` -- is kornia's; the copy builds the 2-D
+    grid with the meshgrid arguments swapped (it returns [1, W, H, (y, x)]), so the comparison is made on the per-axis values, which
+    is where the fp32 rounding the kernels must reproduce (mvwarp_coords.h mesh_coord) lives.  This pins step 4 of SURVEY.md 8c
+    against third-party-held kornia code; the rest of the chain stays pinned by cv2 / scipy / the plain-C restatement only."""
+    mod = pytest.importorskip("transformers.models.efficientloftr.modeling_efficientloftr")
+    for h, w in [(120, 360), (160, 250), (480, 1440), (24, 72), (5, 7), (2, 2)]:
+        theirs = mod.create_meshgrid(h, w, normalized_coordinates=True, dtype=torch.float32)     # [1, W, H, 2], last dim (y, x)
+        ours = K.create_meshgrid(h, w, normalized_coordinates=True)                              # [1, H, W, 2], last dim (x, y)
+        assert theirs.shape == (1, w, h, 2) and ours.shape == (1, h, w, 2)
+        xs_theirs, ys_theirs = theirs[0, :, 0, 1], theirs[0, 0, :, 0]
+        assert torch.equal(ours[0, 0, :, 0], xs_theirs) and torch.equal(ours[0, :, 0, 1], ys_theirs)
+        assert torch.equal(ours[0, :, :, 0], xs_theirs[None, :].expand(h, w))
+        assert torch.equal(ours[0, :, :, 1], ys_theirs[:, None].expand(h, w))
