@@ -13,11 +13,13 @@
 // Replaces: the dense .to('cuda:0') hops of the reference forward (persp_trans_detector.py:63-68) for callers whose
 // features are host-resident; nothing on the device-resident path uses it.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 
 #include "mvwarp_internal.h"
+#include "mvwarp_umma.h"
 
 namespace mvw {
 
@@ -72,6 +74,59 @@ __global__ void __launch_bounds__(COPY_WARPS * 32) copy_touched_kernel(const Cop
   }
 }
 
+#ifdef MVWARP_DEV
+// The same copy on the TMA engine: every THREAD is an independent copier with a ring of NSLOT shared-memory slots -- one bulk
+// async copy global/host -> shared per texel row (completion on the slot's mbarrier), one bulk async copy shared -> global/host
+// back out (bulk group).  No LSU instructions touch the data, the SM only issues descriptors, and the copies are as long as the
+// rows (2 KB), which is what a PCIe link likes.  32 threads x NSLOT rows are in flight per CTA.
+template <int NSLOT>
+__global__ void __launch_bounds__(32) copy_touched_tma_kernel(const CopyParams p) {
+  using namespace umma;
+  extern __shared__ __align__(128) unsigned char tbuf[];
+  __shared__ __align__(8) uint64_t bars[32 * NSLOT];
+  const int t = threadIdx.x, b = blockIdx.y;
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) mbar_init(&bars[t * NSLOT + s], 1);
+  fence_barrier_init();
+  __syncwarp();
+  const uint32_t nthreads = gridDim.x * 32, r0 = blockIdx.x * 32 + t;
+  const uint32_t count = p.nrows > r0 ? (p.nrows - r0 - 1) / nthreads + 1 : 0;
+  const uint32_t bytes = (uint32_t)p.row_bytes;
+  unsigned char* mine = tbuf + (size_t)t * NSLOT * bytes;
+  auto locate = [&](uint32_t i, const char*& s, char*& d) {
+    const uint32_t r = r0 + i * nthreads;
+    int vl = 0;
+    while (r >= p.view_first[vl + 1]) ++vl;
+    const uint32_t id = __ldg(p.touched + p.t0 + r);
+    const int y = id / p.width, x = id - y * p.width;
+    s = p.src + (int64_t)b * p.sB + (int64_t)vl * p.sV + (int64_t)y * p.sH + (int64_t)x * p.sW;
+    d = p.dst + (int64_t)b * p.dB + (int64_t)vl * p.dV + (int64_t)y * p.dH + (int64_t)x * p.dW;
+  };
+  auto load = [&](uint32_t i) {
+    const char* s; char* d;
+    locate(i, s, d);
+    const int slot = i % NSLOT;
+    mbar_expect_tx(&bars[t * NSLOT + slot], bytes);
+    bulk_g2s(mine + (size_t)slot * bytes, s, bytes, &bars[t * NSLOT + slot]);
+  };
+  for (uint32_t i = 0; i < count && i < NSLOT; ++i) load(i);
+  for (uint32_t i = 0; i < count; ++i) {
+    const int slot = i % NSLOT;
+    mbar_wait(&bars[t * NSLOT + slot], (i / NSLOT) & 1);
+    const char* s; char* d;
+    locate(i, s, d);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d), "r"(smem_u32(mine + (size_t)slot * bytes)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (i + NSLOT < count) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store has read the slot: it may be refilled
+      load(i + NSLOT);
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+#endif  // MVWARP_DEV
+
 }  // namespace mvw
 
 using namespace mvw;
@@ -118,6 +173,25 @@ extern "C" int mvwarp_copy_touched_texels(const mvwarp_plan_t* plan, int view0, 
   // ~0.1 MB), few enough that the warp kernels of neighbouring frames keep most of every SM while a copy is in progress.
   const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)p.nrows + COPY_WARPS - 1) / COPY_WARPS, (uint64_t)plan->num_sms * 4);
   dim3 grid(blocks, B), block(COPY_WARPS * 32);
+  // The TMA-engine variant is a development knob: on two boxes of the pool it measured 30.1 vs 26.9 and 30.6 vs 34.3 frames/s end
+  // to end against the LSU kernel below -- the PCIe path of the box, not the copy method, decides (profiles/README.md).
+#ifdef MVWARP_DEV
+  int use_tma = 0, nslot = 2;
+  static const int knob_tma = [] { const char* e = getenv("MVWARP_COPY_TMA"); return e ? atoi(e) : -1; }();   // 0 = LSU kernel, n = CTAs per SM
+  static const int knob_slot = [] { const char* e = getenv("MVWARP_COPY_SLOTS"); return e ? atoi(e) : 0; }();
+  if (knob_tma >= 0) use_tma = knob_tma;
+  if (knob_slot == 4) nslot = 4;
+  if (use_tma && aligned(16) && p.row_bytes <= 2048) {
+    const int smem = 32 * nslot * p.row_bytes;
+    auto kernel = nslot == 4 ? copy_touched_tma_kernel<4> : copy_touched_tma_kernel<2>;
+    cudaError_t ea = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(copy_touched_tma_kernel)");
+    dim3 tgrid((unsigned)std::min<uint64_t>(((uint64_t)p.nrows + 31) / 32, (uint64_t)plan->num_sms * use_tma), B);
+    kernel<<<tgrid, 32, smem, (cudaStream_t)stream>>>(p);
+    const cudaError_t e2 = cudaGetLastError();
+    return e2 == cudaSuccess ? MVWARP_OK : cuda_fail(e2, "copy_touched_texels (TMA) launch");
+  }
+#endif
   if (aligned(16)) copy_touched_kernel<16><<<grid, block, 0, (cudaStream_t)stream>>>(p);
   else if (aligned(4)) copy_touched_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>(p);
   else copy_touched_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>(p);

@@ -42,7 +42,14 @@ struct HostCsr {
   std::vector<uint32_t> heavy_base;  // [V + 1]
   uint64_t nonempty_rows = 0;
   uint32_t max_row = 0;
+  // Staging blocks (forward map of fused up-sample plans only): rows are cut into blocks of STAGE_ROWS consecutive rows (one 8x8
+  // cell tile); per block the DISTINCT columns (low-res texels) it references, ascending, and per entry its index in that list.
+  // The forward kernel brings a block's distinct texel rows into shared memory once (bulk async copies) and blends from there.
+  std::vector<uint32_t> blk_ptr;     // [V * (nblk + 1)] offsets into blk_tex (absolute)
+  std::vector<uint32_t> blk_tex;     // distinct column ids per block
+  std::vector<uint16_t> slot;        // [nnz] slot of every entry within its block's list
 };
+constexpr uint32_t STAGE_ROWS = 64;
 
 struct PlanMaps {
   HostCsr bwd;            // rows = source texels, columns = grid cells (always built)
@@ -72,12 +79,17 @@ struct DevCsr {
   uint32_t* heavy_base_dev = nullptr;
   std::vector<uint32_t> task_base, heavy_base;  // host copies, [V+1]
   uint32_t max_row = 0;                         // longest row (host copy)
+  uint32_t* blk_ptr = nullptr;                  // staging blocks (see HostCsr), or nullptr
+  uint32_t* blk_tex = nullptr;
+  uint16_t* slot = nullptr;
+  uint32_t max_blk_tex = 0;                     // most distinct columns in one block
 };
 
 // Byte offsets of one CSR's arrays inside the plan's single device allocation (also the layout of a saved plan).
 struct CsrLayout {
   uint64_t rows_per_view = 0, max_row = 0;
   uint64_t row_ptr = 0, row_id = 0, entries = 0, view_base = 0, tasks = 0, heavy = 0, heavy_base = 0;
+  uint64_t blk_ptr = 0, blk_tex = 0, slot = 0, n_blk_tex = 0, max_blk_tex = 0;   // staging blocks (n_blk_tex == 0: none)
 };
 struct PlanLayout {
   uint64_t T = 0, grid = 0, coord_x = 0, coord_y = 0;

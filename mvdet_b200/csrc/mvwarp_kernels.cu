@@ -16,6 +16,7 @@
 
 #include "mvwarp_coords.h"
 #include "mvwarp_internal.h"
+#include "mvwarp_umma.h"
 
 namespace mvw {
 
@@ -41,6 +42,10 @@ struct KParams {
   const uint64_t* view_base;
   const Task* tasks;
   const uint32_t* heavy;
+  const uint32_t* blk_ptr;   // staging blocks of the forward map (fused up-sample plans), or nullptr
+  const uint32_t* blk_tex;
+  const uint16_t* slot;
+  int stage_bytes;           // shared-memory staging buffer of fwd_table_stage_kernel
   uint32_t rows_per_view;
   Side gsrc, gdst;
   int Hs, Ws, Hg, Wg;
@@ -806,6 +811,185 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_table_tile_kernel(co
   }
 }
 
+#ifdef MVWARP_DEV
+// ---------------------------------------------------------------------------------------------------
+// forward of fused up-sample plans, STAGED version (channels-last) -- north_star (a): "TMA / shared-memory staging of source
+// tiles that are reused across neighbouring grid cells".
+//
+// An 8x8 cell tile of the ground grid reads 341 low-res taps on average, but only 30 DISTINCT low-res texels (median 21, p99
+// 131; the 3x up-sample makes neighbouring cells share almost all of them).  fwd_table_tile_kernel fetches every tap through
+// L1 (LDG.128, 64 B per data-pipe cycle: the L1 data pipe was 79 % busy and bounded that kernel at 48 % of its HBM roofline).
+// Here the plan lists each block's distinct texels (staging blocks, mvwarp_internal.h); one bulk async copy per texel row
+// (cp.async.bulk, the TMA engine: no LSU wavefronts at all) brings them into shared memory, completion on an mbarrier, and the
+// warps blend from shared memory (LDS.128: 128 B per cycle), same entry order as before -- the same bits.  A block whose rows
+// do not fit the staging buffer is processed in channel slabs; one that does not fit even 512-byte slabs falls back to gathers.
+// NOT the default: measured slower than fwd_table_tile_kernel (see launch_gather_t); kept in the development build as the
+// evidence for that statement (tests/test_gpu_parity.py checks it gives the same bits).
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int UNROLL, int ALIGN>
+__device__ __forceinline__ void stage_cell(const unsigned char* __restrict__ stage, uint32_t slot_bytes, const uint16_t* __restrict__ sslot,
+                                           const float* __restrict__ sw, int n, T* __restrict__ o, int nvec, int lane) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  const unsigned char* sl = stage + lane * 16;
+  T* ol = o + lane * EPV;
+  for (int c0 = 0; c0 < nvec; c0 += 32 * UNROLL) {   // nvec is a multiple of 32 (slabs are multiples of 512 bytes)
+    float acc[UNROLL][EPV];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) acc[u][e] = 0.f;
+    for (int e0 = 0; e0 < n; e0 += 2) {              // n is warp-uniform; two entries in flight
+      const bool two = e0 + 1 < n;
+      const unsigned char* ra = sl + (uint32_t)sslot[e0] * slot_bytes;
+      const unsigned char* rb = sl + (uint32_t)sslot[two ? e0 + 1 : e0] * slot_bytes;
+      const float wa = sw[e0], wb = sw[two ? e0 + 1 : e0];
+      uint4 va[UNROLL], vb[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int c = c0 + 32 * u;
+        const bool ok = c < nvec;
+        va[u] = ok ? *reinterpret_cast<const uint4*>(ra + c * 16) : make_uint4(0, 0, 0, 0);
+        vb[u] = ok ? *reinterpret_cast<const uint4*>(rb + c * 16) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        float f[EPV];
+        VecTraits<T>::unpack(va[u], f);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[u][e] = __fmaf_rn(wa, f[e], acc[u][e]);
+      }
+      if (two) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          float f[EPV];
+          VecTraits<T>::unpack(vb[u], f);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) acc[u][e] = __fmaf_rn(wb, f[e], acc[u][e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int c = c0 + 32 * u;
+      if (c < nvec) stcs16<ALIGN>(ol + c * EPV, VecTraits<T>::pack(acc[u]));
+    }
+  }
+}
+
+template <typename T, int UNROLL, int MINB>
+__global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_table_stage_kernel(const KParams p) {
+  using namespace umma;
+  constexpr int EPV = VecTraits<T>::EPV;
+  extern __shared__ __align__(128) unsigned char stage[];
+  __shared__ uint32_t s_rp[TBL_ROWS + 1];
+  __shared__ uint32_t s_id[TBL_ROWS];
+  __shared__ uint16_t s_slot[TBL_MAX_ENT];
+  __shared__ float s_w[TBL_MAX_ENT];
+  __shared__ __align__(8) uint64_t bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vl = blockIdx.x, v = p.view0 + vl, b = blockIdx.z;   // view fastest: the V slices of a concat row are written together
+  const uint32_t nblk = gridDim.y, blk = blockIdx.y, row0 = blk * TBL_ROWS;
+  const int nrows = min((uint32_t)TBL_ROWS, p.rows_per_view - row0);
+  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (p.rows_per_view + 1) + row0;
+  if (threadIdx.x <= nrows) s_rp[threadIdx.x] = __ldg(rp + threadIdx.x);
+  if (threadIdx.x < nrows) {
+    const uint32_t id = __ldg(p.row_id + (size_t)v * p.rows_per_view + row0 + threadIdx.x);
+    s_id[threadIdx.x] = id;
+    if (p.coord_chan >= 0 && vl == 0) write_coord<T>(p, b, id);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const uint32_t e_begin = s_rp[0], ne = s_rp[nrows] - e_begin;
+  if (ne == 0) {   // no cell of this tile sees the camera: the view's channel slice is all zeros
+    T* __restrict__ gd0 = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.gdst.B + (int64_t)vl * p.gdst.V + p.gdst.chan0;
+    const int nvec = p.C / EPV;
+    for (int i = warp; i < nrows; i += FWD_WARPS) {
+      const uint32_t id = s_id[i];
+      const int yd = id / p.gdst.width, xd = id - yd * p.gdst.width;
+      T* o = gd0 + (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
+      const unsigned oal = (unsigned)(reinterpret_cast<uintptr_t>(o) & 15u);
+      for (int c = lane; c < nvec; c += 32) stcs16_any(o + c * EPV, make_uint4(0, 0, 0, 0), oal);
+    }
+    return;
+  }
+  const uint64_t vbase = __ldg(p.view_base + v);
+  const uint2* __restrict__ en = reinterpret_cast<const uint2*>(p.entries + vbase) + e_begin;
+  const uint16_t* __restrict__ sl = p.slot + vbase + e_begin;
+  for (uint32_t k = threadIdx.x; k < ne; k += blockDim.x) {
+    s_w[k] = __uint_as_float(__ldg(en + k).y);
+    s_slot[k] = __ldg(sl + k);
+  }
+  const uint32_t t0 = __ldg(p.blk_ptr + (size_t)v * (nblk + 1) + blk), nS = __ldg(p.blk_ptr + (size_t)v * (nblk + 1) + blk + 1) - t0;
+  const T* __restrict__ gs = feats_view<const T>(p, p.src, vl, p.gsrc.V) + (int64_t)b * p.gsrc.B + p.gsrc.chan0;
+  T* __restrict__ gd = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.gdst.B + (int64_t)vl * p.gdst.V + p.gdst.chan0;
+  const uint32_t row_bytes = (uint32_t)p.C * sizeof(T);
+  // channel slab: the largest multiple of 512 bytes (one 16-byte vector per lane) per texel row such that all nS rows fit
+  uint32_t slab = row_bytes;
+  if ((uint64_t)nS * row_bytes > (uint32_t)p.stage_bytes) slab = ((uint32_t)p.stage_bytes / nS) / 512u * 512u;
+  __syncthreads();
+  if (slab == 0) {
+    // too many distinct texels even for 512-byte slabs (never on the Wildtrack / MultiviewX rigs with a 96 KB buffer): plain gathers
+    const int nvec = p.C / EPV;
+    for (int i = warp; i < nrows; i += FWD_WARPS) {
+      const uint32_t a = s_rp[i] - e_begin;
+      const int n = (int)(s_rp[i + 1] - s_rp[i]);
+      const uint32_t id = s_id[i];
+      const int yd = id / p.gdst.width, xd = id - yd * p.gdst.width;
+      T* o = gd + (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
+      const unsigned oal = (unsigned)(reinterpret_cast<uintptr_t>(o) & 15u);
+      for (int c = lane; c < nvec; c += 32) {
+        float acc[EPV];
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
+        for (int k = 0; k < n; ++k) {
+          const uint32_t tex = __ldg(p.blk_tex + t0 + s_slot[a + k]);
+          const int cy = tex / p.gsrc.width, cx = tex - cy * p.gsrc.width;
+          float f[EPV];
+          VecTraits<T>::unpack(ldg16(gs + (int64_t)cy * p.gsrc.H + (int64_t)cx * p.gsrc.W + c * EPV), f);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) acc[e] = __fmaf_rn(s_w[a + k], f[e], acc[e]);
+        }
+        stcs16_any(o + c * EPV, VecTraits<T>::pack(acc), oal);
+      }
+    }
+    return;
+  }
+  uint32_t parity = 0;
+  for (uint32_t sb0 = 0; sb0 < row_bytes; sb0 += slab) {
+    const uint32_t cur = min(slab, row_bytes - sb0);
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, nS * cur);
+    fence_proxy_async();     // earlier generic reads of the staging buffer are ordered before the async writes below
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < nS; s += blockDim.x) {
+      const uint32_t tex = __ldg(p.blk_tex + t0 + s);
+      const int cy = tex / p.gsrc.width, cx = tex - cy * p.gsrc.width;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(gs + (int64_t)cy * p.gsrc.H + (int64_t)cx * p.gsrc.W) + sb0;
+      bulk_g2s(stage + (size_t)s * cur, src, cur, &bar);
+    }
+    mbar_wait(&bar, parity);
+    parity ^= 1u;
+    const int nvec = (int)(cur / 16);
+    // round i: the 8 warps take 8 consecutive rows (horizontally adjacent cells of the tile), like fwd_cl_kernel
+    for (int i = warp; i < nrows; i += FWD_WARPS) {
+      const uint32_t a = s_rp[i] - e_begin;
+      const int n = (int)(s_rp[i + 1] - s_rp[i]);
+      const uint32_t id = s_id[i];
+      const int yd = id / p.gdst.width, xd = id - yd * p.gdst.width;
+      T* o = gd + (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W + sb0 / sizeof(T);
+      const unsigned oal = (unsigned)(reinterpret_cast<uintptr_t>(o) & 15u);  // warp-uniform
+      if (oal == 0) stage_cell<T, UNROLL, 16>(stage, cur, s_slot + a, s_w + a, n, o, nvec, lane);
+      else if ((oal & 7u) == 0) stage_cell<T, UNROLL, 8>(stage, cur, s_slot + a, s_w + a, n, o, nvec, lane);
+      else stage_cell<T, UNROLL, 4>(stage, cur, s_slot + a, s_w + a, n, o, nvec, lane);
+    }
+    __syncthreads();
+  }
+}
+
+#endif  // MVWARP_DEV
+
 // CSR gather, arbitrary strides: thread per CSR row (tile-major order), a chunk of GEN_CH channels per thread
 constexpr int GEN_CH = 16;
 template <typename T, bool COORD>
@@ -897,6 +1081,7 @@ static KParams make_params(const LaunchArgs& a) {
 static void set_csr(KParams& p, const DevCsr& c) {
   p.row_ptr = c.row_ptr; p.row_id = c.row_id; p.entries = c.entries; p.view_base = c.view_base;
   p.tasks = c.tasks; p.heavy = c.heavy; p.rows_per_view = c.rows_per_view;
+  p.blk_ptr = c.blk_ptr; p.blk_tex = c.blk_tex; p.slot = c.slot;
 }
 // feature-map side [B, V, C, H, W] and concat side [B, chan0 + vl*C + c, H, W] of a gather
 static Side feats_side(const LaunchArgs& a, int width) {
@@ -907,13 +1092,14 @@ static Side concat_side(const LaunchArgs& a, int width) {
 }
 
 // Tuning knobs exist in the development build only (-DMVWARP_DEV) and are read once; the product library takes the defaults.
-struct WarpKnobs { int fwd = 0, bwd = 0, tbl = 0, nchw = 0; };
+struct WarpKnobs { int fwd = 0, bwd = 0, tbl = 0, nchw = 0, stage_kb = 0; };
 static const WarpKnobs& warp_knobs() {
   static const WarpKnobs k = [] {
     WarpKnobs r;
 #ifdef MVWARP_DEV
     auto get = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
     r.fwd = get("MVWARP_FWD_VARIANT"); r.bwd = get("MVWARP_BWD_VARIANT"); r.tbl = get("MVWARP_TBL_VARIANT"); r.nchw = get("MVWARP_NCHW_VARIANT");
+    r.stage_kb = get("MVWARP_STAGE_KB");
 #endif
     return r;
   }();
@@ -962,6 +1148,32 @@ static int launch_gather_t(const LaunchArgs& a, KParams& p, const DevCsr& csr, b
     if (fullc && dense) KERNEL<T, __VA_ARGS__, true, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev); \
     else KERNEL<T, __VA_ARGS__, false, false><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev);             \
   } while (0)
+#ifdef MVWARP_DEV
+    const bool row16 = ((uint64_t)a.C * sizeof(T)) % 512 == 0;   // a texel row is a whole number of 512-byte lane passes
+    if (FORWARD && csr.blk_ptr && csr.max_row <= 16 && h_hi == h_lo && row16 && warp_knobs().tbl == 3) {
+      // staged forward (MVWARP_TBL_VARIANT=3, development build): distinct texel rows of each cell tile by bulk async copies into
+      // shared memory, blended from there.  Built for VERDICT r01 item 6 and MEASURED SLOWER than the tile kernel below (fp32
+      // Wildtrack 0.28-0.33 ms with a 96 / 64 KB buffer against 0.201 ms): a CTA lives ~25 us in either kernel, bounded by
+      // the drain of its 128 KB of stores and by dependent metadata loads, not by the L1 data pipe; staging adds a serial
+      // copy-and-wait phase and costs occupancy (profiles/README.md).
+      const uint32_t nblk = (csr.rows_per_view + TBL_ROWS - 1) / TBL_ROWS;
+      if (nblk > 65535) { set_error("warp_views_fwd (table): more than 65535 row blocks per view"); return MVWARP_EUNSUPPORTED; }
+      int stage = warp_knobs().stage_kb > 0 ? warp_knobs().stage_kb * 1024 : 64 * 1024;
+      p.stage_bytes = stage;
+      dim3 tgrid(a.nviews, nblk, a.B), tblock(FWD_WARPS * 32);
+      cudaError_t ea = cudaSuccess;
+      auto launch_stage = [&](auto kernel) {
+        ea = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage);
+        // the largest shared-memory carve-out, so that three CTAs fit an SM (made no measurable difference)
+        if (ea == cudaSuccess) ea = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (ea == cudaSuccess) kernel<<<tgrid, tblock, stage, a.stream>>>(p);
+      };
+      // fp32: 4 vectors per lane = a 2 KB texel row in one pass over the entries; bf16: 2 vectors = 1 KB
+      if (sizeof(T) == 4) launch_stage(fwd_table_stage_kernel<T, 4, 2>);
+      else launch_stage(fwd_table_stage_kernel<T, 2, 2>);
+      if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(fwd_table_stage_kernel)");
+    } else
+#endif
     if (FORWARD && sizeof(T) == 4 && csr.max_row <= 16 && h_hi == h_lo && warp_knobs().tbl != 1) {
       // short rows only (always true for fused up-sample plans: <= 16 low-res taps per cell): tile kernel.  fp32 only:
       // measured at the Wildtrack shape, fp32 0.230 -> 0.209 ms against the task kernel, bf16 0.160 -> 0.165 ms (spills)
@@ -974,7 +1186,13 @@ static int launch_gather_t(const LaunchArgs& a, KParams& p, const DevCsr& csr, b
     if (tfull) fwd_table_tile_kernel<T, U, M, true><<<tgrid, tblock, 0, a.stream>>>(p);    \
     else fwd_table_tile_kernel<T, U, M, false><<<tgrid, tblock, 0, a.stream>>>(p);         \
   } while (0)
-      MVW_TBL(2, 4);
+      switch (warp_knobs().tbl) {   // occupancy sweep (development build only)
+        case 4: MVW_TBL(1, 6); break;
+        case 5: MVW_TBL(2, 5); break;
+        case 6: MVW_TBL(1, 8); break;
+        case 7: MVW_TBL(2, 6); break;
+        default: MVW_TBL(2, 4); break;
+      }
 #undef MVW_TBL
     } else if (FORWARD) {
       if (sizeof(T) == 2) MVW_GATHER(fwd_table_cl_kernel, 4);

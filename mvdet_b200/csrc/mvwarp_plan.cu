@@ -215,6 +215,33 @@ static UpsampleAxis upsample_axis(int in, int out) {
   return a;
 }
 
+// Staging blocks of a forward map: distinct columns per block of STAGE_ROWS rows + the slot of every entry (HostCsr).
+static void build_stage_blocks(HostCsr& c, int V) {
+  const size_t R = c.rows_per_view, nblk = (R + STAGE_ROWS - 1) / STAGE_ROWS;
+  c.blk_ptr.assign((size_t)V * (nblk + 1), 0);
+  c.blk_tex.clear();
+  c.slot.assign(c.entries.size(), 0);
+  std::vector<uint32_t> cols;
+  for (int v = 0; v < V; ++v) {
+    const uint32_t* rp = c.row_ptr.data() + (size_t)v * (R + 1);
+    const CsrEntry* en = c.entries.data() + c.view_base[v];
+    uint16_t* sl = c.slot.data() + c.view_base[v];
+    for (size_t b = 0; b < nblk; ++b) {
+      const size_t r0 = b * STAGE_ROWS, r1 = std::min(R, r0 + STAGE_ROWS);
+      const uint32_t k0 = rp[r0], k1 = rp[r1];
+      cols.clear();
+      for (uint32_t k = k0; k < k1; ++k) cols.push_back(en[k].col);
+      std::sort(cols.begin(), cols.end());
+      cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+      c.blk_ptr[(size_t)v * (nblk + 1) + b] = (uint32_t)c.blk_tex.size();
+      for (uint32_t k = k0; k < k1; ++k)
+        sl[k] = (uint16_t)(std::lower_bound(cols.begin(), cols.end(), en[k].col) - cols.begin());
+      c.blk_tex.insert(c.blk_tex.end(), cols.begin(), cols.end());
+    }
+    c.blk_ptr[(size_t)v * (nblk + 1) + nblk] = (uint32_t)c.blk_tex.size();
+  }
+}
+
 void host_build_maps_upsampled(const float* grid, int V, int hl, int wl, int Hs, int Ws, int Hg, int Wg, PlanMaps& maps) {
   const size_t nlow = (size_t)hl * wl, ncell = (size_t)Hg * Wg;
   std::vector<uint32_t> low_of_row, row_of_low, cell_of_row, row_of_cell;
@@ -267,6 +294,7 @@ void host_build_maps_upsampled(const float* grid, int V, int hl, int wl, int Hs,
   });
   csr_assemble(maps.fwd, V, pv_fwd);
   csr_assemble(maps.bwd, V, pv_bwd);
+  build_stage_blocks(maps.fwd, V);
   maps.valid_cells = 0;
   for (int v = 0; v < V; ++v) maps.valid_cells += valid[v];
 }
@@ -319,6 +347,10 @@ static void bind_pointers(mvwarp_plan* p) {
     d.entries = (CsrEntry*)(base + o.entries); d.view_base = (uint64_t*)(base + o.view_base);
     d.tasks = (Task*)(base + o.tasks); d.heavy = (uint32_t*)(base + o.heavy);
     d.heavy_base_dev = (uint32_t*)(base + o.heavy_base);
+    if (o.n_blk_tex) {
+      d.blk_ptr = (uint32_t*)(base + o.blk_ptr); d.blk_tex = (uint32_t*)(base + o.blk_tex); d.slot = (uint16_t*)(base + o.slot);
+      d.max_blk_tex = (uint32_t)o.max_blk_tex;
+    }
   };
   bind(p->bwd, L.bwd);
   bind(p->fwd, L.fwd);
@@ -384,6 +416,16 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int hl,
       o.tasks = carve(c.tasks.size() * sizeof(Task));
       o.heavy = carve(c.heavy.size() * sizeof(uint32_t));
       o.heavy_base = carve(c.heavy_base.size() * sizeof(uint32_t));
+      if (!c.blk_tex.empty()) {
+        o.n_blk_tex = c.blk_tex.size();
+        o.blk_ptr = carve(c.blk_ptr.size() * sizeof(uint32_t));
+        o.blk_tex = carve(c.blk_tex.size() * sizeof(uint32_t));
+        o.slot = carve(c.slot.size() * sizeof(uint16_t));
+        const size_t nb1 = c.blk_ptr.size() / (size_t)V;
+        for (int v = 0; v < V; ++v)
+          for (size_t b = 0; b + 1 < nb1; ++b)
+            o.max_blk_tex = std::max<uint64_t>(o.max_blk_tex, c.blk_ptr[v * nb1 + b + 1] - c.blk_ptr[v * nb1 + b]);
+      }
       return o;
     };
     PlanLayout& L = p->layout;
@@ -432,6 +474,11 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int hl,
       up(d.tasks, c.tasks.data(), c.tasks.size() * sizeof(Task));
       up(d.heavy, c.heavy.data(), c.heavy.size() * sizeof(uint32_t));
       up(d.heavy_base_dev, c.heavy_base.data(), c.heavy_base.size() * sizeof(uint32_t));
+      if (!c.blk_tex.empty()) {
+        up(d.blk_ptr, c.blk_ptr.data(), c.blk_ptr.size() * sizeof(uint32_t));
+        up(d.blk_tex, c.blk_tex.data(), c.blk_tex.size() * sizeof(uint32_t));
+        up(d.slot, c.slot.data(), c.slot.size() * sizeof(uint16_t));
+      }
     };
     e = cudaMemset(p->d_base, 0, p->d_bytes);  // alignment gaps are part of a saved plan's checksum
     if (T) up(p->d_T, T, (size_t)V * 9 * sizeof(float));
@@ -561,7 +608,7 @@ const char kMagic[8] = {'M', 'V', 'W', 'P', 'L', 'A', 'N', '2'};
 
 // Layout / schema hash: any builder change that keeps the constants but changes what the arrays mean must bump PLAN_SCHEMA, so
 // that files cached under $MVWARP_PLAN_DIR by an older build are refused instead of being dereferenced by the gather kernels.
-constexpr uint32_t PLAN_SCHEMA = 2;
+constexpr uint32_t PLAN_SCHEMA = 3;
 constexpr uint32_t plan_schema() {
   return PLAN_SCHEMA * 0x9E3779B1u ^ (uint32_t)(sizeof(mvw::Task) << 24 | sizeof(mvw::CsrEntry) << 16 | sizeof(mvw::PlanLayout));
 }
@@ -734,7 +781,27 @@ int mvwarp_plan_load(const char* path, int device, mvwarp_plan_t** plan_out) {
           if (tasks[t].view != v || tasks[t].nrows == 0 || tasks[t].nrows > TASK_MAX_ROWS || (uint64_t)tasks[t].row0 + tasks[t].nrows > R) return false;
         for (uint32_t i = hb[v]; i < hb[v + 1]; ++i) if (heavy[i] >= R) return false;
       }
-      return hbd[h.V] == hb[h.V];
+      if (hbd[h.V] != hb[h.V]) return false;
+      if (o.n_blk_tex) {   // staging blocks: block lists inside the blob, columns in range, every entry's slot inside its block
+        const uint64_t nblk = (R + STAGE_ROWS - 1) / STAGE_ROWS;
+        if (!inside(o.blk_ptr, (uint64_t)h.V * (nblk + 1) * 4) || !inside(o.blk_tex, o.n_blk_tex * 4) || !inside(o.slot, nnz * 2)) return false;
+        const uint32_t* bp = reinterpret_cast<const uint32_t*>(blob.data() + o.blk_ptr);
+        const uint32_t* bt = reinterpret_cast<const uint32_t*>(blob.data() + o.blk_tex);
+        const uint16_t* sl = reinterpret_cast<const uint16_t*>(blob.data() + o.slot);
+        for (uint64_t i = 0; i < o.n_blk_tex; ++i) if (bt[i] >= n_cols) return false;
+        uint32_t prev = 0;
+        for (int v = 0; v < h.V; ++v) {
+          const uint32_t* r = rp + (uint64_t)v * (R + 1);
+          for (uint64_t b = 0; b < nblk; ++b) {
+            const uint32_t t0 = bp[(uint64_t)v * (nblk + 1) + b], t1 = bp[(uint64_t)v * (nblk + 1) + b + 1];
+            if (t0 < prev || t1 < t0 || t1 > o.n_blk_tex || t1 - t0 > o.max_blk_tex) return false;
+            prev = t0;
+            const uint64_t r0 = b * STAGE_ROWS, r1 = std::min<uint64_t>(R, r0 + STAGE_ROWS);
+            for (uint64_t k = vb[v] + r[r0]; k < vb[v] + r[r1]; ++k) if (sl[k] >= t1 - t0) return false;
+          }
+        }
+      }
+      return true;
     };
     const uint64_t n_cells = (uint64_t)h.Hg * h.Wg, n_src = h.upsampled ? (uint64_t)h.hl * h.wl : (uint64_t)h.Hs * h.Ws;
     {

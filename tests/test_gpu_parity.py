@@ -782,3 +782,109 @@ def test_layout_transpose_round_trip():
         z = torch.empty_like(x)
         L.check(L.load().mvwarp_layout_transpose(C.c_void_p(y.data_ptr()), 0, C.c_void_p(z.data_ptr()), 0, 3, 37, 19 * 23, code, 0, 0, stream), "t")
         assert torch.equal(z, x)
+
+
+@pytest.mark.parametrize("stage_kb", [2, 8, 96])
+def test_staged_upsample_forward_slabs_and_fallback(stage_kb):
+    """fwd_table_stage_kernel (development build, MVWARP_TBL_VARIANT=3: TMA-staged texel rows; measured slower than the default tile
+    kernel and therefore not shipped as the default) with staging buffers of MVWARP_STAGE_KB: 2 KB forces the gather fallback for most
+    blocks, 8 KB forces several channel slabs per block, 96 KB stages whole rows -- every path must give the bits of the default
+    kernel.  Knobs are read once per process, so each setting runs in a child process."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from mvdet_b200.build import build_library
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from mvdet_b200 import ops
+from tests.util import small_rig, to_channels_last_5d
+for dtype in (torch.float32, torch.bfloat16):
+    for V, Cc, seed in ((3, 512, 91), (2, 384, 92)):
+        pm, src_hw, grid_hw = small_rig(num_cam=V, seed=seed)
+        low = (src_hw[0] // 3, src_hw[1] // 3)
+        x = to_channels_last_5d(torch.randn(2, V, Cc, *low, generator=torch.Generator().manual_seed(seed)).to(dtype)).cuda()
+        out = ops.warp_views_upsampled(x, src_hw, pm, grid_hw)
+        torch.save(out.cpu(), sys.argv[1] + f"_{dtype}_{V}.pt")
+print("ok")
+""" % root
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        outs = {}
+        for tag, env_extra in (("default", {}), ("knob", {"MVWARP_LIB": build_library(dev=True), "MVWARP_STAGE_KB": str(stage_kb), "MVWARP_TBL_VARIANT": "3"})):
+            env = dict(os.environ, PYTHONPATH=root, **env_extra)
+            res = subprocess.run([sys.executable, "-c", code, os.path.join(td, tag)], capture_output=True, text=True, env=env, cwd=root, timeout=600)
+            assert res.returncode == 0 and "ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+            outs[tag] = sorted(f for f in os.listdir(td) if f.startswith(tag))
+        assert len(outs["default"]) == len(outs["knob"]) == 4
+        for a, b in zip(outs["default"], outs["knob"]):
+            ta, tb = torch.load(os.path.join(td, a)), torch.load(os.path.join(td, b))
+            assert torch.equal(ta, tb), (stage_kb, a)
+
+
+# ---- memory safety without compute-sanitizer (closed on this pool): canary bands around every written tensor --------------
+@pytest.mark.parametrize("layout", ["cl", "nchw"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_kernels_do_not_write_outside_their_tensors(layout, dtype):
+    """Forward and backward (plain and fused up-sample plans, list variant, touched-texel copy) into tensors carved out of the middle
+    of a larger canary-filled allocation, on ragged shapes (C = 20: vector tails; 54x96 -> 24x72: partial tiles): every byte of the
+    canary bands before and after the tensor must survive, and every element of the tensor itself must have been written."""
+    pm, src_hw, grid_hw = small_rig(num_cam=3, seed=97)
+    low = (src_hw[0] // 3, src_hw[1] // 3)
+    B, V, Cc = 2, 3, 20
+    GUARD = 4096
+
+    def carve(shape5_or_4, cl):
+        """tensor of the logical shape (channels-last physical if cl) in the middle of a canary-filled buffer"""
+        n = 1
+        for s in shape5_or_4:
+            n *= s
+        buf = torch.full((n + 2 * GUARD,), 12345.0, dtype=dtype, device=DEV)
+        core = buf[GUARD:GUARD + n]
+        core.fill_(float("nan"))
+        if len(shape5_or_4) == 5:
+            b, v, c, h, w = shape5_or_4
+            t = core.view(b, v, h, w, c).permute(0, 1, 4, 2, 3) if cl else core.view(b, v, c, h, w)
+        else:
+            b, c, h, w = shape5_or_4
+            t = core.view(b, h, w, c).permute(0, 3, 1, 2) if cl else core.view(b, c, h, w)
+        return buf, t
+
+    def check(buf, t, what):
+        assert bool((buf[:GUARD] == 12345.0).all()) and bool((buf[-GUARD:] == 12345.0).all()), f"{what}: canary band overwritten"
+        assert not bool(t.isnan().any()), f"{what}: part of the tensor was never written"
+
+    cl = layout == "cl"
+    for kind in ("plain", "upsampled"):
+        if kind == "plain":
+            plan, fhw = P.get_plan(pm, src_hw, grid_hw, DEV), src_hw
+        else:
+            plan, fhw = P.get_plan_upsampled(pm, low, src_hw, grid_hw, DEV), low
+        x = _layout(_feats(B, V, Cc, fhw).to(dtype), layout).to(DEV)
+        obuf, out = carve((B, V * Cc + 2, *grid_hw), cl)
+        ops.warp_views_fwd_into(plan, x, out, 0, 0, V * Cc)
+        torch.cuda.synchronize()
+        check(obuf, out, f"{kind} forward")
+        go = torch.randn_like(out)
+        gbuf, gx = carve((B, V, Cc, *fhw), cl)
+        ops.warp_views_bwd_into(plan, go, gx, 0, 0)
+        torch.cuda.synchronize()
+        check(gbuf, gx, f"{kind} backward")
+        # list variant: per-camera gradients, each in its own canary buffer
+        cams = [x[:, v].contiguous(memory_format=torch.channels_last) if cl else x[:, v].contiguous() for v in range(V)]
+        obuf2, out2 = carve((B, V * Cc + 2, *grid_hw), cl)
+        ops._launch_fwd_list(plan, cams, out2, V * Cc)
+        torch.cuda.synchronize()
+        check(obuf2, out2, f"{kind} forward (list)")
+        assert torch.equal(out2, out)
+        pairs = [carve((B, Cc, *fhw), cl) for _ in range(V)]
+        ops._launch_bwd_list(plan, go, [t for _, t in pairs])
+        torch.cuda.synchronize()
+        for v, (bf, t) in enumerate(pairs):
+            check(bf, t, f"{kind} backward (list, view {v})")
+            assert torch.equal(t, gx[:, v])
+        if cl:   # touched-texel copy into a canary-filled destination: only touched rows change, bands survive
+            dbuf, dst = carve((B, V, Cc, *fhw), True)
+            dst.fill_(0)
+            ops.copy_touched_texels(plan, x, dst)
+            torch.cuda.synchronize()
+            check(dbuf, dst, f"{kind} touched copy")
