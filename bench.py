@@ -655,20 +655,38 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("mvwarp_kernels.cu", "mvwarp_coords.h", "mvwarp_internal.h"):
+        with open(os.path.join(ROOT, "mvdet_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def _load_traffic(roofline, extra):
-    """DRAM traffic per launch from the committed ncu capture (profiles/traffic.json), if present."""
+    """DRAM traffic per launch from the committed ncu capture (profiles/traffic.json).  The capture records the hash of the kernel
+    sources it was taken from and the workload's algorithmic bytes: if either differs from this run's, the figure would be stale
+    and `traffic` stays null (with the reason) instead of silently quoting an old measurement."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
         return
     try:
         with open(path) as f:
             traffic = json.load(f)
+        src = kernel_source_hash()
         for r in [roofline] + [v for k, v in extra.items() if k.startswith("roofline_") and "kernel" in v]:
-            key = r["kernel"]
-            # captured at the default workload (Wildtrack, B=1, fp32, channels-last); other workloads report null
-            if key in traffic and traffic[key].get("algorithmic_bytes") == r["algorithmic_bytes"]:
-                r["traffic"] = traffic[key]["dram_bytes"]
-                r["traffic_source"] = "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/" + traffic[key]["report"]
+            t = traffic.get(r["kernel"])
+            if not t:
+                continue
+            if t.get("algorithmic_bytes") != r["algorithmic_bytes"]:
+                r["traffic_source"] = "null: the committed capture is of another workload"
+            elif t.get("kernel_source_sha256") != src:
+                r["traffic_source"] = "null: kernel sources changed since the committed ncu capture (profiles/traffic.json is stale)"
+            else:
+                r["traffic"] = t["dram_bytes"]
+                r["traffic_source"] = ("ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/" + t["report"] +
+                                       ", kernel sources " + src[:12])
     except Exception:
         pass
 

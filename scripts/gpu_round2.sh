@@ -30,6 +30,10 @@ cap() {  # name, kernel regex, skip, count, bench args...
   $CMD "$@" > $O/plain_${TAG}_$name.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:"$rx" -s $skip -c $cnt -f -o $O/${TAG}_prof_$name $CMD "$@" > $O/ncu_$name.log 2>&1
   tail -1 $O/ncu_$name.log
+  # summarise on the box (gpurun_out/ may carry at most 64 MiB back): per-kernel text summary, DRAM bytes into a traffic json;
+  # only the default configuration's report itself travels
+  python scripts/ncu_summary.py $O/${TAG}_prof_$name.ncu-rep --traffic $O/${TAG}_traffic_$name.json > $O/${TAG}_ncu_full_$name.txt 2>> $O/ncu_$name.log
+  [ "$name" = default ] || rm -f $O/${TAG}_prof_$name.ncu-rep
 }
 cap default 'fwd_|bwd_' 6 2
 cap bf16_b8 'fwd_|bwd_' 6 2 --dtype bf16 --batch 8
@@ -38,4 +42,6 @@ cap upsample 'fwd_|bwd_' 6 2 --fuse-upsample
 cap upsample_nchw 'fwd_|bwd_|transpose' 12 4 --fuse-upsample --layout nchw
 TS="python scripts/train_step_bench.py 1 2"
 $TS > $O/plain_${TAG}_train.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'warp_conv1|conv3x3_tc2|relu_bwd|conv1_tail' -s 12 -c 10 -f -o $O/${TAG}_prof_train $TS > $O/ncu_train.log 2>&1
+python scripts/ncu_summary.py $O/${TAG}_prof_train.ncu-rep > $O/${TAG}_ncu_full_train.txt 2>> $O/ncu_train.log; rm -f $O/${TAG}_prof_train.ncu-rep
+du -sh $O
 tail -3 $O/${TAG}_pytest.log; cat $O/${TAG}_rc.txt

@@ -17,7 +17,10 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_static',
         'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__warps_eligible.avg.per_cycle_active', 'sm__cycles_active.avg', 'sm__cycles_active.max', 'sm__cycles_active.min',
-        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts.sum', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
+        'smsp__inst_executed_pipe_tensor.sum', 'sm__inst_executed_pipe_tma.sum']
 for r in rows[2:]:
     print("=" * 100)
     print(r[idx['Kernel Name']], " grid", r[idx.get('Grid Size', 0)], "block", r[idx.get('Block Size', 0)])
@@ -50,6 +53,11 @@ if "--traffic" in sys.argv:
         wr = to_bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
         acc.setdefault(short, []).append(rd + wr)
     prev = json.load(open(out)) if os.path.exists(out) else {}
+    import hashlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha256()
+    for f in ("mvwarp_kernels.cu", "mvwarp_coords.h", "mvwarp_internal.h"):
+        h.update(open(os.path.join(root, "mvdet_b200", "csrc", f), "rb").read())
     for k, v in acc.items():
-        prev[k] = {"dram_bytes": sum(v) / len(v), "launches": len(v), "report": os.path.basename(rep)}
+        prev[k] = {"dram_bytes": sum(v) / len(v), "launches": len(v), "report": os.path.basename(rep), "kernel_source_sha256": h.hexdigest()}
     json.dump(prev, open(out, "w"), indent=1)
