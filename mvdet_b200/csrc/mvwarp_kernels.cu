@@ -426,6 +426,162 @@ __global__ void __launch_bounds__(NCHW_TW * NCHW_TH) fwd_nchw_kernel(const KPara
   }
 }
 
+#ifdef MVWARP_DEV
+// ---------------------------------------------------------------------------------------------------
+// forward, x-contiguous planes, STAGED (development build, MVWARP_NCHW_VARIANT=2; NOT the default: measured 0.94 ms against
+// 0.41 ms for fwd_nchw_kernel at the Wildtrack shape -- built for VERDICT r01 item 4, kept as the evidence; same bits).
+//
+// fwd_nchw_kernel pays one 4-byte gather per tap, channel and cell, and a warp's 32 taps of one kind lie on a slanted line of
+// the source plane: 4.8 L1 wavefronts per warp-level gather, the L1 data pipe bounds it at 40 % of the HBM roofline.  Here a CTA
+// owns a 32 x 8 cell tile; its taps' source footprint is a slanted quadrilateral, covered exactly by one x-range per source row
+// (found with shared-memory atomicMin/Max over the tile's taps).  For NSG_CH channels at a time the ranges are brought into
+// shared memory with coalesced row-segment loads, then every thread blends its cell's four taps out of shared memory (same
+// weights, same FMA order: the same bits) and the warp stores 32 consecutive cells of one output row -- one coalesced 128-byte
+// store.  Tiles whose footprint does not fit (cells near the camera sample sparsely: thousands of texels for 256 cells) take the
+// direct-gather path inside the same kernel.
+// ---------------------------------------------------------------------------------------------------
+constexpr int NSG_TW = 32, NSG_TH = 8, NSG_ROWS = 96, NSG_CH = 16;
+
+template <typename T, bool kInline>
+__global__ void __launch_bounds__(NSG_TW * NSG_TH) fwd_nchw_stage_kernel(const KParams p, int smax, int chunk) {
+  extern __shared__ __align__(16) unsigned char nsg_raw[];
+  T* s_in = reinterpret_cast<T*>(nsg_raw);                      // [NSG_CH][smax]
+  int* s_src = reinterpret_cast<int*>(nsg_raw + (size_t)NSG_CH * smax * sizeof(T));   // [smax] plane offset of every staged texel
+  __shared__ int s_xmin[NSG_ROWS], s_xmax[NSG_ROWS], s_off[NSG_ROWS + 1];
+  __shared__ int s_ymin, s_ymax, s_total;
+  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = tx * NSG_TW + lane, y = ty * NSG_TH + warp;
+  const int vl = blockIdx.y, v = p.view0 + vl;
+  const int nchunk = (p.C + chunk - 1) / chunk;
+  const int b = blockIdx.z / nchunk, c_begin = (blockIdx.z % nchunk) * chunk, c_end = min(p.C, c_begin + chunk);
+  const bool incell = x < p.Wg && y < p.Hg;
+  Taps tp;
+  tp.mask = 0; tp.x0 = tp.y0 = 0; tp.w[0] = tp.w[1] = tp.w[2] = tp.w[3] = 0.f;
+  if (incell) {
+    float Tm[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Tm[i] = kInline ? __ldg(p.T + 9 * v + i) : 0.f;
+    tp = cell_taps<kInline>(p, Tm, v, x, y);
+  }
+  if (threadIdx.x == 0) { s_ymin = 0x7fffffff; s_ymax = -1; }
+  for (int i = threadIdx.x; i < NSG_ROWS; i += blockDim.x) { s_xmin[i] = 0x7fffffff; s_xmax[i] = -1; }
+  __syncthreads();
+  // footprint: source rows touched by any in-range tap of the tile
+  if (tp.mask & 3u) { atomicMin(&s_ymin, tp.y0); atomicMax(&s_ymax, tp.y0); }
+  if (tp.mask & 12u) { atomicMin(&s_ymin, tp.y0 + 1); atomicMax(&s_ymax, tp.y0 + 1); }
+  __syncthreads();
+  const int ymin = s_ymin, nrow = s_ymax - ymin + 1;
+  const bool rows_ok = nrow <= NSG_ROWS;             // nrow <= 0: no tap of the tile is in range
+  if (rows_ok) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (tp.mask >> k & 1) {
+        const int r = tp.y0 + (k >> 1) - ymin, xx = tp.x0 + (k & 1);
+        atomicMin(&s_xmin[r], xx);
+        atomicMax(&s_xmax[r], xx);
+      }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    if (rows_ok)
+      for (int r = 0; r < nrow; ++r) {
+        s_off[r] = tot;
+        if (s_xmax[r] >= s_xmin[r]) tot += s_xmax[r] - s_xmin[r] + 1;
+      }
+    s_total = rows_ok ? tot : 0x7fffffff;
+  }
+  __syncthreads();
+  const int total = s_total;
+  const T* __restrict__ src = feats_view<const T>(p, p.src, vl, p.fV) + (int64_t)b * p.fB;
+  T* __restrict__ o = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (int64_t)y * p.oH + x;
+  if (incell && p.coord_chan >= 0 && vl == 0 && c_begin == 0) {
+    o[(int64_t)p.coord_chan * p.oC] = from_float<T>(__ldg(p.coord_x + x));
+    o[(int64_t)(p.coord_chan + 1) * p.oC] = from_float<T>(__ldg(p.coord_y + y));
+  }
+  T* oc = o + (int64_t)(p.out_chan0 + (int64_t)vl * p.C + c_begin) * p.oC;
+  if (total <= 0) {                                    // nothing in range: zeros (the 0 * w chain of the oracle)
+    if (incell) {
+      const T z = from_float<T>(blend4(0.f, 0.f, 0.f, 0.f, tp.w));
+      for (int c = c_begin; c < c_end; ++c, oc += p.oC) __stcs(oc, z);
+    }
+    return;
+  }
+  if (total > smax) {                                  // sparse footprint: direct gathers (the fwd_nchw_kernel body)
+    if (!incell) return;
+    int64_t off[4];
+    bool on[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      on[k] = tp.mask >> k & 1;
+      off[k] = on[k] ? (int64_t)(tp.y0 + (k >> 1)) * p.fH + (tp.x0 + (k & 1)) : 0;
+    }
+    const T* sc = src + (int64_t)c_begin * p.fC;
+    int c = c_begin;
+    for (; c + 4 <= c_end; c += 4) {                   // 16 independent gathers in flight, as in fwd_nchw_kernel
+      float f[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[u][k] = on[k] ? to_float(__ldg(sc + (int64_t)u * p.fC + off[k])) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) __stcs(oc + (int64_t)u * p.oC, from_float<T>(blend4(f[u][0], f[u][1], f[u][2], f[u][3], tp.w)));
+      sc += 4 * p.fC;
+      oc += 4 * p.oC;
+    }
+    for (; c < c_end; ++c, sc += p.fC, oc += p.oC) {
+      float f[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) f[k] = on[k] ? to_float(__ldg(sc + off[k])) : 0.f;
+      __stcs(oc, from_float<T>(blend4(f[0], f[1], f[2], f[3], tp.w)));
+    }
+    return;
+  }
+  int idx[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = tp.y0 + (k >> 1) - ymin;
+    idx[k] = (tp.mask >> k & 1) ? s_off[r] + (tp.x0 + (k & 1)) - s_xmin[r] : -1;
+  }
+  // plane offset of every staged texel, once per tile: position s_off[r] + i  <->  texel (ymin + r, xmin[r] + i)
+  for (int r = warp; r < nrow; r += NSG_TH) {
+    const int x0 = s_xmin[r], len = s_xmax[r] - x0 + 1, base = (int)((ymin + r) * p.fH) + x0;
+    for (int i = lane; i < len; i += 32) s_src[s_off[r] + i] = base + i;
+  }
+  __syncthreads();
+  for (int c0 = c_begin; c0 < c_end; c0 += NSG_CH) {
+    const int nc = min(NSG_CH, c_end - c0);
+    // stage: thread t brings positions t, t + 256, ... of all NSG_CH planes -- NSG_CH independent loads in flight per position,
+    // consecutive threads read consecutive texels of a row segment
+    const T* plane0 = src + (int64_t)c0 * p.fC;
+    for (int pos = threadIdx.x; pos < total; pos += NSG_TW * NSG_TH) {
+      const int off = s_src[pos];
+      T val[NSG_CH];
+#pragma unroll
+      for (int ch = 0; ch < NSG_CH; ++ch)
+        if (ch < nc) val[ch] = __ldg(plane0 + (int64_t)ch * p.fC + off);
+#pragma unroll
+      for (int ch = 0; ch < NSG_CH; ++ch)
+        if (ch < nc) s_in[(size_t)ch * smax + pos] = val[ch];
+    }
+    __syncthreads();
+    if (incell) {
+      for (int ch = 0; ch < nc; ++ch) {
+        const T* sp = s_in + (size_t)ch * smax;
+        float f[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = idx[k] >= 0 ? to_float(sp[idx[k]]) : 0.f;
+        __stcs(oc, from_float<T>(blend4(f[0], f[1], f[2], f[3], tp.w)));
+        oc += p.oC;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+#endif  // MVWARP_DEV
+
 // ---------------------------------------------------------------------------------------------------
 // CSR gather, channels-last:  dst[row] = sum over the row's entries of  w * src[col]
 //
@@ -990,6 +1146,166 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_table_stage_kernel(c
 
 #endif  // MVWARP_DEV
 
+#ifdef MVWARP_DEV
+// ---------------------------------------------------------------------------------------------------
+// CSR gather, x-contiguous planes, STAGED (development build, MVWARP_NCHW_VARIANT=2; NOT the default: 3.1 ms against 1.1 ms for
+// bwd_generic_kernel at the Wildtrack shape -- the block-wide barriers make every thread of a strip wait for its longest row).
+//
+// bwd_generic_kernel gathers one 4-byte value per entry and channel from the grad_out planes and writes 32-byte pieces of the
+// gradient planes (a warp = four rows of an 8 x 8 texel tile).  Here a CTA owns a STRIP of 256 consecutive CSR rows = four 8 x 8
+// tiles side by side = 32 x 8 texels, thread t <-> texel (x = t % 32, y = t / 32), so a warp stores 32 consecutive texels of one
+// gradient row: one coalesced 128-byte store per channel.  The cells the strip's entries reference form a compact region of the
+// grid; as in fwd_nchw_stage_kernel it is covered by one x-range per grid row, brought into shared memory for NSG_CH channels at
+// a time with coalesced row-segment loads, and every thread runs down its own row's entries (ascending cell: the CSR order, the
+// same summation order as every other backward kernel) with NSG_CH register accumulators fed from shared memory.  Strips near
+// a camera's horizon reference thousands of cells: their footprint is processed in BANDS of grid rows that fit the buffer, the
+// per-thread entry cursor and the accumulators carrying over from band to band.
+// ---------------------------------------------------------------------------------------------------
+constexpr int NSB_ROWS = 256;
+
+constexpr int NSB_SRC_MAX = 4096;   // staged positions of a strip's whole footprint (all bands): 16 KB of offsets
+
+template <typename T, bool COORD>
+__global__ void __launch_bounds__(NSB_ROWS) gather_nchw_stage_kernel(const KParams p, int smax, int chunk, uint32_t regular_rows) {
+  extern __shared__ __align__(16) unsigned char nsb_raw[];
+  T* s_in = reinterpret_cast<T*>(nsb_raw);                      // [NSG_CH][smax]
+  __shared__ int s_src[NSB_SRC_MAX];                            // plane offset of every position of the footprint
+  __shared__ int s_xmin[NSG_ROWS], s_xmax[NSG_ROWS], s_off[NSG_ROWS], s_band[NSG_ROWS + 2], s_bpos[NSG_ROWS + 2];
+  __shared__ int s_ymin, s_ymax, s_nband;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t strip0 = blockIdx.x * NSB_ROWS;
+  // regular strips (four whole 8 x 8 tiles side by side): thread (lane, warp) takes texel (x = lane, y = warp) of the 32 x 8 strip,
+  // i.e. CSR row tile * 64 + y * 8 + x % 8 with tile = lane / 8; ragged ends of the row order keep the identity mapping
+  const uint32_t rl = strip0 + NSB_ROWS <= regular_rows ? (uint32_t)((lane >> 3) * 64 + warp * 8 + (lane & 7)) : threadIdx.x;
+  const uint32_t r = strip0 + rl;
+  const bool valid = r < p.rows_per_view;
+  const int vl = blockIdx.y, v = p.view0 + vl;
+  const int nchunk = (p.C + chunk - 1) / chunk;
+  const int b = blockIdx.z / nchunk, c_begin = (blockIdx.z % nchunk) * chunk, c_end = min(p.C, c_begin + chunk);
+  const uint32_t* __restrict__ rp = p.row_ptr + (size_t)v * (p.rows_per_view + 1);
+  const CsrEntry* __restrict__ en = p.entries + __ldg(p.view_base + v);
+  const uint32_t k0 = valid ? __ldg(rp + r) : 0u, k1 = valid ? __ldg(rp + r + 1) : 0u;
+  const uint32_t id = valid ? __ldg(p.row_id + (size_t)v * p.rows_per_view + r) : 0u;
+  if (COORD && valid && p.coord_chan >= 0 && vl == 0 && c_begin == 0) write_coord<T>(p, b, id);
+  const int yd = id / p.gdst.width, xd = id - yd * p.gdst.width;
+  const int sw = p.gsrc.width;
+  if (threadIdx.x == 0) { s_ymin = 0x7fffffff; s_ymax = -1; }
+  for (int i = threadIdx.x; i < NSG_ROWS; i += blockDim.x) { s_xmin[i] = 0x7fffffff; s_xmax[i] = -1; }
+  __syncthreads();
+  if (k1 > k0) {   // entries of a row are sorted by column: first / last entry bound the row's grid rows
+    atomicMin(&s_ymin, (int)(__ldg(&en[k0].col) / sw));
+    atomicMax(&s_ymax, (int)(__ldg(&en[k1 - 1].col) / sw));
+  }
+  __syncthreads();
+  const int ymin = s_ymin, nrow = s_ymax - ymin + 1;
+  const T* __restrict__ gs = (p.feats_is_src ? feats_view<const T>(p, p.src, vl, p.gsrc.V) : reinterpret_cast<const T*>(p.src) + (int64_t)vl * p.gsrc.V) +
+                             (int64_t)b * p.gsrc.B + p.gsrc.chan0;
+  T* __restrict__ o = (p.feats_is_src ? reinterpret_cast<T*>(p.dst) + (int64_t)vl * p.gdst.V : feats_view<T>(p, p.dst, vl, p.gdst.V)) +
+                      (int64_t)b * p.gdst.B + p.gdst.chan0 + (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
+  if (nrow <= 0) {                                   // the whole strip is untouched: zeros
+    if (valid)
+      for (int c = c_begin; c < c_end; ++c) __stcs(o + (int64_t)c * p.gdst.C, from_float<T>(0.f));
+    return;
+  }
+  const bool rows_ok = nrow <= NSG_ROWS;
+  if (rows_ok) {
+    for (uint32_t k = k0; k < k1; ++k) {
+      const int col = (int)__ldg(&en[k].col), cy = col / sw, cx = col - cy * sw;
+      atomicMin(&s_xmin[cy - ymin], cx);
+      atomicMax(&s_xmax[cy - ymin], cx);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // positions: s_off[q] = first position of grid row q in the footprint; bands = runs of rows whose positions fit the buffer
+    int nb = 0, tot = 0, band_first = 0;
+    bool ok = rows_ok;
+    s_band[0] = 0; s_bpos[0] = 0;
+    for (int q = 0; q < nrow && ok; ++q) {
+      const int len = s_xmax[q] >= s_xmin[q] ? s_xmax[q] - s_xmin[q] + 1 : 0;
+      if (len > smax || tot + len > NSB_SRC_MAX) { ok = false; break; }
+      if (tot + len - band_first > smax) { ++nb; s_band[nb] = q; s_bpos[nb] = tot; band_first = tot; }
+      s_off[q] = tot;
+      tot += len;
+    }
+    ++nb; s_band[nb] = nrow; s_bpos[nb] = tot;
+    s_nband = ok ? nb : -1;
+  }
+  __syncthreads();
+  const int nband = s_nband;
+  if (nband < 0) {
+    // footprint too tall / too wide for the buffers (never on the Wildtrack / MultiviewX rigs): direct gathers, same order
+    if (!valid) return;
+    for (int c0 = c_begin; c0 < c_end; c0 += NSG_CH) {
+      const int nc = min(NSG_CH, c_end - c0);
+      float acc[NSG_CH];
+#pragma unroll
+      for (int i = 0; i < NSG_CH; ++i) acc[i] = 0.f;
+      for (uint32_t k = k0; k < k1; ++k) {
+        const CsrEntry e = en[k];
+        const int cy = e.col / sw, cx = e.col - cy * sw;
+        const T* g = gs + (int64_t)c0 * p.gsrc.C + (int64_t)cy * p.gsrc.H + (int64_t)cx * p.gsrc.W;
+#pragma unroll
+        for (int i = 0; i < NSG_CH; ++i)
+          if (i < nc) acc[i] = __fmaf_rn(e.w, to_float(__ldg(g + (int64_t)i * p.gsrc.C)), acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < NSG_CH; ++i)
+        if (i < nc) __stcs(o + (int64_t)(c0 + i) * p.gdst.C, from_float<T>(acc[i]));
+    }
+    return;
+  }
+  const int total = s_bpos[nband];
+  for (int q = warp; q < nrow; q += NSB_ROWS / 32) {   // plane offset of every position, once per strip
+    const int x0 = s_xmin[q], len = s_xmax[q] - x0 + 1, base = (int)((ymin + q) * p.gsrc.H) + x0 * (int)p.gsrc.W;
+    for (int i = lane; i < len; i += 32) s_src[s_off[q] + i] = base + i * (int)p.gsrc.W;
+  }
+  __syncthreads();
+  for (int c0 = c_begin; c0 < c_end; c0 += NSG_CH) {
+    const int nc = min(NSG_CH, c_end - c0);
+    float acc[NSG_CH];
+#pragma unroll
+    for (int i = 0; i < NSG_CH; ++i) acc[i] = 0.f;
+    uint32_t k = k0;
+    const T* plane0 = gs + (int64_t)c0 * p.gsrc.C;
+    for (int j = 0; j < nband; ++j) {
+      const int p0 = s_bpos[j], p1 = s_bpos[j + 1];
+      // stage the band: NSG_CH independent loads in flight per position, consecutive threads read consecutive cells of a row
+      for (int pos = p0 + (int)threadIdx.x; pos < p1; pos += NSB_ROWS) {
+        const int off = s_src[pos];
+        T val[NSG_CH];
+#pragma unroll
+        for (int ch = 0; ch < NSG_CH; ++ch)
+          if (ch < nc) val[ch] = __ldg(plane0 + (int64_t)ch * p.gsrc.C + off);
+#pragma unroll
+        for (int ch = 0; ch < NSG_CH; ++ch)
+          if (ch < nc) s_in[(size_t)ch * smax + (pos - p0)] = val[ch];
+      }
+      __syncthreads();
+      const uint32_t limit = (uint32_t)(ymin + s_band[j + 1]) * (uint32_t)sw;   // first column of the next band
+      while (k < k1) {
+        const CsrEntry e = en[k];
+        if (e.col >= limit) break;
+        const int cy = e.col / sw, cx = e.col - cy * sw;
+        const T* sp = s_in + (s_off[cy - ymin] + (cx - s_xmin[cy - ymin]) - p0);
+#pragma unroll
+        for (int i = 0; i < NSG_CH; ++i)
+          if (i < nc) acc[i] = __fmaf_rn(e.w, to_float(sp[(size_t)i * smax]), acc[i]);
+        ++k;
+      }
+      __syncthreads();
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < NSG_CH; ++i)
+        if (i < nc) __stcs(o + (int64_t)(c0 + i) * p.gdst.C, from_float<T>(acc[i]));
+    }
+  }
+  (void)total;
+}
+
+#endif  // MVWARP_DEV
+
 // CSR gather, arbitrary strides: thread per CSR row (tile-major order), a chunk of GEN_CH channels per thread
 constexpr int GEN_CH = 16;
 template <typename T, bool COORD>
@@ -1209,6 +1525,28 @@ static int launch_gather_t(const LaunchArgs& a, KParams& p, const DevCsr& csr, b
       }
     }
 #undef MVW_GATHER
+#ifdef MVWARP_DEV
+  } else if (p.gsrc.W == 1 && p.gdst.W == 1 && warp_knobs().nchw == 2) {
+    // x-contiguous planes on both sides (NCHW): strips of 256 rows, the referenced columns staged in shared memory band by band
+    const int chunk = 64, smax = sizeof(T) == 4 ? 768 : 1536;         // 16 channels x smax values = 48 KB of shared memory
+    const int nchunk = (a.C + chunk - 1) / chunk;
+    int rc = check_grid_dims(a, (int64_t)a.B * nchunk);
+    if (rc) return rc;
+    const int dw = p.gdst.width, dh = (int)(csr.rows_per_view / (uint32_t)dw);
+    // rows below this index belong to whole 8 x 8 tiles arranged in strips of four (see the kernel): needs width % 32 == 0
+    const uint32_t regular_rows = dw % 32 == 0 ? (uint32_t)(dh / CSR_TILE * CSR_TILE) * (uint32_t)dw : 0u;
+    dim3 grid((csr.rows_per_view + NSB_ROWS - 1) / NSB_ROWS, a.nviews, a.B * nchunk), block(NSB_ROWS);
+    const int smem = NSG_CH * smax * (int)sizeof(T);
+    cudaError_t ea;
+    if (FORWARD) {
+      ea = cudaFuncSetAttribute(gather_nchw_stage_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (ea == cudaSuccess) gather_nchw_stage_kernel<T, true><<<grid, block, smem, a.stream>>>(p, smax, chunk, regular_rows);
+    } else {
+      ea = cudaFuncSetAttribute(gather_nchw_stage_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (ea == cudaSuccess) gather_nchw_stage_kernel<T, false><<<grid, block, smem, a.stream>>>(p, smax, chunk, regular_rows);
+    }
+    if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(gather_nchw_stage_kernel)");
+#endif
   } else {
     const int nchunk = (a.C + p.cchunk - 1) / p.cchunk;
     int rc = check_grid_dims(a, (int64_t)a.B * nchunk);
@@ -1258,7 +1596,28 @@ static int launch_fwd_t(const LaunchArgs& a) {
       default: MVW_FWD(2, 4, false); break;
     }
 #undef MVW_FWD
-  } else if (a.fs[4] == 1 && a.os[3] == 1 && warp_knobs().nchw == 0) {
+#ifdef MVWARP_DEV
+  } else if (a.fs[4] == 1 && a.os[3] == 1 && warp_knobs().nchw == 2) {
+    // x-contiguous planes (NCHW, the reference's layout): 32 x 8 cell tiles, source footprint staged in shared memory
+    const int chunk = 64, smax = sizeof(T) == 4 ? 1024 : 2048;        // 16 channels x smax texels = 64 KB of shared memory
+    const int nchunk = (a.C + chunk - 1) / chunk;
+    int rc = check_grid_dims(a, (int64_t)a.B * nchunk);
+    if (rc) return rc;
+    p.tiles_x = (p.Wg + NSG_TW - 1) / NSG_TW;
+    p.tiles_y = (p.Hg + NSG_TH - 1) / NSG_TH;
+    dim3 grid(p.tiles_x * p.tiles_y, a.nviews, a.B * nchunk), block(NSG_TW * NSG_TH);
+    const int smem = NSG_CH * smax * (int)sizeof(T) + smax * (int)sizeof(int);
+    cudaError_t ea;
+    if (inl) {
+      ea = cudaFuncSetAttribute(fwd_nchw_stage_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (ea == cudaSuccess) fwd_nchw_stage_kernel<T, true><<<grid, block, smem, a.stream>>>(p, smax, chunk);
+    } else {
+      ea = cudaFuncSetAttribute(fwd_nchw_stage_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (ea == cudaSuccess) fwd_nchw_stage_kernel<T, false><<<grid, block, smem, a.stream>>>(p, smax, chunk);
+    }
+    if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(fwd_nchw_stage_kernel)");
+#endif
+  } else if (a.fs[4] == 1 && a.os[3] == 1 && warp_knobs().nchw != 1) {
     // x-contiguous planes (NCHW, the reference's layout): 2-D cell tiles, 64 channels per thread
     const int nchunk = (a.C + NCHW_CH - 1) / NCHW_CH;
     int rc = check_grid_dims(a, (int64_t)a.B * nchunk);

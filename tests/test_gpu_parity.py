@@ -888,3 +888,48 @@ def test_kernels_do_not_write_outside_their_tensors(layout, dtype):
             ops.copy_touched_texels(plan, x, dst)
             torch.cuda.synchronize()
             check(dbuf, dst, f"{kind} touched copy")
+
+
+def test_staged_nchw_kernels_give_the_default_bits():
+    """fwd_nchw_stage_kernel / gather_nchw_stage_kernel (development build, MVWARP_NCHW_VARIANT=2: source footprint staged in shared
+    memory; measured 2-3x SLOWER than the shipped planar kernels and therefore not the default) must still be correct: same bits as
+    the default kernels on NCHW tensors, forward and backward, plain and fused up-sample plans."""
+    import os, subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from mvdet_b200.build import build_library
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from mvdet_b200 import ops, plan as P
+from tests.util import small_rig
+res = {}
+for dtype in (torch.float32, torch.bfloat16):
+    for V, Cc, seed in ((3, 70, 93), (2, 16, 94)):
+        pm, src_hw, grid_hw = small_rig(num_cam=V, seed=seed)
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(2, V, Cc, *src_hw, generator=g).to(dtype).cuda().requires_grad_(True)
+        out = ops.warp_views(x, pm, grid_hw)
+        go = torch.randn(out.shape, generator=g).to(dtype).cuda()
+        (gx,) = torch.autograd.grad(out, x, go)
+        plan = P.get_plan_upsampled(pm, (src_hw[0] // 3, src_hw[1] // 3), src_hw, grid_hw, "cuda:0")
+        xl = torch.randn(2, V, Cc, src_hw[0] // 3, src_hw[1] // 3, generator=g).to(dtype).cuda()
+        o2 = torch.empty(2, V * Cc + 2, *grid_hw, dtype=dtype, device="cuda")
+        ops.warp_views_fwd_into(plan, xl, o2, 0, 0, V * Cc)           # raw planar launch (no transposing route)
+        g2 = torch.empty_like(xl)
+        ops.warp_views_bwd_into(plan, torch.randn(o2.shape, generator=g).to(dtype).cuda(), g2, 0, 0)
+        res[f"{dtype}_{V}"] = [t.cpu() for t in (out.detach(), gx, o2, g2)]
+torch.save(res, sys.argv[1])
+print("ok")
+""" % root
+    with tempfile.TemporaryDirectory() as td:
+        files = {}
+        for tag, extra in (("default", {}), ("staged", {"MVWARP_LIB": build_library(dev=True), "MVWARP_NCHW_VARIANT": "2"})):
+            files[tag] = os.path.join(td, tag + ".pt")
+            res = subprocess.run([sys.executable, "-c", code, files[tag]], capture_output=True, text=True,
+                                 env=dict(os.environ, PYTHONPATH=root, **extra), cwd=root, timeout=600)
+            assert res.returncode == 0 and "ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+        a, b = torch.load(files["default"]), torch.load(files["staged"])
+        assert a.keys() == b.keys() and len(a) == 4
+        for k in a:
+            for i, (ta, tb) in enumerate(zip(a[k], b[k])):
+                assert torch.equal(ta, tb), (k, i)
