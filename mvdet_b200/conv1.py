@@ -181,6 +181,7 @@ def conv1_wgrad_gemm(plan, feats: torch.Tensor, Xp: torch.Tensor, Gp: torch.Tens
 
 
 _dgrad_cache = {}
+_wpack_cache = {}
 
 
 def _dgrad_packs(weight: torch.Tensor, V: int, Cc: int):
@@ -258,7 +259,13 @@ def warp_conv1_trainable(img_feats: torch.Tensor, weight: torch.Tensor, bias: Op
     and ``bias``: fused tcgen05 forward, unfused backward (cuDNN conv backward + the deterministic CSR warp backward).
     Pass ``wpack`` (from :func:`pack_conv1_weight`) to skip re-packing when the weight has not changed."""
     if wpack is None:
-        wpack = pack_conv1_weight(weight, img_feats.shape[1], img_feats.shape[2])
+        # re-packed only when the weight changed (storage address + version counter): once per optimizer step in training,
+        # never in an evaluation loop
+        key = (weight.data_ptr(), weight._version, weight.device, img_feats.shape[1], img_feats.shape[2])
+        hit = _wpack_cache.get("k")
+        if hit is None or hit[0] != key:
+            _wpack_cache["k"] = (key, pack_conv1_weight(weight, img_feats.shape[1], img_feats.shape[2]))
+        wpack = _wpack_cache["k"][1]
     return _WarpConv1Fn.apply(img_feats, weight, bias, proj_mats, grid_shape, wpack, relu)
 
 
