@@ -241,6 +241,8 @@ def _reduce_my_inbox(inbox: "Conv1Inbox", bias: Optional[torch.Tensor], relu: bo
     rows = y1 - y0
     dev = inbox.buf.device
     band = torch.empty((inbox.B, rows, inbox.Wg, 512), dtype=out_dtype, device=dev)
+    if rows == 0:                      # more ranks than tile rows of the grid: this rank owns no band
+        return band.permute(0, 3, 1, 2)
     bias_ptr = None
     if bias is not None:
         bias = bias.detach().to(device=dev, dtype=torch.float32).contiguous()

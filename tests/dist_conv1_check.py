@@ -20,9 +20,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    # a scaled-down version of BASELINE.json configs[3]: 2 cameras per rank + one extra on rank 0, 54x96 features -> 48x144 grid
+    # a scaled-down version of BASELINE.json configs[3]: 2 cameras per rank + one extra on rank 0, 54x96 features -> 48x144 grid.
+    # With 4 ranks the grid shrinks to 24x72 = 3 tile rows, so that the last rank owns an EMPTY row band (more ranks than tile rows).
     V, Cc, B = 2 * world + 1, 64, 2
-    spec = RigSpec("dist", V, img_shape=(1080, 1920), worldgrid_shape=(480, 1440), img_reduce=20, grid_reduce=10, seed=51)
+    spec = RigSpec("dist", V, img_shape=(1080, 1920), worldgrid_shape=(480, 1440), img_reduce=20, grid_reduce=10 if world <= 2 else 20, seed=51)
     pm = synthetic_rig(spec)
     Hg, Wg = spec.grid_shape
     g = torch.Generator().manual_seed(0)
@@ -51,10 +52,11 @@ def main():
     ref = ref.to(dev)
     dist.broadcast(ref, src=0)
     scale = float(ref.abs().max())
-    errs = {"allreduce": float((full - ref).abs().max()) / scale,
-            "allreduce_banded": float((banded - ref).abs().max()) / scale,
-            "reduce_scatter_p2p": float((band_p2p - ref[:, :, y0:y1]).abs().max()) / scale,
-            "reduce_scatter_ce": float((band_ce - ref[:, :, y0:y1]).abs().max()) / scale}
+    amax = lambda t: float(t.abs().max()) if t.numel() else 0.0          # an empty band has nothing to compare
+    errs = {"allreduce": amax(full - ref) / scale,
+            "allreduce_banded": amax(banded - ref) / scale,
+            "reduce_scatter_p2p": amax(band_p2p - ref[:, :, y0:y1]) / scale,
+            "reduce_scatter_ce": amax(band_ce - ref[:, :, y0:y1]) / scale}
     t = torch.tensor(list(errs.values()) + [0.0 if torch.equal(band_ce, band_ce2) else 1.0], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("world", [2, 4])
 def test_sharded_conv1_exchanges_match_the_unsharded_result(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, this box has {torch.cuda.device_count()}")
