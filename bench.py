@@ -227,7 +227,10 @@ def parallelism_note(args, spec, world):
     how = (f"cameras [{spec.num_cam}r, {spec.num_cam}r+{spec.num_cam}) of one {spec.num_cam * world}-camera ring (work differs per rank)"
            if getattr(args, "distinct_cameras", False) and world > 1 else
            f"ring r of {world} identical {spec.num_cam}-camera rings (the N=1 work on every GPU)")
-    return f"view-sharded: each of {world} ranks warps its own {spec.num_cam} cameras - {how}; no data-path collective"
+    return (f"DATA-PARALLEL REPLICAS of the view-sharded warp: each of {world} ranks warps its own {spec.num_cam} cameras - {how}; the warp "
+            f"needs no data-path collective, so `value` is replica throughput (weak scaling, near 1.0 by construction). The path that "
+            f"COMMUNICATES -- one rig's cameras partitioned across the ranks, conv1 partial sums reduce-scattered over NVLink -- is the "
+            f"`sharded_conv1` key of this line (strong scaling)")
 
 
 def workload_config(args, spec, world):
