@@ -1,15 +1,26 @@
 #!/bin/bash
-# SASS listings of the production kernels (fp32 instantiations the Wildtrack bench launches) -> profiles/
-OUT=${1:-profiles}
+# SASS listings of the production kernels (cuobjdump works without a GPU) -> profiles/${TAG}_sass_*.txt
+#   bash scripts/sass_listing.sh profiles r02
+OUT=${1:-profiles}; TAG=${2:-r02}
 LIB=mvdet_b200/libmvwarp.so
-for k in "fwd_cl_kernelIfLb1ELi2ELi4ELb1ELb0" "bwd_cl_kernelIfLi3ELb1ELb1ELb1" "fwd_generic_kernelIfLb1" "bwd_generic_kernelIf"; do
-  name=$(echo $k | sed 's/If.*//')
-  cuobjdump -sass -fun "$(cuobjdump -elf $LIB | grep -o "_ZN3mvw[0-9]*${k}[A-Za-z0-9_]*" | sort -u | head -1)" $LIB | grep -v "^\s*/\* 0x[0-9a-f]* \*/\s*$" | grep -v "^Fatbin\|^=====\|^arch =\|^code version\|^host =\|^compile_size\|^identifier\|^$" > $OUT/r01_sass_${name}_f32.txt
-  echo "$name: $(grep -c '^\s*/\*[0-9a-f]\{4\}\*/' $OUT/r01_sass_${name}_f32.txt) instructions, LDG.E.128: $(grep -c 'LDG.E.128' $OUT/r01_sass_${name}_f32.txt), STG.*128: $(grep -c 'STG.E.*128' $OUT/r01_sass_${name}_f32.txt), FFMA: $(grep -c FFMA $OUT/r01_sass_${name}_f32.txt), SHFL: $(grep -c SHFL $OUT/r01_sass_${name}_f32.txt)"
-done
-# tensor-core / TMA kernels
-for k in warp_conv1_direct_kernel warp_conv1_pipe_kernelILi1ELb1 conv3x3_tc2_kernel conv3x3_tc_kernelILi1 conv3x3_head_kernelILi2; do
-  name=$(echo $k | sed 's/IL.*//')
-  cuobjdump -sass -fun "$(cuobjdump -elf $LIB | grep -o "_ZN3mvw[0-9]*${k}[A-Za-z0-9_]*" | sort -u | head -1)" $LIB | grep -v "^\s*/\* 0x[0-9a-f]* \*/\s*$" | grep -v "^Fatbin\|^=====\|^arch =\|^code version\|^host =\|^compile_size\|^identifier\|^$" > $OUT/r01_sass_${name}.txt
-  echo "$name: UTCHMMA $(grep -c UTCHMMA $OUT/r01_sass_${name}.txt) (2CTA: $(grep -c "UTCHMMA.2CTA" $OUT/r01_sass_${name}.txt)), UTMALDG $(grep -c UTMALDG $OUT/r01_sass_${name}.txt), UBLKCP $(grep -c UBLKCP $OUT/r01_sass_${name}.txt), LDTM $(grep -c LDTM $OUT/r01_sass_${name}.txt), UTCBAR $(grep -c UTCBAR $OUT/r01_sass_${name}.txt)"
-done
+ELF=$(cuobjdump -elf $LIB)
+dump() {  # mangled-name fragment, output name
+  local sym=$(echo "$ELF" | grep -o "_ZN3mvw[0-9]*$1[A-Za-z0-9_]*" | sort -u | head -1)
+  [ -z "$sym" ] && { echo "$2: kernel not found ($1)"; return; }
+  cuobjdump -sass -fun "$sym" $LIB 2>/dev/null | grep -v "^\s*/\* 0x[0-9a-f]* \*/\s*$" | grep -v "^Fatbin\|^=====\|^arch =\|^code version\|^host =\|^compile_size\|^identifier\|^$" > $OUT/${TAG}_sass_$2.txt
+  local f=$OUT/${TAG}_sass_$2.txt
+  echo "$2: $(grep -c '^\s*/\*[0-9a-f]\{4\}\*/' $f) instr | LDG.E.128 $(grep -c 'LDG.E.128' $f) STG.*128 $(grep -c 'STG.E.*128' $f) FFMA $(grep -c FFMA $f) SHFL $(grep -c SHFL $f) ATOM/RED $(grep -c 'ATOM\|RED\.' $f) | UTCHMMA $(grep -c UTCHMMA $f) (2CTA $(grep -c 'UTCHMMA.2CTA' $f)) UTMALDG $(grep -c UTMALDG $f) UBLKCP $(grep -c UBLKCP $f) LDTM $(grep -c LDTM $f) UTCBAR $(grep -c UTCBAR $f)"
+}
+dump "fwd_cl_kernelIfLb1ELi2ELi4ELb1ELb0" fwd_cl_kernel_f32
+dump "bwd_cl_kernelIfLi3ELb1ELb1ELb1" bwd_cl_kernel_f32
+dump "fwd_cl_kernelI13__nv_bfloat16Lb1ELi2ELi4ELb1ELb0" fwd_cl_kernel_bf16
+dump "bwd_cl_kernelI13__nv_bfloat16Li4ELb1ELb1ELb1" bwd_cl_kernel_bf16
+dump "fwd_nchw_kernelIfLb1" fwd_nchw_kernel_f32
+dump "bwd_generic_kernelIf" bwd_generic_kernel_f32
+dump "fwd_table_tile_kernelIfLi2ELi4ELb1" fwd_table_tile_kernel_f32
+dump "transpose_tiles_kernelIf" transpose_tiles_kernel_f32
+dump "copy_touched_kernelILi16" copy_touched_kernel
+dump "relu_bwd_cast_kernel" relu_bwd_cast_kernel
+dump "warp_conv1_direct_kernel" warp_conv1_direct_kernel
+dump "conv3x3_tc2_kernel" conv3x3_tc2_kernel
+dump "conv3x3_head_kernelILi2" conv3x3_head_kernel
