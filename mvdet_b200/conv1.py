@@ -193,6 +193,14 @@ def _dgrad_packs(weight: torch.Tensor, V: int, Cc: int):
     return _dgrad_cache["k"][1]
 
 
+def clear_caches() -> None:
+    """Drop the training path's cached buffers: the zero-bordered ``Xp`` / ``Gp`` (2.9 GB at the Wildtrack shape with B=8), the packed
+    forward weight and the packed data-gradient weights.  They are rebuilt on the next call."""
+    _pad_cache.clear()
+    _dgrad_cache.clear()
+    _wpack_cache.clear()
+
+
 class _WarpConv1Fn(torch.autograd.Function):
     """Training wrapper: fused tcgen05 forward.  Backward, no cuDNN anywhere:
     * ``mvwarp_relu_bwd_cast``: ReLU mask + bf16 rounding + bias gradient in one pass, written into the zero-bordered buffer ``Gp``;

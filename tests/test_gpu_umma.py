@@ -514,3 +514,33 @@ def test_patch_detector_fused_head_follows_weight_updates():
     with torch.no_grad():
         doubled, _ = model(imgs)
     assert rel_errors(doubled, 2 * after)[1] <= 1e-3
+
+
+def test_conv1_training_backward_at_the_wildtrack_shape(monkeypatch):
+    """The cuDNN-free backward of warp_conv1_trainable (fused ReLU/bf16/bias kernel, data gradient on the TMA tcgen05 convolution, weight
+    gradient as batched GEMMs on shifted views) at the benchmark's own size -- V=7, C=512, 270x480 -> 120x360, B=1 -- against
+    aten.convolution_backward (cuDNN) fed the same bf16 operands: same four rounding points, so only summation order differs."""
+    from mvdet_b200 import conv1
+    from tests.util import to_channels_last_5d, rel_errors
+    spec, pm, x, weight, bias = _wildtrack_conv1_case(1, seed=3)
+    xd = to_channels_last_5d(x).cuda().requires_grad_(True)
+    wd = weight.cuda().requires_grad_(True)
+    bd = bias.cuda().requires_grad_(True)
+    go = torch.randn(1, *spec.grid_shape, 512, generator=torch.Generator().manual_seed(5)).permute(0, 3, 1, 2).cuda()
+    wpack = conv1.pack_conv1_weight(wd, spec.num_cam, 512)
+
+    def grads():
+        out = conv1.warp_conv1_trainable(xd, wd, bd, pm, spec.grid_shape, wpack=wpack)
+        return [g.float() for g in torch.autograd.grad(out, [xd, wd, bd], go)]
+
+    gx, gw, gb = grads()                                              # own kernels + GEMMs
+    monkeypatch.setenv("MVWARP_CUDNN_DGRAD", "1")
+    monkeypatch.setenv("MVWARP_CUDNN_WGRAD", "1")
+    rx, rw, rb = grads()                                              # cuDNN for both convolution gradients
+    assert rel_errors(gx, rx)[1] <= 3e-3, rel_errors(gx, rx)          # both round the input gradient to bf16 after different sums
+    assert rel_errors(gw, rw)[1] <= 3e-3, rel_errors(gw, rw)          # GEMM path: fp32 out; cuDNN: bf16 out (2^-9 per element)
+    assert rel_errors(gb, rb)[1] <= 1e-6, rel_errors(gb, rb)
+    monkeypatch.delenv("MVWARP_CUDNN_DGRAD"); monkeypatch.delenv("MVWARP_CUDNN_WGRAD")
+    gx2, gw2, gb2 = grads()
+    assert torch.equal(gx, gx2) and torch.equal(gb, gb2)              # deterministic where we own the kernels
+    conv1.clear_caches()
