@@ -402,3 +402,74 @@ def test_plan_table_holds_no_strong_references():
     import weakref
     from mvdet_b200 import ops
     assert isinstance(ops._plans_by_id, weakref.WeakValueDictionary)
+
+
+def test_weight_gradient_as_gemms_on_shifted_views_is_the_convolution_weight_gradient():
+    """The identity conv1_wgrad_gemm rests on, checked on the CPU in fp32: with X in the interior of a zero-bordered
+    buffer Xp[B,H+2,W+2,P] and g in the top-left corner of an equally bordered Gp, tap (ky,kx) is the constant shift ky*(W+2)+kx of the
+    flattened position index, so gW[:,:,ky,kx] = Gp[:K].T @ Xp[shift:shift+K] -- including the overlapping batched view used for kx."""
+    import torch.nn.functional as F
+    g0 = torch.Generator().manual_seed(0)
+    B, Cin, Cout, H, W = 2, 5, 4, 6, 9
+    X = torch.randn(B, Cin, H, W, generator=g0)
+    g = torch.randn(B, Cout, H, W, generator=g0)
+    ref = torch.nn.grad.conv2d_weight(X, (Cout, Cin, 3, 3), g, padding=1)
+    P_ = 8
+    Xp = torch.zeros(B, H + 2, W + 2, P_)
+    Xp[:, 1:H + 1, 1:W + 1, :Cin] = X.permute(0, 2, 3, 1)
+    Gp = torch.zeros(B, H + 2, W + 2, Cout)
+    Gp[:, :H, :W] = g.permute(0, 2, 3, 1)
+    Xf, Gf = Xp.view(-1, P_), Gp.view(-1, Cout)
+    K = Xf.shape[0] - (2 * (W + 2) + 2)
+    Gt = Gf[:K].t()
+    rows = []
+    for ky in range(3):
+        Xk = torch.as_strided(Xf, (3, K, P_), (P_, P_, 1), Xf.storage_offset() + ky * (W + 2) * P_)   # the three kx taps: one bmm
+        rows.append(torch.bmm(Gt.unsqueeze(0).expand(3, Cout, K), Xk))
+    gw = torch.stack(rows).view(3, 3, Cout, P_)[..., :Cin].permute(2, 3, 0, 1)
+    assert torch.allclose(gw, ref, rtol=1e-5, atol=1e-5)
+    assert float(torch.stack(rows).view(3, 3, Cout, P_)[..., Cin:].abs().max()) == 0.0     # pad channels stay zero
+
+
+def test_data_gradient_weights_are_the_transposed_flipped_convolution():
+    """pack_conv1_dgrad_weight: the gradient w.r.t. view v's warped channels is conv3x3(g, W'_v, padding=1) with
+    W'_v[c,n,ky,kx] = W[n, v*C+c, 2-ky, 2-kx] -- checked against torch's conv2d_input on the CPU through unpack_conv1_weight."""
+    import torch.nn.functional as F
+    from mvdet_b200 import conv1
+    g0 = torch.Generator().manual_seed(1)
+    V, Cc, H, W = 2, 512, 5, 7
+    weight = (torch.randn(512, V * Cc + 2, 3, 3, generator=g0) * 0.05).bfloat16().float()
+    g = torch.randn(1, 512, H, W, generator=g0)
+    ref = torch.nn.grad.conv2d_input((1, V * Cc + 2, H, W), weight, g, padding=1)
+    packs = conv1.pack_conv1_dgrad_weight(weight, V, Cc)
+    assert len(packs) == V
+    for v, wp in enumerate(packs):
+        wt = conv1.unpack_conv1_weight(wp, 1, 512, with_coord=False).float()        # [c, n, 3, 3]
+        got = F.conv2d(g, wt, None, padding=1)
+        assert torch.allclose(got, ref[:, v * Cc:(v + 1) * Cc], rtol=1e-4, atol=1e-4)
+    with pytest.raises(ValueError):
+        conv1.pack_conv1_dgrad_weight(torch.randn(512, 2 * 64 + 2, 3, 3), 2, 64)   # the tcgen05 convolution has 512 outputs per view
+
+
+def test_row_bands_with_more_ranks_than_tile_rows():
+    from mvdet_b200 import sharding as S
+    assert S.row_bands(24, 4) == [0, 8, 16, 24, 24]           # 3 tile rows over 4 ranks: the last rank owns an empty band
+    assert S.row_bands(20, 2) == [0, 16, 20]
+    e = S.row_bands(480, 8)
+    assert e[0] == 0 and e[-1] == 480 and all(b >= a and a % 8 == 0 for a, b in zip(e[:-1], e[1:]))
+
+
+def test_new_ops_refuse_cpu_tensors_and_bad_arguments_without_a_gpu():
+    """warp_views_list / copy_touched_texels: CUDA only, kornia-style argument errors first -- all checkable on a box with no GPU."""
+    import mvdet_b200 as mv
+    from mvdet_b200 import ops
+    pm, src_hw, grid_hw = small_rig(num_cam=2, seed=3)
+    cams = [torch.zeros(1, 4, *src_hw) for _ in range(2)]
+    with pytest.raises(mv.MvwarpError):
+        ops.warp_views_list(cams, pm, grid_hw)                 # CPU tensors: no fallback
+    with pytest.raises(ValueError):
+        ops.warp_views_list([], pm, grid_hw)
+    with pytest.raises(TypeError):
+        ops.warp_views_list(["x", cams[0]], pm, grid_hw)
+    assert _lib.load().mvwarp_layout_transpose(None, 0, None, 0, 1, 4, 4, 0, 1, 0, None) == _lib.EINVAL
+    assert _lib.load().mvwarp_relu_bwd_scratch_floats(0, 0) == 0
