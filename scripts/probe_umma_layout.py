@@ -4,7 +4,7 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mvdet_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_dev()
 g = torch.Generator().manual_seed(0)
 M, K = 128, 128
 A = torch.randn(M, K, generator=g).bfloat16().cuda()

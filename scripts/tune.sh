@@ -1,4 +1,6 @@
 #!/bin/bash
+# Tuning knobs (MVWARP_*) exist in the development build only: exports MVWARP_LIB=mvdet_b200/libmvwarp_dev.so (python -m mvdet_b200.build --dev)
+export MVWARP_LIB=${MVWARP_LIB:-$PWD/mvdet_b200/libmvwarp_dev.so}
 # development: sweep kernel tuning variants on one GPU; prints kernel times per variant
 B="python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline"
 for bv in ${BWD_VARIANTS:-0}; do

@@ -1,4 +1,6 @@
 #!/bin/bash
+# Tuning knobs (MVWARP_*) exist in the development build only: exports MVWARP_LIB=mvdet_b200/libmvwarp_dev.so (python -m mvdet_b200.build --dev)
+export MVWARP_LIB=${MVWARP_LIB:-$PWD/mvdet_b200/libmvwarp_dev.so}
 B="python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline"
 for cfg in "16 15" "24 23" "32 31" "40 39" "48 47" "20 19" "28 27"; do
   set -- $cfg
