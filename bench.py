@@ -659,11 +659,13 @@ def run_ours(args):
 
 
 def kernel_source_hash():
-    import hashlib
+    """sha256 of the warp kernels' sources AS THE PRODUCT LIBRARY COMPILES THEM: `#ifdef MVWARP_DEV ... #endif` blocks (tuning knobs,
+    experimental kernels of the development build) are cut out first, so experiments there do not invalidate a capture."""
+    import hashlib, re
     h = hashlib.sha256()
     for f in ("mvwarp_kernels.cu", "mvwarp_coords.h", "mvwarp_internal.h"):
-        with open(os.path.join(ROOT, "mvdet_b200", "csrc", f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(ROOT, "mvdet_b200", "csrc", f)) as fh:
+            h.update(re.sub(r"#ifdef MVWARP_DEV.*?#endif[^\n]*\n", "", fh.read(), flags=re.S).encode())
     return h.hexdigest()
 
 

@@ -55,9 +55,9 @@ if "--traffic" in sys.argv:
     prev = json.load(open(out)) if os.path.exists(out) else {}
     import hashlib
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    h = hashlib.sha256()
+    h = hashlib.sha256()   # same rule as bench.py kernel_source_hash(): development-only blocks do not count
     for f in ("mvwarp_kernels.cu", "mvwarp_coords.h", "mvwarp_internal.h"):
-        h.update(open(os.path.join(root, "mvdet_b200", "csrc", f), "rb").read())
+        h.update(re.sub(r"#ifdef MVWARP_DEV.*?#endif[^\n]*\n", "", open(os.path.join(root, "mvdet_b200", "csrc", f)).read(), flags=re.S).encode())
     for k, v in acc.items():
         prev[k] = {"dram_bytes": sum(v) / len(v), "launches": len(v), "report": os.path.basename(rep), "kernel_source_sha256": h.hexdigest()}
     json.dump(prev, open(out, "w"), indent=1)
