@@ -15,12 +15,11 @@ namespace mvw {
 // src: [N][R][S] (S contiguous)  ->  dst: [N][S][R] (R contiguous).  NCHW -> NHWC: R = C, S = H*W.  NHWC -> NCHW: R = H*W, S = C.
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_tiles_kernel(const T* __restrict__ src, T* __restrict__ dst, int R, int S,
-                                                              int64_t src_n, int64_t dst_n, const uint64_t* __restrict__ src_ptrs,
-                                                              const uint64_t* __restrict__ dst_ptrs) {
+                                                              int64_t src_n, int64_t dst_n) {
   __shared__ T tile[32][33];
   const int n = blockIdx.z;
-  const T* s = src_ptrs ? reinterpret_cast<const T*>(src_ptrs[n]) : src + (int64_t)n * src_n;
-  T* d = dst_ptrs ? reinterpret_cast<T*>(dst_ptrs[n]) : dst + (int64_t)n * dst_n;
+  const T* s = src + (int64_t)n * src_n;
+  T* d = dst + (int64_t)n * dst_n;
   const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
@@ -55,10 +54,9 @@ extern "C" int mvwarp_layout_transpose(const void* src, int64_t src_image_stride
   const int64_t sn = src_image_stride > 0 ? src_image_stride : per, dn = dst_image_stride > 0 ? dst_image_stride : per;
   if (sn < per || dn < per) { set_error("layout_transpose: image stride smaller than an image"); return MVWARP_EINVAL; }
   if (dtype == MVWARP_F32)
-    transpose_tiles_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, R, S, sn, dn, nullptr, nullptr);
+    transpose_tiles_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, R, S, sn, dn);
   else
-    transpose_tiles_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, R, S, sn, dn,
-                                                                                   nullptr, nullptr);
+    transpose_tiles_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, R, S, sn, dn);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "layout_transpose launch");
 }
