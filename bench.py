@@ -324,6 +324,26 @@ def run_conv1_fused(args, spec, pm, dev, rank, world, dist):
            "peak_bf16_tflops": {"sustained": sustained, "burst": burst, "source": src},
            "vs_cudnn_ms": tc["median"], "speedup_vs_cudnn_unfused": tc["median"] / t["median"],
            "frames_per_s": B / (t["median"] * 1e-3), "dtype": "bf16 operands, fp32 accumulate"}
+    # persp_trans_detector.py:65 fused in as well: the kernel reads the trunk's LOW-RES map (1/3 resolution) and composes up-sample
+    # and warp per halo cell; beside it the two-step path it replaces (bf16 F.interpolate of all views, then the fused kernel)
+    if Hs % 3 == 0 and Ws % 3 == 0:
+        del feats
+        low = torch.randn((B, V, Hs // 3, Ws // 3, Cc), device=dev, generator=gen).to(torch.bfloat16).permute(0, 1, 4, 2, 3)
+
+        def two_step():
+            up = F.interpolate(low.flatten(0, 1), (Hs, Ws), mode="bilinear").unflatten(0, (B, V))
+            return conv1.warp_conv1(up, pm, (Hg, Wg), wpack, bias, relu=True)
+        with torch.no_grad():
+            tu = _event_times(lambda: conv1.warp_conv1(low, pm, (Hg, Wg), wpack, bias, relu=True, upsample_shape=(Hs, Ws)), steps, 3, sync)
+            t2 = _event_times(two_step, steps, 3, sync)
+            a, b2 = conv1.warp_conv1(low, pm, (Hg, Wg), wpack, bias, relu=True, upsample_shape=(Hs, Ws)), two_step()
+            diff = float((a - b2).norm() / b2.norm())
+        res["upsample_fused"] = {
+            "workload": f"relu(conv3x3(warp_views(F.interpolate(low {Hs // 3}x{Ws // 3} -> {Hs}x{Ws}, bilinear))) + bias): low-res map in, "
+                        "up-sample + warp composed per halo cell into a 3x3 low-res window (warp_conv1_direct_kernel<UPS>)",
+            "ms_median": tu["median"], "ms_min": tu["min"], "tflops": flops / (tu["median"] * 1e-3) / 1e12,
+            "two_step_ms_median": t2["median"], "speedup_vs_two_step": t2["median"] / tu["median"],
+            "l2_rel_diff_vs_two_step": diff, "frames_per_s": B / (tu["median"] * 1e-3)}
     if world > 1:
         x = torch.tensor([res["ms_median"]], device=dev, dtype=torch.float64)
         dist.all_reduce(x, op=dist.ReduceOp.MAX)

@@ -89,6 +89,14 @@ int mvwarp_host_csr_upsampled(const float* grid_host, int V, int hl, int wl, int
                               mvwarp_stats_t* stats_out, uint32_t* tex_of_out, uint32_t* row_ptr_out, uint32_t* cells_out,
                               float* weights_out, uint64_t capacity);
 
+/* The composed 3 x 3 low-res windows the fused warp -> conv1 kernel uses on fused up-sample plans (mvwarp_warp_conv1_fwd_ex with a
+ * plan from mvwarp_plan_create_upsampled), computed on the host by the kernel's own source (csrc/mvwarp_uptaps.h):
+ *   warp(up-sample(low))[v, cell] = sum_{j,i<3, bit j*3+i of mask set} wy[j] * wx[i] * low[v][oy + j][ox + i].
+ * T [V,9] as for mvwarp_host_grid; origin_out [V*Hg*Wg][2] = (ox, oy); mask_out [V*Hg*Wg]; wx_out, wy_out [V*Hg*Wg][3].
+ * Needs hl <= Hs and wl <= Ws (an up-sample).  Test / introspection entry point: no GPU needed. */
+int mvwarp_host_upsample_windows(const float* T, int V, int hl, int wl, int Hs, int Ws, int Hg, int Wg, int32_t* origin_out,
+                                 uint32_t* mask_out, float* wx_out, float* wy_out);
+
 /* ---- plan: everything that depends only on the camera rig ---------------------------------------
  * Built once per (proj_mats, shapes, device); holds the per-view matrices (or grid table) and the
  * inverse CSR map used by the deterministic backward.

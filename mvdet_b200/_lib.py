@@ -40,6 +40,8 @@ SIGNATURES = {
                                   _U32P, _U32P, _U32P, _F32P, C.c_uint64]),
     "mvwarp_host_csr_upsampled": (C.c_int, [_F32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(Stats), _U32P, _U32P, _U32P, _F32P, C.c_uint64]),
+    "mvwarp_host_upsample_windows": (C.c_int, [_F32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(C.c_int32), _U32P, _F32P, _F32P]),
     "mvwarp_plan_create_upsampled": (C.c_int, [_F32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.c_int, C.POINTER(_P)]),
     "mvwarp_plan_create": (C.c_int, [_F32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libmvwarp.so")
 DEV_LIB_PATH = os.path.join(PKG_DIR, "libmvwarp_dev.so")
 OBJ_DIR = os.path.join(PKG_DIR, "csrc", "_obj")
 SOURCES = ["mvwarp_plan.cu", "mvwarp_kernels.cu", "mvwarp_conv1.cu", "mvwarp_conv2.cu", "mvwarp_conv1_bwd.cu", "mvwarp_host_io.cu", "mvwarp_layout.cu"]
-HEADERS = ["mvwarp_coords.h", "mvwarp_internal.h", "mvwarp_umma.h", os.path.join("..", "..", "include", "mvwarp.h")]
+HEADERS = ["mvwarp_coords.h", "mvwarp_internal.h", "mvwarp_umma.h", "mvwarp_uptaps.h", os.path.join("..", "..", "include", "mvwarp.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from .plan import get_plan
+from .plan import get_plan, get_plan_upsampled
 
 KB = 64          # channels per K block
 N_OUT = 512
@@ -211,22 +211,27 @@ class _WarpConv1Fn(torch.autograd.Function):
     ``MVWARP_CUDNN_DGRAD=1`` / ``MVWARP_CUDNN_WGRAD=1`` switch either gradient back to ``aten.convolution_backward`` (comparison runs)."""
 
     @staticmethod
-    def forward(ctx, img_feats, weight, bias, proj_mats, grid_shape, wpack, relu):
-        out = warp_conv1(img_feats, proj_mats, grid_shape, wpack, bias, relu=relu)
+    def forward(ctx, img_feats, weight, bias, proj_mats, grid_shape, wpack, relu, upsample_shape=None):
+        out = warp_conv1(img_feats, proj_mats, grid_shape, wpack, bias, relu=relu, upsample_shape=upsample_shape)
         ctx.save_for_backward(img_feats, weight, bias if bias is not None else torch.empty(0), out if relu else torch.empty(0))
         ctx.proj_mats, ctx.grid_shape, ctx.relu, ctx.has_bias = proj_mats, tuple(int(g) for g in grid_shape), relu, bias is not None
+        ctx.upsample_shape = None if upsample_shape is None else tuple(int(u) for u in upsample_shape)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         from . import ops
         from .map_head import conv3x3_cl
-        from .plan import get_plan
         img_feats, weight, bias, out = ctx.saved_tensors
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
         feats = img_feats.detach()
         B, V, Cc, Hs, Ws = feats.shape
-        plan = get_plan(ctx.proj_mats, (Hs, Ws), ctx.grid_shape, feats.device)
+        # fused up-sample: the SAME backward over the composed plan -- the re-materialised warp reads the low-res map through the
+        # composed forward CSR, and the CSR warp backward writes the low-res gradient directly (no F.interpolate backward)
+        if ctx.upsample_shape is not None:
+            plan = get_plan_upsampled(ctx.proj_mats, (Hs, Ws), ctx.upsample_shape, ctx.grid_shape, feats.device)
+        else:
+            plan = get_plan(ctx.proj_mats, (Hs, Ws), ctx.grid_shape, feats.device)
         Hg, Wg = plan.grid_hw
         ctot = V * Cc + 2
         Xp, Gp = _padded_buffers(feats.device, B, Hg, Wg, (ctot + 7) // 8 * 8)
@@ -258,14 +263,18 @@ class _WarpConv1Fn(torch.autograd.Function):
             g_feats = torch.empty((B, V, Hs, Ws, Cc), dtype=feats.dtype, device=feats.device).permute(0, 1, 4, 2, 3)
             ops.warp_views_bwd_into(plan, gx, g_feats)        # deterministic CSR gather; the two coord channels of gx get no gradient
         g_w = gw.to(weight.dtype) if need_w else None
-        return g_feats, g_w, (g_b.to(bias.dtype) if need_b else None), None, None, None, None
+        return g_feats, g_w, (g_b.to(bias.dtype) if need_b else None), None, None, None, None, None
 
 
 def warp_conv1_trainable(img_feats: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], proj_mats: torch.Tensor,
-                         grid_shape: Sequence[int], wpack: Optional[torch.Tensor] = None, relu: bool = True) -> torch.Tensor:
+                         grid_shape: Sequence[int], wpack: Optional[torch.Tensor] = None, relu: bool = True,
+                         upsample_shape: Optional[Sequence[int]] = None) -> torch.Tensor:
     """``relu(map_classifier[0](warp_views(img_feats)))`` with gradients for ``img_feats``, ``weight`` [512, V*C+2, 3, 3]
-    and ``bias``: fused tcgen05 forward, unfused backward (cuDNN conv backward + the deterministic CSR warp backward).
-    Pass ``wpack`` (from :func:`pack_conv1_weight`) to skip re-packing when the weight has not changed."""
+    and ``bias``: fused tcgen05 forward; backward = ReLU-mask / bias-gradient kernel, data gradient on the TMA tcgen05 convolution,
+    weight gradient as GEMMs on shifted views, deterministic CSR warp backward (see :class:`_WarpConv1Fn`).
+    Pass ``wpack`` (from :func:`pack_conv1_weight`) to skip re-packing when the weight has not changed.  With ``upsample_shape``
+    ``img_feats`` is the trunk's low-res output and ``F.interpolate`` (persp_trans_detector.py:65) is fused into forward and
+    backward alike (see :func:`warp_conv1`): the gradient comes back at low resolution."""
     if wpack is None:
         # re-packed only when the weight changed (storage address + version counter): once per optimizer step in training,
         # never in an evaluation loop
@@ -274,14 +283,21 @@ def warp_conv1_trainable(img_feats: torch.Tensor, weight: torch.Tensor, bias: Op
         if hit is None or hit[0] != key:
             _wpack_cache["k"] = (key, pack_conv1_weight(weight, img_feats.shape[1], img_feats.shape[2]))
         wpack = _wpack_cache["k"][1]
-    return _WarpConv1Fn.apply(img_feats, weight, bias, proj_mats, grid_shape, wpack, relu)
+    return _WarpConv1Fn.apply(img_feats, weight, bias, proj_mats, grid_shape, wpack, relu, upsample_shape)
 
 
 def warp_conv1(img_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Sequence[int], wpack: torch.Tensor,
                bias: Optional[torch.Tensor] = None, relu: bool = True, with_coord: bool = True,
                out: Optional[torch.Tensor] = None, rows: Optional[Sequence[int]] = None,
-               out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+               out_dtype: torch.dtype = torch.float32, upsample_shape: Optional[Sequence[int]] = None) -> torch.Tensor:
     """relu(conv3x3(warp_views(img_feats, proj_mats, grid_shape), W) + bias) as one fused kernel (forward only).
+
+    ``upsample_shape`` (the reference's ``upsample_shape``, persp_trans_detector.py:41): ``img_feats`` is then the trunk's LOW-RES
+    output and the kernel computes ``conv(warp_views(F.interpolate(img_feats, upsample_shape, mode='bilinear')))`` -- line 65 of
+    the reference fused in as well: the producers compose up-sample and warp per halo cell into one 3 x 3 low-res window
+    (csrc/mvwarp_uptaps.h), so the 512-channel up-sampled tensor never exists.  ``proj_mats`` stay the reference's matrices (built
+    for the up-sampled map).  The blend runs in fp32 from the bf16 low-res values: one bf16 rounding (of the blended value) where
+    the two-step path rounds twice.
 
     img_feats [B,V,C,H,W] bf16 CUDA, channel-contiguous; wpack from :func:`pack_conv1_weight`; bias fp32 [512] or None.
     Returns [B,512,Hg,Wg] (channels-last) in ``out_dtype``: fp32, or bf16 to feed :func:`mvdet_b200.map_head.conv3x3_cl`
@@ -296,7 +312,12 @@ def warp_conv1(img_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Seq
     nblocks = V * (Cc // KB) * 9 + (1 if with_coord else 0)
     if wpack.dtype != torch.bfloat16 or tuple(wpack.shape) != (nblocks, N_OUT, KB) or not wpack.is_contiguous():
         raise ValueError(f"wpack must be a contiguous bf16 [{nblocks}, 512, 64] tensor from pack_conv1_weight")
-    plan = get_plan(proj_mats, (Hs, Ws), grid_shape, img_feats.device)
+    if upsample_shape is not None:
+        if Hs > int(upsample_shape[0]) or Ws > int(upsample_shape[1]):
+            raise ValueError(f"upsample_shape {tuple(upsample_shape)} is smaller than the feature map {(Hs, Ws)}")
+        plan = get_plan_upsampled(proj_mats, (Hs, Ws), upsample_shape, grid_shape, img_feats.device)
+    else:
+        plan = get_plan(proj_mats, (Hs, Ws), grid_shape, img_feats.device)
     Hg, Wg = plan.grid_hw
     if out_dtype not in (torch.float32, torch.bfloat16):
         raise ValueError("warp_conv1 writes fp32 or bf16")

@@ -148,6 +148,7 @@ extern "C" int mvwarp_debug_gemm_layout(const void* A, const void* B, void* D, i
 // (view, channel block, tap), and arrives by one bulk async copy (TMA engine) per block.
 // =====================================================================================================
 #include "mvwarp_coords.h"
+#include "mvwarp_uptaps.h"
 
 namespace mvw {
 
@@ -160,6 +161,8 @@ struct ConvParams {
   const float* coord_x;
   const float* coord_y;
   int Hs, Ws, Hg, Wg, view0, nviews, C, B;
+  int hl, wl;                  // fused up-sample plans (direct kernel, UPS): feats is the LOW-RES map [hl][wl]; (Hs, Ws) is the size it is
+                               // up-sampled to before the warp (persp_trans_detector.py:65).  0, 0: feats is the map the warp reads
   const __nv_bfloat16* feats;
   int64_t fB, fV, fH, fW;
   const __nv_bfloat16* wpack;  // [nviews * C/64 * 9 (+1 coord block)][512][64] bf16, rows pre-swizzled
@@ -738,6 +741,15 @@ constexpr int NPATCH = 3, DPB = 4;                                             /
 constexpr int D_SBO = DP_Y * 128;                                              // 1280 bytes between the 8-row groups of a tap
 constexpr int DP_TASKS = DP_CELLS * 8, DP_ROUNDS = (DP_TASKS + NPROD - 1) / NPROD;
 
+// UPS (fused up-sample plans): the warp reads F.interpolate(low-res, (Hs, Ws), bilinear, align_corners=False) -- which is never
+// materialised.  Both steps are bilinear and separable: a high-res tap column X is the two low-res columns (i0, i1) with weights
+// (l0, l1) (ATen upsample_bilinear2d: mvwarp_plan.cu upsample_axis, the same fp32 formulas), two neighbouring high-res columns
+// fall into a window of at most THREE low-res columns when the map is up-sampled (scale <= 1), and the out-of-range mask of
+// grid_sample's zero padding is a product of an x flag and a y flag.  So a halo cell is a 3 x 3 low-res window with weights
+// wy[j] * wx[i]: 32 bytes per cell like ConvTap, nine (masked) 16-byte gathers per task instead of four.
+static_assert(sizeof(ConvTapUp) == sizeof(ConvTap), "both tap records share the shared-memory budget");
+
+template <bool UPS>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sPatch = smem;                                        // NPATCH x 23 KB
@@ -856,6 +868,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
     }
   } else {
     // ===== producers (256 threads), then epilogue =====
+    auto publish = [&](uint64_t* bar) {   // all of this warp's writes -> async proxy, then one arrival per warp
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    if constexpr (!UPS) {
     auto compute_taps = [&](int vl, ConvTap* dst) {   // patch cell i = (px = i / 10, py = i % 10) <-> grid cell (tx0 + px - 1, ty0 + py - 1)
       const int v = p.view0 + vl;
       for (int i = tid; i < DP_CELLS; i += NPROD) {
@@ -914,11 +932,6 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
         }
       }
     };
-    auto publish = [&](uint64_t* bar) {   // all of this warp's writes -> async proxy, then one arrival per warp
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar);
-    };
 
     if (npatch > 0) {
       compute_taps(vlo, sT + (vlo & 1) * DP_CELLS);
@@ -940,6 +953,94 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
         }
         issue_gathers(nvl, ncbi, sT + (nvl & 1) * DP_CELLS);
       }
+    }
+    } else {
+    // ----- UPS: the patch is warp(up-sample(low-res)) composed per halo cell into a 3 x 3 low-res window (ConvTapUp) -----
+    static_assert(DP_ROUNDS == 6, "the round schedule below is written out for six rounds");
+    ConvTapUp* sU = reinterpret_cast<ConvTapUp*>(sT);
+    const float scx = upsample_scale(p.wl, p.Ws), scy = upsample_scale(p.hl, p.Hs);
+    auto compute_taps_up = [&](int vl, ConvTapUp* dst) {
+      const int v = p.view0 + vl;
+      for (int i = tid; i < DP_CELLS; i += NPROD) {
+        const int gx = tx0 + i / DP_Y - 1, gy = ty0 + i % DP_Y - 1;
+        ConvTapUp t;
+        t.mask = 0; t.xy = 0;
+        t.wx[0] = t.wx[1] = t.wx[2] = t.wy[0] = t.wy[1] = t.wy[2] = 0.f;
+        if (gy >= 0 && gy < p.Hg && gx >= 0 && gx < p.Wg) {
+          float Tm[9];
+#pragma unroll
+          for (int q = 0; q < 9; ++q) Tm[q] = __ldg(p.T + 9 * v + q);
+          float sx, sy;
+          norm_src_coord(Tm, gx, gy, p.Hg, p.Wg, sx, sy);
+          t = compose_cell(sx, sy, p.Hs, p.Ws, p.hl, p.wl, scx, scy);
+        }
+        dst[i] = t;
+      }
+    };
+    // round j of a patch: task = tid + j * 256 -> (halo cell, 16-byte channel chunk); nine masked gathers, then the blend
+    auto issue = [&](uint4 (&g)[9], int vl, int cb, int j, const ConvTapUp* taps) {
+      const int task = tid + j * NPROD;
+      if (task < DP_TASKS) {
+        const int cell = task >> 3, ch = task & 7;
+        const ConvTapUp t = taps[cell];
+        const __nv_bfloat16* f0 = p.feats + (int64_t)b * p.fB + (int64_t)vl * p.fV + cb * CV_KB + ch * 8 +
+                                  (int64_t)(t.xy >> 16) * p.fH + (int64_t)(t.xy & 0xffff) * p.fW;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+          g[k] = (t.mask >> k & 1) ? __ldg(reinterpret_cast<const uint4*>(f0 + (int64_t)(k / 3) * p.fH + (int64_t)(k % 3) * p.fW))
+                                   : make_uint4(0, 0, 0, 0);
+      }
+    };
+    auto blend = [&](const uint4 (&g)[9], int j, const ConvTapUp* taps, uint8_t* patch) {
+      const int task = tid + j * NPROD;
+      if (task < DP_TASKS) {
+        const int cell = task >> 3, ch = task & 7;
+        const ConvTapUp t = taps[cell];
+        float lo[4] = {0.f, 0.f, 0.f, 0.f}, hi[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {     // ascending low-res texel; a dead slot holds zeros and a zero weight
+          const float wk = __fmul_rn(t.wy[k / 3], t.wx[k % 3]);
+          const unsigned* q = &g[k].x;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            lo[c] = __fmaf_rn(bf_lo(q[c]), wk, lo[c]);
+            hi[c] = __fmaf_rn(bf_hi(q[c]), wk, hi[c]);
+          }
+        }
+        *reinterpret_cast<uint4*>(patch + cell * 128 + ((ch ^ (cell & 7)) << 4)) =
+            t.mask ? make_uint4(pack_bf2(lo[0], hi[0]), pack_bf2(lo[1], hi[1]), pack_bf2(lo[2], hi[2]), pack_bf2(lo[3], hi[3]))
+                   : make_uint4(0, 0, 0, 0);
+      }
+    };
+    uint4 g0[9], g1[9];   // two rounds of gathers in flight: the low-res map is L2-resident (103 MB bf16 on Wildtrack) and a patch's
+                          // 180 cells share ~60 texel rows, so two rounds cover the latency; nine K blocks of MMA hide the rest
+    if (npatch > 0) {
+      compute_taps_up(vlo, sU + (vlo & 1) * DP_CELLS);
+      producers_sync();
+      issue(g0, vlo, 0, 0, sU + (vlo & 1) * DP_CELLS);
+    }
+    for (int pk = 0; pk < npatch; ++pk) {
+      const int blk = vlo * ncb + pk, vl = blk / ncb, cb = blk % ncb;
+      const int i = pk % NPATCH;
+      const ConvTapUp* taps = sU + (vl & 1) * DP_CELLS;
+      uint8_t* patch = sPatch + (size_t)i * DPATCH_BYTES;
+      if (pk >= NPATCH) mbar_wait(&p_empty[i], ((pk / NPATCH) - 1) & 1);   // the nine K blocks that read this buffer are done
+      issue(g1, vl, cb, 1, taps); blend(g0, 0, taps, patch);
+      issue(g0, vl, cb, 2, taps); blend(g1, 1, taps, patch);
+      issue(g1, vl, cb, 3, taps); blend(g0, 2, taps, patch);
+      issue(g0, vl, cb, 4, taps); blend(g1, 3, taps, patch);
+      issue(g1, vl, cb, 5, taps); blend(g0, 4, taps, patch);
+      const bool more = pk + 1 < npatch;
+      const int nvl = (blk + 1) / ncb, ncbi = (blk + 1) % ncb;
+      if (more && ncbi != 0) issue(g0, nvl, ncbi, 0, taps);               // same view: the next patch's first round flies already
+      blend(g1, 5, taps, patch);
+      publish(&p_full[i]);
+      if (more && ncbi == 0) {            // next patch opens a new view: its taps go to the other buffer (last read one view ago,
+        compute_taps_up(nvl, sU + (nvl & 1) * DP_CELLS);   // and every thread has passed this view's barrier since)
+        producers_sync();
+        issue(g0, nvl, 0, 0, sU + (nvl & 1) * DP_CELLS);
+      }
+    }
     }
     if (coord_here) {  // the two coord_map channels: all 9 taps x 2 channels in one K block (k = tap*2 + ch), canonical layout
       const int m = tid & 127, half = tid >> 7, mx = m / DT_Y, my = m % DT_Y;
@@ -1238,7 +1339,13 @@ int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* f
   if (out_dtype != MVWARP_F32 && out_dtype != MVWARP_BF16) { set_error("warp_conv1_fwd: unknown output dtype"); return MVWARP_EINVAL; }
   if (!plan || !feats || !feat_strides || !wpack || !out || !out_strides) { set_error("warp_conv1_fwd: null argument"); return MVWARP_EINVAL; }
   if (B <= 0 || nviews <= 0 || view0 < 0 || view0 > plan->V || nviews > plan->V - view0) { set_error("warp_conv1_fwd: bad B / view range"); return MVWARP_EINVAL; }
-  if (plan->upsampled || !plan->inline_coords) { set_error("warp_conv1_fwd: needs a plain matrix plan"); return MVWARP_EUNSUPPORTED; }
+  if (!plan->inline_coords) { set_error("warp_conv1_fwd: needs a plan made from matrices (not from a sampling grid)"); return MVWARP_EUNSUPPORTED; }
+  // fused up-sample plans (mvwarp_plan_create_upsampled): `feats` is the low-res map [B,V,C,hl,wl]; the producers compose the two
+  // bilinear steps per halo cell into a 3 x 3 low-res window, which holds for an up-sampling ratio only
+  if (plan->upsampled && (plan->hl > plan->Hs || plan->wl > plan->Ws || plan->hl > 32767 || plan->wl > 32767)) {
+    set_error("warp_conv1_fwd: a fused up-sample plan must up-sample (low-res size <= up-sampled size, below 32768)");
+    return MVWARP_EUNSUPPORTED;
+  }
   if (C <= 0 || C % CV_KB || feat_strides[2] != 1 || (reinterpret_cast<uintptr_t>(feats) & 15u) || feat_strides[0] % 8 ||
       feat_strides[1] % 8 || feat_strides[3] % 8 || feat_strides[4] % 8) {
     set_error("warp_conv1_fwd: feats must be bf16 channels-last with C % 64 == 0 and 16-byte aligned texel rows");
@@ -1255,6 +1362,7 @@ int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* f
   ConvParams p{};
   p.T = plan->d_T; p.coord_x = plan->d_coord_x; p.coord_y = plan->d_coord_y;
   p.Hs = plan->Hs; p.Ws = plan->Ws; p.Hg = plan->Hg; p.Wg = plan->Wg;
+  p.hl = plan->upsampled ? plan->hl : 0; p.wl = plan->upsampled ? plan->wl : 0;
   p.view0 = view0; p.nviews = nviews; p.C = C; p.B = B;
   p.feats = (const __nv_bfloat16*)feats;
   p.fB = feat_strides[0]; p.fV = feat_strides[1]; p.fH = feat_strides[3]; p.fW = feat_strides[4];
@@ -1300,6 +1408,11 @@ int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* f
       if (wrc) { if (prev >= 0 && prev != plan->device) cudaSetDevice(prev); return wrc; }
     }
     p.pair_mode = pmode;
+    if (plan->upsampled && pmode != 2) {
+      if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
+      set_error("warp_conv1_fwd: fused up-sample plans run on the direct kernel only (unset MVWARP_CONV1_PAIR / _VARIANT)");
+      return MVWARP_EUNSUPPORTED;
+    }
     if (p2p.n > 0) {
       if (pmode != 2) {
         if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
@@ -1348,7 +1461,8 @@ int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* f
     }
     if (pmode == 2) {
       const int smem_d = NPATCH * DPATCH_BYTES + 16384 + DPB * (int)CV_B2_BYTES + 2 * DP_CELLS * (int)sizeof(ConvTap) + 1024;
-      e = cudaFuncSetAttribute(warp_conv1_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
+      auto kern = plan->upsampled ? warp_conv1_direct_kernel<true> : warp_conv1_direct_kernel<false>;
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
       if (e == cudaSuccess) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(p.n_full + (p.nitems - p.n_full + 1) / 2 * 2 * p.split, 1, 1);
@@ -1359,7 +1473,7 @@ int conv1_launch(const mvwarp_plan_t* plan, int view0, int nviews, const void* f
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, warp_conv1_direct_kernel, tmap_w, p);
+        e = cudaLaunchKernelEx(&cfg, kern, tmap_w, p);
       }
     }
 #ifdef MVWARP_DEV

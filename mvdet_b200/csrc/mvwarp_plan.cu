@@ -14,6 +14,7 @@
 #include <thread>
 
 #include "mvwarp_coords.h"
+#include "mvwarp_uptaps.h"
 #include "mvwarp_internal.h"
 
 namespace mvw {
@@ -567,6 +568,31 @@ int mvwarp_host_csr_upsampled(const float* grid_host, int V, int hl, int wl, int
     set_error("host_csr: unknown C++ exception");
     return MVWARP_EINVAL;
   }
+}
+
+int mvwarp_host_upsample_windows(const float* T, int V, int hl, int wl, int Hs, int Ws, int Hg, int Wg, int32_t* origin_out,
+                                 uint32_t* mask_out, float* wx_out, float* wy_out) {
+  if (!T || !origin_out || !mask_out || !wx_out || !wy_out) { set_error("host_upsample_windows: null argument"); return MVWARP_EINVAL; }
+  int rc = check_shapes(V, Hs, Ws, Hg, Wg);
+  if (rc) return rc;
+  if (hl <= 0 || wl <= 0 || hl > Hs || wl > Ws || hl > 32767 || wl > 32767) {
+    set_error("host_upsample_windows: the low-res size must be positive, at most the up-sampled size and below 32768");
+    return MVWARP_EINVAL;
+  }
+  // exactly what the fused warp -> conv1 producers compute per halo cell (mvwarp_uptaps.h, shared source)
+  const float scx = upsample_scale(wl, Ws), scy = upsample_scale(hl, Hs);
+  for (int v = 0; v < V; ++v)
+    for (int y = 0; y < Hg; ++y)
+      for (int x = 0; x < Wg; ++x) {
+        float sx, sy;
+        norm_src_coord(T + 9 * v, x, y, Hg, Wg, sx, sy);
+        const ConvTapUp t = compose_cell(sx, sy, Hs, Ws, hl, wl, scx, scy);
+        const size_t i = ((size_t)v * Hg + y) * Wg + x;
+        origin_out[2 * i] = t.xy & 0xffff; origin_out[2 * i + 1] = t.xy >> 16;
+        mask_out[i] = t.mask;
+        for (int k = 0; k < 3; ++k) { wx_out[3 * i + k] = t.wx[k]; wy_out[3 * i + k] = t.wy[k]; }
+      }
+  return MVWARP_OK;
 }
 
 int mvwarp_plan_create(const float* T, int V, int Hs, int Ws, int Hg, int Wg, int device, mvwarp_plan_t** plan_out) {

@@ -116,8 +116,9 @@ def warped_forward(model, imgs: torch.Tensor, visualize: bool = False, warp_fn: 
     (:68-81) by three fused kernels whenever autograd is off: fused warp -> conv1 on tcgen05, dilated conv by TMA, 512 -> 1 head,
     bf16 activations with fp32 accumulation.  With autograd on the un-fused path runs (the fused kernels are forward-only) --
     unless ``fused_conv1`` is set: then ``map_classifier[0]`` + ReLU run as :func:`mvdet_b200.conv1.warp_conv1_trainable` (fused
-    tcgen05 forward on bf16 features; backward = re-materialised warp + cuDNN's convolution backward + the deterministic CSR warp
-    backward; BASELINE.json configs[2]) and the rest of ``map_classifier`` follows in torch."""
+    tcgen05 forward on bf16 features; backward = own ReLU-mask / data-gradient / weight-gradient kernels + the deterministic CSR
+    warp backward, no cuDNN; BASELINE.json configs[2]) and the rest of ``map_classifier`` follows in torch.  With ``fuse_upsample``
+    both fused paths read the low-res features (``upsample_shape=`` of ``warp_conv1``): line 65 disappears for the map branch."""
     if visualize:
         raise NotImplementedError("visualize=True is the reference's matplotlib debugging path; call the original forward for it")
     list_fn = None
@@ -166,7 +167,8 @@ def warped_forward(model, imgs: torch.Tensor, visualize: bool = False, warp_fn: 
         x = img_feats.to(torch.bfloat16)
         if x.stride(2) != 1:                                                                    # NCHW trunk: one transposing copy
             x = x.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
-        map_result = fused_head(x, proj_mats, model.reducedgrid_shape)                          # :68-81
+        up = {"upsample_shape": tuple(model.upsample_shape)} if fuse_upsample else {}            # :65 fused in as well
+        map_result = fused_head(x, proj_mats, model.reducedgrid_shape, **up)                    # :68-81
         return F.interpolate(map_result, model.reducedgrid_shape, mode="bilinear"), imgs_result # :82
     if fused_conv1:
         from .conv1 import warp_conv1_trainable
@@ -174,7 +176,8 @@ def warped_forward(model, imgs: torch.Tensor, visualize: bool = False, warp_fn: 
         if x.stride(2) != 1:
             x = x.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
         conv = model.map_classifier[0]
-        a1 = warp_conv1_trainable(x, conv.weight, conv.bias, proj_mats, model.reducedgrid_shape, relu=True)   # :68-77 + map_classifier[0:2]
+        a1 = warp_conv1_trainable(x, conv.weight, conv.bias, proj_mats, model.reducedgrid_shape, relu=True,
+                                  upsample_shape=tuple(model.upsample_shape) if fuse_upsample else None)   # (:65) :68-77 + map_classifier[0:2]
         map_result = model.map_classifier[2:](a1)                                               # :81, the rest
         return F.interpolate(map_result, model.reducedgrid_shape, mode="bilinear"), imgs_result # :82
     if fuse_upsample:
@@ -196,15 +199,14 @@ def patch_detector(model, channels_last: bool = True, warp_fn: Optional[Callable
     full effect.  ``fuse_upsample``: see :func:`warped_forward`.  ``fused_head=True`` packs ``map_classifier``'s weights into a
     :class:`mvdet_b200.map_head.MapHead` behind a :class:`FusedHeadCache` (stored as ``model.fused_map_head``; it re-packs by itself
     when an optimizer step or ``load_state_dict`` changes the weights) and uses it under ``torch.no_grad()`` -- inference: 1.14 ms per Wildtrack frame for the warp + ``map_classifier`` against 2.01 ms un-fused.
-    It needs the up-sampled features, so it excludes ``fuse_upsample``.  ``fused_conv1=True`` (training; also excludes ``fuse_upsample``)
-    runs ``map_classifier[0]`` + ReLU as the fused warp -> conv1 kernel with gradients, see :func:`warped_forward`.  The original forward stays reachable as
-    ``model.reference_forward``."""
+    ``fused_conv1=True`` (training) runs ``map_classifier[0]`` + ReLU as the fused warp -> conv1 kernel with gradients, see
+    :func:`warped_forward`.  Both combine with ``fuse_upsample``: the fused kernel then reads the trunk's low-res output and composes
+    up-sample and warp per halo cell (``warp_conv1(..., upsample_shape=)``), so no 512-channel ``F.interpolate`` runs at all -- in
+    training neither its backward: the CSR warp backward over the composed plan writes the low-res gradient.  The original forward
+    stays reachable as ``model.reference_forward``."""
     missing = [a for a in _ATTRS if not hasattr(model, a)]
     if missing:
         raise TypeError(f"patch_detector needs a PerspTransDetector-like model; missing attributes: {missing}")
-    if fuse_upsample and (fused_head or fused_conv1):
-        raise ValueError("fused_head / fused_conv1 need the up-sampled features (the fused conv1 kernel warps them itself); "
-                         "they exclude fuse_upsample")
     if fused_conv1:
         mc = model.map_classifier
         ok = (isinstance(mc, torch.nn.Sequential) and len(mc) >= 2 and isinstance(mc[0], torch.nn.Conv2d) and

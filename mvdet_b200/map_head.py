@@ -105,9 +105,12 @@ class MapHead:
         self.b2 = get("2.bias").float().contiguous()
         self.w3 = pack_head_weight(get("4.weight"))
 
-    def __call__(self, img_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Sequence[int]) -> torch.Tensor:
+    def __call__(self, img_feats: torch.Tensor, proj_mats: torch.Tensor, grid_shape: Sequence[int],
+                 upsample_shape: Optional[Sequence[int]] = None) -> torch.Tensor:
         """img_feats [B,V,C,H,W] bf16 channels-last -> map_result fp32 [B,1,Hg,Wg] (before the reference's final
-        same-size F.interpolate, persp_trans_detector.py:82, which is the identity)."""
-        a1 = warp_conv1(img_feats, proj_mats, grid_shape, self.w1, self.b1, relu=True, out_dtype=torch.bfloat16)
+        same-size F.interpolate, persp_trans_detector.py:82, which is the identity).  With ``upsample_shape`` img_feats is the
+        trunk's low-res output and the 512-channel F.interpolate of persp_trans_detector.py:65 is fused into the first kernel."""
+        a1 = warp_conv1(img_feats, proj_mats, grid_shape, self.w1, self.b1, relu=True, out_dtype=torch.bfloat16,
+                        upsample_shape=upsample_shape)
         a2 = conv3x3_cl(a1, self.w2, self.b2, dilation=2, relu=True, out_dtype=torch.bfloat16)
         return conv3x3_head(a2, self.w3, dilation=4)

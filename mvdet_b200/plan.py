@@ -99,6 +99,25 @@ def host_csr(grid: torch.Tensor, src_hw: Sequence[int], with_map: bool = False, 
     return d, tex_of.view(V, nrow), row_ptr.view(V, nrow + 1), cells[:d["nnz"]], weights[:d["nnz"]]
 
 
+def host_upsample_windows(T: torch.Tensor, lowres_hw: Sequence[int], src_hw: Sequence[int], dst_hw: Sequence[int]):
+    """The composed 3 x 3 low-res windows of ``warp(F.interpolate(low, src_hw, bilinear))`` that the fused warp -> conv1 kernel uses
+    on fused up-sample plans, computed on the host by the kernel's own source (``mvwarp_host_upsample_windows``; no GPU needed).
+    ``T`` [V,3,3] from :func:`src_norm_trans_dst_norm`.  Returns ``origin`` int32 [V,Hg,Wg,2] (ox, oy), ``mask`` int64 [V,Hg,Wg]
+    (bit j*3+i: slot live), ``wx``, ``wy`` fp32 [V,Hg,Wg,3]:  ``out[v,y,x] = sum_{j,i} wy[j] * wx[i] * low[v, oy+j, ox+i]``."""
+    lib = _lib.load()
+    T = T.contiguous().float()
+    V, (Hg, Wg) = T.shape[0], (int(dst_hw[0]), int(dst_hw[1]))
+    origin = torch.empty(V, Hg, Wg, 2, dtype=torch.int32)
+    mask = torch.empty(V, Hg, Wg, dtype=torch.int32)
+    wx = torch.empty(V, Hg, Wg, 3, dtype=torch.float32)
+    wy = torch.empty(V, Hg, Wg, 3, dtype=torch.float32)
+    _lib.check(lib.mvwarp_host_upsample_windows(_fptr(T), V, int(lowres_hw[0]), int(lowres_hw[1]), int(src_hw[0]), int(src_hw[1]), Hg, Wg,
+                                                C.cast(origin.data_ptr(), C.POINTER(C.c_int32)),
+                                                C.cast(mask.data_ptr(), C.POINTER(C.c_uint32)), _fptr(wx), _fptr(wy)),
+               "mvwarp_host_upsample_windows")
+    return origin, mask.long() & 0x1ff, wx, wy
+
+
 class WarpPlan:
     """Opaque device-resident plan for one camera rig (wraps mvwarp_plan_t*)."""
 

@@ -360,8 +360,6 @@ def test_patch_detector_fused_head_inference():
     assert all(torch.equal(a, b) for a, b in zip(res_f, res_p))
     plain.square().sum().backward()
     assert model.map_classifier[0].weight.grad is not None and model.base_pt1.weight.grad is not None
-    with pytest.raises(ValueError):
-        integration.patch_detector(Det().cuda(), fused_head=True, fuse_upsample=True)
 
     # fused_conv1: the training path through warp_conv1_trainable agrees with the un-fused autograd path to bf16 rounding
     for p_ in model.parameters():
@@ -544,3 +542,144 @@ def test_conv1_training_backward_at_the_wildtrack_shape(monkeypatch):
     gx2, gw2, gb2 = grads()
     assert torch.equal(gx, gx2) and torch.equal(gb, gb2)              # deterministic where we own the kernels
     conv1.clear_caches()
+
+
+# ---- fused conv1 over fused up-sample plans (VERDICT r01 "missing" #5 / "next" #7): F.interpolate of :65 inside the kernel -------
+def _conv1_upsampled_reference(low_bf16, up_hw, pm, grid_hw, weight, bias, relu, device="cpu"):
+    """conv3x3(bf16(warp_views_oracle(F.interpolate(low, up_hw, bilinear)))) with bf16-rounded weights, fp32 accumulate: the
+    reference's persp_trans_detector.py:65, :68-77 and map_classifier[0] on the bf16 low-res features, ONE rounding of the warped
+    value (the up-sampled tensor stays fp32) -- what the fused kernel computes."""
+    import torch.nn.functional as F
+    from oracle import kornia_warp as K
+    B, V, Cc, hl, wl = low_bf16.shape
+    up = F.interpolate(low_bf16.float().reshape(B * V, Cc, hl, wl), tuple(up_hw), mode="bilinear").reshape(B, V, Cc, *up_hw)
+    X = torch.cat([K.warp_views_oracle(up[b:b + 1], pm, grid_hw) for b in range(B)]).bfloat16().float()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        out = F.conv2d(X.to(device), weight.bfloat16().float().to(device), bias.to(device), padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    return F.relu(out) if relu else out
+
+
+# tolerance of the up-sampled variant: the kernel composes the two bilinear steps into one fp32 blend, the reference blends twice;
+# the fp32 values differ by ~1e-6 relative, which flips the bf16 rounding of about one warped value in a thousand by one bf16 ulp
+# (2^-8): a few 1e-4 of the output's scale after the K-sum.  A wrong or dropped tap shows up at >= 1e-2.
+UP_TOL = (2e-3, 5e-4)
+
+
+@pytest.mark.parametrize("V,Cc,low_hw,grid,B", [(2, 128, (18, 32), (24, 72), 2), (5, 64, (27, 48), (20, 60), 3), (1, 64, (54, 96), (24, 72), 1),
+                                                (3, 64, (20, 37), (24, 72), 1)])
+def test_fused_conv1_upsampled_matches_two_step_reference(V, Cc, low_hw, grid, B):
+    """warp_conv1(upsample_shape=): 3x, 2x, 1:1 and a non-integer ratio; ragged grid + five views (unequal K-split parts) + odd item count."""
+    from mvdet_b200 import conv1
+    from tests.util import small_rig, to_channels_last_5d, rel_errors
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=53, grid=grid)
+    g = torch.Generator().manual_seed(0)
+    low = torch.randn(B, V, Cc, *low_hw, generator=g).bfloat16()
+    weight = torch.randn(512, V * Cc + 2, 3, 3, generator=g) * 0.05
+    bias = torch.randn(512, generator=g)
+    ref = _conv1_upsampled_reference(low, src_hw, pm, grid_hw, weight, bias, relu=True)
+    wpack = conv1.pack_conv1_weight(weight, V, Cc).cuda()
+    xd = to_channels_last_5d(low).cuda()
+    out = conv1.warp_conv1(xd, pm, grid_hw, wpack, bias, relu=True, upsample_shape=src_hw)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape == (B, 512, *grid_hw)
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= UP_TOL[0] and el2 <= UP_TOL[1], (emax, el2)
+    # deterministic; bf16 output = the rounded fp32 output; a band of rows equals the same rows of the whole map
+    assert torch.equal(out, conv1.warp_conv1(xd, pm, grid_hw, wpack, bias, relu=True, upsample_shape=src_hw))
+    out16 = conv1.warp_conv1(xd, pm, grid_hw, wpack, bias, relu=True, upsample_shape=src_hw, out_dtype=torch.bfloat16)
+    assert rel_errors(out16, out)[0] <= 2 ** -8
+    band = torch.zeros_like(out)
+    conv1.warp_conv1(xd, pm, grid_hw, wpack, bias, relu=True, upsample_shape=src_hw, out=band, rows=(8, 16))
+    assert rel_errors(band[:, :, 8:16], out[:, :, 8:16])[0] <= 1e-5 and float(band[:, :, :8].abs().max()) == 0.0
+    # 1:1 "up-sample": every window is a single texel, the result is the plain fused kernel's
+    if tuple(low_hw) == tuple(src_hw):
+        plain = conv1.warp_conv1(xd, pm, grid_hw, wpack, bias, relu=True)
+        assert rel_errors(out, plain)[0] <= 1e-5
+
+
+def test_fused_conv1_upsampled_rejects_a_down_sample():
+    from mvdet_b200 import conv1
+    from tests.util import small_rig, to_channels_last_5d
+    pm, src_hw, grid_hw = small_rig(num_cam=1, seed=3)
+    x = to_channels_last_5d(torch.zeros(1, 1, 64, src_hw[0] + 2, src_hw[1]).bfloat16()).cuda()
+    wpack = conv1.pack_conv1_weight(torch.zeros(512, 66, 3, 3), 1, 64).cuda()
+    with pytest.raises(ValueError):
+        conv1.warp_conv1(x, pm, grid_hw, wpack, upsample_shape=src_hw)
+
+
+def test_fused_conv1_upsampled_at_the_wildtrack_shape():
+    """V=7, C=512, 90x160 -> (270x480) -> 120x360, B=1: the benchmark's own size (K split of the last wave, 56 patches per tile).
+    Reference: CPU oracle warp of the fp32 up-sampled features, rounded to bf16, conv3x3 in fp32 on the GPU; and the plain fused
+    kernel on the bf16-rounded up-sampled features (two roundings: looser)."""
+    import torch.nn.functional as F
+    from mvdet_b200 import conv1
+    from mvdet_b200.geometry import WILDTRACK, synthetic_rig
+    from tests.util import to_channels_last_5d, rel_errors
+    spec = WILDTRACK
+    pm = synthetic_rig(spec)
+    g = torch.Generator().manual_seed(5)
+    low = torch.randn(1, spec.num_cam, 512, 90, 160, generator=g).bfloat16()
+    weight = torch.randn(512, spec.num_cam * 512 + 2, 3, 3, generator=g) * 0.02
+    bias = torch.randn(512, generator=g)
+    ref = _conv1_upsampled_reference(low, spec.feat_shape, pm, spec.grid_shape, weight, bias, relu=True, device="cuda")
+    wpack = conv1.pack_conv1_weight(weight, spec.num_cam, 512).cuda()
+    xd = to_channels_last_5d(low).cuda()
+    out = conv1.warp_conv1(xd, pm, spec.grid_shape, wpack, bias, relu=True, upsample_shape=spec.feat_shape)
+    torch.cuda.synchronize()
+    emax, el2 = rel_errors(out, ref)
+    assert emax <= UP_TOL[0] and el2 <= UP_TOL[1], (emax, el2)
+    assert torch.equal(out, conv1.warp_conv1(xd, pm, spec.grid_shape, wpack, bias, relu=True, upsample_shape=spec.feat_shape))
+    up16 = F.interpolate(xd[0], spec.feat_shape, mode="bilinear")[None]              # bf16 in, bf16 out: a second rounding
+    two_step = conv1.warp_conv1(up16, pm, spec.grid_shape, wpack, bias, relu=True)
+    assert rel_errors(out, two_step)[1] <= 5e-3
+
+
+def test_upsampled_map_head_and_detector_paths(monkeypatch):
+    """MapHead(upsample_shape=) and patch_detector(fuse_upsample=True, fused_head=True / fused_conv1=True): no 512-channel
+    F.interpolate on the map branch, in inference and in training; results against the model's own un-fused forward."""
+    import torch.nn as nn
+    from mvdet_b200 import integration
+    from tests.util import small_rig, rel_errors
+    V, Cc = 2, 64
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=37)
+
+    class Det(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.num_cam = V
+            self.base_pt1, self.base_pt2 = nn.Conv2d(3, Cc, 3, padding=1), nn.Sequential(nn.ReLU(), nn.Conv2d(Cc, Cc, 1))
+            self.img_classifier = nn.Sequential(nn.Conv2d(Cc, 8, 1), nn.ReLU(), nn.Conv2d(8, 2, 1, bias=False))
+            self.map_classifier = nn.Sequential(nn.Conv2d(Cc * V + 2, 512, 3, padding=1), nn.ReLU(),
+                                                nn.Conv2d(512, 512, 3, padding=2, dilation=2), nn.ReLU(),
+                                                nn.Conv2d(512, 1, 3, padding=4, dilation=4, bias=False))
+            self.proj_mats = [pm[v] for v in range(V)]
+            self.upsample_shape, self.reducedgrid_shape = list(src_hw), list(grid_hw)
+
+        def forward(self, imgs, visualize=False):
+            raise RuntimeError("replaced by patch_detector")
+
+    torch.manual_seed(0)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    base = Det().cuda().eval()
+    imgs = torch.randn(2, V, 3, 18, 32, generator=torch.Generator().manual_seed(1))     # trunk output 18x32, up-sampled to 54x96
+    plain_model = integration.patch_detector(base)                                       # un-fused: F.interpolate + warp_views + cuDNN
+    plain, res_p = plain_model(imgs)
+    g_plain = torch.autograd.grad(plain.square().sum(), [base.map_classifier[0].weight, base.base_pt1.weight])
+    model = integration.patch_detector(base, fuse_upsample=True, fused_head=True)
+    with torch.no_grad():
+        fused, res_f = model(imgs)
+    assert fused.shape == plain.shape == (2, 1, *grid_hw)
+    emax, el2 = rel_errors(fused, plain)
+    assert emax <= 3e-2 and el2 <= 2e-2, (emax, el2)        # bf16 activations + weights against fp32
+    for a, b in zip(res_f, res_p):                           # img_classifier: up-sample after the 1x1 convolution (commutes)
+        assert rel_errors(a, b)[0] <= 1e-4
+    trained = integration.patch_detector(base, fuse_upsample=True, fused_conv1=True)
+    out_f, _ = trained(imgs)
+    assert out_f.requires_grad and rel_errors(out_f, plain)[1] <= 2e-2
+    g_fused = torch.autograd.grad(out_f.square().sum(), [base.map_classifier[0].weight, base.base_pt1.weight])
+    for a, b in zip(g_fused, g_plain):
+        assert rel_errors(a, b)[1] <= 6e-2, rel_errors(a, b)

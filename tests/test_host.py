@@ -473,3 +473,48 @@ def test_new_ops_refuse_cpu_tensors_and_bad_arguments_without_a_gpu():
         ops.warp_views_list(["x", cams[0]], pm, grid_hw)
     assert _lib.load().mvwarp_layout_transpose(None, 0, None, 0, 1, 4, 4, 0, 1, 0, None) == _lib.EINVAL
     assert _lib.load().mvwarp_relu_bwd_scratch_floats(0, 0) == 0
+
+
+def _apply_upsample_windows(low, origin, mask, wx, wy):
+    """out[v,c,y,x] = sum_{j,i<3} wy[j] wx[i] low[v,c,oy+j,ox+i] over the live slots, in float64 (low [V,C,hl,wl])."""
+    V, Cc, hl, wl = low.shape
+    out = torch.zeros(V, Cc, *origin.shape[1:3], dtype=torch.float64)
+    for v in range(V):
+        for j in range(3):
+            for i in range(3):
+                live = ((mask[v] >> (j * 3 + i)) & 1).bool()
+                yy, xx = origin[v, ..., 1].long() + j, origin[v, ..., 0].long() + i
+                # a live slot always addresses a texel of the low-res map (the kernel gathers it without a bounds test)
+                assert bool(((yy[live] >= 0) & (yy[live] < hl) & (xx[live] >= 0) & (xx[live] < wl)).all())
+                w = wy[v, ..., j].double() * wx[v, ..., i].double() * live
+                out[v] += low[v].double()[:, yy.clamp(0, hl - 1), xx.clamp(0, wl - 1)] * w
+    return out
+
+
+@pytest.mark.parametrize("low_hw", [(18, 32), (27, 48), (54, 96), (20, 37), (1, 1)])
+def test_fused_conv1_upsample_windows_equal_the_two_step_oracle(low_hw):
+    """Fused warp -> conv1 over fused up-sample plans: the 3 x 3 low-res window the kernel's producers compose per halo cell
+    (csrc/mvwarp_uptaps.h, run here on the host through mvwarp_host_upsample_windows -- the same source) reproduces
+    warp(F.interpolate(low, bilinear)) -- persp_trans_detector.py:65 followed by :68-69 -- for integer, non-integer and 1:1 ratios."""
+    import torch.nn.functional as F
+    pm, src_hw, grid_hw = small_rig()
+    V, Cc = pm.shape[0], 3
+    T = P.src_norm_trans_dst_norm(pm, src_hw, grid_hw)
+    origin, mask, wx, wy = P.host_upsample_windows(T, low_hw, src_hw, grid_hw)
+    torch.manual_seed(1)
+    low = torch.randn(V, Cc, *low_hw)
+    mine = _apply_upsample_windows(low, origin, mask, wx, wy)
+    up = F.interpolate(low, src_hw, mode="bilinear")
+    ref = K.warp_views_oracle(up.reshape(1, V, Cc, *src_hw), pm, grid_hw)[0, :V * Cc].reshape(V, Cc, *grid_hw)
+    assert float(ref.abs().max()) > 0.5                                    # the rig sees the grid
+    assert float((mine - ref.double()).abs().max()) <= 1e-5 * float(ref.abs().max())
+    # cells the warp leaves empty have no live slot, and every other cell has at least one
+    empty = (ref == 0).all(dim=1)
+    assert bool((mask[empty] == 0).all()) and bool((mask[~empty] != 0).all())
+
+
+def test_upsample_windows_reject_a_down_sample():
+    pm, src_hw, grid_hw = small_rig()
+    T = P.src_norm_trans_dst_norm(pm, src_hw, grid_hw)
+    with pytest.raises(_lib.MvwarpError):
+        P.host_upsample_windows(T, (src_hw[0] + 1, src_hw[1]), src_hw, grid_hw)
