@@ -9,6 +9,8 @@ from a synthetic trunk output [B,7,512,90,160].  Four wirings of the same module
                   low-res maps once and returns a channels-last result
   seam2+up bf16   the same under torch.autocast(bfloat16) for the convolutions, features in bf16
   seam2 conv1 bf16  patch_detector(model, fused_conv1=True) under autocast: fused tcgen05 conv1 forward, backward without cuDNN
+  seam2 conv1+up bf16  the same with fuse_upsample=True: the fused kernels read the low-res trunk output, no 512-channel F.interpolate
+Then INFERENCE (torch.no_grad, bf16 autocast): seam2, seam2 + fused_head, seam2 + fused_head + fuse_upsample.
 Prints one JSON line.   usage: detector_head_bench.py [B] [iters]"""
 import copy, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -89,13 +91,28 @@ def main():
     for name, kw, ac in (("seam2", {}, False), ("seam2_fused_upsample", {"fuse_upsample": True}, False),
                          ("seam2_nchw_model_fused_upsample", {"fuse_upsample": True, "channels_last": False}, False),
                          ("seam2_fused_upsample_bf16", {"fuse_upsample": True}, True),
-                         ("seam2_fused_conv1_bf16", {"fused_conv1": True}, True)):
+                         ("seam2_fused_conv1_bf16", {"fused_conv1": True}, True),
+                         ("seam2_fused_conv1_fused_upsample_bf16", {"fused_conv1": True, "fuse_upsample": True}, True)):
         model = copy.deepcopy(ref)
         kw = dict({"channels_last": True}, **kw)
         integration.patch_detector(model, **kw)
         x = feats_low if not kw["channels_last"] else (x_cl.bfloat16() if ac else x_cl)
         m = run(model, x, ac)
         out[name + "_ms"] = round(timeit(lambda: run(model, x, ac)), 3)
+        out[name + "_map_rel_diff"] = float((m.float() - m_ref).abs().max() / m_ref.abs().max())
+        del model
+        torch.cuda.empty_cache()
+    def infer(model, x):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return model(x)[0]
+
+    for name, kw in (("infer_seam2", {}), ("infer_fused_head", {"fused_head": True}),
+                     ("infer_fused_head_fused_upsample", {"fused_head": True, "fuse_upsample": True})):
+        model = copy.deepcopy(ref).eval()
+        integration.patch_detector(model, channels_last=True, **kw)
+        x = x_cl.bfloat16()
+        m = infer(model, x)
+        out[name + "_ms"] = round(timeit(lambda: infer(model, x)), 3)
         out[name + "_map_rel_diff"] = float((m.float() - m_ref).abs().max() / m_ref.abs().max())
         del model
         torch.cuda.empty_cache()
