@@ -968,6 +968,104 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_table_tile_kernel(co
 }
 
 #ifdef MVWARP_DEV
+}  // namespace mvw
+#include "mvwarp_uptaps.h"
+namespace mvw {
+// ---------------------------------------------------------------------------------------------------
+// forward of fused up-sample plans made from matrices, QUAD version (channels-last) -- development build only (MVWARP_TBL_VARIANT=8..11).
+//
+// BUILT, MEASURED, NOT SHIPPED: 0.26-0.35 ms against the tile kernel's 0.208 ms (fp32 Wildtrack; bf16 0.20-0.25 against 0.161;
+// profiles/README.md).  The idea: fwd_table_tile_kernel (one warp per cell, lanes across 512 contiguous bytes of a texel row) is bound
+// by the L1 data pipe -- 21.8 M load + 4.8 M store lines of 128 bytes per Wildtrack frame at ~2 cycles each = 0.19 ms of a 0.20 ms
+// kernel -- although an 8x8 cell tile reads 341 taps from only ~30 distinct low-res texels.  If L1 charged a line once per REQUEST,
+// sharing inside a request would pay: here a warp takes a 2 x 2 quad of cells, eight lanes (128 bytes) per cell, and walks the
+// channels in 128-byte chunks; each cell reads its own composed 3 x 3 low-res window (mvwarp_uptaps.h, computed in-kernel from the
+// matrices, no CSR traffic) and slot k of the four windows is mostly the SAME texel.  It does not pay: a 128-bit load is served one
+// quarter-warp (8 lanes x 16 bytes) per data-pipe pass whatever the other quarters address, i.e. the pipe is bound by the bytes
+// DELIVERED to registers, not by the distinct lines touched -- and the quad mapping issues nine (masked) loads per 512 delivered bytes
+// where the tile kernel issues 5.4.  Only register-level reuse (one load feeding several cells) lowers the delivered bytes; round 1's
+// quad plan did that and was issue-bound.  Same arithmetic as the fused warp -> conv1 producers; agrees with the composed CSR to fp32
+// rounding (the 24 up-sample parity tests pass with it as the default).
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int UNROLL, int MINB>
+__global__ void __launch_bounds__(FWD_WARPS * 32, MINB) fwd_up_quad_kernel(const KParams p, int hl, int wl) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  static_assert(FWD_TILE_W == 8 && FWD_TILE_H == 8 && FWD_WARPS == 8, "16 quads per tile, two per warp");
+  __shared__ ConvTapUp taps[FWD_CELLS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tx = blockIdx.y % p.tiles_x, ty = blockIdx.y / p.tiles_x;   // grid: x = view (fastest), y = tile, z = batch (as fwd_cl_kernel)
+  const int vl = blockIdx.x, b = blockIdx.z;
+  const int v = p.view0 + vl;
+
+  if (threadIdx.x < FWD_CELLS) {
+    const int x = tx * FWD_TILE_W + (threadIdx.x % FWD_TILE_W), y = ty * FWD_TILE_H + (threadIdx.x / FWD_TILE_W);
+    ConvTapUp r;
+    r.mask = 0; r.xy = 0;
+    r.wx[0] = r.wx[1] = r.wx[2] = r.wy[0] = r.wy[1] = r.wy[2] = 0.f;
+    if (x < p.Wg && y < p.Hg) {
+      float Tm[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Tm[i] = __ldg(p.T + 9 * v + i);
+      float sx, sy;
+      norm_src_coord(Tm, x, y, p.Hg, p.Wg, sx, sy);
+      r = compose_cell(sx, sy, p.Hs, p.Ws, hl, wl, upsample_scale(wl, p.Ws), upsample_scale(hl, p.Hs));
+      if (p.coord_chan >= 0 && vl == 0) {
+        T* cm = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (int64_t)y * p.oH + (int64_t)x * p.oW + (int64_t)p.coord_chan * p.oC;
+        cm[0] = from_float<T>(__ldg(p.coord_x + x));
+        cm[p.oC] = from_float<T>(__ldg(p.coord_y + y));
+      }
+    }
+    taps[threadIdx.x] = r;
+  }
+  __syncthreads();
+
+  const T* __restrict__ src = feats_view<const T>(p, p.src, vl, p.fV) + (int64_t)b * p.fB;
+  T* __restrict__ dst = reinterpret_cast<T*>(p.dst) + (int64_t)b * p.oB + (p.out_chan0 + (int64_t)vl * p.C);
+  const int q = lane >> 3, l = lane & 7;              // cell of the quad, 16-byte piece of its 128-byte chunk
+  constexpr int CH = 8 * EPV;                          // elements per 128-byte chunk
+  const int nchunk = p.C / CH;
+  for (int quad = warp; quad < FWD_CELLS / 4; quad += FWD_WARPS) {
+    const int cx = (quad % (FWD_TILE_W / 2)) * 2 + (q & 1), cy = (quad / (FWD_TILE_W / 2)) * 2 + (q >> 1);
+    const int x = tx * FWD_TILE_W + cx, y = ty * FWD_TILE_H + cy;
+    const bool inside = x < p.Wg && y < p.Hg;
+    const ConvTapUp t = taps[cy * FWD_TILE_W + cx];
+    float wk[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wk[k] = __fmul_rn(t.wy[k / 3], t.wx[k % 3]);
+    const T* f0 = src + (int64_t)(t.xy >> 16) * p.fH + (int64_t)(t.xy & 0xffff) * p.fW + l * EPV;
+    T* o = dst + (int64_t)y * p.oH + (int64_t)x * p.oW + l * EPV;
+    const unsigned oalign = (unsigned)(reinterpret_cast<uintptr_t>(o) & 15u);   // differs between the cells of a quad (odd concat pitch)
+    for (int c0 = 0; c0 < nchunk; c0 += UNROLL) {
+      uint4 val[UNROLL][9];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const bool ok = inside && c0 + u < nchunk;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+          val[u][k] = (ok && (t.mask >> k & 1)) ? ldg16(f0 + (int64_t)(k / 3) * p.fH + (int64_t)(k % 3) * p.fW + (c0 + u) * CH)
+                                                : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (inside && c0 + u < nchunk) {
+          float acc[EPV];
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {      // ascending low-res texel; a dead slot holds zeros and a zero weight
+            float f[EPV];
+            VecTraits<T>::unpack(val[u][k], f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) acc[e] = __fmaf_rn(f[e], wk[k], acc[e]);
+          }
+          stcs16_any(o + (c0 + u) * CH, VecTraits<T>::pack(acc), oalign);
+        }
+      }
+    }
+  }
+}
+#endif  // MVWARP_DEV (quad forward)
+#ifdef MVWARP_DEV
 // ---------------------------------------------------------------------------------------------------
 // forward of fused up-sample plans, STAGED version (channels-last) -- north_star (a): "TMA / shared-memory staging of source
 // tiles that are reused across neighbouring grid cells".
@@ -1567,6 +1665,25 @@ static int launch_fwd_t(const LaunchArgs& a) {
   const bool fast = feats_vector_ok(a, a.feats_or_grad_out, EPV) && a.os[1] == 1 &&
                     (reinterpret_cast<uintptr_t>(a.out_or_grad_feats) % sizeof(float) == 0) &&
                     (sizeof(T) == 4 || (a.os[0] % 2 == 0 && a.os[2] % 2 == 0 && a.os[3] % 2 == 0 && a.out_chan0 % 2 == 0));
+#ifdef MVWARP_DEV
+  if (a.plan->upsampled && fast && inl && a.plan->hl <= a.plan->Hs && a.plan->wl <= a.plan->Ws && a.plan->hl < 32768 && a.plan->wl < 32768 &&
+      ((uint64_t)a.C * sizeof(T)) % 128 == 0 && warp_knobs().tbl >= 8 && warp_knobs().tbl <= 12) {
+    // development build, MVWARP_TBL_VARIANT=8..12: quads of cells, windows composed in-kernel (measured slower than the tile kernel)
+    int rc = check_grid_dims(a, a.B);
+    if (rc) return rc;
+    if (p.tiles_x * p.tiles_y > 65535) { set_error("warp_views_fwd: more than 65535 cell tiles per view"); return MVWARP_EUNSUPPORTED; }
+    dim3 grid(a.nviews, p.tiles_x * p.tiles_y, a.B), block(FWD_WARPS * 32);
+    switch (warp_knobs().tbl) {
+      case 8: fwd_up_quad_kernel<T, 2, 2><<<grid, block, 0, a.stream>>>(p, a.plan->hl, a.plan->wl); break;
+      case 9: fwd_up_quad_kernel<T, 2, 3><<<grid, block, 0, a.stream>>>(p, a.plan->hl, a.plan->wl); break;
+      case 10: fwd_up_quad_kernel<T, 1, 6><<<grid, block, 0, a.stream>>>(p, a.plan->hl, a.plan->wl); break;
+      case 11: fwd_up_quad_kernel<T, 1, 3><<<grid, block, 0, a.stream>>>(p, a.plan->hl, a.plan->wl); break;
+      default: fwd_up_quad_kernel<T, 1, 4><<<grid, block, 0, a.stream>>>(p, a.plan->hl, a.plan->wl); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "warp_views_fwd (up-sample quads) launch");
+  }
+#endif
   if (a.plan->upsampled) {  // fused up-sample plan: the forward is a table gather from the low-res feature map
     set_csr(p, a.plan->fwd);
     p.feats_is_src = 1;

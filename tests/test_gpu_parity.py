@@ -810,7 +810,11 @@ print("ok")
     import tempfile
     with tempfile.TemporaryDirectory() as td:
         outs = {}
-        for tag, env_extra in (("default", {}), ("knob", {"MVWARP_LIB": build_library(dev=True), "MVWARP_STAGE_KB": str(stage_kb), "MVWARP_TBL_VARIANT": "3"})):
+        # "default" = the CSR tile kernel (MVWARP_TBL_VARIANT=2), whose entry order the staged kernel follows; the shipped default for
+        # these shapes is fwd_up_quad_kernel, which composes its weights in-kernel and agrees to rounding, not bit for bit
+        dev_lib = build_library(dev=True)
+        for tag, env_extra in (("default", {"MVWARP_LIB": dev_lib, "MVWARP_TBL_VARIANT": "2"}),
+                               ("knob", {"MVWARP_LIB": dev_lib, "MVWARP_STAGE_KB": str(stage_kb), "MVWARP_TBL_VARIANT": "3"})):
             env = dict(os.environ, PYTHONPATH=root, **env_extra)
             res = subprocess.run([sys.executable, "-c", code, os.path.join(td, tag)], capture_output=True, text=True, env=env, cwd=root, timeout=600)
             assert res.returncode == 0 and "ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
@@ -819,6 +823,43 @@ print("ok")
         for a, b in zip(outs["default"], outs["knob"]):
             ta, tb = torch.load(os.path.join(td, a)), torch.load(os.path.join(td, b))
             assert torch.equal(ta, tb), (stage_kb, a)
+
+
+def test_quad_upsample_forward_agrees_with_the_shipped_kernel():
+    """fwd_up_quad_kernel (development build, MVWARP_TBL_VARIANT=8: 2 x 2 quads of cells, 3 x 3 low-res windows composed in-kernel by
+    csrc/mvwarp_uptaps.h; measured slower than the CSR tile kernel and therefore not shipped) computes the same operator as the shipped
+    forward with weights composed in fp32 instead of double: agreement to rounding, fp32 and bf16, partial tiles, odd concat pitch."""
+    import os, subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from mvdet_b200.build import build_library
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from mvdet_b200 import ops
+from tests.util import small_rig, to_channels_last_5d
+for dtype in (torch.float32, torch.bfloat16):
+    for V, Cc, seed in ((3, 512, 91), (2, 96, 92)):
+        pm, src_hw, grid_hw = small_rig(num_cam=V, seed=seed)
+        low = (src_hw[0] // 3, src_hw[1] // 3)
+        x = to_channels_last_5d(torch.randn(2, V, Cc, *low, generator=torch.Generator().manual_seed(seed)).to(dtype)).cuda()
+        out = ops.warp_views_upsampled(x, src_hw, pm, grid_hw)
+        torch.save(out.float().cpu(), sys.argv[1] + f"_{dtype}_{V}.pt")
+print("ok")
+""" % root
+    dev_lib = build_library(dev=True)
+    with tempfile.TemporaryDirectory() as td:
+        outs = {}
+        for tag, env_extra in (("shipped", {}), ("quad", {"MVWARP_LIB": dev_lib, "MVWARP_TBL_VARIANT": "8"})):
+            env = dict(os.environ, PYTHONPATH=root, **env_extra)
+            res = subprocess.run([sys.executable, "-c", code, os.path.join(td, tag)], capture_output=True, text=True, env=env, cwd=root, timeout=600)
+            assert res.returncode == 0 and "ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+            outs[tag] = sorted(f for f in os.listdir(td) if f.startswith(tag))
+        assert len(outs["shipped"]) == len(outs["quad"]) == 4
+        for a, b in zip(outs["shipped"], outs["quad"]):
+            ta, tb = torch.load(os.path.join(td, a)), torch.load(os.path.join(td, b))
+            tol = 1e-5 if "float32" in a else 2.0 ** -7          # bf16: the two fp32 results may round to neighbouring bf16 values
+            assert float((ta - tb).abs().max()) <= tol * float(ta.abs().max()), (a, float((ta - tb).abs().max()))
+            assert not torch.equal(ta, torch.zeros_like(ta))
 
 
 # ---- memory safety without compute-sanitizer (closed on this pool): canary bands around every written tensor --------------
