@@ -229,3 +229,43 @@ def test_patch_detector_fused_upsample_agrees_to_rounding(reference_model):
     model.img_classifier = torch.nn.Sequential(torch.nn.Conv2d(512, 2, 3, padding=1))
     with pytest.raises(TypeError):
         integration.patch_detector(model, fuse_upsample=True)          # a 3x3 first layer does not commute with the up-sample
+
+
+def test_fused_head_over_lowres_features_on_the_reference_model(reference_model):
+    """fuse_upsample=True together with a fused head (integration.warped_forward, the wiring behind patch_detector(fuse_upsample=True,
+    fused_head=True)): under no_grad the head receives the trunk's LOW-RES features in bf16 plus upsample_shape -- lines 65 and 68-81 of
+    persp_trans_detector.py collapse into one call -- and with a stand-in head that does the reference's arithmetic (F.interpolate,
+    oracle warp, the model's own map_classifier) the unmodified reference model returns the same map_result to bf16 rounding."""
+    from mvdet_b200 import integration
+    from oracle import kornia_warp as K
+    model, calls = reference_model
+    ds = _fake_dataset()
+    imgs = torch.randn(1, ds.num_cam, 3, 144, 256, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        map_ref, img_ref = model(imgs)
+    seen = []
+
+    def head(img_feats_low, proj_mats, grid_shape, upsample_shape=None):
+        seen.append((tuple(img_feats_low.shape), img_feats_low.dtype, tuple(upsample_shape)))
+        V = img_feats_low.shape[1]
+        up = torch.stack([F.interpolate(img_feats_low[:, v].float(), upsample_shape, mode="bilinear") for v in range(V)], dim=1)   # :65
+        return model.map_classifier(K.warp_views_oracle(up, proj_mats, grid_shape))                                              # :68-81
+
+    with torch.no_grad():
+        map_new, img_new = integration.warped_forward(model, imgs, fuse_upsample=True, fused_head=head,
+                                                      warp_fn=lambda *a, **k: pytest.fail("the un-fused warp must not run"))
+    assert seen == [((1, ds.num_cam, 512, 18, 32), torch.bfloat16, (54, 96))]
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert rel(map_new, map_ref) <= 3e-2                                  # bf16 features
+    assert all(rel(a, b) <= 1e-5 for a, b in zip(img_new, img_ref))       # img branch: fp32, up-sample after the 1x1 convolution
+    # with autograd on and no fused_conv1 the un-fused path runs (the fused head is forward-only)
+    ran = []
+
+    def warp_up(img_feats_low, upsample_shape, proj_mats, grid_shape):
+        ran.append(tuple(img_feats_low.shape))
+        V = img_feats_low.shape[1]
+        up = torch.stack([F.interpolate(img_feats_low[:, v], upsample_shape, mode="bilinear") for v in range(V)], dim=1)
+        return K.warp_views_oracle(up, proj_mats, grid_shape)
+
+    map_g, _ = integration.warped_forward(model, imgs, fuse_upsample=True, fused_head=head, warp_fn=warp_up)
+    assert ran == [(1, ds.num_cam, 512, 18, 32)] and len(seen) == 1 and map_g.requires_grad
