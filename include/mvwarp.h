@@ -292,6 +292,13 @@ int mvwarp_conv3x3_fwd(const void* x, const int64_t x_strides[4], const void* wp
                        int device, void* stream);
 int mvwarp_conv3x3_head_fwd(const void* x, const int64_t x_strides[4], const void* w, float* out, const int64_t out_strides[4],
                             int B, int H, int W, int Cin, int dilation, int device, void* stream);
+/* The same with caller-provided scratch (mvwarp_conv3x3_head_scratch_bytes(B, H, W) bytes, 16-byte aligned; any allocator): with it
+ * and Cin % 32 == 0 the convolution runs in two passes that read every activation ONCE -- nine partial dot products per cell
+ * (P[cell][tap], a skinny GEMM on the tensor cores), then a 9-term stencil over P.  Without scratch: the one-pass kernel. */
+int64_t mvwarp_conv3x3_head_scratch_bytes(int B, int H, int W);
+int mvwarp_conv3x3_head_fwd_ex(const void* x, const int64_t x_strides[4], const void* w, float* out, const int64_t out_strides[4],
+                               int B, int H, int W, int Cin, int dilation, void* scratch, int64_t scratch_bytes, int device,
+                               void* stream);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,9 @@ SIGNATURES = {
     "mvwarp_conv3x3_fwd": (C.c_int, [_P, _I64P, _P, _P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, _P]),
     "mvwarp_conv3x3_head_fwd": (C.c_int, [_P, _I64P, _P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "mvwarp_conv3x3_head_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "mvwarp_conv3x3_head_fwd_ex": (C.c_int, [_P, _I64P, _P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int64,
+                                             C.c_int, _P]),
     "mvwarp_warp_views_fwd_list": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), _I64P, _P, _I64P, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_int, _P]),
     "mvwarp_warp_views_bwd_list": (C.c_int, [_P, C.c_int, C.c_int, _P, _I64P, C.c_int, C.POINTER(_P), _I64P,

@@ -406,6 +406,116 @@ __global__ void __launch_bounds__(HD_WARPS * 32, 1) conv3x3_head_kernel(const __
   }
 }
 
+// -----------------------------------------------------------------------------------------------------
+// map_classifier[4] in two passes (the default when the caller provides scratch): every activation is read ONCE.
+//   pass 1  P[cell][tap] = sum_c x[cell][c] * w[tap][c]      nine partial dot products per cell (head_partial_kernel)
+//   pass 2  out[y][x]    = sum_tap P[(y + dy*d, x + dx*d)][tap]   a 9-term stencil over the 36-byte rows of P (head_stencil_kernel)
+// The one-pass kernel above reads each cell's 1 KB row nine times (once per tap; three from registers) through L1 / L2 and lost to
+// cuDNN at B >= 4.  Pass 1 is a skinny GEMM -- M = cells, N = 9, K = Cin -- and runs on the tensor cores with mma.sync
+// (m16n8k16, bf16 x bf16 -> fp32; two n-tiles of eight taps, the second holds tap 8 only): with N = 9 the contraction is far below
+// the HBM ridge whatever issues it, so this is a bandwidth kernel, and mma.sync takes its A fragments straight from registers --
+// no shared-memory staging of the activations, no TMEM round trip.  The K order inside a k-step is a free choice as long as both
+// operands agree, so lane (g, t) of a warp reads 16 contiguous bytes (channels c0 + 8t .. + 8 of rows g and g + 8: LDG.128) and uses
+// register pairs (0, 1) as the first k-step and (2, 3) as the second; the weights follow the same rule from shared memory.
+// -----------------------------------------------------------------------------------------------------
+constexpr int HP_WARPS = 8, HP_MT = 2, HP_CELLS = HP_WARPS * HP_MT * 16;   // 256 cells per CTA
+constexpr int HP_TAPS = 9;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(HP_WARPS * 32, 2) head_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t xB, int64_t xH, int64_t xW,
+                                                                        const __nv_bfloat16* __restrict__ w /*[9][Cin]*/, float* __restrict__ P,
+                                                                        int64_t ncells, int H, int W, int Cin) {
+  extern __shared__ __align__(16) uint8_t hp_smem[];
+  const int pitch = Cin * 2 + 16;                        // bytes; +16: the eight tap rows of a quarter-warp's LDS.128 fall into different banks
+  for (int i = threadIdx.x; i < HP_TAPS * (Cin / 8); i += blockDim.x) {
+    const int tap = i / (Cin / 8), c8 = i % (Cin / 8);
+    *reinterpret_cast<uint4*>(hp_smem + (size_t)tap * pitch + c8 * 16) = __ldg(reinterpret_cast<const uint4*>(w + (size_t)tap * Cin + c8 * 8));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t base = (int64_t)blockIdx.x * HP_CELLS + (int64_t)warp * (HP_MT * 16);
+  if (base >= ncells) return;
+  const __nv_bfloat16* pa[HP_MT][2];
+#pragma unroll
+  for (int m = 0; m < HP_MT; ++m)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int64_t cell = base + m * 16 + h * 8 + g;
+      if (cell >= ncells) cell = ncells - 1;             // a clamped row is computed and dropped at the store
+      const int64_t hw = (int64_t)H * W, b = cell / hw, r = cell - b * hw;
+      const int y = (int)(r / W), xx = (int)(r - (int64_t)y * W);
+      pa[m][h] = x + b * xB + (int64_t)y * xH + (int64_t)xx * xW + 8 * t;
+    }
+  const uint8_t* wb0 = hp_smem + (size_t)g * pitch + 16 * t;            // taps 0..7 (n-tile 0, column g)
+  const uint8_t* wb1 = hp_smem + (size_t)8 * pitch + 16 * t;            // tap 8 (n-tile 1, column 0; the other columns are zero)
+  float acc[HP_MT][2][4];
+#pragma unroll
+  for (int m = 0; m < HP_MT; ++m)
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
+  constexpr int UB = 4;                                  // channel blocks (32 channels each) per trip: 2 * HP_MT * UB loads in flight per lane
+  for (int c0 = 0; c0 < Cin; c0 += 32 * UB) {
+    uint4 a[UB][HP_MT][2];
+#pragma unroll
+    for (int u = 0; u < UB; ++u)
+#pragma unroll
+      for (int m = 0; m < HP_MT; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          a[u][m][h] = (c0 + 32 * u < Cin) ? __ldg(reinterpret_cast<const uint4*>(pa[m][h] + c0 + 32 * u)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      if (c0 + 32 * u < Cin) {
+        const uint4 b0 = *reinterpret_cast<const uint4*>(wb0 + (c0 + 32 * u) * 2);
+        const uint4 b1 = g == 0 ? *reinterpret_cast<const uint4*>(wb1 + (c0 + 32 * u) * 2) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int m = 0; m < HP_MT; ++m) {
+          const uint4 lo = a[u][m][0], hi = a[u][m][1];
+          mma_bf16_16816(acc[m][0], lo.x, hi.x, lo.y, hi.y, b0.x, b0.y);
+          mma_bf16_16816(acc[m][0], lo.z, hi.z, lo.w, hi.w, b0.z, b0.w);
+          mma_bf16_16816(acc[m][1], lo.x, hi.x, lo.y, hi.y, b1.x, b1.y);
+          mma_bf16_16816(acc[m][1], lo.z, hi.z, lo.w, hi.w, b1.z, b1.w);
+        }
+      }
+    }
+  }
+  // accumulator (row g / g + 8, columns 2t, 2t + 1) -> P[cell][tap]: n-tile 0 = taps 2t, 2t + 1; n-tile 1 = tap 8 in column 0 (t == 0)
+#pragma unroll
+  for (int m = 0; m < HP_MT; ++m)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t cell = base + m * 16 + h * 8 + g;
+      if (cell < ncells) {
+        float* o = P + cell * HP_TAPS;
+        o[2 * t] = acc[m][0][2 * h];
+        o[2 * t + 1] = acc[m][0][2 * h + 1];
+        if (t == 0) o[8] = acc[m][1][2 * h];
+      }
+    }
+}
+
+__global__ void __launch_bounds__(256) head_stencil_kernel(const float* __restrict__ P, float* __restrict__ out, int64_t oB, int64_t oH, int64_t oW,
+                                                           int64_t ncells, int H, int W, int dilation) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ncells) return;
+  const int64_t hw = (int64_t)H * W, b = cell / hw, r = cell - b * hw;
+  const int y = (int)(r / W), x = (int)(r - (int64_t)y * W);
+  float acc = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < HP_TAPS; ++tap) {              // tap order = the one-pass kernel's: (dy, dx) row-major
+    const int yy = y + (tap / 3 - 1) * dilation, xx = x + (tap % 3 - 1) * dilation;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc += __ldg(P + ((b * H + yy) * (int64_t)W + xx) * HP_TAPS + tap);
+  }
+  out[b * oB + (int64_t)y * oH + (int64_t)x * oW] = acc;
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -536,8 +646,19 @@ extern "C" int mvwarp_conv3x3_fwd(const void* x, const int64_t x_strides[4], con
   return e == cudaSuccess ? MVWARP_OK : cuda_fail(e, "conv3x3_fwd launch");
 }
 
+extern "C" int64_t mvwarp_conv3x3_head_scratch_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (int64_t)B * H * W * HP_TAPS * (int64_t)sizeof(float);
+}
+
 extern "C" int mvwarp_conv3x3_head_fwd(const void* x, const int64_t x_strides[4], const void* w, float* out, const int64_t out_strides[4],
                                        int B, int H, int W, int Cin, int dilation, int device, void* stream) {
+  return mvwarp_conv3x3_head_fwd_ex(x, x_strides, w, out, out_strides, B, H, W, Cin, dilation, nullptr, 0, device, stream);
+}
+
+extern "C" int mvwarp_conv3x3_head_fwd_ex(const void* x, const int64_t x_strides[4], const void* w, float* out, const int64_t out_strides[4],
+                                          int B, int H, int W, int Cin, int dilation, void* scratch, int64_t scratch_bytes, int device,
+                                          void* stream) {
   if (!x || !x_strides || !w || !out || !out_strides) { set_error("conv3x3_head_fwd: null argument"); return MVWARP_EINVAL; }
   if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || dilation <= 0) { set_error("conv3x3_head_fwd: bad B / H / W / Cin / dilation"); return MVWARP_EINVAL; }
   if (Cin % 8 || Cin > 512 || x_strides[1] != 1 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15u) || x_strides[0] % 8 ||
@@ -551,6 +672,23 @@ extern "C" int mvwarp_conv3x3_head_fwd(const void* x, const int64_t x_strides[4]
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != device && cudaSetDevice(device) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+  const int64_t ncells = (int64_t)B * H * W;
+  if (scratch && Cin % 32 == 0 && !(reinterpret_cast<uintptr_t>(scratch) & 15u) && scratch_bytes >= ncells * HP_TAPS * (int64_t)sizeof(float) &&
+      (ncells + HP_CELLS - 1) / HP_CELLS <= 0x7fffffff) {
+    // two passes: nine partial dot products per cell on the tensor cores (every activation read once), then the 9-term stencil
+    float* P = reinterpret_cast<float*>(scratch);
+    const int smem = HP_TAPS * (Cin * 2 + 16);
+    head_partial_kernel<<<(unsigned)((ncells + HP_CELLS - 1) / HP_CELLS), HP_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, x_strides[0], x_strides[2], x_strides[3], (const __nv_bfloat16*)w, P, ncells, H, W, Cin);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 == cudaSuccess) {
+      head_stencil_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, out, out_strides[0], out_strides[2], out_strides[3],
+                                                                                           ncells, H, W, dilation);
+      e2 = cudaGetLastError();
+    }
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    return e2 == cudaSuccess ? MVWARP_OK : cuda_fail(e2, "conv3x3_head_fwd (two-pass) launch");
+  }
   const int grid = (int)((nwarps + HD_WARPS - 1) / HD_WARPS);
   if (Cin <= 256)
     conv3x3_head_kernel<1><<<grid, HD_WARPS * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, x_strides[0], x_strides[2], x_strides[3],

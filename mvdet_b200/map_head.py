@@ -72,17 +72,22 @@ def conv3x3_cl(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
-def conv3x3_head(x: torch.Tensor, w9: torch.Tensor, dilation: int = 1) -> torch.Tensor:
-    """``conv2d(x, W[1,Cin,3,3], None, padding=dilation, dilation=dilation)`` -> fp32 [B,1,H,W]; w9 from :func:`pack_head_weight`."""
+def conv3x3_head(x: torch.Tensor, w9: torch.Tensor, dilation: int = 1, two_pass: bool = True) -> torch.Tensor:
+    """``conv2d(x, W[1,Cin,3,3], None, padding=dilation, dilation=dilation)`` -> fp32 [B,1,H,W]; w9 from :func:`pack_head_weight`.
+    ``two_pass`` (default; needs Cin % 32 == 0, else the one-pass kernel runs): nine partial dot products per cell on the tensor cores
+    into a ``[B*H*W, 9]`` fp32 scratch from torch's allocator, then a 9-term stencil -- every activation is read once."""
     _check_cl_bf16(x, "conv3x3_head")
     B, Cin, H, W = x.shape
     if w9.dtype != torch.bfloat16 or tuple(w9.shape) != (9, Cin) or not w9.is_contiguous():
         raise ValueError(f"w9 must be a contiguous bf16 [9, {Cin}] tensor from pack_head_weight")
     out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
     stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-    rc = _lib.load().mvwarp_conv3x3_head_fwd(C.c_void_p(x.data_ptr()), _lib.i64x(x.stride()), C.c_void_p(w9.data_ptr()),
-                                             C.c_void_p(out.data_ptr()), _lib.i64x(out.stride()), B, H, W, Cin, int(dilation),
-                                             x.device.index, stream)
+    lib = _lib.load()
+    nbytes = int(lib.mvwarp_conv3x3_head_scratch_bytes(B, H, W)) if two_pass and Cin % 32 == 0 else 0
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
+    rc = lib.mvwarp_conv3x3_head_fwd_ex(C.c_void_p(x.data_ptr()), _lib.i64x(x.stride()), C.c_void_p(w9.data_ptr()),
+                                        C.c_void_p(out.data_ptr()), _lib.i64x(out.stride()), B, H, W, Cin, int(dilation),
+                                        C.c_void_p(scratch.data_ptr()) if scratch is not None else None, nbytes, x.device.index, stream)
     _lib.check(rc, "mvwarp_conv3x3_head_fwd")
     return out
 

@@ -58,6 +58,7 @@ def main():
             "conv2_tma_ms": timeit(lambda: MH.conv3x3_cl(a1, head.w2, head.b2, dilation=2, relu=True), iters),
             "conv2_cudnn_ms": timeit(lambda: F.relu(cudnn_head[2](a1)), iters),
             "conv3_head_ms": timeit(lambda: MH.conv3x3_head(a2, head.w3, dilation=4), iters),
+            "conv3_head_one_pass_ms": timeit(lambda: MH.conv3x3_head(a2, head.w3, dilation=4, two_pass=False), iters),
             "conv3_cudnn_ms": timeit(lambda: cudnn_head[4](a2), iters),
         }
     flops2 = 2.0 * B * Hg * Wg * 512 * 512 * 9

@@ -145,18 +145,25 @@ def test_tcgen05_tma_conv3x3_matches_conv2d(B, Cin, H, W, d, relu, odt):
     assert emax <= tol and el2 <= tol, (emax, el2)
 
 
-def test_conv3x3_head_matches_conv2d():
+@pytest.mark.parametrize("two_pass", [True, False])
+@pytest.mark.parametrize("B,Cin,H,W,d", [(2, 512, 21, 35, 4), (1, 96, 9, 70, 2), (3, 256, 17, 16, 1), (1, 40, 12, 20, 4)])
+def test_conv3x3_head_matches_conv2d(two_pass, B, Cin, H, W, d):
+    """map_classifier[4] (512 -> 1, dilation 4, no bias): the two-pass path (nine partial dot products per cell by mma.sync, then a
+    9-term stencil; needs Cin % 32 == 0 -- Cin = 40 falls back) and the one-pass kernel against F.conv2d in fp32.  Cell counts that
+    are no multiple of the 256-cell CTA / 16-cell MMA tile, Cin that is no multiple of the 128-channel trip."""
     import torch.nn.functional as F
     from mvdet_b200 import map_head as MH
     from tests.util import rel_errors
     g = torch.Generator().manual_seed(6)
-    x = torch.randn(2, 512, 21, 35, generator=g).bfloat16()
-    w = torch.randn(1, 512, 3, 3, generator=g) * 0.05
-    ref = F.conv2d(x.float(), w.bfloat16().float(), None, padding=4, dilation=4)
-    out = MH.conv3x3_head(x.cuda().contiguous(memory_format=torch.channels_last), MH.pack_head_weight(w).cuda(), dilation=4)
+    x = torch.randn(B, Cin, H, W, generator=g).bfloat16()
+    w = torch.randn(1, Cin, 3, 3, generator=g) * 0.05
+    ref = F.conv2d(x.float(), w.bfloat16().float(), None, padding=d, dilation=d)
+    xd = x.cuda().contiguous(memory_format=torch.channels_last)
+    out = MH.conv3x3_head(xd, MH.pack_head_weight(w).cuda(), dilation=d, two_pass=two_pass)
     assert out.shape == ref.shape
     emax, el2 = rel_errors(out, ref)
     assert emax <= 1e-5 and el2 <= 1e-5, (emax, el2)
+    assert torch.equal(out, MH.conv3x3_head(xd, MH.pack_head_weight(w).cuda(), dilation=d, two_pass=two_pass))   # deterministic
 
 
 def test_map_head_matches_the_reference_module():

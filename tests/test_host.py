@@ -72,6 +72,8 @@ def test_every_entry_point_rejects_null_arguments_without_a_gpu():
                                                                   None, 0, None),
         "conv3x3_fwd": lambda: lib.mvwarp_conv3x3_fwd(None, i4, None, None, None, i4, 1, 8, 8, 64, 1, 1, 0, 0, None),
         "conv3x3_head_fwd": lambda: lib.mvwarp_conv3x3_head_fwd(None, i4, None, None, i4, 1, 8, 8, 64, 1, 0, None),
+        "conv3x3_head_fwd_ex": lambda: lib.mvwarp_conv3x3_head_fwd_ex(None, i4, None, None, i4, 1, 8, 8, 64, 1, None, 0, 0, None),
+        "host_upsample_windows": lambda: lib.mvwarp_host_upsample_windows(nine, 1, 2, 2, 4, 4, 4, 4, None, None, None, None),
         "inbox_reduce": lambda: lib.mvwarp_inbox_reduce(None, 2, 0, 0, 1, 512, None, 0, None, 0, 0, None),
         "warp_conv1_fwd_p2p": lambda: lib.mvwarp_warp_conv1_fwd_p2p(None, 0, 1, None, i5, None, 1, 64, 1, 2, 0, None, None, 8, None),
         "warp_views_fwd_list": lambda: lib.mvwarp_warp_views_fwd_list(None, 0, 1, None, i4, None, i4, 0, -1, 1, 4, 0, None),
@@ -88,6 +90,7 @@ def test_every_entry_point_rejects_null_arguments_without_a_gpu():
         assert call() == _lib.EINVAL, name
         assert len(lib.mvwarp_last_error()) > 0, name
     assert lib.mvwarp_warp_conv1_scratch_bytes(None, 1, 1, 0, 0) == 0
+    assert lib.mvwarp_conv3x3_head_scratch_bytes(0, 8, 8) == 0 and lib.mvwarp_conv3x3_head_scratch_bytes(2, 8, 8) == 2 * 64 * 9 * 4
 
 
 def test_matrix_chain_matches_oracle_bits():
