@@ -419,6 +419,49 @@ def run_conv1_train_step(args, spec, pm, dev):
     return res
 
 
+def run_map_head(args, spec, pm, dev):
+    """SURVEY.md 8(f) rank 2 (+ rank 1): the whole ground-plane head in inference -- map_classifier(warp_views(F.interpolate(feats)))
+    (persp_trans_detector.py:65, 68-81) -- as MapHead's kernels on the trunk's LOW-RES output (fused up-sample conv1 on tcgen05, TMA-fed
+    tcgen05 dilated conv, two-pass 512 -> 1 head), against the same modules on library kernels (torch's F.interpolate, our warp_views,
+    three cuDNN convolutions; bf16 channels-last)."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from mvdet_b200 import map_head as MH, ops
+    V, Cc, B = spec.num_cam, args.channels, args.batch
+    Hs, Ws = spec.feat_shape
+    Hg, Wg = spec.grid_shape
+    if Hs % 3 or Ws % 3:
+        return {"skipped": "feature map is not a 3x up-sample"}
+    torch.manual_seed(400)
+    gen = torch.Generator(device=dev).manual_seed(400)
+    low = torch.randn((B, V, Hs // 3, Ws // 3, Cc), device=dev, generator=gen).to(torch.bfloat16).permute(0, 1, 4, 2, 3)
+    ref = nn.Sequential(nn.Conv2d(Cc * V + 2, 512, 3, padding=1), nn.ReLU(), nn.Conv2d(512, 512, 3, padding=2, dilation=2), nn.ReLU(),
+                        nn.Conv2d(512, 1, 3, padding=4, dilation=4, bias=False)).to(dev)
+    head = MH.MapHead({"map_classifier." + k: v for k, v in ref.state_dict().items()}, V, Cc, device=dev)
+    cudnn = ref.to(torch.bfloat16).to(memory_format=torch.channels_last)
+    sync = torch.cuda.synchronize
+    steps = max(5, min(args.steps, 20))
+
+    def library():
+        ups = [F.interpolate(low[:, v], (Hs, Ws), mode="bilinear") for v in range(V)]       # :65, per camera like the reference
+        return cudnn(ops.warp_views_list(ups, pm, (Hg, Wg)))
+
+    with torch.no_grad():
+        a = head(low, pm, (Hg, Wg), upsample_shape=(Hs, Ws))
+        b = library().float()
+        t = _event_times(lambda: head(low, pm, (Hg, Wg), upsample_shape=(Hs, Ws)), steps, 3, sync)
+        tl = _event_times(library, max(3, steps // 2), 2, sync)
+        up = torch.stack([F.interpolate(low[:, v], (Hs, Ws), mode="bilinear") for v in range(V)], dim=1)
+        tf = _event_times(lambda: head(up, pm, (Hg, Wg)), steps, 3, sync)
+    return {"workload": f"{spec.name} B={B} inference: map_classifier(warp_views(F.interpolate(trunk output {Hs // 3}x{Ws // 3}))) -> [B,1,{Hg},{Wg}]",
+            "kernels": "warp_conv1_direct_kernel<UPS> (+ conv1_tail_reduce_kernel), conv3x3_tc2_kernel, head_partial_kernel, head_stencil_kernel",
+            "ms_median": t["median"], "ms_min": t["min"], "frames_per_s": B / (t["median"] * 1e-3),
+            "from_upsampled_features_ms": tf["median"], "library_interpolate_warp_cudnn_ms": tl["median"],
+            "speedup_vs_library": tl["median"] / t["median"], "max_rel_diff_vs_library_bf16": float((a - b).abs().max() / b.abs().max()),
+            "dtype": "bf16 activations and weights, fp32 accumulate"}
+
+
 def run_sharded_conv1(args, dev, rank, world, dist):
     """BASELINE.json configs[3] / north_star's multi-GPU design, STRONG scaling: ONE 32-camera rig (512 ch x 270x480 -> the
     full-resolution 480x1440 grid), its cameras partitioned across the N ranks.  Each rank runs the fused warp -> conv1 kernel on
@@ -664,6 +707,9 @@ def run_ours(args):
         torch.cuda.empty_cache()
         if world == 1 and Cc == 512:
             legs["conv1_train_step"] = guarded(run_conv1_train_step, args, base, pm, dev)
+            torch.cuda.empty_cache()
+        if world == 1 and Cc % 64 == 0:
+            legs["map_head"] = guarded(run_map_head, args, base, pm, dev)
             torch.cuda.empty_cache()
     if not args.no_sharded_conv1 and not args.fuse_upsample and args.layout == "cl":
         legs["sharded_conv1"] = guarded(run_sharded_conv1, args, dev, rank, world, dist if world > 1 else None)
