@@ -690,3 +690,46 @@ def test_upsampled_map_head_and_detector_paths(monkeypatch):
     g_fused = torch.autograd.grad(out_f.square().sum(), [base.map_classifier[0].weight, base.base_pt1.weight])
     for a, b in zip(g_fused, g_plain):
         assert rel_errors(a, b)[1] <= 6e-2, rel_errors(a, b)
+
+
+@pytest.mark.parametrize("V,Cc", [(2, 64), (1, 512)])
+def test_fused_conv1_trainable_upsampled_gradients_same_roundings(V, Cc):
+    """warp_conv1_trainable(upsample_shape=): forward AND backward on the trunk's low-res map.  Reference: autograd through
+    F.interpolate -> oracle warp (fp32), with the training path's bf16 roundings (warped value, weight, masked gradient, data gradient,
+    feature gradient) and the same ReLU mask.  C = 512 takes the tcgen05 data gradient; C = 64 the comparison path.  The low-res
+    feature gradient, the weight gradient (re-materialised warp through the composed forward CSR) and the bias gradient must agree
+    to 2e-3 -- a wrong composed tap or a gradient left at high resolution would be off by O(1)."""
+    import torch.nn.functional as F
+    from mvdet_b200 import conv1
+    from oracle import kornia_warp as K
+    from tests.util import small_rig, to_channels_last_5d, rel_errors
+    pm, src_hw, grid_hw = small_rig(num_cam=V, seed=35)
+    low_hw = (src_hw[0] // 3, src_hw[1] // 3)
+    g = torch.Generator().manual_seed(0)
+    low = torch.randn(1, V, Cc, *low_hw, generator=g).bfloat16()
+    weight = (torch.randn(512, V * Cc + 2, 3, 3, generator=g) * 0.05)
+    bias = torch.randn(512, generator=g)
+    go = torch.randn(1, 512, *grid_hw, generator=g)
+    xd = to_channels_last_5d(low).cuda().requires_grad_(True)
+    wd = weight.cuda().requires_grad_(True)
+    bd = bias.cuda().requires_grad_(True)
+    out = conv1.warp_conv1_trainable(xd, wd, bd, pm, grid_hw, upsample_shape=src_hw)
+    gx, gw, gb = torch.autograd.grad(out, [xd, wd, bd], go.cuda())
+    assert gx.shape == xd.shape                                           # the gradient comes back at LOW resolution
+    mask = (out.detach().cpu() > 0).float()
+    bf = lambda t: t.bfloat16().float()
+    xr = low.float().requires_grad_(True)
+    up = torch.stack([F.interpolate(xr[:, v], src_hw, mode="bilinear") for v in range(V)], dim=1)      # persp_trans_detector.py:65
+    Xo = K.warp_views_oracle(up, pm, grid_hw)
+    X, w16 = bf(Xo.detach()), bf(weight)
+    ref_out = F.relu(F.conv2d(X, w16, bias, padding=1))
+    assert float(((ref_out > 0).float() == mask).float().mean()) >= 0.999
+    g16 = bf(go * mask)
+    gX = bf(torch.nn.grad.conv2d_input(X.shape, w16, g16, padding=1))
+    gwr = torch.nn.grad.conv2d_weight(X, w16.shape, g16, padding=1)
+    gbr = (go * mask).sum(dim=(0, 2, 3))
+    (gxr,) = torch.autograd.grad(Xo, xr, gX)
+    assert rel_errors(out, ref_out)[1] <= 5e-4
+    assert rel_errors(gx.float(), bf(gxr))[1] <= 2e-3, rel_errors(gx.float(), bf(gxr))
+    assert rel_errors(gw, gwr)[1] <= 2e-3, rel_errors(gw, gwr)
+    assert rel_errors(gb, gbr)[1] <= 1e-5, rel_errors(gb, gbr)
