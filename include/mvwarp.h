@@ -57,6 +57,9 @@ typedef struct mvwarp_stats {
   uint32_t fwd_tasks;         /* fused up-sample plans: warp-sized tasks of the forward table gather (else 0) */
   int32_t  lowres_h, lowres_w;/* fused up-sample plans: the low-res feature map the kernels read (else 0); for such plans
                                  unique_texels / nnz / max_row describe the composed map on the low-res image */
+  uint32_t zero_segments;     /* backward: runs of <= 8 consecutive texels (one image row of one 8x8 tile) whose rows are all empty;
+                                 dedicated CTAs stream zeros over them, they belong to no task */
+  uint32_t zero_rows;         /* texels covered by those segments, summed over views */
   uint64_t device_bytes;      /* HBM held by the plan */
 } mvwarp_stats_t;
 

@@ -20,7 +20,8 @@ class Stats(C.Structure):
     _fields_ = [("V", C.c_int32), ("Hs", C.c_int32), ("Ws", C.c_int32), ("Hg", C.c_int32), ("Wg", C.c_int32),
                 ("inline_coords", C.c_int32), ("unique_texels", C.c_uint64), ("nnz", C.c_uint64),
                 ("valid_cells", C.c_uint64), ("max_row", C.c_uint32), ("bwd_tasks", C.c_uint32), ("heavy_rows", C.c_uint32),
-                ("fwd_tasks", C.c_uint32), ("lowres_h", C.c_int32), ("lowres_w", C.c_int32), ("device_bytes", C.c_uint64)]
+                ("fwd_tasks", C.c_uint32), ("lowres_h", C.c_int32), ("lowres_w", C.c_int32), ("zero_segments", C.c_uint32),
+                ("zero_rows", C.c_uint32), ("device_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_}

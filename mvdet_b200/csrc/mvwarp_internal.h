@@ -22,6 +22,11 @@ struct CsrEntry {
 constexpr uint32_t TASK_BUDGET = 32, TASK_MAX_ROWS = 31, HEAVY_LEN = 31;  // swept on B200: profiles/README.md
 constexpr int CSR_TILE = 8;  // rows are ordered tile-major over CSR_TILE x CSR_TILE tiles of the row image
 
+struct ZeroSeg {
+  uint32_t id;     // linear index of the segment's first texel in the destination image
+  uint32_t view;
+};
+
 struct Task {
   uint32_t row0;   // first row (tile-major position, view-relative)
   uint16_t nrows;  // <= TASK_MAX_ROWS
@@ -42,6 +47,12 @@ struct HostCsr {
   std::vector<uint32_t> heavy_base;  // [V + 1]
   uint64_t nonempty_rows = 0;
   uint32_t max_row = 0;
+  // Zero segments (backward maps): tile-row segments -- the <= CSR_TILE consecutive rows that are one image row of one tile, i.e.
+  // consecutive texels in memory -- in which EVERY row is empty (60 % of a Wildtrack feature map lies outside the cameras' ground
+  // footprints).  They belong to no task: dedicated CTAs of the same launch stream zeros over them with no per-row bookkeeping,
+  // and the gather warps only walk rows inside the footprints.  {first texel id (y * W + x, x a multiple of CSR_TILE), view}.
+  std::vector<ZeroSeg> zseg;
+  std::vector<uint32_t> zseg_base;   // [V + 1]
   // Staging blocks (forward map of fused up-sample plans only): rows are cut into blocks of STAGE_ROWS consecutive rows (one 8x8
   // cell tile); per block the DISTINCT columns (low-res texels) it references, ascending, and per entry its index in that list.
   // The forward kernel brings a block's distinct texel rows into shared memory once (bulk async copies) and blends from there.
@@ -77,7 +88,8 @@ struct DevCsr {
   Task* tasks = nullptr;
   uint32_t* heavy = nullptr;
   uint32_t* heavy_base_dev = nullptr;
-  std::vector<uint32_t> task_base, heavy_base;  // host copies, [V+1]
+  ZeroSeg* zseg = nullptr;                      // zero segments (see HostCsr), or nullptr
+  std::vector<uint32_t> task_base, heavy_base, zseg_base;  // host copies, [V+1]
   uint32_t max_row = 0;                         // longest row (host copy)
   uint32_t* blk_ptr = nullptr;                  // staging blocks (see HostCsr), or nullptr
   uint32_t* blk_tex = nullptr;
@@ -90,6 +102,7 @@ struct CsrLayout {
   uint64_t rows_per_view = 0, max_row = 0;
   uint64_t row_ptr = 0, row_id = 0, entries = 0, view_base = 0, tasks = 0, heavy = 0, heavy_base = 0;
   uint64_t blk_ptr = 0, blk_tex = 0, slot = 0, n_blk_tex = 0, max_blk_tex = 0;   // staging blocks (n_blk_tex == 0: none)
+  uint64_t zseg = 0, n_zseg = 0;                                                 // zero segments (n_zseg == 0: none)
 };
 struct PlanLayout {
   uint64_t T = 0, grid = 0, coord_x = 0, coord_y = 0;

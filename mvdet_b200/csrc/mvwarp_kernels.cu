@@ -42,6 +42,7 @@ struct KParams {
   const uint64_t* view_base;
   const Task* tasks;
   const uint32_t* heavy;
+  const ZeroSeg* zseg;       // zero segments of the map (mvwarp_internal.h HostCsr), or nullptr
   const uint32_t* blk_ptr;   // staging blocks of the forward map (fused up-sample plans), or nullptr
   const uint32_t* blk_tex;
   const uint16_t* slot;
@@ -819,16 +820,55 @@ __device__ __forceinline__ void gather_heavy_row(const KParams& p, uint32_t hid,
   }
 }
 
-// One launch: the first n_heavy CTAs take one heavy row each (longest chains start first), the rest take
-// BWD_WARPS tasks each.  Two entry points over the same body so that profiles name the two uses apart.
+// Zero segments (backward maps): a warp streams zeros over ZSEG_PER_WARP tile-row segments -- up to CSR_TILE consecutive texels, whose
+// rows are all empty -- with one address computation per segment and no per-row bookkeeping: 60 % of a Wildtrack feature gradient
+// lies outside every camera's ground footprint and is written here; the gather warps only walk rows inside the footprints.
+constexpr int ZSEG_PER_WARP = 4, ZSEG_PER_CTA = ZSEG_PER_WARP * BWD_WARPS;
+
+template <typename T, bool FULLC>
+__device__ __forceinline__ void zero_segments(const KParams& p, uint32_t first, uint32_t zseg_hi) {
+  constexpr int EPV = VecTraits<T>::EPV;
+  const int lane = threadIdx.x & 31, b = blockIdx.z;
+  const int nvec = p.C / EPV;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+  for (int i = 0; i < ZSEG_PER_WARP; ++i) {
+    const uint32_t s = first + i;
+    if (s >= zseg_hi) return;
+    const ZeroSeg zs = p.zseg[s];
+    const int vl = (int)zs.view - p.view0;
+    const int yd = zs.id / p.gdst.width, xd = zs.id - yd * p.gdst.width;
+    const int tw = min(CSR_TILE, p.gdst.width - xd);
+    T* o = feats_view<T>(p, p.dst, vl, p.gdst.V) + (int64_t)b * p.gdst.B + p.gdst.chan0 + (int64_t)yd * p.gdst.H + (int64_t)xd * p.gdst.W;
+    for (int t = 0; t < tw; ++t, o += p.gdst.W)
+      for (int c = lane; c < nvec; c += 32) stcs16<16>(o + c * EPV, z);
+  }
+}
+
+// One launch: the first n_heavy CTAs take one heavy row each (longest chains start first), the next n_task_ctas take
+// BWD_WARPS tasks each, the rest stream zeros over the map's zero segments (backward only).  Two entry points over the same
+// body so that profiles name the two uses apart.
 template <typename T, bool KEEP, bool FULLC, bool DENSE, bool DSTANY>
 __device__ __forceinline__ void csr_gather_body(const KParams& p, uint32_t task_lo, uint32_t task_hi, uint32_t heavy_lo,
                                                 uint32_t n_heavy, int view_lo, const uint32_t* __restrict__ heavy_base,
-                                                float (*part)[BWD_PASS_FLOATS]) {
-  if (blockIdx.x < n_heavy) {
-    gather_heavy_row<T, KEEP, FULLC, DENSE, DSTANY>(p, heavy_lo + blockIdx.x, view_lo, heavy_base, part);
+                                                uint32_t n_task_ctas, uint32_t zseg_lo, uint32_t zseg_hi, float (*part)[BWD_PASS_FLOATS]) {
+  uint32_t bid = blockIdx.x;
+  if (!DSTANY && zseg_hi > zseg_lo) {
+    // the zero-segment CTAs are spread evenly over the launch (every `period`-th CTA) instead of queued behind the gathers: the
+    // gather warps are latency-bound and leave DRAM bandwidth idle, which the streaming zero stores then use
+    const uint32_t n_zero = (zseg_hi - zseg_lo + ZSEG_PER_CTA - 1) / ZSEG_PER_CTA;
+    const uint32_t period = max(1u, gridDim.x / n_zero);        // n_zero * period <= gridDim.x: every zero CTA has a slot
+    const uint32_t q = bid / period;
+    if (bid % period == period - 1 && q < n_zero) {
+      zero_segments<T, FULLC>(p, zseg_lo + q * ZSEG_PER_CTA + (threadIdx.x >> 5) * ZSEG_PER_WARP, zseg_hi);
+      return;
+    }
+    bid -= min(q, n_zero);                                       // index among the heavy / task CTAs
+  }
+  if (bid < n_heavy) {
+    gather_heavy_row<T, KEEP, FULLC, DENSE, DSTANY>(p, heavy_lo + bid, view_lo, heavy_base, part);
   } else {
-    gather_task<T, KEEP, FULLC, DENSE, DSTANY>(p, task_lo + (blockIdx.x - n_heavy) * BWD_WARPS + (threadIdx.x >> 5), task_hi);
+    gather_task<T, KEEP, FULLC, DENSE, DSTANY>(p, task_lo + (bid - n_heavy) * BWD_WARPS + (threadIdx.x >> 5), task_hi);
   }
 }
 
@@ -836,18 +876,18 @@ __device__ __forceinline__ void csr_gather_body(const KParams& p, uint32_t task_
 template <typename T, int MINB, bool KEEP, bool FULLC, bool DENSE>
 __global__ void __launch_bounds__(BWD_WARPS * 32, MINB)
     bwd_cl_kernel(const KParams p, uint32_t task_lo, uint32_t task_hi, uint32_t heavy_lo, uint32_t n_heavy, int view_lo,
-                  const uint32_t* __restrict__ heavy_base) {
+                  const uint32_t* __restrict__ heavy_base, uint32_t n_task_ctas, uint32_t zseg_lo, uint32_t zseg_hi) {
   __shared__ __align__(16) float part[BWD_WARPS][BWD_PASS_FLOATS];
-  csr_gather_body<T, KEEP, FULLC, DENSE, false>(p, task_lo, task_hi, heavy_lo, n_heavy, view_lo, heavy_base, part);
+  csr_gather_body<T, KEEP, FULLC, DENSE, false>(p, task_lo, task_hi, heavy_lo, n_heavy, view_lo, heavy_base, n_task_ctas, zseg_lo, zseg_hi, part);
 }
 
 // forward of fused up-sample plans: out[cell] = sum w * feats_lowres[texel]  (+ coord_map channels)
 template <typename T, int MINB, bool FULLC, bool DENSE>
 __global__ void __launch_bounds__(BWD_WARPS * 32, MINB)
     fwd_table_cl_kernel(const KParams p, uint32_t task_lo, uint32_t task_hi, uint32_t heavy_lo, uint32_t n_heavy, int view_lo,
-                        const uint32_t* __restrict__ heavy_base) {
+                        const uint32_t* __restrict__ heavy_base, uint32_t n_task_ctas, uint32_t zseg_lo, uint32_t zseg_hi) {
   __shared__ __align__(16) float part[BWD_WARPS][BWD_PASS_FLOATS];
-  csr_gather_body<T, false, FULLC, DENSE, true>(p, task_lo, task_hi, heavy_lo, n_heavy, view_lo, heavy_base, part);
+  csr_gather_body<T, false, FULLC, DENSE, true>(p, task_lo, task_hi, heavy_lo, n_heavy, view_lo, heavy_base, n_task_ctas, zseg_lo, zseg_hi, part);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1494,7 +1534,7 @@ static KParams make_params(const LaunchArgs& a) {
 
 static void set_csr(KParams& p, const DevCsr& c) {
   p.row_ptr = c.row_ptr; p.row_id = c.row_id; p.entries = c.entries; p.view_base = c.view_base;
-  p.tasks = c.tasks; p.heavy = c.heavy; p.rows_per_view = c.rows_per_view;
+  p.tasks = c.tasks; p.heavy = c.heavy; p.zseg = c.zseg; p.rows_per_view = c.rows_per_view;
   p.blk_ptr = c.blk_ptr; p.blk_tex = c.blk_tex; p.slot = c.slot;
 }
 // feature-map side [B, V, C, H, W] and concat side [B, chan0 + vl*C + c, H, W] of a gather
@@ -1553,14 +1593,20 @@ static int launch_gather_t(const LaunchArgs& a, KParams& p, const DevCsr& csr, b
     const uint32_t t_lo = csr.task_base[a.view0], t_hi = csr.task_base[a.view0 + a.nviews];
     const uint32_t h_lo = csr.heavy_base[a.view0], h_hi = csr.heavy_base[a.view0 + a.nviews];
     const uint32_t n_heavy = h_hi - h_lo, n_task_ctas = (t_hi - t_lo + BWD_WARPS - 1) / BWD_WARPS;
-    if (n_heavy + n_task_ctas == 0) return MVWARP_OK;
-    dim3 grid(n_heavy + n_task_ctas, 1, a.B), block(BWD_WARPS * 32);
+    // zero segments exist on backward maps only; the forward table kernel writes its (few) empty rows from its tasks
+    const bool zs = !FORWARD && csr.zseg && !csr.zseg_base.empty();
+    const uint32_t z_lo = zs ? csr.zseg_base[a.view0] : 0u, z_hi = zs ? csr.zseg_base[a.view0 + a.nviews] : 0u;
+    const uint32_t n_zero_ctas = (z_hi - z_lo + ZSEG_PER_CTA - 1) / ZSEG_PER_CTA;
+    if (n_heavy + n_task_ctas + n_zero_ctas == 0) return MVWARP_OK;
+    dim3 grid(n_heavy + n_task_ctas + n_zero_ctas, 1, a.B), block(BWD_WARPS * 32);
     const bool fullc = (a.C / EPV) % (32 * (BWD_ACC_FLOATS / EPV)) == 0;      // a pass never has a channel tail
     const bool dense = p.gsrc.H == (int64_t)p.gsrc.width * p.gsrc.W;           // source rows are col * W apart
 #define MVW_GATHER(KERNEL, ...)                                                                                                  \
   do {                                                                                                                           \
-    if (fullc && dense) KERNEL<T, __VA_ARGS__, true, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev); \
-    else KERNEL<T, __VA_ARGS__, false, false><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev);             \
+    if (fullc && dense)                                                                                                          \
+      KERNEL<T, __VA_ARGS__, true, true><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev, n_task_ctas, z_lo, z_hi); \
+    else                                                                                                                         \
+      KERNEL<T, __VA_ARGS__, false, false><<<grid, block, 0, a.stream>>>(p, t_lo, t_hi, h_lo, n_heavy, a.view0, csr.heavy_base_dev, n_task_ctas, z_lo, z_hi); \
   } while (0)
 #ifdef MVWARP_DEV
     const bool row16 = ((uint64_t)a.C * sizeof(T)) % 512 == 0;   // a texel row is a whole number of 512-byte lane passes

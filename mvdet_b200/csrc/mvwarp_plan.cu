@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <memory>
 #include <new>
+#include <stdexcept>
 #include <thread>
 
 #include "mvwarp_coords.h"
@@ -65,13 +66,17 @@ struct ViewCsr {
   std::vector<CsrEntry> entries;
   std::vector<Task> tasks;
   std::vector<uint32_t> heavy;
+  std::vector<ZeroSeg> zseg;
   uint64_t nonempty = 0;
   uint32_t max_row = 0;
 };
 
 // Stable counting sort of one view's triplets by row (entry order inside a row = insertion order), then the
 // gather tasks: greedy runs of consecutive light rows under TASK_BUDGET, heavy rows apart.
-static void csr_from_triplets(const std::vector<Triplet>& trip, size_t nrows, int view, uint32_t* row_ptr, ViewCsr& out) {
+// zero_width > 0 (backward maps; the width of the destination image whose tile-major order the rows follow): tile-row segments
+// whose rows are all empty become zero segments instead of task rows (HostCsr::zseg).
+static void csr_from_triplets(const std::vector<Triplet>& trip, size_t nrows, int view, uint32_t* row_ptr, ViewCsr& out,
+                              const uint32_t* id_of_row = nullptr, int zero_width = 0) {
   std::vector<uint32_t> cursor(nrows + 1, 0);
   for (const Triplet& t : trip) ++cursor[t.row];
   uint32_t run = 0;
@@ -105,6 +110,22 @@ static void csr_from_triplets(const std::vector<Triplet>& trip, size_t nrows, in
   };
   for (size_t r = 0; r < nrows; ++r) {
     const uint32_t len = row_ptr[r + 1] - row_ptr[r];
+    if (zero_width > 0 && len == 0) {
+      // start of a tile-row segment (x a multiple of CSR_TILE; its rows are consecutive in tile-major order and in memory)?
+      const uint32_t id = id_of_row[r];
+      const int x = (int)(id % (uint32_t)zero_width);
+      if (x % CSR_TILE == 0) {
+        const size_t tw = (size_t)std::min(CSR_TILE, zero_width - x);
+        bool all_empty = r + tw <= nrows;
+        for (size_t i = 0; all_empty && i < tw; ++i) all_empty = row_ptr[r + i + 1] == row_ptr[r + i] && id_of_row[r + i] == id + i;
+        if (all_empty) {
+          flush();   // tasks are runs of CONSECUTIVE rows
+          out.zseg.push_back(ZeroSeg{id, (uint32_t)view});
+          r += tw - 1;
+          continue;
+        }
+      }
+    }
     if (len > heavy_len) {
       flush();
       out.heavy.push_back((uint32_t)r);
@@ -127,6 +148,7 @@ static void csr_init(HostCsr& csr, int V, size_t rows_per_view, const std::vecto
   csr.view_base.assign(V + 1, 0);
   csr.task_base.assign(V + 1, 0);
   csr.heavy_base.assign(V + 1, 0);
+  csr.zseg_base.assign(V + 1, 0);
 }
 
 static void csr_assemble(HostCsr& csr, int V, std::vector<ViewCsr>& per_view) {
@@ -136,6 +158,7 @@ static void csr_assemble(HostCsr& csr, int V, std::vector<ViewCsr>& per_view) {
     total += per_view[v].entries.size();
     csr.task_base[v + 1] = csr.task_base[v] + (uint32_t)per_view[v].tasks.size();
     csr.heavy_base[v + 1] = csr.heavy_base[v] + (uint32_t)per_view[v].heavy.size();
+    csr.zseg_base[v + 1] = csr.zseg_base[v] + (uint32_t)per_view[v].zseg.size();
   }
   csr.view_base[V] = total;
   csr.entries.resize(total);
@@ -149,9 +172,45 @@ static void csr_assemble(HostCsr& csr, int V, std::vector<ViewCsr>& per_view) {
       memcpy(csr.entries.data() + csr.view_base[v], pv.entries.data(), pv.entries.size() * sizeof(CsrEntry));
     csr.tasks.insert(csr.tasks.end(), pv.tasks.begin(), pv.tasks.end());
     csr.heavy.insert(csr.heavy.end(), pv.heavy.begin(), pv.heavy.end());
+    csr.zseg.insert(csr.zseg.end(), pv.zseg.begin(), pv.zseg.end());
     std::vector<CsrEntry>().swap(pv.entries);
     csr.nonempty_rows += pv.nonempty;
     csr.max_row = std::max(csr.max_row, pv.max_row);
+  }
+}
+
+// Every row of every view must belong to exactly one task, be a heavy row, or lie in a zero segment: a row left out would keep
+// whatever the output buffer held.  Checked once per plan on the host (cheap: one pass over the work lists).
+static void csr_check_coverage(const HostCsr& csr, int V, int zero_width) {
+  const size_t R = csr.rows_per_view;
+  std::vector<uint8_t> seen(R);
+  std::vector<uint32_t> row_of_id;
+  if (!csr.zseg.empty()) {
+    row_of_id.resize(R);
+    for (size_t r = 0; r < R; ++r) row_of_id[csr.row_id[r]] = (uint32_t)r;   // the same order for every view
+  }
+  for (int v = 0; v < V; ++v) {
+    std::fill(seen.begin(), seen.end(), 0);
+    auto mark = [&](size_t r) {
+      if (r >= R || seen[r]) throw std::logic_error("plan: a CSR row is covered twice or lies outside the map");
+      seen[r] = 1;
+    };
+    for (uint32_t t = csr.task_base[v]; t < csr.task_base[v + 1]; ++t)
+      for (uint32_t i = 0; i < csr.tasks[t].nrows; ++i) mark((size_t)csr.tasks[t].row0 + i);
+    for (uint32_t i = csr.heavy_base[v]; i < csr.heavy_base[v + 1]; ++i) mark(csr.heavy[i]);
+    for (uint32_t i = csr.zseg_base[v]; i < csr.zseg_base[v + 1]; ++i) {
+      const uint32_t id = csr.zseg[i].id;
+      const int tw = std::min<int>(CSR_TILE, zero_width - (int)(id % (uint32_t)zero_width));
+      for (int k = 0; k < tw; ++k) {
+        if ((size_t)id + k >= R) throw std::logic_error("plan: a zero segment leaves the map");
+        const size_t r = row_of_id[id + k];
+        const uint32_t* rp = csr.row_ptr.data() + (size_t)v * (R + 1);
+        if (rp[r + 1] != rp[r]) throw std::logic_error("plan: a zero segment covers a non-empty row");
+        mark(r);
+      }
+    }
+    for (size_t r = 0; r < R; ++r)
+      if (!seen[r]) throw std::logic_error("plan: a CSR row belongs to no task, heavy row or zero segment");
   }
 }
 
@@ -186,9 +245,10 @@ void host_build_maps(const float* grid, int V, int Hs, int Ws, int Hg, int Wg, P
         if (t.mask >> k & 1)
           trip.push_back({row_of_tex[(size_t)(t.y0 + kDy[k]) * Ws + (t.x0 + kDx[k])], CsrEntry{(uint32_t)cell, t.w[k]}});
     }
-    csr_from_triplets(trip, ntex, v, maps.bwd.row_ptr.data() + (size_t)v * (ntex + 1), per_view[v]);
+    csr_from_triplets(trip, ntex, v, maps.bwd.row_ptr.data() + (size_t)v * (ntex + 1), per_view[v], tex_of_row.data(), Ws);
   });
   csr_assemble(maps.bwd, V, per_view);
+  csr_check_coverage(maps.bwd, V, Ws);
   maps.valid_cells = 0;
   for (int v = 0; v < V; ++v) maps.valid_cells += valid[v];
 }
@@ -291,10 +351,12 @@ void host_build_maps_upsampled(const float* grid, int V, int hl, int wl, int Hs,
       }
     }
     csr_from_triplets(tf, ncell, v, maps.fwd.row_ptr.data() + (size_t)v * (ncell + 1), pv_fwd[v]);
-    csr_from_triplets(tb, nlow, v, maps.bwd.row_ptr.data() + (size_t)v * (nlow + 1), pv_bwd[v]);
+    csr_from_triplets(tb, nlow, v, maps.bwd.row_ptr.data() + (size_t)v * (nlow + 1), pv_bwd[v], low_of_row.data(), wl);
   });
   csr_assemble(maps.fwd, V, pv_fwd);
   csr_assemble(maps.bwd, V, pv_bwd);
+  csr_check_coverage(maps.fwd, V, Wg);
+  csr_check_coverage(maps.bwd, V, wl);
   build_stage_blocks(maps.fwd, V);
   maps.valid_cells = 0;
   for (int v = 0; v < V; ++v) maps.valid_cells += valid[v];
@@ -330,6 +392,11 @@ static void fill_stats(mvwarp_stats_t& st, const PlanMaps& maps, int V, int Hs, 
   st.heavy_rows = maps.bwd.heavy_base[V];
   st.lowres_h = hl; st.lowres_w = wl;
   st.fwd_tasks = maps.fwd.task_base.empty() ? 0 : maps.fwd.task_base[V];
+  const int zw = hl > 0 ? wl : Ws;   // width of the image the backward's rows are texels of
+  st.zero_segments = (uint32_t)maps.bwd.zseg.size();
+  uint64_t zr = 0;
+  for (const ZeroSeg& z : maps.bwd.zseg) zr += (uint64_t)std::min<int>(CSR_TILE, zw - (int)(z.id % (uint32_t)zw));
+  st.zero_rows = (uint32_t)zr;
 }
 
 // Device pointers of a plan from its layout (shared by plan creation and mvwarp_plan_load).
@@ -352,6 +419,7 @@ static void bind_pointers(mvwarp_plan* p) {
       d.blk_ptr = (uint32_t*)(base + o.blk_ptr); d.blk_tex = (uint32_t*)(base + o.blk_tex); d.slot = (uint16_t*)(base + o.slot);
       d.max_blk_tex = (uint32_t)o.max_blk_tex;
     }
+    d.zseg = o.n_zseg ? (ZeroSeg*)(base + o.zseg) : nullptr;
   };
   bind(p->bwd, L.bwd);
   bind(p->fwd, L.fwd);
@@ -417,6 +485,10 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int hl,
       o.tasks = carve(c.tasks.size() * sizeof(Task));
       o.heavy = carve(c.heavy.size() * sizeof(uint32_t));
       o.heavy_base = carve(c.heavy_base.size() * sizeof(uint32_t));
+      if (!c.zseg.empty()) {
+        o.n_zseg = c.zseg.size();
+        o.zseg = carve(c.zseg.size() * sizeof(ZeroSeg));
+      }
       if (!c.blk_tex.empty()) {
         o.n_blk_tex = c.blk_tex.size();
         o.blk_ptr = carve(c.blk_ptr.size() * sizeof(uint32_t));
@@ -458,8 +530,8 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int hl,
     p->d_bytes = off;
     e = cudaMalloc(&p->d_base, p->d_bytes);
     if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(plan)"); }
-    p->bwd.task_base = maps.bwd.task_base; p->bwd.heavy_base = maps.bwd.heavy_base;
-    p->fwd.task_base = maps.fwd.task_base; p->fwd.heavy_base = maps.fwd.heavy_base;
+    p->bwd.task_base = maps.bwd.task_base; p->bwd.heavy_base = maps.bwd.heavy_base; p->bwd.zseg_base = maps.bwd.zseg_base;
+    p->fwd.task_base = maps.fwd.task_base; p->fwd.heavy_base = maps.fwd.heavy_base; p->fwd.zseg_base = maps.fwd.zseg_base;
     if (T) p->h_T.assign(T, T + (size_t)V * 9);
     bind_pointers(p);
 
@@ -475,6 +547,7 @@ static int plan_create_impl(const float* T, const float* grid_in, int V, int hl,
       up(d.tasks, c.tasks.data(), c.tasks.size() * sizeof(Task));
       up(d.heavy, c.heavy.data(), c.heavy.size() * sizeof(uint32_t));
       up(d.heavy_base_dev, c.heavy_base.data(), c.heavy_base.size() * sizeof(uint32_t));
+      if (!c.zseg.empty()) up(d.zseg, c.zseg.data(), c.zseg.size() * sizeof(ZeroSeg));
       if (!c.blk_tex.empty()) {
         up(d.blk_ptr, c.blk_ptr.data(), c.blk_ptr.size() * sizeof(uint32_t));
         up(d.blk_tex, c.blk_tex.data(), c.blk_tex.size() * sizeof(uint32_t));
@@ -615,7 +688,7 @@ int mvwarp_plan_create_upsampled(const float* T, int V, int hl, int wl, int Hs, 
 }
 
 // ---- plan persistence ----------------------------------------------------------------------
-// File = PlanFileHeader | bwd task_base[V+1] | bwd heavy_base[V+1] | fwd task_base[V+1] | fwd heavy_base[V+1] (fused
+// File = PlanFileHeader | bwd task_base[V+1] | bwd heavy_base[V+1] | bwd zseg_base[V+1] | fwd task_base, heavy_base, zseg_base (fused
 // up-sample plans only) | matrices [V*9] (inline plans only) | the device allocation, byte for byte.
 namespace {
 struct PlanFileHeader {
@@ -634,7 +707,7 @@ const char kMagic[8] = {'M', 'V', 'W', 'P', 'L', 'A', 'N', '2'};
 
 // Layout / schema hash: any builder change that keeps the constants but changes what the arrays mean must bump PLAN_SCHEMA, so
 // that files cached under $MVWARP_PLAN_DIR by an older build are refused instead of being dereferenced by the gather kernels.
-constexpr uint32_t PLAN_SCHEMA = 3;
+constexpr uint32_t PLAN_SCHEMA = 4;   // 4: zero segments (rows of all-empty tile-row segments belong to no task)
 constexpr uint32_t plan_schema() {
   return PLAN_SCHEMA * 0x9E3779B1u ^ (uint32_t)(sizeof(mvw::Task) << 24 | sizeof(mvw::CsrEntry) << 16 | sizeof(mvw::PlanLayout));
 }
@@ -688,8 +761,8 @@ int mvwarp_plan_save(const mvwarp_plan_t* plan, const char* path) {
       auto put = [&](const std::vector<uint32_t>& v) {
         ok = ok && v.size() == (size_t)plan->V + 1 && fwrite(v.data(), sizeof(uint32_t), v.size(), fc.f) == v.size();
       };
-      put(plan->bwd.task_base); put(plan->bwd.heavy_base);
-      if (h.has_fwd) { put(plan->fwd.task_base); put(plan->fwd.heavy_base); }
+      put(plan->bwd.task_base); put(plan->bwd.heavy_base); put(plan->bwd.zseg_base);
+      if (h.has_fwd) { put(plan->fwd.task_base); put(plan->fwd.heavy_base); put(plan->fwd.zseg_base); }
       if (h.inline_coords) ok = ok && plan->h_T.size() == (size_t)plan->V * 9 &&
                                 fwrite(plan->h_T.data(), sizeof(float), plan->h_T.size(), fc.f) == plan->h_T.size();
       ok = ok && fwrite(blob.data(), 1, blob.size(), fc.f) == blob.size();
@@ -745,8 +818,8 @@ int mvwarp_plan_load(const char* path, int device, mvwarp_plan_t** plan_out) {
       v.resize((size_t)h.V + 1);
       ok = ok && fread(v.data(), sizeof(uint32_t), v.size(), fc.f) == v.size();
     };
-    get(p->bwd.task_base); get(p->bwd.heavy_base);
-    if (h.has_fwd) { get(p->fwd.task_base); get(p->fwd.heavy_base); }
+    get(p->bwd.task_base); get(p->bwd.heavy_base); get(p->bwd.zseg_base);
+    if (h.has_fwd) { get(p->fwd.task_base); get(p->fwd.heavy_base); get(p->fwd.zseg_base); }
     if (h.inline_coords) {
       p->h_T.resize((size_t)h.V * 9);
       ok = ok && fread(p->h_T.data(), sizeof(float), p->h_T.size(), fc.f) == p->h_T.size();
@@ -761,24 +834,25 @@ int mvwarp_plan_load(const char* path, int device, mvwarp_plan_t** plan_out) {
     // every array must lie inside the blob (a corrupt header must not become a wild device pointer)
     const uint64_t nrows_b = h.layout.bwd.rows_per_view, nrows_f = h.layout.fwd.rows_per_view;
     auto inside = [&](uint64_t off, uint64_t bytes) { return off <= h.d_bytes && bytes <= h.d_bytes - off; };
-    auto csr_ok = [&](const CsrLayout& o, const std::vector<uint32_t>& tb, const std::vector<uint32_t>& hb) {
+    auto csr_ok = [&](const CsrLayout& o, const std::vector<uint32_t>& tb, const std::vector<uint32_t>& hb, const std::vector<uint32_t>& zb) {
       if (o.rows_per_view == 0) return true;
+      if (zb.back() != o.n_zseg || (o.n_zseg && !inside(o.zseg, o.n_zseg * sizeof(ZeroSeg)))) return false;
       return inside(o.row_ptr, (uint64_t)h.V * (o.rows_per_view + 1) * 4) && inside(o.row_id, (uint64_t)h.V * o.rows_per_view * 4) &&
              inside(o.view_base, ((uint64_t)h.V + 1) * 8) && inside(o.tasks, (uint64_t)tb.back() * sizeof(Task)) &&
              inside(o.heavy, (uint64_t)hb.back() * 4) && inside(o.heavy_base, ((uint64_t)h.V + 1) * 4) && inside(o.entries, 0);
     };
     if (!inside(h.layout.T, (uint64_t)h.V * 36) || !inside(h.layout.coord_x, (uint64_t)h.Wg * 4) ||
         !inside(h.layout.coord_y, (uint64_t)h.Hg * 4) || nrows_b == 0 || (h.has_fwd != 0) != (nrows_f != 0) ||
-        !csr_ok(h.layout.bwd, p->bwd.task_base, p->bwd.heavy_base) ||
-        (h.has_fwd && !csr_ok(h.layout.fwd, p->fwd.task_base, p->fwd.heavy_base)) ||
+        !csr_ok(h.layout.bwd, p->bwd.task_base, p->bwd.heavy_base, p->bwd.zseg_base) ||
+        (h.has_fwd && !csr_ok(h.layout.fwd, p->fwd.task_base, p->fwd.heavy_base, p->fwd.zseg_base)) ||
         (!h.inline_coords && !inside(h.layout.grid, (uint64_t)h.V * h.Hg * h.Wg * 8))) {
       set_error(std::string("plan_load: inconsistent layout in ") + path);
       return MVWARP_EINVAL;
     }
     // ... and every INDEX the gather kernels will dereference must be in range: a well-formed file with a valid checksum but
     // wrong contents (a foreign tool, a shared cache directory) must be refused here, not found out by an out-of-bounds read.
-    auto contents_ok = [&](const CsrLayout& o, const std::vector<uint32_t>& tb, const std::vector<uint32_t>& hb, uint64_t n_dst,
-                           uint64_t n_cols) {
+    auto contents_ok = [&](const CsrLayout& o, const std::vector<uint32_t>& tb, const std::vector<uint32_t>& hb, const std::vector<uint32_t>& zb,
+                           uint64_t n_dst, uint64_t dst_width, uint64_t n_cols) {
       if (o.rows_per_view == 0) return true;
       const uint64_t R = o.rows_per_view;
       if (R > n_dst) return false;
@@ -808,6 +882,16 @@ int mvwarp_plan_load(const char* path, int device, mvwarp_plan_t** plan_out) {
         for (uint32_t i = hb[v]; i < hb[v + 1]; ++i) if (heavy[i] >= R) return false;
       }
       if (hbd[h.V] != hb[h.V]) return false;
+      if (zb[0] != 0) return false;
+      for (int v = 0; v < h.V; ++v) if (zb[v + 1] < zb[v]) return false;
+      if (o.n_zseg) {   // zero segments: whole tile-row segments inside the destination image, filed under their own view
+        const ZeroSeg* zs = reinterpret_cast<const ZeroSeg*>(blob.data() + o.zseg);
+        for (int v = 0; v < h.V; ++v)
+          for (uint32_t i = zb[v]; i < zb[v + 1]; ++i) {
+            const uint64_t x = zs[i].id % dst_width;
+            if (zs[i].view != (uint32_t)v || zs[i].id >= n_dst || x % CSR_TILE != 0) return false;
+          }
+      }
       if (o.n_blk_tex) {   // staging blocks: block lists inside the blob, columns in range, every entry's slot inside its block
         const uint64_t nblk = (R + STAGE_ROWS - 1) / STAGE_ROWS;
         if (!inside(o.blk_ptr, (uint64_t)h.V * (nblk + 1) * 4) || !inside(o.blk_tex, o.n_blk_tex * 4) || !inside(o.slot, nnz * 2)) return false;
@@ -845,8 +929,10 @@ int mvwarp_plan_load(const char* path, int device, mvwarp_plan_t** plan_out) {
       }
       if (!tok) { set_error(std::string("plan_load: bad touched-texel list in ") + path); return MVWARP_EINVAL; }
     }
-    if ((h.upsampled && (h.hl <= 0 || h.wl <= 0)) || !contents_ok(h.layout.bwd, p->bwd.task_base, p->bwd.heavy_base, n_src, n_cells) ||
-        (h.has_fwd && !contents_ok(h.layout.fwd, p->fwd.task_base, p->fwd.heavy_base, n_cells, n_src))) {
+    const uint64_t w_src = h.upsampled ? (uint64_t)h.wl : (uint64_t)h.Ws;
+    if ((h.upsampled && (h.hl <= 0 || h.wl <= 0)) ||
+        !contents_ok(h.layout.bwd, p->bwd.task_base, p->bwd.heavy_base, p->bwd.zseg_base, n_src, w_src, n_cells) ||
+        (h.has_fwd && !contents_ok(h.layout.fwd, p->fwd.task_base, p->fwd.heavy_base, p->fwd.zseg_base, n_cells, (uint64_t)h.Wg, n_src))) {
       set_error(std::string("plan_load: index out of range in ") + path + " (corrupt or foreign contents)");
       return MVWARP_EINVAL;
     }

@@ -35,8 +35,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_stats_struct_layout_matches_header():
-    # int32 x6, uint64 x3, uint32 x4, int32 x2, uint64: 24 + 24 + 16 + 8 + 8
-    assert ctypes.sizeof(_lib.Stats) == 80
+    # int32 x6, uint64 x3, uint32 x4, int32 x2, uint32 x2, uint64: 24 + 24 + 16 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.Stats) == 88
 
 
 def test_bad_arguments_return_error_codes_not_crashes():
@@ -187,10 +187,12 @@ def test_backward_task_decomposition_covers_every_row_once():
     lens = (row_ptr[:, 1:] - row_ptr[:, :-1]).long()
     heavy = int((lens > 31).sum())
     assert st["heavy_rows"] == heavy and heavy > 0
-    light_weight = int((lens[lens <= 31] + 1).sum())
-    # every task weighs at most 32 (rows + entries): the task count is bounded both ways
+    # rows of zero segments (all-empty runs of 8 texels) are in no task; what is left weighs 1 per row + 1 per entry
+    light_weight = int((lens[lens <= 31] + 1).sum()) - st["zero_rows"]
+    # every task weighs at most 32 (rows + entries): the task count is bounded both ways (a task ends at every heavy row and at
+    # every zero segment that interrupts a run)
     assert st["bwd_tasks"] >= light_weight / 32
-    assert st["bwd_tasks"] <= light_weight / 8 + 2 * heavy + 7 * 2040
+    assert st["bwd_tasks"] <= light_weight / 8 + 2 * heavy + 7 * 2040 + st["zero_segments"]
 
 
 @pytest.mark.parametrize("Wg", [2, 44, 45, 64])
@@ -521,3 +523,20 @@ def test_upsample_windows_reject_a_down_sample():
     T = P.src_norm_trans_dst_norm(pm, src_hw, grid_hw)
     with pytest.raises(_lib.MvwarpError):
         P.host_upsample_windows(T, (src_hw[0] + 1, src_hw[1]), src_hw, grid_hw)
+
+
+@pytest.mark.parametrize("spec", [WILDTRACK, MULTIVIEWX], ids=lambda s: s.name)
+def test_zero_segments_cover_the_area_outside_the_footprints(spec):
+    """Backward work decomposition: runs of 8 consecutive texels (one image row of one 8x8 tile) with no tap at all are zero segments
+    -- streamed by dedicated CTAs, in no task.  The builder checks on the host that every row is in exactly one task, heavy row or
+    zero segment (a plan that left a row out would raise here); the statistics must add up, for plain and fused up-sample plans."""
+    pm = synthetic_rig(spec)
+    g = P.host_grid(P.src_norm_trans_dst_norm(pm, spec.feat_shape, spec.grid_shape), spec.grid_shape)
+    total = spec.num_cam * spec.feat_shape[0] * spec.feat_shape[1]
+    st = P.host_csr(g, spec.feat_shape)
+    assert st["zero_rows"] <= total - st["unique_texels"]
+    assert st["zero_rows"] >= 0.5 * total                         # most of a feature map lies outside the ground rectangle
+    assert st["zero_segments"] * 8 >= st["zero_rows"] > st["zero_segments"]
+    low = (spec.feat_shape[0] // 3, spec.feat_shape[1] // 3)
+    st_up = P.host_csr(g, spec.feat_shape, lowres_hw=low)
+    assert 0 < st_up["zero_rows"] <= spec.num_cam * low[0] * low[1] - st_up["unique_texels"]
