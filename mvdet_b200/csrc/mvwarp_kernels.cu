@@ -825,7 +825,7 @@ __device__ __forceinline__ void gather_heavy_row(const KParams& p, uint32_t hid,
 // lies outside every camera's ground footprint and is written here; the gather warps only walk rows inside the footprints.
 constexpr int ZSEG_PER_WARP = 4, ZSEG_PER_CTA = ZSEG_PER_WARP * BWD_WARPS;
 
-template <typename T, bool FULLC>
+template <typename T>
 __device__ __forceinline__ void zero_segments(const KParams& p, uint32_t first, uint32_t zseg_hi) {
   constexpr int EPV = VecTraits<T>::EPV;
   const int lane = threadIdx.x & 31, b = blockIdx.z;
@@ -845,9 +845,10 @@ __device__ __forceinline__ void zero_segments(const KParams& p, uint32_t first, 
   }
 }
 
-// One launch: the first n_heavy CTAs take one heavy row each (longest chains start first), the next n_task_ctas take
-// BWD_WARPS tasks each, the rest stream zeros over the map's zero segments (backward only).  Two entry points over the same
-// body so that profiles name the two uses apart.
+// One launch: CTAs that stream zeros over the map's zero segments (backward only) sit at every `period`-th block index; of the
+// others the first n_heavy take one heavy row each (longest chains start first), the rest BWD_WARPS tasks each.  Two entry points
+// over the same body so that profiles name the two uses apart.  Measured (Wildtrack): fp32 B=1 0.447 -> 0.434 ms with the zero CTAs
+// queued behind the gathers, 0.428 ms interleaved; bf16 B=8 2.06 -> 2.05 -> 1.94 ms (profiles/r02_logs/r02_bwd_zero_segments_*.txt).
 template <typename T, bool KEEP, bool FULLC, bool DENSE, bool DSTANY>
 __device__ __forceinline__ void csr_gather_body(const KParams& p, uint32_t task_lo, uint32_t task_hi, uint32_t heavy_lo,
                                                 uint32_t n_heavy, int view_lo, const uint32_t* __restrict__ heavy_base,
@@ -860,7 +861,7 @@ __device__ __forceinline__ void csr_gather_body(const KParams& p, uint32_t task_
     const uint32_t period = max(1u, gridDim.x / n_zero);        // n_zero * period <= gridDim.x: every zero CTA has a slot
     const uint32_t q = bid / period;
     if (bid % period == period - 1 && q < n_zero) {
-      zero_segments<T, FULLC>(p, zseg_lo + q * ZSEG_PER_CTA + (threadIdx.x >> 5) * ZSEG_PER_WARP, zseg_hi);
+      zero_segments<T>(p, zseg_lo + q * ZSEG_PER_CTA + (threadIdx.x >> 5) * ZSEG_PER_WARP, zseg_hi);
       return;
     }
     bid -= min(q, n_zero);                                       // index among the heavy / task CTAs
