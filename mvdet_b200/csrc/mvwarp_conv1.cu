@@ -770,6 +770,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
       slot = q * 2 + (int)prank;
     }
   }
+  const int item_peer = min(item ^ 1, p.nitems - 1);          // the other CTA of the pair (n_full is even: items pair as 2k, 2k + 1)
   const bool real_tile = item < p.nitems;
   if (!real_tile) item = p.nitems - 1;
   const int b = item / p.ntiles, tile = p.tile0 + (item % p.ntiles + p.p2p_tile_shift) % p.ntiles;
@@ -778,9 +779,52 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
   const int vlo = (part * p.nviews) / nparts, vhi = ((part + 1) * p.nviews) / nparts;
   const bool coord_here = p.with_coord && part == nparts - 1;
   const bool partial = nparts > 1;
-  const int npatch = (vhi - vlo) * ncb;                       // patches = (view, channel block) pairs of this CTA
+
+  // ----- views that reach neither tile of the pair are skipped: their K blocks would multiply zeros -----
+  // A camera sees only part of the ground plane (81 % of the cells on Wildtrack, 72 % on MultiviewX), and the area it misses is
+  // contiguous, so for 12.5 % (Wildtrack) to 22 % (MultiviewX, the 32-camera rig) of the (tile pair, view) combinations every halo
+  // cell of BOTH tiles falls outside the view's image: the whole patch is zero and its 9 * C/64 K blocks add +0 to the accumulator.
+  // Both CTAs of a pair walk the same weight blocks, so a view is dropped only when it misses both tiles; every thread of both CTAs
+  // evaluates the same predicate (the coordinate chain of the 2 x 180 halo cells per view, ~1 us per tile) and so arrives at the
+  // same list without any exchange.  Same bits as the dense loop.
+  constexpr int SKIP_MAX_VIEWS = 128;   // 276 bytes of static shared memory: the kernel is within 1 KB of the 227 KB limit
+  __shared__ uint32_t s_vmask[SKIP_MAX_VIEWS / 32];
+  __shared__ uint16_t s_av[SKIP_MAX_VIEWS];
+  __shared__ int s_nav;
+  const int nv_part = vhi - vlo;
+  const bool sparse = nv_part <= SKIP_MAX_VIEWS;
+  if (tid < SKIP_MAX_VIEWS / 32) s_vmask[tid] = 0u;
+  __syncthreads();
+  if (sparse) {
+    const int tile_p = p.tile0 + (item_peer % p.ntiles + p.p2p_tile_shift) % p.ntiles;
+    const int tx0_p = (tile_p % p.tiles_x) * DT_X, ty0_p = (tile_p / p.tiles_x) * DT_Y;
+    for (int w = tid; w < nv_part * 2 * DP_CELLS; w += PIPE_THREADS) {
+      const int vi = w / (2 * DP_CELLS), r = w - vi * (2 * DP_CELLS), which = r / DP_CELLS, i = r - which * DP_CELLS;
+      if ((*reinterpret_cast<volatile uint32_t*>(&s_vmask[vi >> 5]) >> (vi & 31)) & 1u) continue;   // already known to be seen
+      const int gx = (which ? tx0_p : tx0) + i / DP_Y - 1, gy = (which ? ty0_p : ty0) + i % DP_Y - 1;
+      if (gy < 0 || gy >= p.Hg || gx < 0 || gx >= p.Wg) continue;
+      float Tm[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) Tm[q] = __ldg(p.T + 9 * (p.view0 + vlo + vi) + q);
+      float sx, sy;
+      norm_src_coord(Tm, gx, gy, p.Hg, p.Wg, sx, sy);
+      if (make_taps(sx, sy, p.Hs, p.Ws).mask) atomicOr(&s_vmask[vi >> 5], 1u << (vi & 31));
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int n = 0;
+    if (sparse)
+      for (int vi = 0; vi < nv_part; ++vi)
+        if ((s_vmask[vi >> 5] >> (vi & 31)) & 1u) s_av[n++] = (uint16_t)(vlo + vi);
+    s_nav = sparse ? n : nv_part;
+  }
+  __syncthreads();
+  const int nav = s_nav;                                       // active views of this CTA pair (and K part)
+  auto view_of = [&](int idx) -> int { return sparse ? (int)s_av[idx] : vlo + idx; };   // idx-th active view (local index)
+  const int npatch = nav * ncb;                               // patches = (active view, channel block) pairs of this CTA
   const int NK = npatch * 9 + (coord_here ? 1 : 0);
-  const int wblk0 = vlo * ncb * 9, wblk_coord = p.nviews * ncb * 9;
+  const int wblk_coord = p.nviews * ncb * 9;
 
   if (warp == 0) tmem_alloc_2cta(&tmem_holder, CV_N);
   if (tid == 0) {
@@ -801,7 +845,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
     if (lane == 0) {
       for (int kb = 0; kb < NK; ++kb) {
         const int s = kb % DPB;
-        const int wblk = kb < npatch * 9 ? wblk0 + kb : wblk_coord;
+        const int pkb = kb / 9;                                   // patch of this K block -> (active view, channel block), tap
+        const int wblk = kb < npatch * 9 ? (view_of(pkb / ncb) * ncb + pkb % ncb) * 9 + (kb - 9 * pkb) : wblk_coord;
         if (kb >= DPB) mbar_wait(&b_empty[s], ((kb / DPB) - 1) & 1);
         if (prank == 0) mbar_expect_tx(&b_full[s], CV_B_BYTES);
         const uint32_t dst = smem_u32(sB + (size_t)s * CV_B2_BYTES), bar = map_to_cta(smem_u32(&b_full[s]), 0);
@@ -933,25 +978,26 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
       }
     };
 
+    // tap buffers alternate with the INDEX of the active view (two consecutive active views may both be even)
     if (npatch > 0) {
-      compute_taps(vlo, sT + (vlo & 1) * DP_CELLS);
+      compute_taps(view_of(0), sT);
       producers_sync();
-      issue_gathers(vlo, 0, sT + (vlo & 1) * DP_CELLS);
+      issue_gathers(view_of(0), 0, sT);
     }
     for (int pk = 0; pk < npatch; ++pk) {
-      const int blk = vlo * ncb + pk, vl = blk / ncb;
+      const int vidx = pk / ncb;
       const int i = pk % NPATCH;
       if (pk >= NPATCH) mbar_wait(&p_empty[i], ((pk / NPATCH) - 1) & 1);   // the nine K blocks that read this buffer are done
-      blend_patch(sT + (vl & 1) * DP_CELLS, sPatch + (size_t)i * DPATCH_BYTES);    // consumes the gathers issued one patch earlier
+      blend_patch(sT + (vidx & 1) * DP_CELLS, sPatch + (size_t)i * DPATCH_BYTES);    // consumes the gathers issued one patch earlier
       publish(&p_full[i]);
       if (pk + 1 < npatch) {             // the next patch's gathers fly while the tensor core works on this one
-        const int nvl = (blk + 1) / ncb, ncbi = (blk + 1) % ncb;
+        const int nidx = (pk + 1) / ncb, ncbi = (pk + 1) % ncb, nvl = view_of(nidx);
         if (ncbi == 0) {                 // next patch opens a new view: its taps go to the other buffer
           producers_sync();              // everybody is done reading the buffer of the view before this one
-          compute_taps(nvl, sT + (nvl & 1) * DP_CELLS);
+          compute_taps(nvl, sT + (nidx & 1) * DP_CELLS);
           producers_sync();
         }
-        issue_gathers(nvl, ncbi, sT + (nvl & 1) * DP_CELLS);
+        issue_gathers(nvl, ncbi, sT + (nidx & 1) * DP_CELLS);
       }
     }
     } else {
@@ -1015,14 +1061,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
     uint4 g0[9], g1[9];   // two rounds of gathers in flight: the low-res map is L2-resident (103 MB bf16 on Wildtrack) and a patch's
                           // 180 cells share ~60 texel rows, so two rounds cover the latency; nine K blocks of MMA hide the rest
     if (npatch > 0) {
-      compute_taps_up(vlo, sU + (vlo & 1) * DP_CELLS);
+      compute_taps_up(view_of(0), sU);
       producers_sync();
-      issue(g0, vlo, 0, 0, sU + (vlo & 1) * DP_CELLS);
+      issue(g0, view_of(0), 0, 0, sU);
     }
     for (int pk = 0; pk < npatch; ++pk) {
-      const int blk = vlo * ncb + pk, vl = blk / ncb, cb = blk % ncb;
+      const int vidx = pk / ncb, cb = pk % ncb, vl = view_of(vidx);
       const int i = pk % NPATCH;
-      const ConvTapUp* taps = sU + (vl & 1) * DP_CELLS;
+      const ConvTapUp* taps = sU + (vidx & 1) * DP_CELLS;          // tap buffers alternate with the INDEX of the active view
       uint8_t* patch = sPatch + (size_t)i * DPATCH_BYTES;
       if (pk >= NPATCH) mbar_wait(&p_empty[i], ((pk / NPATCH) - 1) & 1);   // the nine K blocks that read this buffer are done
       issue(g1, vl, cb, 1, taps); blend(g0, 0, taps, patch);
@@ -1031,14 +1077,15 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
       issue(g0, vl, cb, 4, taps); blend(g1, 3, taps, patch);
       issue(g1, vl, cb, 5, taps); blend(g0, 4, taps, patch);
       const bool more = pk + 1 < npatch;
-      const int nvl = (blk + 1) / ncb, ncbi = (blk + 1) % ncb;
-      if (more && ncbi != 0) issue(g0, nvl, ncbi, 0, taps);               // same view: the next patch's first round flies already
+      const int nidx = (pk + 1) / ncb, ncbi = (pk + 1) % ncb;
+      if (more && ncbi != 0) issue(g0, vl, ncbi, 0, taps);                // same view: the next patch's first round flies already
       blend(g1, 5, taps, patch);
       publish(&p_full[i]);
       if (more && ncbi == 0) {            // next patch opens a new view: its taps go to the other buffer (last read one view ago,
-        compute_taps_up(nvl, sU + (nvl & 1) * DP_CELLS);   // and every thread has passed this view's barrier since)
+        const int nvl = view_of(nidx);    // and every thread has passed this view's barrier since)
+        compute_taps_up(nvl, sU + (nidx & 1) * DP_CELLS);
         producers_sync();
-        issue(g0, nvl, 0, 0, sU + (nvl & 1) * DP_CELLS);
+        issue(g0, nvl, 0, 0, sU + (nidx & 1) * DP_CELLS);
       }
     }
     }
@@ -1085,7 +1132,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) warp_conv1_direct_kernel(cons
 #pragma unroll 1
     for (int c0 = cbeg; c0 < cbeg + 256; c0 += 32) {
       float vv[32];
-      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, vv);
+      if (NK > 0) {
+        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, vv);
+      } else {   // no K block at all (every view skipped and no coord block here): the sum is zero, TMEM was never written
+#pragma unroll
+        for (int i = 0; i < 32; ++i) vv[i] = 0.f;
+      }
       if (partial) {
         float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)slot * 128 + er) * CV_N + c0);
 #pragma unroll
