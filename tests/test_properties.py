@@ -127,3 +127,42 @@ def test_composed_upsample_map_equals_the_two_step_matrix(seed, hl, wl, fy, fx, 
         mine[:, int(tex_of[0][r])].index_add_(0, cells[seg].long(), weights[seg].double())
     assert int(rp[-1]) == stt["nnz"]
     assert float((mine - A).abs().max()) <= 2e-6, float((mine - A).abs().max())
+
+
+@settings(max_examples=20, deadline=None, derandomize=True)
+@given(seed=st.integers(0, 10_000), hl=st.integers(1, 6), wl=st.integers(1, 7), fy=st.sampled_from([1, 2, 3, 2.5, 1.4]),
+       fx=st.sampled_from([1, 2, 3, 1.75]), hg=st.integers(2, 7), wg=st.integers(2, 9))
+def test_upsample_windows_equal_the_two_step_matrix(seed, hl, wl, fy, fx, hg, wg):
+    """The 3 x 3 low-res windows of the fused warp -> conv1 kernel (csrc/mvwarp_uptaps.h, run on the host by mvwarp_host_upsample_windows)
+    for ANY low-res size and up-sample ratio >= 1 (integer, non-integer, 1:1): as a dense matrix they equal
+    grid_sample(F.interpolate(., bilinear, align_corners=False)) in float64, every live slot addresses a texel of the map, and
+    they agree with the plan builder's composed CSR (weights composed in double) to fp32 rounding."""
+    import torch.nn.functional as F
+    hs, ws = max(hl, max(2, int(round(hl * fy)))), max(wl, max(2, int(round(wl * fx))))
+    spec = RigSpec("rnd", 1, img_shape=(1080, 1920), worldgrid_shape=(480, 1440), img_reduce=4, grid_reduce=4, seed=seed)
+    pm = synthetic_rig(spec)
+    T = P.src_norm_trans_dst_norm(pm, (hs, ws), (hg, wg))
+    g = P.host_grid(T, (hg, wg))
+    origin, mask, wx, wy = P.host_upsample_windows(T, (hl, wl), (hs, ws), (hg, wg))
+    nlow = hl * wl
+    eye = torch.eye(nlow, dtype=torch.float64).reshape(1, nlow, hl, wl)
+    up = F.interpolate(eye.float(), (hs, ws), mode="bilinear").double()
+    A = F.grid_sample(up, g[0][None].double(), mode="bilinear", padding_mode="zeros", align_corners=True)[0].reshape(nlow, hg * wg).T
+    mine = torch.zeros_like(A)
+    for cell in range(hg * wg):
+        y, x = divmod(cell, wg)
+        for j in range(3):
+            for i in range(3):
+                if (int(mask[0, y, x]) >> (j * 3 + i)) & 1:
+                    yy, xx = int(origin[0, y, x, 1]) + j, int(origin[0, y, x, 0]) + i
+                    assert 0 <= yy < hl and 0 <= xx < wl
+                    mine[cell, yy * wl + xx] += float(wy[0, y, x, j]) * float(wx[0, y, x, i])
+    assert float((mine - A).abs().max()) <= 2e-6, float((mine - A).abs().max())
+    # the composed CSR of the plan (the backward's weights) describes the same operator
+    stt, tex_of, row_ptr, cells, weights = P.host_csr(g, (hs, ws), with_map=True, lowres_hw=(hl, wl))
+    csr = torch.zeros_like(A)
+    rp = row_ptr[0].long()
+    for r in range(nlow):
+        seg = slice(int(rp[r]), int(rp[r + 1]))
+        csr[:, int(tex_of[0][r])].index_add_(0, cells[seg].long(), weights[seg].double())
+    assert float((mine - csr).abs().max()) <= 2e-6
